@@ -1,0 +1,157 @@
+/*
+ * qrag.h -- C ABI of libqrag.so, the B200 (sm_100a) reranking hot path behind
+ * the quantum-rag reranker API.
+ *
+ * The reference (jon-fox/quantum-rag) has no native/FFI interface on this path:
+ * its boundary is the Python class API of src/reranker (app.py:12-13 imports
+ * it).  These entry points are what a ctypes binding inside those classes
+ * calls; each one names the reference code it replaces.  INTEGRATION.md shows
+ * the binding.
+ *
+ * Conventions
+ *  - every function returns 0 (QRAG_OK) or a negative QRAG_ERR_* code;
+ *    qrag_last_error() returns a thread-local, human-readable message;
+ *  - all data pointers are DEVICE pointers owned by the caller (row-major,
+ *    densely packed unless a leading dimension is given); nothing is allocated
+ *    inside except where a workspace is passed in explicitly;
+ *  - `stream` is a cudaStream_t / CUstream passed as void*; kernels are
+ *    enqueued on it and the call returns without synchronising;
+ *  - there is NO CPU fallback: without a CUDA device the calls fail with
+ *    QRAG_ERR_CUDA.
+ *
+ * Ordering contract (bit-exact with the reference's `sorted(..., reverse=True)`,
+ * quantum.py:70-72 / classical.py:302-304): best score first, ties broken by
+ * the smaller input position / id.
+ */
+#ifndef QRAG_H_
+#define QRAG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QRAG_OK               0
+#define QRAG_ERR_INVALID     -1   /* bad argument (null pointer, size, alignment) */
+#define QRAG_ERR_CUDA        -2   /* CUDA runtime / driver error, or no device    */
+#define QRAG_ERR_UNSUPPORTED -3   /* shape outside what the kernels implement     */
+#define QRAG_ERR_WORKSPACE   -4   /* workspace too small                           */
+#define QRAG_ERR_INEXACT     -5   /* tensor-core search could not certify exactness (never silent) */
+
+#define QRAG_METRIC_IP     0      /* inner product, descending                     */
+#define QRAG_METRIC_L2     1      /* squared L2, ascending (faiss METRIC_L2 == 1)  */
+#define QRAG_METRIC_COSINE 2      /* cosine similarity, descending                 */
+
+#define QRAG_MAX_QUBITS      12   /* 2^12 complex128 amplitudes staged in shared memory */
+#define QRAG_MAX_SORT_LEN  4096   /* longest per-query list the in-kernel sorts accept   */
+
+const char* qrag_last_error(void);
+int         qrag_version(void);
+/* sm count / compute capability of the current device */
+int         qrag_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------
+ * (1a) Reference circuit, exact statevector, complex128.
+ * Replaces QuantumReranker._quantum_similarity + _vector_to_circuit
+ * (quantum.py:108-167) for a whole batch in one launch.
+ *
+ *   qvec [nq, vec_len], dvec [nd, vec_len]  fp64 embeddings (not necessarily
+ *   normalised; the kernel renormalises like quantum.py:149-151).
+ *   Document j is scored against query doc_query[j]; if doc_query is NULL the
+ *   layout is dense: query = j / docs_per_query.
+ *   layers == 1 is the reference circuit: RY(pi v_i), RZ(pi v_i / 2) on qubit
+ *   i < min(vec_len, n_qubits), then CX(i, i+1) for i = 0..n-2.  layers > 1
+ *   repeats the block, layer l reading v[(l*n + i) % vec_len].
+ *   out_scores[j] = |<psi_d|psi_q>|^2  (qiskit state_fidelity).
+ * ------------------------------------------------------------------------- */
+int qrag_sv_fidelity_angle(const double* qvec, int nq,
+                           const double* dvec, int64_t nd,
+                           const int32_t* doc_query, int64_t docs_per_query,
+                           int vec_len, int n_qubits, int layers,
+                           double* out_scores, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * (1b) Amplitude encoding (+ optional feature-map layers) on fp32 embeddings.
+ * The encoding quantum.py:156 names as the real scheme; builder-defined.
+ *
+ *   Q [nq, D] fp32.  Candidates are either dense  cand [nq, C, D]  (X, idx NULL)
+ *   or gathered rows  X[idx[q, c]]  of a corpus X [N, D] (cand NULL).
+ *   State = zero-pad(x) / |x| on n_qubits (needs D <= 2^n_qubits), followed by
+ *   `layers` blocks of the reference circuit with angles x^[(l*n+i) % D].
+ *   layers == 0: F = (q.d)^2 / (|q|^2 |d|^2), evaluated with fp64 accumulation.
+ *   out64 [nq, C] (required), out32 [nq, C] (optional, rounded from out64).
+ * ------------------------------------------------------------------------- */
+int qrag_amp_fidelity(const float* Q, int nq,
+                      const float* cand, const float* X, const int64_t* idx,
+                      int64_t C, int D, int n_qubits, int layers,
+                      double* out64, float* out32, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * (1c) Fused amplitude-encoded rerank: score + stable descending sort + top_k
+ * in one launch.  Replaces QuantumReranker.rerank (quantum.py:44-78) at tensor
+ * level.  C <= QRAG_MAX_SORT_LEN, 0 < top_k <= C, layers == 0.
+ *   out_scores [nq, top_k] fp64, out_pos [nq, top_k] position in the candidate
+ *   list, out_ids [nq, top_k] = idx[q, pos] (optional; needs idx).
+ * ------------------------------------------------------------------------- */
+int qrag_amp_rerank(const float* Q, int nq,
+                    const float* cand, const float* X, const int64_t* idx,
+                    int64_t C, int D, int n_qubits, int top_k,
+                    double* out_scores, int32_t* out_pos, int64_t* out_ids,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------
+ * (1d) Stable segmented sort: the `sorted(scored, key=score, reverse=True)[:top_k]`
+ * of quantum.py:70-76 / classical.py:302-308 for nq lists of C scores.
+ *   descending != 0: (score desc, position asc); else (score asc, position asc).
+ *   out_perm [nq, top_k] int32 positions; out_sorted [nq, top_k] optional.
+ * ------------------------------------------------------------------------- */
+int qrag_sort_scores_stable(const double* scores, int nq, int64_t C, int top_k, int descending,
+                            int32_t* out_perm, double* out_sorted, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * (1e) The reference's text-hash embedding (quantum.py:169-185) for a batch of
+ * seeds: legacy MT19937 seeded with sum(ord(c)), 2*n_qubits doubles in [0,1),
+ * L2-normalised.  out [n, 2*n_qubits] fp64.
+ * ------------------------------------------------------------------------- */
+int qrag_mock_embedding(const uint32_t* seeds, int64_t n, int n_qubits, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * (2) Brute-force search over a flat index (the IndexFlatL2 the ingest tool
+ * writes at store_in_faiss.py:99-109; `.search` is never called by the
+ * reference, semantics follow faiss's API).  Exact: fp32 inputs, fp64
+ * accumulation, order (best, id asc), ids = id_base + row, -1 padding if k > N.
+ *
+ *   qrag_search_topk       CUDA-core exact path (any nq; the checker for (2b)).
+ *   qrag_search_topk_tc    tcgen05 path: bf16 GEMM + fused threshold filter,
+ *                          exact fp64 rescore of the survivors, and a per-query
+ *                          certificate that no discarded row can belong to the
+ *                          top-k; returns QRAG_ERR_INEXACT if it cannot certify.
+ * ------------------------------------------------------------------------- */
+int qrag_search_workspace(int nq, int64_t N, int D, int k, size_t* bytes);
+int qrag_search_topk(const float* Q, int nq, const float* X, int64_t N, int D, int k,
+                     int metric, int64_t id_base,
+                     double* out_scores, int64_t* out_ids,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* bf16 shadow copy + squared norms of the corpus (built once per index). */
+int qrag_index_prepare(const float* X, int64_t N, int D,
+                       uint16_t* Xb /* [N, D] bf16 */, float* xnorm2 /* [N] */, void* stream);
+int qrag_search_tc_workspace(int nq, int64_t N, int D, int k, size_t* bytes);
+int qrag_search_topk_tc(const float* Q, int nq, const float* X, const uint16_t* Xb, const float* xnorm2,
+                        int64_t N, int D, int k, int metric, int64_t id_base,
+                        double* out_scores, int64_t* out_ids,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * (3) Merge of per-shard top-k lists after the all-gather: scores/ids
+ * [G, nq, k] -> [nq, k_out] in the canonical order; id < 0 is padding.
+ * ------------------------------------------------------------------------- */
+int qrag_topk_merge(const double* scores, const int64_t* ids, int G, int nq, int k, int k_out,
+                    int metric, double* out_scores, int64_t* out_ids, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QRAG_H_ */

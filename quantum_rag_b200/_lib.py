@@ -1,0 +1,116 @@
+"""Loader and in-tree builder for ``libqrag.so`` (the C ABI in ``include/qrag.h``).
+
+The library is plain CUDA runtime code with C linkage: no torch types cross the
+boundary, only device pointers, sizes and a stream handle.  There is no CPU
+fallback -- if the library or a CUDA device is missing the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint16, c_uint32, c_void_p
+from typing import Dict, List, Optional
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC_DIR = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libqrag.so")
+SOURCES = ["lib.cu", "amp_fidelity.cu", "sv_kernels.cu", "search_exact.cu", "search_tc.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+# name -> (restype, argtypes); mirrors include/qrag.h
+PROTOTYPES: Dict[str, tuple] = {
+    "qrag_last_error": (c_char_p, []),
+    "qrag_version": (c_int, []),
+    "qrag_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "qrag_sv_fidelity_angle": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
+                                       c_void_p, c_void_p]),
+    "qrag_amp_fidelity": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                                  c_void_p, c_void_p, c_void_p]),
+    "qrag_amp_rerank": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                                c_void_p, c_void_p, c_void_p, c_void_p]),
+    "qrag_sort_scores_stable": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "qrag_mock_embedding": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "qrag_search_workspace": (c_int, [c_int, c_int64, c_int, c_int, POINTER(c_size_t)]),
+    "qrag_search_topk": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_void_p,
+                                 c_void_p, c_void_p, c_size_t, c_void_p]),
+    "qrag_index_prepare": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "qrag_search_tc_workspace": (c_int, [c_int, c_int64, c_int, c_int, POINTER(c_size_t)]),
+    "qrag_search_topk_tc": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                                    c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "qrag_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                c_void_p]),
+}
+
+ERROR_NAMES = {-1: "QRAG_ERR_INVALID", -2: "QRAG_ERR_CUDA", -3: "QRAG_ERR_UNSUPPORTED", -4: "QRAG_ERR_WORKSPACE",
+               -5: "QRAG_ERR_INEXACT"}
+
+
+class QragError(RuntimeError):
+    """Raised for every non-zero return code of libqrag (no silent fallback)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libqrag.so")
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR)] + [
+        os.path.join(os.path.dirname(PKG_DIR), "include", "qrag.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into the in-tree ``libqrag.so``."""
+    if not force and not _stale():
+        return LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC_DIR, s) for s in SOURCES]
+    if verbose:
+        print(" ".join(cmd))
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    return LIB_PATH
+
+
+_LIB: Optional[ctypes.CDLL] = None
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the in-tree library and attach the prototypes.  Raises if it is missing."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(libqrag has no CPU fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def exported_symbols() -> List[str]:
+    return list(PROTOTYPES)
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise QragError(rc, load().qrag_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,230 @@
+"""Tensor-level API over libqrag (what the reranker classes and the benchmarks call).
+
+torch is used for device memory, streams and (elsewhere) torch.distributed only;
+every computation is a hand-written sm_100a kernel reached through the C ABI.
+Inputs on the host are copied to the current CUDA device; outputs stay on the
+device unless stated otherwise.  No CPU fallback: without CUDA these raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+
+METRIC_IP = 0
+METRIC_L2 = 1
+METRIC_COSINE = 2
+_METRICS = {"ip": METRIC_IP, "inner_product": METRIC_IP, "l2": METRIC_L2, "cosine": METRIC_COSINE,
+            "cos": METRIC_COSINE, METRIC_IP: METRIC_IP, METRIC_L2: METRIC_L2, METRIC_COSINE: METRIC_COSINE}
+
+MAX_QUBITS = 12
+MAX_SORT_LEN = 4096
+
+ArrayLike = Union[torch.Tensor, np.ndarray]
+
+
+def metric_id(metric) -> int:
+    try:
+        return _METRICS[metric.lower() if isinstance(metric, str) else metric]
+    except KeyError:
+        raise ValueError(f"unknown metric {metric!r}; expected one of ip, l2, cosine") from None
+
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("quantum_rag_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _dev(x: Optional[ArrayLike], dtype: torch.dtype) -> Optional[torch.Tensor]:
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(x)
+    return x.to(device=_device(), dtype=dtype, non_blocking=True).contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def qubits_for(dim: int) -> int:
+    """Smallest n with 2**n >= dim (amplitude encoding zero-pads to 2**n)."""
+    return max(1, int(dim - 1).bit_length())
+
+
+# ---------------------------------------------------------------------------
+def sv_fidelity_angle(qvec: ArrayLike, dvec: ArrayLike, doc_query: Optional[ArrayLike] = None,
+                      docs_per_query: Optional[int] = None, n_qubits: int = 4, layers: int = 1) -> torch.Tensor:
+    """Fidelity of the reference circuit for every document (quantum.py:108-167).
+
+    qvec [nq, L] / dvec [nd, L] fp64.  ``doc_query[j]`` names the query of document j;
+    without it the layout is dense (``docs_per_query`` consecutive documents per query,
+    default nd // nq).  Returns fp64 [nd] on the device.
+    """
+    q = _dev(qvec, torch.float64)
+    d = _dev(dvec, torch.float64)
+    if q.dim() == 1:
+        q = q[None, :]
+    if d.dim() == 1:
+        d = d[None, :]
+    if q.shape[1] != d.shape[1]:
+        raise ValueError("query and document vectors must have the same length")
+    nq, nd = q.shape[0], d.shape[0]
+    dq = _dev(doc_query, torch.int32) if doc_query is not None else None
+    if dq is not None and dq.numel() != nd:
+        raise ValueError("doc_query must have one entry per document")
+    if dq is None and docs_per_query is None:
+        docs_per_query = max(1, -(-nd // max(nq, 1)))
+    out = torch.empty(nd, dtype=torch.float64, device=q.device)
+    lib = _lib.load()
+    _lib.check(lib.qrag_sv_fidelity_angle(_ptr(q), nq, _ptr(d), nd, _ptr(dq), int(docs_per_query or 0),
+                                          q.shape[1], n_qubits, layers, _ptr(out), _stream()))
+    return out
+
+
+def _cand_args(Q, cand, X, idx, check_bounds=False):
+    Qd = _dev(Q, torch.float32)
+    if Qd.dim() != 2:
+        raise ValueError("Q must be [nq, D]")
+    nq, D = Qd.shape
+    if cand is not None:
+        if X is not None or idx is not None:
+            raise ValueError("pass either cand, or X together with idx")
+        c = _dev(cand, torch.float32)
+        if c.dim() != 3 or c.shape[0] != nq or c.shape[2] != D:
+            raise ValueError("cand must be [nq, C, D]")
+        return Qd, c, None, None, c.shape[1]
+    if X is None or idx is None:
+        raise ValueError("pass either cand, or X together with idx")
+    Xd = _dev(X, torch.float32)
+    i = _dev(idx, torch.int64)
+    if Xd.dim() != 2 or Xd.shape[1] != D or i.dim() != 2 or i.shape[0] != nq:
+        raise ValueError("X must be [N, D] and idx [nq, C]")
+    if check_bounds and i.numel() and (int(i.max()) >= Xd.shape[0]):     # device sync; opt-in
+        raise IndexError("idx out of range for X")
+    return Qd, None, Xd, i, i.shape[1]
+
+
+def amp_fidelity(Q: ArrayLike, cand: Optional[ArrayLike] = None, X: Optional[ArrayLike] = None,
+                 idx: Optional[ArrayLike] = None, n_qubits: Optional[int] = None, layers: int = 0,
+                 want_fp32: bool = False):
+    """Amplitude-encoded fidelity |<q^|d^>|^2 (optionally after ``layers`` feature-map blocks).
+
+    Returns fp64 [nq, C] (and the fp32 rounding if ``want_fp32``).
+    """
+    Qd, c, Xd, i, C = _cand_args(Q, cand, X, idx)
+    nq, D = Qd.shape
+    n = qubits_for(D) if n_qubits is None else n_qubits
+    out = torch.empty((nq, C), dtype=torch.float64, device=Qd.device)
+    out32 = torch.empty((nq, C), dtype=torch.float32, device=Qd.device) if want_fp32 else None
+    lib = _lib.load()
+    _lib.check(lib.qrag_amp_fidelity(_ptr(Qd), nq, _ptr(c), _ptr(Xd), _ptr(i), C, D, n, layers, _ptr(out),
+                                     _ptr(out32), _stream()))
+    return (out, out32) if want_fp32 else out
+
+
+def sort_scores(scores: ArrayLike, top_k: Optional[int] = None, descending: bool = True):
+    """Stable segmented sort: the order Python's ``sorted(key=score, reverse=True)`` gives.
+
+    scores [nq, C] fp64 -> (perm int32 [nq, k], sorted fp64 [nq, k]).
+    """
+    s = _dev(scores, torch.float64)
+    if s.dim() == 1:
+        s = s[None, :]
+    nq, C = s.shape
+    k = C if top_k is None else max(0, min(int(top_k), C))
+    perm = torch.empty((nq, k), dtype=torch.int32, device=s.device)
+    srt = torch.empty((nq, k), dtype=torch.float64, device=s.device)
+    lib = _lib.load()
+    _lib.check(lib.qrag_sort_scores_stable(_ptr(s), nq, C, k, 1 if descending else 0, _ptr(perm), _ptr(srt),
+                                           _stream()))
+    return perm, srt
+
+
+def quantum_rerank_batch(Q: ArrayLike, cand: Optional[ArrayLike] = None, X: Optional[ArrayLike] = None,
+                         idx: Optional[ArrayLike] = None, top_k: Optional[int] = None,
+                         n_qubits: Optional[int] = None, layers: int = 0):
+    """Tensor-level ``QuantumReranker.rerank`` with amplitude encoding.
+
+    Returns ``(scores fp64 [nq, k], pos int32 [nq, k], ids int64 [nq, k] | None)`` ordered
+    by (score desc, candidate position asc); ``ids`` is ``idx[q, pos]`` in the gathered form.
+    """
+    Qd, c, Xd, i, C = _cand_args(Q, cand, X, idx)
+    nq, D = Qd.shape
+    n = qubits_for(D) if n_qubits is None else n_qubits
+    k = C if top_k is None else max(0, min(int(top_k), C))
+    lib = _lib.load()
+    if layers == 0 and 1 <= C <= MAX_SORT_LEN and k >= 1:
+        scores = torch.empty((nq, k), dtype=torch.float64, device=Qd.device)
+        pos = torch.empty((nq, k), dtype=torch.int32, device=Qd.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=Qd.device) if i is not None else None
+        _lib.check(lib.qrag_amp_rerank(_ptr(Qd), nq, _ptr(c), _ptr(Xd), _ptr(i), C, D, n, k, _ptr(scores),
+                                       _ptr(pos), _ptr(ids), _stream()))
+        return scores, pos, ids
+    full = torch.empty((nq, C), dtype=torch.float64, device=Qd.device)
+    _lib.check(lib.qrag_amp_fidelity(_ptr(Qd), nq, _ptr(c), _ptr(Xd), _ptr(i), C, D, n, layers, _ptr(full), None,
+                                     _stream()))
+    pos, scores = sort_scores(full, k)
+    ids = torch.gather(i, 1, pos.long()) if i is not None else None
+    return scores, pos, ids
+
+
+def mock_embedding(seeds: ArrayLike, n_qubits: int = 4) -> torch.Tensor:
+    """quantum.py:169-185 for a batch of seeds (= sum(ord(c))), fp64 [n, 2*n_qubits]."""
+    host = np.asarray(seeds.cpu() if isinstance(seeds, torch.Tensor) else seeds, dtype=np.int64).reshape(-1)
+    if host.size and (host.min() < 0 or host.max() > 0xFFFFFFFF):
+        raise ValueError("Seed must be between 0 and 2**32 - 1")      # numpy's own error text
+    s32 = _dev(host.astype(np.uint32).view(np.int32), torch.int32)     # same 32 bits
+    out = torch.empty((host.size, 2 * n_qubits), dtype=torch.float64, device=s32.device)
+    lib = _lib.load()
+    _lib.check(lib.qrag_mock_embedding(_ptr(s32), host.size, n_qubits, _ptr(out), _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------
+def search_topk(Q: ArrayLike, X: ArrayLike, k: int, metric="l2", id_base: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exact brute-force top-k (CUDA-core fp64 path).  Returns (scores fp64 [nq,k], ids int64 [nq,k])."""
+    Qd = _dev(Q, torch.float32)
+    Xd = _dev(X, torch.float32)
+    if Qd.dim() == 1:
+        Qd = Qd[None, :]
+    if Xd.dim() != 2 or Qd.shape[1] != Xd.shape[1]:
+        raise ValueError("Q [nq, D] and X [N, D] must share D")
+    nq, D = Qd.shape
+    N = Xd.shape[0]
+    m = metric_id(metric)
+    lib = _lib.load()
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(lib.qrag_search_workspace(nq, N, D, k, ctypes.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=Qd.device)
+    scores = torch.empty((nq, k), dtype=torch.float64, device=Qd.device)
+    ids = torch.empty((nq, k), dtype=torch.int64, device=Qd.device)
+    _lib.check(lib.qrag_search_topk(_ptr(Qd), nq, _ptr(Xd), N, D, k, m, id_base, _ptr(scores), _ptr(ids), _ptr(ws),
+                                    nbytes.value, _stream()))
+    return scores, ids
+
+
+def topk_merge(scores: ArrayLike, ids: ArrayLike, k_out: int, metric="l2") -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge per-shard lists [G, nq, k] into [nq, k_out] (id < 0 = padding)."""
+    s = _dev(scores, torch.float64)
+    i = _dev(ids, torch.int64)
+    if s.dim() != 3 or s.shape != i.shape:
+        raise ValueError("scores and ids must both be [G, nq, k]")
+    G, nq, k = s.shape
+    out_s = torch.empty((nq, k_out), dtype=torch.float64, device=s.device)
+    out_i = torch.empty((nq, k_out), dtype=torch.int64, device=s.device)
+    lib = _lib.load()
+    _lib.check(lib.qrag_topk_merge(_ptr(s), _ptr(i), G, nq, k, k_out, metric_id(metric), _ptr(out_s), _ptr(out_i),
+                                   _stream()))
+    return out_s, out_i

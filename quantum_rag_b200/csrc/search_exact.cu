@@ -1,0 +1,376 @@
+// K3a / K5: exact brute-force search over a flat index and top-k list merging.
+//
+// The flat index is what the ingest tool builds with faiss.IndexFlatL2
+// (/root/reference/mcp/server/tools/store_in_faiss.py:99-109); the reference never
+// searches it, so the semantics are faiss's API contract made canonical:
+// fp32 inputs, fp64 accumulation, order (best score, smaller id), ids int64,
+// padding id -1 when k > N.
+//
+// Phase 1 (search_chunk_kernel): one CTA scores one chunk of rows against one query
+//   (query staged in shared memory as fp64, 4 rows in flight per warp, warp-shuffle
+//   reductions), sorts the chunk in shared memory and emits its best kk entries.
+// Phase 2 (merge_lists_kernel): groups of lists are sorted together in shared memory
+//   until one list per query remains.  The same kernel merges the per-shard lists
+//   after the NCCL all-gather (qrag_topk_merge).
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace qrag {
+
+constexpr int SE_THREADS = 256;
+constexpr int SE_WARPS = SE_THREADS / 32;
+constexpr int SE_ROWS = 4;
+constexpr int MERGE_MAX = 8192;          // pairs sorted at once by merge_lists_kernel (128 KB smem)
+constexpr long long TAG_PAD = 0x7fffffffffffffffLL;
+
+struct ChunkParams {
+    const float* Q; const float* X;
+    int nq; int64_t N; int D; int metric; int64_t id_base;
+    int chunk, kk, nchunks;
+    double* ws_key; long long* ws_tag;    // [nq, nchunks, kk]
+};
+
+__device__ __forceinline__ double reduce4pairs(const double (&v)[8], int lane) {
+    // same transposed butterfly as amp_fidelity.cu::reduce8
+    double w4[4], w2[2], w1;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double send = b4 ? v[i] : v[i + 4];
+        const double keep = b4 ? v[i + 4] : v[i];
+        w4[i] = keep + __shfl_xor_sync(FULL_MASK, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double send = b3 ? w4[i] : w4[i + 2];
+        const double keep = b3 ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(FULL_MASK, send, 8);
+    }
+    const double send = b2 ? w2[0] : w2[1];
+    const double keep = b2 ? w2[1] : w2[0];
+    w1 = keep + __shfl_xor_sync(FULL_MASK, send, 4);
+    w1 += __shfl_xor_sync(FULL_MASK, w1, 2);
+    w1 += __shfl_xor_sync(FULL_MASK, w1, 1);
+    return w1;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(SE_THREADS) search_chunk_kernel(const ChunkParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int D = p.D, Dpad = (D + 3) & ~3;
+    double* qs = reinterpret_cast<double*>(smem_raw);
+    double* red = qs + Dpad;
+    double* key = red + SE_WARPS;
+    long long* tag = reinterpret_cast<long long*>(key + p.chunk);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = blockIdx.x;
+    const int64_t row0 = (int64_t)c * p.chunk;
+    const int rows = (int)((p.N - row0) < p.chunk ? (p.N - row0) : p.chunk);
+    int P = 1;
+    while (P < rows) P <<= 1;
+    const bool l2 = p.metric == QRAG_METRIC_L2;
+
+    for (int q = blockIdx.y; q < p.nq; q += gridDim.y) {
+        const float* qrow = p.Q + (size_t)q * D;
+        double part = 0.0;
+        for (int i = tid; i < D; i += SE_THREADS) {
+            const double v = (double)qrow[i];
+            qs[i] = v;
+            part = fma(v, v, part);
+        }
+        part = warp_sum(part);
+        if (lane == 0) red[warp] = part;
+        __syncthreads();
+        double nq2 = 0.0;
+#pragma unroll
+        for (int w = 0; w < SE_WARPS; ++w) nq2 += red[w];
+
+        for (int r0 = warp * SE_ROWS; r0 < P; r0 += SE_WARPS * SE_ROWS) {
+            if (r0 >= rows) {                                   // padding slots of the sort
+                if (lane < SE_ROWS && r0 + lane < P) { key[r0 + lane] = pos_inf(); tag[r0 + lane] = TAG_PAD; }
+                continue;
+            }
+            const float* rp[SE_ROWS];
+#pragma unroll
+            for (int i = 0; i < SE_ROWS; ++i) {
+                const int r = (r0 + i < rows) ? r0 + i : r0;
+                rp[i] = p.X + (size_t)(row0 + r) * D;
+            }
+            double acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.0;
+            if (VEC) {
+                const int D4 = D >> 2;
+#pragma unroll 2
+                for (int j = lane; j < D4; j += 32) {
+                    float4 v[SE_ROWS];
+#pragma unroll
+                    for (int i = 0; i < SE_ROWS; ++i) v[i] = ldg_stream(reinterpret_cast<const float4*>(rp[i]) + j);
+                    const double2 qa = *reinterpret_cast<const double2*>(qs + 4 * j);
+                    const double2 qb = *reinterpret_cast<const double2*>(qs + 4 * j + 2);
+                    const double qv[4] = {qa.x, qa.y, qb.x, qb.y};
+#pragma unroll
+                    for (int i = 0; i < SE_ROWS; ++i) {
+                        const double d[4] = {(double)v[i].x, (double)v[i].y, (double)v[i].z, (double)v[i].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (l2) {
+                                const double t = qv[e] - d[e];
+                                acc[2 * i] = fma(t, t, acc[2 * i]);
+                            } else {
+                                acc[2 * i] = fma(qv[e], d[e], acc[2 * i]);
+                                acc[2 * i + 1] = fma(d[e], d[e], acc[2 * i + 1]);
+                            }
+                        }
+                    }
+                }
+            } else {
+                for (int j = lane; j < D; j += 32) {
+                    const double qv = qs[j];
+#pragma unroll
+                    for (int i = 0; i < SE_ROWS; ++i) {
+                        const double d = (double)__ldg(rp[i] + j);
+                        if (l2) {
+                            const double t = qv - d;
+                            acc[2 * i] = fma(t, t, acc[2 * i]);
+                        } else {
+                            acc[2 * i] = fma(qv, d, acc[2 * i]);
+                            acc[2 * i + 1] = fma(d, d, acc[2 * i + 1]);
+                        }
+                    }
+                }
+            }
+            const double tot = reduce4pairs(acc, lane);
+            const double nd2 = __shfl_down_sync(FULL_MASK, tot, 4);
+            if ((lane & 7) == 0) {
+                const int i = lane >> 3, r = r0 + i;
+                if (r < rows) {
+                    double kv;
+                    if (l2) kv = tot;
+                    else if (p.metric == QRAG_METRIC_IP) kv = -tot;
+                    else {
+                        const double den = nq2 * nd2;
+                        kv = den > 0.0 ? -(tot / sqrt(den)) : -0.0;
+                    }
+                    key[r] = kv;
+                    tag[r] = p.id_base + row0 + r;
+                } else if (r < P) {
+                    key[r] = pos_inf();
+                    tag[r] = TAG_PAD;
+                }
+            }
+        }
+        __syncthreads();
+        block_bitonic_sort<long long>(key, tag, P);
+        double* ok = p.ws_key + ((size_t)q * p.nchunks + c) * p.kk;
+        long long* ot = p.ws_tag + ((size_t)q * p.nchunks + c) * p.kk;
+        for (int i = tid; i < p.kk; i += SE_THREADS) {
+            const bool have = i < P;
+            ok[i] = have ? key[i] : pos_inf();
+            ot[i] = have ? tag[i] : TAG_PAD;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// merge: for each query, lists [l0, l0+g) of length kin -> one list of length kout
+// ---------------------------------------------------------------------------
+struct MergeParams {
+    const double* in_key; const long long* in_tag;      // element (l, q, i) at l*stride_l + q*stride_q + i
+    int64_t stride_l, stride_q;
+    int nlists, kin, group, nq;
+    int raw_scores;         // inputs are scores/ids (id < 0 = padding) rather than keys/tags
+    int metric;
+    double* out_key; long long* out_tag;                // [nq, ngroups, kout]
+    int kout;
+    int final_out;          // write scores/ids (convert keys back, pads -> id -1)
+    int pmax;               // capacity (pairs) of the shared-memory sort arrays
+};
+
+__global__ void __launch_bounds__(256) merge_lists_kernel(const MergeParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ngroups = (p.nlists + p.group - 1) / p.group;
+    const int gi = blockIdx.x;
+    const int l0 = gi * p.group;
+    const int nl = (p.nlists - l0) < p.group ? (p.nlists - l0) : p.group;
+    const int total = nl * p.kin;
+    int P = 1;
+    while (P < total) P <<= 1;
+    double* key = reinterpret_cast<double*>(smem_raw);
+    long long* tag = reinterpret_cast<long long*>(key + p.pmax);
+    const bool l2 = p.metric == QRAG_METRIC_L2;
+    for (int q = blockIdx.y; q < p.nq; q += gridDim.y) {
+        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+            double kv = pos_inf();
+            long long tv = TAG_PAD;
+            if (i < total) {
+                const int l = l0 + i / p.kin, e = i % p.kin;
+                const size_t off = (size_t)l * p.stride_l + (size_t)q * p.stride_q + e;
+                kv = p.in_key[off];
+                tv = p.in_tag[off];
+                if (p.raw_scores) {
+                    if (tv < 0) { kv = pos_inf(); tv = TAG_PAD; }
+                    else if (!l2) kv = -kv;
+                }
+            }
+            key[i] = kv;
+            tag[i] = tv;
+        }
+        __syncthreads();
+        block_bitonic_sort<long long>(key, tag, P);
+        double* ok = p.out_key + ((size_t)q * ngroups + gi) * p.kout;
+        long long* ot = p.out_tag + ((size_t)q * ngroups + gi) * p.kout;
+        for (int i = threadIdx.x; i < p.kout; i += blockDim.x) {
+            double kv = i < P ? key[i] : pos_inf();
+            long long tv = i < P ? tag[i] : TAG_PAD;
+            if (p.final_out) {
+                if (tv == TAG_PAD) { tv = -1; kv = l2 ? pos_inf() : -pos_inf(); }
+                else if (!l2) kv = -kv;
+            }
+            ok[i] = kv;
+            ot[i] = tv;
+        }
+        __syncthreads();
+    }
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int search_plan(int nq, int64_t N, int k, int* chunk, int* kk, int* nchunks, int* group) {
+    QRAG_REQUIRE(k >= 1 && k <= 2048, QRAG_ERR_UNSUPPORTED, "exact search supports 1 <= k <= 2048 (got %d)", k);
+    *chunk = k > 1024 ? 4096 : 2048;
+    *kk = k;
+    const int64_t nc = N > 0 ? ceil_div(N, *chunk) : 1;
+    QRAG_REQUIRE(nc <= 0x7fffffff, QRAG_ERR_UNSUPPORTED, "N too large");
+    *nchunks = (int)nc;
+    int g = MERGE_MAX / *kk;
+    if (g < 2) g = 2;
+    *group = g;
+    (void)nq;
+    return QRAG_OK;
+}
+
+static int launch_merge(const MergeParams& p, cudaStream_t st) {
+    const int ngroups = (p.nlists + p.group - 1) / p.group;
+    const size_t P = (size_t)next_pow2((int64_t)p.group * p.kin);
+    const size_t smem = P * (sizeof(double) + sizeof(long long));
+    QRAG_REQUIRE(smem <= (size_t)device_props().max_smem_optin, QRAG_ERR_UNSUPPORTED,
+                 "merge of %d lists x %d entries needs %zu B shared memory", p.group, p.kin, smem);
+    if (smem > 48 * 1024)
+        QRAG_CUDA_CHECK(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ngroups, p.nq < 65535 ? p.nq : 65535);
+    MergeParams pp = p;
+    pp.pmax = (int)P;
+    merge_lists_kernel<<<grid, 256, smem, st>>>(pp);
+    QRAG_LAUNCH_CHECK("merge_lists_kernel");
+    return QRAG_OK;
+}
+
+}  // namespace qrag
+
+using namespace qrag;
+
+extern "C" int qrag_search_workspace(int nq, int64_t N, int D, int k, size_t* bytes) {
+    QRAG_REQUIRE(bytes != nullptr, QRAG_ERR_INVALID, "bytes is null");
+    QRAG_REQUIRE(nq >= 0 && N >= 0 && D > 0, QRAG_ERR_INVALID, "bad sizes");
+    int chunk, kk, nchunks, group;
+    int rc = search_plan(nq, N, k, &chunk, &kk, &nchunks, &group);
+    if (rc) return rc;
+    const size_t lvl0 = (size_t)nq * nchunks * kk;
+    const size_t lvl1 = (size_t)nq * ceil_div(nchunks, group) * kk;
+    *bytes = align_up(lvl0 * 16, 256) + align_up(lvl1 * 16, 256) + 256;
+    return QRAG_OK;
+}
+
+extern "C" int qrag_search_topk(const float* Q, int nq, const float* X, int64_t N, int D, int k, int metric,
+                                int64_t id_base, double* out_scores, int64_t* out_ids, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+    QRAG_REQUIRE(Q && out_scores && out_ids, QRAG_ERR_INVALID, "null pointer argument");
+    QRAG_REQUIRE(X != nullptr || N == 0, QRAG_ERR_INVALID, "X is null");
+    QRAG_REQUIRE(nq >= 0 && N >= 0 && D > 0, QRAG_ERR_INVALID, "bad sizes nq=%d N=%lld D=%d", nq, (long long)N, D);
+    QRAG_REQUIRE(metric >= 0 && metric <= 2, QRAG_ERR_INVALID, "unknown metric %d", metric);
+    int chunk, kk, nchunks, group;
+    int rc = search_plan(nq, N, k, &chunk, &kk, &nchunks, &group);
+    if (rc) return rc;
+    if (nq == 0) return QRAG_OK;
+    size_t need;
+    rc = qrag_search_workspace(nq, N, D, k, &need);
+    if (rc) return rc;
+    QRAG_REQUIRE(workspace != nullptr && workspace_bytes >= need, QRAG_ERR_WORKSPACE,
+                 "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+    const DeviceProps& dp = device_props();
+    QRAG_REQUIRE(dp.ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    // carve workspace: two ping-pong levels of (key, tag)
+    const size_t lvl0 = (size_t)nq * nchunks * kk;
+    const size_t lvl1 = (size_t)nq * ceil_div(nchunks, group) * kk;
+    unsigned char* base = reinterpret_cast<unsigned char*>(align_up((size_t)workspace, 256));
+    double* key0 = reinterpret_cast<double*>(base);
+    long long* tag0 = reinterpret_cast<long long*>(key0 + lvl0);
+    unsigned char* base1 = base + align_up(lvl0 * 16, 256);
+    double* key1 = reinterpret_cast<double*>(base1);
+    long long* tag1 = reinterpret_cast<long long*>(key1 + lvl1);
+
+    ChunkParams cp{Q, X, nq, N, D, metric, id_base, chunk, kk, nchunks, key0, tag0};
+    const int Dpad = (D + 3) & ~3;
+    const size_t smem = (size_t)(Dpad + SE_WARPS) * sizeof(double) + (size_t)chunk * 16;
+    QRAG_REQUIRE(smem <= (size_t)dp.max_smem_optin, QRAG_ERR_UNSUPPORTED, "D=%d too large for the exact search", D);
+    const bool vec = (D % 4 == 0) && ((uintptr_t)X % 16 == 0);
+    dim3 grid(nchunks, nq < 65535 ? nq : 65535);
+    if (vec) {
+        if (smem > 48 * 1024)
+            QRAG_CUDA_CHECK(cudaFuncSetAttribute(search_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        search_chunk_kernel<true><<<grid, SE_THREADS, smem, st>>>(cp);
+    } else {
+        if (smem > 48 * 1024)
+            QRAG_CUDA_CHECK(cudaFuncSetAttribute(search_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        search_chunk_kernel<false><<<grid, SE_THREADS, smem, st>>>(cp);
+    }
+    QRAG_LAUNCH_CHECK("search_chunk_kernel");
+
+    // merge levels
+    const double* in_key = key0; const long long* in_tag = tag0;
+    double* out_key = key1; long long* out_tag = tag1;
+    int nlists = nchunks;
+    while (true) {
+        const int ngroups = (nlists + group - 1) / group;
+        MergeParams mp{};
+        mp.in_key = in_key; mp.in_tag = in_tag;
+        mp.stride_q = (int64_t)nlists * kk; mp.stride_l = kk;
+        mp.nlists = nlists; mp.kin = kk; mp.group = group; mp.nq = nq; mp.metric = metric;
+        mp.kout = kk;
+        if (ngroups == 1) {
+            mp.final_out = 1;
+            mp.out_key = out_scores; mp.out_tag = reinterpret_cast<long long*>(out_ids);
+            return launch_merge(mp, st);
+        }
+        mp.out_key = out_key; mp.out_tag = out_tag;
+        rc = launch_merge(mp, st);
+        if (rc) return rc;
+        // swap
+        const double* nk = out_key; const long long* nt = out_tag;
+        out_key = const_cast<double*>(in_key); out_tag = const_cast<long long*>(in_tag);
+        in_key = nk; in_tag = nt;
+        nlists = ngroups;
+    }
+}
+
+extern "C" int qrag_topk_merge(const double* scores, const int64_t* ids, int G, int nq, int k, int k_out, int metric,
+                               double* out_scores, int64_t* out_ids, void* stream) {
+    QRAG_REQUIRE(scores && ids && out_scores && out_ids, QRAG_ERR_INVALID, "null pointer argument");
+    QRAG_REQUIRE(G >= 1 && nq >= 0 && k >= 1 && k_out >= 1, QRAG_ERR_INVALID, "bad sizes G=%d nq=%d k=%d k_out=%d", G,
+                 nq, k, k_out);
+    QRAG_REQUIRE(metric >= 0 && metric <= 2, QRAG_ERR_INVALID, "unknown metric %d", metric);
+    QRAG_REQUIRE((int64_t)G * k <= MERGE_MAX, QRAG_ERR_UNSUPPORTED, "G*k=%lld exceeds %d", (long long)G * k, MERGE_MAX);
+    if (nq == 0) return QRAG_OK;
+    QRAG_REQUIRE(device_props().ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
+    MergeParams mp{};
+    mp.in_key = scores; mp.in_tag = reinterpret_cast<const long long*>(ids);
+    mp.stride_l = (int64_t)nq * k; mp.stride_q = k;
+    mp.nlists = G; mp.kin = k; mp.group = G; mp.nq = nq; mp.raw_scores = 1; mp.metric = metric;
+    mp.out_key = out_scores; mp.out_tag = reinterpret_cast<long long*>(out_ids);
+    mp.kout = k_out; mp.final_out = 1;
+    return launch_merge(mp, (cudaStream_t)stream);
+}

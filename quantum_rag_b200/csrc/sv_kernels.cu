@@ -1,0 +1,480 @@
+// K1: exact statevector simulation of the reference fidelity circuit, batched.
+//
+// Reference being replaced (one pair at a time, two Qiskit execute() calls per
+// pair): QuantumReranker._quantum_similarity / _vector_to_circuit,
+// /root/reference/src/reranker/quantum.py:108-167.
+//
+// Two kernels, both complex128:
+//  * sv_angle_warp_kernel  (n_qubits <= 5): 2^n lanes hold one amplitude each of the
+//    query state and of the document state; gates are __shfl_xor exchanges, the CX
+//    chain is a single arbitrary-lane shuffle, the overlap a shuffle butterfly.
+//  * sv_cta_kernel (n_qubits <= 12): the 2^n amplitudes are staged in shared memory
+//    (double2, XOR-swizzled so that all radix-8 passes are bank-conflict free); each
+//    pass applies up to three qubits' RY/RZ in registers; the pass that finishes a
+//    layer scatters through the CX-chain permutation into the other buffer.
+//    Also serves the amplitude-encoded feature map (fp32 rows, `layers` >= 1).
+//
+// Gate semantics (Qiskit, little-endian): RY(t) = [[c,-s],[s,c]], c = cos t/2;
+// RZ(p) = diag(e^{-ip/2}, e^{+ip/2}); CX(i,i+1) for i = 0..n-2 maps basis x to
+// y with y_k = x_0 ^ ... ^ x_k (prefix xor).
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace qrag {
+
+constexpr double kPi = 3.141592653589793238462643383279502884;
+
+struct GateParams { double c, s, cp, sp; };   // RY half-angle cos/sin, RZ half-angle cos/sin
+
+__device__ __forceinline__ GateParams gate_params(double a) {
+    // quantum.py:160-161: ry(a*pi), rz(a*pi/2)
+    GateParams g;
+    const double theta = a * kPi;
+    const double phi = a * kPi / 2.0;
+    sincos(theta / 2.0, &g.s, &g.c);
+    sincos(0.5 * phi, &g.sp, &g.cp);
+    return g;
+}
+
+// Apply RZ(phi) RY(theta) to the amplitude pair (a0 = bit clear, a1 = bit set).
+__device__ __forceinline__ void apply_gate(const GateParams& g, double2& a0, double2& a1) {
+    const double t0r = g.c * a0.x - g.s * a1.x, t0i = g.c * a0.y - g.s * a1.y;
+    const double t1r = g.s * a0.x + g.c * a1.x, t1i = g.s * a0.y + g.c * a1.y;
+    a0.x = t0r * g.cp + t0i * g.sp;  a0.y = t0i * g.cp - t0r * g.sp;   // * e^{-i phi/2}
+    a1.x = t1r * g.cp - t1i * g.sp;  a1.y = t1i * g.cp + t1r * g.sp;   // * e^{+i phi/2}
+}
+
+__device__ __forceinline__ int prefix_xor(int x) {
+    x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8;
+    return x;
+}
+
+// ===========================================================================
+// warp path, n <= 5
+// ===========================================================================
+struct SvAngleParams {
+    const double* qvec; const double* dvec; const int32_t* doc_query;
+    int64_t nd, docs_per_query; int nq, vec_len, n, layers;
+    double* out;
+};
+
+__device__ __forceinline__ double group_sum(double v, int n) {
+    for (int o = 1; o < (1 << n); o <<= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(128) sv_angle_warp_kernel(const SvAngleParams p) {
+    const int n = p.n, dim = 1 << n;
+    const int lane = threadIdx.x & 31;
+    const int a = lane & (dim - 1);                       // amplitude index owned by this lane
+    const int per_warp = 32 >> n;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t jraw = warp_global * per_warp + (lane >> n);
+    const bool live = jraw < p.nd;
+    const int64_t j = live ? jraw : p.nd - 1;             // clamp so every lane joins the shuffles
+    const int64_t qi = p.doc_query ? (int64_t)p.doc_query[j] : j / p.docs_per_query;
+    const double* v[2] = {p.qvec + qi * p.vec_len, p.dvec + j * p.vec_len};
+
+    double vnorm[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        double n2 = 0.0;
+        for (int i = 0; i < p.vec_len; ++i) n2 = fma(v[s][i], v[s][i], n2);
+        const double nrm = sqrt(n2);
+        vnorm[s] = nrm;                                    // divide by it like quantum.py:151
+    }
+    double2 st[2];
+    st[0] = make_double2(a == 0 ? 1.0 : 0.0, 0.0);
+    st[1] = st[0];
+    const int limit = p.vec_len < n ? p.vec_len : n;       // quantum.py:158
+    const int src_lane = (lane & ~(dim - 1)) | ((a ^ (a << 1)) & (dim - 1));   // CX chain: new[y] = old[y ^ (y<<1)]
+    for (int layer = 0; layer < p.layers; ++layer) {
+        for (int k = 0; k < n; ++k) {
+            if (p.layers == 1 && k >= limit) continue;
+            const int comp = (layer * n + k) % p.vec_len;
+            const bool hi = (a >> k) & 1;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const double x = v[s][comp];
+                const double an = vnorm[s] > 0.0 ? x / vnorm[s] : x;
+                const GateParams g = gate_params(an);
+                double2 other;
+                other.x = __shfl_xor_sync(FULL_MASK, st[s].x, 1 << k);
+                other.y = __shfl_xor_sync(FULL_MASK, st[s].y, 1 << k);
+                double2 a0 = hi ? other : st[s];
+                double2 a1 = hi ? st[s] : other;
+                apply_gate(g, a0, a1);
+                st[s] = hi ? a1 : a0;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            st[s].x = __shfl_sync(FULL_MASK, st[s].x, src_lane);
+            st[s].y = __shfl_sync(FULL_MASK, st[s].y, src_lane);
+        }
+    }
+    // <psi_d | psi_q> = sum conj(d) q
+    double re = st[1].x * st[0].x + st[1].y * st[0].y;
+    double im = st[1].x * st[0].y - st[1].y * st[0].x;
+    re = group_sum(re, n);
+    im = group_sum(im, n);
+    if (live && a == 0) p.out[j] = re * re + im * im;
+}
+
+// ===========================================================================
+// CTA path, n <= 12
+// ===========================================================================
+struct SvCtaParams {
+    // ANGLE mode
+    const double* qvec; const double* dvec; const int32_t* doc_query;
+    int64_t nd, docs_per_query; int vec_len;
+    // FMAP mode
+    const float* Q; const float* cand; const float* X; const int64_t* idx; int64_t C; int D;
+    int nq, n, layers;
+    int64_t docs_per_cta;
+    double* out; float* out32;
+};
+
+__device__ __forceinline__ int swz(int i) { return i ^ ((i >> 3) & 7); }
+
+// block-wide sum, result broadcast to all threads; `red` has >= 32 doubles.
+__device__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();                 // protect red[] from the previous use
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += red[w];
+    return t;
+}
+
+// One radix-8 pass over qubits [k0, k0+g).  If `nxt` is non-null this pass ends the
+// layer: amplitudes are scattered through the CX-chain permutation into `nxt`.
+__device__ void apply_pass(double2* __restrict__ cur, double2* __restrict__ nxt, const GateParams* __restrict__ par,
+                           int n, int k0, int g) {
+    const int dim = 1 << n, ngroups = dim >> g, na = 1 << g;
+    const int lowmask = (1 << k0) - 1;
+    for (int t = threadIdx.x; t < ngroups; t += blockDim.x) {
+        const int base = ((t & ~lowmask) << g) | (t & lowmask);
+        double2 a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < na) a[j] = cur[swz(base | (j << k0))];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            if (b < g) {
+                const GateParams gp = par[k0 + b];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (!((j >> b) & 1) && (j | (1 << b)) < na) apply_gate(gp, a[j], a[j | (1 << b)]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < na) {
+                const int x = base | (j << k0);
+                if (nxt) nxt[swz(prefix_xor(x) & (dim - 1))] = a[j];
+                else     cur[swz(x)] = a[j];
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Runs `layers` blocks on the state in buf[which]; returns the buffer index holding the result.
+__device__ int run_layers(double2* buf0, double2* buf1, int which, const GateParams* par, int n, int layers) {
+    for (int layer = 0; layer < layers; ++layer) {
+        double2* cur = which ? buf1 : buf0;
+        double2* nxt = which ? buf0 : buf1;
+        for (int k0 = 0; k0 < n; k0 += 3) {
+            const int g = (n - k0) < 3 ? (n - k0) : 3;
+            const bool last = (k0 + 3 >= n);
+            apply_pass(cur, last ? nxt : nullptr, par + layer * n, n, k0, g);
+        }
+        which ^= 1;
+    }
+    return which;
+}
+
+// Builds one state; returns buffer index.  MODE 0: angle vector (fp64), start |0..0>.
+// MODE 1: fp32 row, amplitude-encoded start, angles from the normalised row.
+template <int MODE>
+__device__ int build_state(const void* src, int len, double2* buf0, double2* buf1, GateParams* par, double* red,
+                           int n, int layers, bool* is_zero) {
+    const int dim = 1 << n;
+    double part = 0.0;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        const double x = MODE == 0 ? static_cast<const double*>(src)[i] : (double)static_cast<const float*>(src)[i];
+        part = fma(x, x, part);
+    }
+    const double nrm = sqrt(block_sum(part, red));
+    *is_zero = (nrm == 0.0);
+    const int limit = len < n ? len : n;
+    for (int t = threadIdx.x; t < layers * n; t += blockDim.x) {
+        const int k = t % n;
+        GateParams g;
+        if (len == 0 || (MODE == 0 && layers == 1 && k >= limit)) {
+            g.c = 1.0; g.s = 0.0; g.cp = 1.0; g.sp = 0.0;              // qubit not rotated (quantum.py:158)
+        } else {
+            const int comp = t % len;
+            const double x = MODE == 0 ? static_cast<const double*>(src)[comp]
+                                       : (double)static_cast<const float*>(src)[comp];
+            g = gate_params(nrm > 0.0 ? x / nrm : x);
+        }
+        par[t] = g;
+    }
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+        double2 v = make_double2(0.0, 0.0);
+        if (MODE == 0) {
+            if (i == 0) v.x = 1.0;
+        } else if (i < len && nrm > 0.0) {
+            v.x = (double)static_cast<const float*>(src)[i] / nrm;
+        }
+        buf0[swz(i)] = v;
+    }
+    __syncthreads();
+    return run_layers(buf0, buf1, 0, par, n, layers);
+}
+
+template <int MODE>
+__global__ void sv_cta_kernel(const SvCtaParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = p.n, dim = 1 << n;
+    double2* qstate = reinterpret_cast<double2*>(smem_raw);
+    double2* buf0 = qstate + dim;
+    double2* buf1 = buf0 + dim;
+    GateParams* par = reinterpret_cast<GateParams*>(buf1 + dim);
+    double* red = reinterpret_cast<double*>(par + p.layers * n);
+
+    const int64_t total = MODE == 0 ? p.nd : (int64_t)p.nq * p.C;
+    const int64_t per_query = MODE == 0 ? p.docs_per_query : p.C;
+    const int len = MODE == 0 ? p.vec_len : p.D;
+    const int64_t j0 = (int64_t)blockIdx.x * p.docs_per_cta;
+    int64_t j1 = j0 + p.docs_per_cta;
+    if (j1 > total) j1 = total;
+    int64_t cur_q = -1;
+    bool q_zero = false;
+
+    for (int64_t j = j0; j < j1; ++j) {
+        const int64_t qi = (MODE == 0 && p.doc_query) ? (int64_t)p.doc_query[j] : j / per_query;
+        if (qi != cur_q) {
+            const void* qsrc = MODE == 0 ? (const void*)(p.qvec + qi * len) : (const void*)(p.Q + qi * len);
+            bool z;
+            const int w = build_state<MODE>(qsrc, len, buf0, buf1, par, red, n, p.layers, &z);
+            const double2* res = w ? buf1 : buf0;
+            for (int i = threadIdx.x; i < dim; i += blockDim.x) qstate[i] = res[i];
+            __syncthreads();
+            q_zero = z;
+            cur_q = qi;
+        }
+        const void* dsrc;
+        bool missing = false;
+        if (MODE == 0) {
+            dsrc = p.dvec + j * len;
+        } else if (p.cand) {
+            dsrc = p.cand + (size_t)j * len;
+        } else {
+            const int64_t id = p.idx[j];
+            missing = id < 0;
+            dsrc = p.X + (size_t)(missing ? 0 : id) * len;
+        }
+        bool d_zero;
+        const int w = build_state<MODE>(dsrc, len, buf0, buf1, par, red, n, p.layers, &d_zero);
+        const double2* ds = w ? buf1 : buf0;
+        double re = 0.0, im = 0.0;
+        for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+            const double2 d = ds[i], q = qstate[i];
+            re += d.x * q.x + d.y * q.y;
+            im += d.x * q.y - d.y * q.x;
+        }
+        re = block_sum(re, red);
+        im = block_sum(im, red);
+        if (threadIdx.x == 0) {
+            double f = re * re + im * im;
+            if (MODE == 1 && (q_zero || d_zero)) f = 0.0;
+            if (missing) f = -pos_inf();
+            p.out[j] = f;
+            if (p.out32) p.out32[j] = (float)f;
+        }
+        __syncthreads();
+    }
+}
+
+static size_t sv_cta_smem(int n, int layers) {
+    return (size_t)3 * ((size_t)1 << n) * sizeof(double2) + (size_t)layers * n * sizeof(GateParams) + 32 * sizeof(double);
+}
+
+template <int MODE>
+static int launch_sv_cta(SvCtaParams p, cudaStream_t st) {
+    const DeviceProps& dp = device_props();
+    QRAG_REQUIRE(dp.ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
+    const size_t smem = sv_cta_smem(p.n, p.layers);
+    QRAG_REQUIRE(smem <= (size_t)dp.max_smem_optin, QRAG_ERR_UNSUPPORTED,
+                 "statevector kernel: n_qubits=%d layers=%d needs %zu B shared memory", p.n, p.layers, smem);
+    const int64_t total = MODE == 0 ? p.nd : (int64_t)p.nq * p.C;
+    int threads = (1 << p.n) / 8;
+    if (threads < 32) threads = 32;
+    if (threads > 256) threads = 256;
+    int64_t per_cta = total / ((int64_t)dp.sm_count * 16);
+    if (per_cta < 1) per_cta = 1;
+    if (per_cta > 32) per_cta = 32;
+    p.docs_per_cta = per_cta;
+    const int64_t grid = ceil_div(total, per_cta);
+    QRAG_REQUIRE(grid <= 0x7fffffff, QRAG_ERR_UNSUPPORTED, "too many documents for one launch");
+    auto kern = sv_cta_kernel<MODE>;
+    if (smem > 48 * 1024)
+        QRAG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, threads, smem, st>>>(p);
+    QRAG_LAUNCH_CHECK("sv_cta_kernel");
+    return QRAG_OK;
+}
+
+int fmap_fidelity(const float* Q, int nq, const float* cand, const float* X, const int64_t* idx, int64_t C, int D,
+                  int n_qubits, int layers, double* out64, float* out32, cudaStream_t st) {
+    QRAG_REQUIRE(n_qubits <= QRAG_MAX_QUBITS, QRAG_ERR_UNSUPPORTED, "feature map: n_qubits=%d > %d", n_qubits,
+                 QRAG_MAX_QUBITS);
+    QRAG_REQUIRE(layers <= 64, QRAG_ERR_UNSUPPORTED, "feature map: layers=%d > 64", layers);
+    SvCtaParams p{};
+    p.Q = Q; p.cand = cand; p.X = X; p.idx = idx; p.C = C; p.D = D; p.nq = nq; p.n = n_qubits; p.layers = layers;
+    p.out = out64; p.out32 = out32;
+    return launch_sv_cta<1>(p, st);
+}
+
+// ===========================================================================
+// Legacy MT19937 text-hash embedding, quantum.py:169-185
+// ===========================================================================
+__global__ void mock_embedding_kernel(const uint32_t* __restrict__ seeds, int64_t n, int n_qubits,
+                                      double* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int m = 4 * n_qubits;              // 32-bit outputs needed (two per double)
+    constexpr int MAXM = 4 * QRAG_MAX_QUBITS;
+    uint32_t lo[MAXM + 1];                   // mt[0 .. m]
+    uint32_t hi[MAXM];                       // mt[397 .. 397+m-1]
+    uint32_t x = seeds[t];                   // init_genrand (np.random.seed with a 32-bit int)
+    lo[0] = x;
+    for (int i = 1; i < 397 + m; ++i) {
+        x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)i;
+        if (i <= m) lo[i] = x;
+        if (i >= 397) hi[i - 397] = x;
+    }
+    double* o = out + t * (2 * n_qubits);
+    double n2 = 0.0;
+    uint32_t prev = 0;
+    for (int i = 0; i < m; ++i) {
+        uint32_t y = (lo[i] & 0x80000000u) | (lo[i + 1] & 0x7fffffffu);
+        y = hi[i] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        if (i & 1) {
+            const double d = ((double)(prev >> 5) * 67108864.0 + (double)(y >> 6)) / 9007199254740992.0;
+            o[i >> 1] = d;
+            n2 = fma(d, d, n2);
+        }
+        prev = y;
+    }
+    const double nrm = sqrt(n2);
+    for (int i = 0; i < 2 * n_qubits; ++i) o[i] = o[i] / nrm;
+}
+
+// ===========================================================================
+// Segmented stable sort (quantum.py:70-76, classical.py:302-308)
+// ===========================================================================
+__global__ void __launch_bounds__(256) sort_scores_kernel(const double* __restrict__ scores, int nq, int64_t C,
+                                                          int top_k, int descending, int32_t* __restrict__ out_perm,
+                                                          double* __restrict__ out_sorted) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int P = 1;
+    while (P < C) P <<= 1;
+    double* key = reinterpret_cast<double*>(smem_raw);
+    int* tag = reinterpret_cast<int*>(key + P);
+    for (int q = blockIdx.x; q < nq; q += gridDim.x) {
+        const double* s = scores + (size_t)q * C;
+        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+            const bool real = i < C;
+            const double v = real ? s[i] : 0.0;
+            key[i] = real ? (descending ? -v : v) : pos_inf();
+            tag[i] = real ? i : TagPad<int>::value();
+        }
+        __syncthreads();
+        block_bitonic_sort<int>(key, tag, P);
+        for (int i = threadIdx.x; i < top_k; i += blockDim.x) {
+            out_perm[(size_t)q * top_k + i] = tag[i];
+            if (out_sorted) out_sorted[(size_t)q * top_k + i] = descending ? -key[i] : key[i];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace qrag
+
+using namespace qrag;
+
+extern "C" int qrag_sv_fidelity_angle(const double* qvec, int nq, const double* dvec, int64_t nd,
+                                      const int32_t* doc_query, int64_t docs_per_query, int vec_len, int n_qubits,
+                                      int layers, double* out_scores, void* stream) {
+    QRAG_REQUIRE(qvec && dvec && out_scores, QRAG_ERR_INVALID, "null pointer argument");
+    QRAG_REQUIRE(nq >= 1 && nd >= 0, QRAG_ERR_INVALID, "bad sizes nq=%d nd=%lld", nq, (long long)nd);
+    QRAG_REQUIRE(vec_len >= 1, QRAG_ERR_INVALID, "vec_len=%d", vec_len);
+    QRAG_REQUIRE(n_qubits >= 1 && n_qubits <= QRAG_MAX_QUBITS, QRAG_ERR_UNSUPPORTED,
+                 "n_qubits=%d outside [1, %d]", n_qubits, QRAG_MAX_QUBITS);
+    QRAG_REQUIRE(layers >= 1 && layers <= 64, QRAG_ERR_INVALID, "layers=%d outside [1, 64]", layers);
+    QRAG_REQUIRE(doc_query != nullptr || docs_per_query >= 1, QRAG_ERR_INVALID,
+                 "need doc_query or docs_per_query >= 1");
+    QRAG_REQUIRE(doc_query != nullptr || nd <= (int64_t)nq * docs_per_query, QRAG_ERR_INVALID,
+                 "nd=%lld exceeds nq*docs_per_query", (long long)nd);
+    if (nd == 0) return QRAG_OK;
+    const DeviceProps& dp = device_props();
+    QRAG_REQUIRE(dp.ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_qubits <= 5) {
+        SvAngleParams p{qvec, dvec, doc_query, nd, docs_per_query, nq, vec_len, n_qubits, layers, out_scores};
+        const int per_warp = 32 >> n_qubits;
+        const int64_t warps = ceil_div(nd, per_warp);
+        const int64_t grid = ceil_div(warps, 4);
+        QRAG_REQUIRE(grid <= 0x7fffffff, QRAG_ERR_UNSUPPORTED, "too many documents for one launch");
+        sv_angle_warp_kernel<<<(unsigned)grid, 128, 0, st>>>(p);
+        QRAG_LAUNCH_CHECK("sv_angle_warp_kernel");
+        return QRAG_OK;
+    }
+    SvCtaParams p{};
+    p.qvec = qvec; p.dvec = dvec; p.doc_query = doc_query; p.nd = nd;
+    p.docs_per_query = doc_query ? 1 : docs_per_query;
+    p.vec_len = vec_len; p.nq = nq; p.n = n_qubits; p.layers = layers; p.out = out_scores;
+    return launch_sv_cta<0>(p, st);
+}
+
+extern "C" int qrag_mock_embedding(const uint32_t* seeds, int64_t n, int n_qubits, double* out, void* stream) {
+    QRAG_REQUIRE(seeds && out, QRAG_ERR_INVALID, "null pointer argument");
+    QRAG_REQUIRE(n >= 0, QRAG_ERR_INVALID, "n=%lld", (long long)n);
+    QRAG_REQUIRE(n_qubits >= 1 && n_qubits <= QRAG_MAX_QUBITS, QRAG_ERR_UNSUPPORTED,
+                 "n_qubits=%d outside [1, %d]", n_qubits, QRAG_MAX_QUBITS);
+    if (n == 0) return QRAG_OK;
+    QRAG_REQUIRE(device_props().ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
+    const int64_t grid = ceil_div(n, 128);
+    mock_embedding_kernel<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(seeds, n, n_qubits, out);
+    QRAG_LAUNCH_CHECK("mock_embedding_kernel");
+    return QRAG_OK;
+}
+
+extern "C" int qrag_sort_scores_stable(const double* scores, int nq, int64_t C, int top_k, int descending,
+                                       int32_t* out_perm, double* out_sorted, void* stream) {
+    QRAG_REQUIRE(scores && out_perm, QRAG_ERR_INVALID, "null pointer argument");
+    QRAG_REQUIRE(nq >= 0 && C >= 0, QRAG_ERR_INVALID, "bad sizes nq=%d C=%lld", nq, (long long)C);
+    QRAG_REQUIRE(C <= QRAG_MAX_SORT_LEN, QRAG_ERR_UNSUPPORTED, "C=%lld > %d", (long long)C, QRAG_MAX_SORT_LEN);
+    QRAG_REQUIRE(top_k >= 0 && top_k <= C, QRAG_ERR_INVALID, "top_k=%d outside [0, C=%lld]", top_k, (long long)C);
+    if (nq == 0 || C == 0 || top_k == 0) return QRAG_OK;
+    const DeviceProps& dp = device_props();
+    QRAG_REQUIRE(dp.ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
+    const size_t smem = (size_t)next_pow2(C) * (sizeof(double) + sizeof(int));
+    if (smem > 48 * 1024)
+        QRAG_CUDA_CHECK(cudaFuncSetAttribute(sort_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = nq < dp.sm_count * 32 ? nq : dp.sm_count * 32;
+    sort_scores_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(scores, nq, C, top_k, descending, out_perm,
+                                                                  out_sorted);
+    QRAG_LAUNCH_CHECK("sort_scores_kernel");
+    return QRAG_OK;
+}

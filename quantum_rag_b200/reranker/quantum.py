@@ -1,0 +1,128 @@
+"""Drop-in for ``src/reranker/quantum.py`` of jon-fox/quantum-rag, on a B200.
+
+``QuantumReranker(config).rerank(query, documents, top_k)`` keeps the reference's
+behaviour (quantum.py:44-78): empty input -> ``[]``; every document scored by the
+state fidelity of the reference circuit (or the constant 0.5 for any other
+``method``, quantum.py:134-136); stable descending sort; ``[:top_k]`` whenever
+``top_k is not None``.  What runs underneath is one batched launch of the
+hand-written statevector kernel instead of two Qiskit ``execute`` calls per
+document.
+
+Extensions (all default to the reference behaviour):
+    config["encoding"]  "angle" (reference circuit on the text-hash embedding) or
+                        "amplitude" (real embeddings from config["embedder"] /
+                        Document.metadata["embedding"], as quantum.py:93,99,156 anticipate)
+    config["layers"]    repetitions of the circuit block (1 = reference; amplitude: 0)
+    config["embedding_backend"]  "host" (NumPy legacy MT19937, bit-identical to the
+                        reference's np.random.seed stream) or "device" (MT19937 kernel)
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .classical import ClassicalReranker, Document
+
+# Kept for import compatibility (quantum.py:11-17).  The statevector engine is built
+# into libqrag, so the quantum path is always "available"; when the library or a CUDA
+# device is missing, rerank() raises instead of silently going classical.
+QISKIT_AVAILABLE = True
+
+
+def _char_sum(text: str) -> int:
+    """sum(ord(c)) -- quantum.py:182 (vectorised over the UTF-32 code units)."""
+    if not text:
+        return 0
+    return int(np.frombuffer(text.encode("utf-32-le", "surrogatepass"), dtype="<u4").sum(dtype=np.uint64))
+
+
+class QuantumReranker:
+    """Quantum-circuit similarity reranker backed by batched statevector kernels."""
+
+    def __init__(self, config: Dict[str, Any] = None):
+        self.config = config or {}
+        self.method = self.config.get("method", "state_fidelity")
+        self.n_qubits = self.config.get("n_qubits", 4)
+        self.encoding = self.config.get("encoding", "angle")
+        self.layers = self.config.get("layers", 1 if self.encoding == "angle" else 0)
+        self.embedding_backend = self.config.get("embedding_backend", "host")
+        self.embedder = self.config.get("embedder")
+        self.embedding_key = self.config.get("embedding_key", "embedding")
+        # the reference builds a ClassicalReranker from the same dict (quantum.py:37); kept as an attribute
+        self.classical_fallback = ClassicalReranker(config)
+        self._embedding_memo: Dict[int, np.ndarray] = {}
+
+    # ------------------------------------------------------------------ API
+    def rerank(self, query: str, documents: List[Document], top_k: int = None) -> List[Tuple[Document, float]]:
+        if not documents:                                           # quantum.py:63-64
+            return []
+        order, scores = self._rank(query, documents)
+        ranked = [(documents[i], s) for i, s in zip(order, scores)]
+        if top_k is not None:                                       # quantum.py:75-76 (plain slice)
+            ranked = ranked[:top_k]
+        return ranked
+
+    def _quantum_score_documents(self, query: str, documents: List[Document]) -> List[Tuple[Document, float]]:
+        """Scores in input order (quantum.py:80-106)."""
+        scores = self._scores(query, documents).cpu().tolist()
+        return list(zip(documents, scores))
+
+    # ------------------------------------------------------------ internals
+    def _mock_embedding(self, text: str) -> np.ndarray:
+        """quantum.py:169-185 without touching NumPy's global RNG; memoised by seed."""
+        seed = _char_sum(text)
+        vec = self._embedding_memo.get(seed)
+        if vec is None:
+            raw = np.random.RandomState(seed).random_sample(self.n_qubits * 2)
+            vec = raw / np.linalg.norm(raw)
+            self._embedding_memo[seed] = vec
+        return vec
+
+    def _text_embeddings(self, query: str, documents: List[Document]):
+        from .. import api
+        if self.embedding_backend == "device":
+            seeds = np.array([_char_sum(query)] + [_char_sum(d.content) for d in documents], dtype=np.int64)
+            emb = api.mock_embedding(seeds, self.n_qubits)
+            return emb[:1], emb[1:]
+        q = self._mock_embedding(query)[None, :]
+        d = np.stack([self._mock_embedding(doc.content) for doc in documents])
+        return q, d
+
+    def _real_embeddings(self, query: str, documents: List[Document]):
+        docs_e = [d.metadata.get(self.embedding_key) if isinstance(d.metadata, dict) else None for d in documents]
+        if any(e is None for e in docs_e):
+            if self.embedder is None:
+                raise ValueError("encoding='amplitude' needs config['embedder'] or Document.metadata['embedding']")
+            docs_e = self.embedder([d.content for d in documents])
+        q_e = self.config.get("query_embedding")
+        if q_e is None:
+            if self.embedder is None:
+                raise ValueError("encoding='amplitude' needs config['embedder'] or config['query_embedding']")
+            q_e = self.embedder([query])
+        q = np.asarray(q_e, dtype=np.float32).reshape(1, -1)
+        x = np.asarray(docs_e, dtype=np.float32).reshape(len(documents), -1)
+        return q, x
+
+    def _scores(self, query: str, documents: List[Document]):
+        """fp64 device tensor [len(documents)] of similarity scores, input order."""
+        import torch
+        from .. import api
+        if self.method != "state_fidelity":                         # quantum.py:134-136
+            return torch.full((len(documents),), 0.5, dtype=torch.float64, device=api._device())
+        if self.encoding == "angle":
+            q, d = self._text_embeddings(query, documents)
+            return api.sv_fidelity_angle(q, d, docs_per_query=len(documents), n_qubits=self.n_qubits,
+                                         layers=self.layers)
+        if self.encoding == "amplitude":
+            q, x = self._real_embeddings(query, documents)
+            n = max(self.n_qubits, api.qubits_for(q.shape[1])) if "n_qubits" not in self.config else self.n_qubits
+            return api.amp_fidelity(q, cand=x[None, :, :], n_qubits=n, layers=self.layers)[0]
+        raise ValueError(f"unknown encoding {self.encoding!r}")
+
+    def _rank(self, query: str, documents: List[Document]):
+        """(input positions, scores) in final order: score desc, input position asc."""
+        from .. import api
+        scores = self._scores(query, documents)
+        perm, srt = api.sort_scores(scores[None, :], None, descending=True)
+        return perm[0].cpu().tolist(), srt[0].cpu().tolist()

@@ -1,0 +1,138 @@
+"""Drop-in API surface and host-side logic, runnable without a GPU."""
+import random
+import string
+
+import numpy as np
+import pytest
+
+from oracle import reranker as orr
+from src.reranker.classical import ClassicalReranker, Document
+from src.reranker.controller import RerankerController
+from src.reranker.quantum import QISKIT_AVAILABLE, QuantumReranker
+from quantum_rag_b200.reranker.quantum import _char_sum
+
+
+def test_import_paths_match_reference_app():
+    # reference app.py:12-13
+    import src.reranker.classical as c
+    import src.reranker.controller as k
+    import src.reranker.quantum as q
+    assert k.RerankerController is RerankerController and c.Document is Document
+    assert q.QuantumReranker is QuantumReranker and isinstance(QISKIT_AVAILABLE, bool)
+
+
+def test_document_defaults():
+    d = Document("1", "text")
+    assert (d.id, d.content, d.source, d.metadata) == ("1", "text", None, {})
+    d2 = Document("2", "t", "src", {"a": 1})
+    assert d2.source == "src" and d2.metadata == {"a": 1}
+    assert Document("3", "t", metadata=None).metadata == {}
+
+
+def test_controller_defaults_and_keywords():
+    ctl = RerankerController()
+    assert ctl.complexity_threshold == 8
+    assert ctl.quantum_keywords == list(orr.QUANTUM_KEYWORDS)
+    assert isinstance(ctl.classical_reranker, ClassicalReranker)
+    assert isinstance(ctl.quantum_reranker, QuantumReranker)
+    assert ctl.quantum_reranker.n_qubits == 4 and ctl.quantum_reranker.method == "state_fidelity"
+    assert isinstance(ctl.quantum_reranker.classical_fallback, ClassicalReranker)
+    assert RerankerController({"complexity_threshold": 2}).complexity_threshold == 2
+
+
+@pytest.mark.parametrize("query,want", [
+    ("had a good time", "quantum"),            # "ad" is a substring of "had"
+    ("what is the weather", "classical"),
+    ("one two three four five six seven eight", "classical"),
+    ("one two three four five six seven eight nine", "quantum"),
+    ("SPONSOR segment", "quantum"),
+    ("", "classical"),
+    ("ideal", "quantum"),                       # contains "deal"
+])
+def test_select_reranker_examples(query, want):
+    assert RerankerController().select_reranker(query) == want
+    assert orr.select_reranker(query) == want
+
+
+def test_select_reranker_random_against_oracle():
+    rnd = random.Random(5)
+    vocab = ["ad", "bad", "offer", "coffee", "the", "a", "brand", "xyz", "Deal", "pro", "motion", "q"]
+    ctl = RerankerController({"complexity_threshold": 5})
+    for _ in range(300):
+        words = [rnd.choice(vocab) if rnd.random() < 0.5 else
+                 "".join(rnd.choice(string.ascii_letters) for _ in range(rnd.randint(1, 6)))
+                 for _ in range(rnd.randint(0, 9))]
+        q = rnd.choice([" ", "  ", "\t"]).join(words)
+        assert ctl.select_reranker(q) == orr.select_reranker(q, 5)
+    assert ctl.select_rerankers(["ad", "x"]) == ["quantum", "classical"]
+
+
+def test_classical_validation_returns_neutral_scores_in_order():
+    r = ClassicalReranker()
+    docs = [Document("a", "x"), Document("b", "y")]
+    assert r.rerank("", docs) == [(docs[0], 0.5), (docs[1], 0.5)]
+    assert r.rerank("   ", docs, top_k=1) == [(docs[0], 0.5), (docs[1], 0.5)]     # no slicing on this route
+    assert r.rerank("q", []) == []
+    bad = [Document("a", "x"), Document("b", "")]
+    assert r.rerank("q", bad) == [(bad[0], 0.5), (bad[1], 0.5)]
+    mixed = [Document("a", "x"), "not a document"]
+    assert r.rerank("q", mixed) == [(mixed[0], 0.5), (mixed[1], 0.5)]
+    assert not r._validate_inputs(123, docs)
+    assert orr.classical_inputs_valid("q", ["x", ""], [True, True]) is False
+
+
+def test_classical_cross_encoder_unavailable_is_the_reference_failure_route():
+    r = ClassicalReranker()
+    assert r.method == "cross-encoder" and r.batch_size == 32 and r.max_sequence_length == 512
+    if r.model_loaded:
+        pytest.skip("sentence_transformers present")
+    docs = [Document(str(i), f"doc {i}") for i in range(4)]
+    out = r.rerank("query", docs, top_k=2)
+    assert out == [(d, 0.5) for d in docs]           # classical.py:258-260: not sliced, original order
+
+
+def test_sanitize_and_cache_key():
+    r = ClassicalReranker({"max_sequence_length": 2})
+    assert r._sanitize_text("  a \n\t b  ") == "a b"
+    assert r._sanitize_text("x" * 100) == "x" * 8
+    assert r._sanitize_text(12) == "12"
+    assert r._get_cache_key("q", "d") == f"{hash('q')}_{hash('d')}"
+
+
+def test_embedding_method_requires_embeddings():
+    r = ClassicalReranker({"method": "cosine"})
+    with pytest.raises(ValueError):
+        r.rerank("q", [Document("a", "x")])
+
+
+def test_quantum_empty_and_config():
+    q = QuantumReranker()
+    assert q.rerank("anything", []) == []
+    assert q.rerank("anything", None) == []
+    q9 = QuantumReranker({"n_qubits": 9, "method": "other"})
+    assert q9.n_qubits == 9 and q9.method == "other"
+    assert QuantumReranker({"encoding": "amplitude"}).layers == 0
+
+
+def test_mock_embedding_matches_numpy_global_stream():
+    q = QuantumReranker()
+    for text in ["hello", "", "naïve café", "ab", "ba", "\U0001F600 emoji"]:
+        seed = sum(ord(c) for c in text)
+        assert _char_sum(text) == seed
+        np.random.seed(seed)                       # what the reference does (quantum.py:183)
+        v = np.random.random(8)
+        want = v / np.linalg.norm(v)
+        assert np.array_equal(q._mock_embedding(text), want)
+    state = np.random.get_state()[1].copy()
+    q._mock_embedding("does not touch the global generator")
+    assert np.array_equal(np.random.get_state()[1], state)
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        QuantumReranker().rerank("query", [Document("a", "x")])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        RerankerController().rerank("sponsor ad", [Document("a", "x")], reranker_type="quantum")
