@@ -228,3 +228,53 @@ def topk_merge(scores: ArrayLike, ids: ArrayLike, k_out: int, metric="l2") -> Tu
     _lib.check(lib.qrag_topk_merge(_ptr(s), _ptr(i), G, nq, k, k_out, metric_id(metric), _ptr(out_s), _ptr(out_i),
                                    _stream()))
     return out_s, out_i
+
+
+# ---------------------------------------------------------------------------
+class HostRerankPipeline:
+    """End-to-end amplitude-encoded rerank from HOST buffers (what a serving process calls).
+
+    Queries are processed in ``chunks`` slices on two CUDA streams so the host->device
+    copy of slice i+1 overlaps the kernel of slice i; results come back in pinned host
+    tensors.  ``__call__`` returns after everything has landed on the host.
+    """
+
+    def __init__(self, nq: int, C: int, D: int, top_k: int, n_qubits: Optional[int] = None, chunks: int = 4):
+        dev = _device()
+        self.nq, self.C, self.D, self.k = nq, C, D, top_k
+        self.n = qubits_for(D) if n_qubits is None else n_qubits
+        self.chunks = max(1, min(chunks, nq))
+        self.step = -(-nq // self.chunks)
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        self.dQ = [torch.empty((self.step, D), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.dC = [torch.empty((self.step, C, D), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.dS = torch.empty((nq, top_k), dtype=torch.float64, device=dev)
+        self.dP = torch.empty((nq, top_k), dtype=torch.int32, device=dev)
+        self.hS = torch.empty((nq, top_k), dtype=torch.float64).pin_memory()
+        self.hP = torch.empty((nq, top_k), dtype=torch.int32).pin_memory()
+        self.h2d_bytes = nq * D * 4 + nq * C * D * 4
+        self.d2h_bytes = nq * top_k * (8 + 4)
+        self.launches_per_call = self.chunks
+
+    def __call__(self, Q_host: torch.Tensor, cand_host: torch.Tensor):
+        lib = _lib.load()
+        cur = torch.cuda.current_stream()
+        for s in self.streams:
+            s.wait_stream(cur)
+        for c in range(self.chunks):
+            a, b = c * self.step, min(self.nq, (c + 1) * self.step)
+            if a >= b:
+                break
+            s = self.streams[c & 1]
+            dq, dc = self.dQ[c & 1][: b - a], self.dC[c & 1][: b - a]
+            with torch.cuda.stream(s):
+                dq.copy_(Q_host[a:b], non_blocking=True)
+                dc.copy_(cand_host[a:b], non_blocking=True)
+                _lib.check(lib.qrag_amp_rerank(_ptr(dq), b - a, _ptr(dc), None, None, self.C, self.D, self.n, self.k,
+                                               _ptr(self.dS[a:b]), _ptr(self.dP[a:b]), None,
+                                               ctypes.c_void_p(s.cuda_stream)))
+                self.hS[a:b].copy_(self.dS[a:b], non_blocking=True)
+                self.hP[a:b].copy_(self.dP[a:b], non_blocking=True)
+        for s in self.streams:
+            s.synchronize()
+        return self.hS, self.hP

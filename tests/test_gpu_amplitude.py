@@ -1,0 +1,137 @@
+"""K2 parity: amplitude-encoded fidelity, fused rerank and feature-map layers vs the oracle."""
+import numpy as np
+import pytest
+
+from oracle import quantum as oq
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-12
+
+
+@pytest.mark.parametrize("D", [3, 10, 128, 256, 384, 512, 1000, 1024, 1536])
+@pytest.mark.parametrize("C", [1, 5, 100])
+def test_amp_fidelity_dense(cuda, D, C):
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(D + C)
+    nq = 4
+    Q = rng.standard_normal((nq, D)).astype(np.float32)
+    cand = rng.standard_normal((nq, C, D)).astype(np.float32)
+    if C > 2:
+        cand[1, 2] = 0.0                              # zero candidate -> fidelity 0
+        cand[2, 1] = Q[2] * 3.0                       # parallel -> fidelity 1
+    got, got32 = api.amp_fidelity(Q, cand=cand, want_fp32=True)
+    want = oq.amplitude_fidelity_batch(Q, cand)
+    assert np.allclose(got.cpu().numpy(), want, rtol=REL, atol=1e-300)
+    assert np.allclose(got32.cpu().numpy(), want, rtol=1e-5, atol=1e-30)      # north_star: 1e-5 relative in fp32
+    if C > 2:
+        assert float(got[1, 2]) == 0.0
+        assert float(got[2, 1]) == pytest.approx(1.0, abs=1e-14)
+
+
+def test_amp_fidelity_gather_and_padding_ids(cuda):
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(11)
+    X = rng.standard_normal((300, 384)).astype(np.float32)
+    Q = rng.standard_normal((6, 384)).astype(np.float32)
+    idx = rng.randint(0, 300, size=(6, 33)).astype(np.int64)
+    idx[0, 4] = idx[0, 9]                             # same row twice -> exact tie
+    idx[3, 30:] = -1                                  # padding ids from a short search
+    got = api.amp_fidelity(Q, X=X, idx=idx).cpu().numpy()
+    want = oq.amplitude_fidelity_batch(Q, X[np.maximum(idx, 0)])
+    want[3, 30:] = -np.inf
+    assert np.allclose(got, want, rtol=REL)
+    assert got[0, 4] == got[0, 9]
+    scores, pos, ids = api.quantum_rerank_batch(Q, X=X, idx=idx, top_k=33)
+    order = oq.rank_rows(want)
+    assert np.array_equal(pos.cpu().numpy(), order)
+    assert np.array_equal(ids.cpu().numpy(), np.take_along_axis(idx, order, 1))
+    assert ids[3, -3:].cpu().tolist() == [-1, -1, -1]
+
+
+@pytest.mark.parametrize("C,top_k", [(1, 1), (20, 20), (100, 10), (128, 128), (129, 7), (1000, 10), (4096, 100)])
+def test_fused_rerank_order_is_bit_exact(cuda, C, top_k):
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(C)
+    nq, D = 5, 384
+    Q = rng.standard_normal((nq, D)).astype(np.float32)
+    cand = rng.standard_normal((nq, C, D)).astype(np.float32)
+    if C >= 20:
+        cand[:, 11] = cand[:, 3]                      # duplicate rows must tie and keep input order
+        cand[:, 17] = cand[:, 3]
+    scores, pos, ids = api.quantum_rerank_batch(Q, cand=cand, top_k=top_k, n_qubits=9)
+    assert ids is None
+    want = oq.amplitude_fidelity_batch(Q, cand)
+    order = oq.rank_rows(want, top_k)
+    assert np.array_equal(pos.cpu().numpy(), order)
+    assert np.allclose(scores.cpu().numpy(), np.take_along_axis(want, order, 1), rtol=REL)
+    # unfused path must agree bit for bit with the fused one
+    full = api.amp_fidelity(Q, cand=cand)
+    perm, srt = api.sort_scores(full, top_k)
+    assert np.array_equal(perm.cpu().numpy(), pos.cpu().numpy())
+    assert np.array_equal(srt.cpu().numpy(), scores.cpu().numpy())
+
+
+def test_golden_amplitude_and_feature_map(cuda, kat):
+    from quantum_rag_b200 import api
+    for c in kat["oracle"]["amplitude"]:
+        q = np.float32(c["q"])[None]
+        d = np.float32(c["d"])[None, None]
+        assert float(api.amp_fidelity(q, cand=d, n_qubits=c["n"])[0, 0]) == pytest.approx(c["f"], rel=REL)
+    for c in kat["oracle"]["feature_map"]:
+        q = np.float32(c["q"])[None]
+        d = np.float32(c["d"])[None, None]
+        got = float(api.amp_fidelity(q, cand=d, n_qubits=c["n"], layers=c["layers"])[0, 0])
+        assert got == pytest.approx(c["f"], rel=REL)
+
+
+@pytest.mark.parametrize("D,n,layers", [(5, 3, 1), (20, 5, 2), (48, 6, 3), (384, 9, 2), (1024, 10, 4)])
+def test_feature_map_layers_match_oracle(cuda, D, n, layers):
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(D)
+    nq, C = 2, 4
+    Q = rng.standard_normal((nq, D)).astype(np.float32)
+    cand = rng.standard_normal((nq, C, D)).astype(np.float32)
+    cand[1, 1] = 0.0
+    cand[0, 2] = Q[0]
+    got = api.amp_fidelity(Q, cand=cand, n_qubits=n, layers=layers).cpu().numpy()
+    want = np.array([[oq.feature_map_fidelity(Q[i], cand[i, j], n, layers) for j in range(C)] for i in range(nq)])
+    assert np.allclose(got, want, rtol=1e-11, atol=1e-15)
+    assert got[1, 1] == 0.0 and got[0, 2] == pytest.approx(1.0, abs=1e-12)
+
+
+def test_too_few_qubits_is_an_error(cuda):
+    from quantum_rag_b200 import api
+    from quantum_rag_b200._lib import QragError
+    with pytest.raises(QragError, match="does not fit"):
+        api.amp_fidelity(np.ones((1, 384), np.float32), cand=np.ones((1, 2, 384), np.float32), n_qubits=8)
+
+
+def test_config2_full_size_properties(cuda):
+    """BASELINE config 2 (1k queries x 100 candidates x 384-d, 9 qubits) through size-independent properties."""
+    import torch
+    from quantum_rag_b200 import api
+    g = torch.Generator(device="cpu").manual_seed(1234 + 2)
+    nq, C, D = 1000, 100, 384
+    Q = torch.nn.functional.normalize(torch.randn(nq, D, generator=g), dim=1).cuda()
+    cand = torch.nn.functional.normalize(torch.randn(nq, C, D, generator=g), dim=2).cuda()
+    cand[:, 42] = Q                                    # planted self-match: fidelity 1, must rank first
+    cand[:, 77] = cand[:, 5]                           # planted tie
+    scores, pos, _ = api.quantum_rerank_batch(Q, cand=cand, top_k=C, n_qubits=9)
+    full = api.amp_fidelity(Q, cand=cand)
+    assert torch.all(pos[:, 0] == 42) and torch.allclose(scores[:, 0], torch.ones(nq, dtype=torch.float64, device="cuda"),
+                                                         atol=1e-6)
+    assert torch.all(scores[:, :-1] >= scores[:, 1:])                          # sortedness
+    assert torch.equal(torch.gather(full, 1, pos.long()), scores)              # scores are the gathered fidelities
+    assert torch.all(torch.sort(pos.long(), dim=1).values == torch.arange(C, device="cuda"))   # a permutation
+    p5 = (pos == 5).nonzero()[:, 1]
+    p77 = (pos == 77).nonzero()[:, 1]
+    assert torch.all(p77 == p5 + 1)                                            # tie keeps input order, adjacent
+    assert float(full.min()) >= 0.0 and float(full.max()) <= 1.0 + 1e-12
+    # scale invariance of the state preparation
+    full2 = api.amp_fidelity(Q * 3.0, cand=cand * 0.5)
+    assert torch.allclose(full, full2, rtol=1e-6, atol=1e-12)
+    # sample rows against the oracle
+    rows = [0, 499, 999]
+    want = oq.amplitude_fidelity_batch(Q[rows].cpu().numpy(), cand[rows].cpu().numpy())
+    assert np.allclose(full[rows].cpu().numpy(), want, rtol=REL)

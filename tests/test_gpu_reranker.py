@@ -1,0 +1,114 @@
+"""Drop-in reranker classes on the GPU vs the restated reference (string API, config 1)."""
+import random
+import string
+
+import numpy as np
+import pytest
+
+from oracle import quantum as oq
+from oracle import reranker as orr
+from oracle import search as osr
+from src.reranker.classical import ClassicalReranker, Document
+from src.reranker.controller import RerankerController
+from src.reranker.quantum import QuantumReranker
+
+pytestmark = pytest.mark.gpu
+
+
+def _texts(rnd, n):
+    out = []
+    for _ in range(n):
+        out.append("".join(rnd.choice(string.ascii_letters + "  .,") for _ in range(rnd.randint(0, 60))))
+    return out
+
+
+@pytest.mark.parametrize("n_qubits", [4, 5, 9])
+@pytest.mark.parametrize("backend", ["host", "device"])
+def test_quantum_reranker_matches_reference_semantics(cuda, n_qubits, backend):
+    rnd = random.Random(n_qubits)
+    rr = QuantumReranker({"n_qubits": n_qubits, "embedding_backend": backend})
+    for trial in range(4):
+        texts = _texts(rnd, rnd.randint(1, 40)) + ["ab", "ba", "ab"]           # anagrams collide (same char sum)
+        rnd.shuffle(texts)
+        docs = [Document(str(i), t) for i, t in enumerate(texts)]
+        query = "".join(rnd.choice(string.ascii_lowercase + " ") for _ in range(30))
+        for top_k in (None, 0, 1, 5, len(docs) + 3, -2):
+            got = rr.rerank(query, docs, top_k)
+            want = oq.quantum_rerank_strings(query, texts, top_k, n_qubits)
+            assert [docs.index(d) for d, _ in got] == [i for i, _ in want], (trial, top_k)
+            assert all(d is docs[i] for (d, _), (i, _) in zip(got, want))      # identity preserved
+            assert np.allclose([s for _, s in got], [s for _, s in want], rtol=1e-12, atol=0)
+            assert all(isinstance(s, float) for _, s in got)
+
+
+def test_known_answers_through_the_class(cuda, kat):
+    s = kat["survey"]
+    rr = QuantumReranker()
+    docs = [Document(str(i), t) for i, (t, _, _) in enumerate(s["docs_n4"])]
+    scored = rr._quantum_score_documents(s["query"], docs)
+    assert np.allclose([v for _, v in scored], [f for _, _, f in s["docs_n4"]], rtol=1e-12)
+    ranked = rr.rerank(s["query"], docs)
+    ab = [d.content for d, _ in ranked if d.content in ("ab", "ba")]
+    assert ab == ["ab", "ba"]                          # exact tie keeps input order
+
+
+def test_other_method_gives_half_in_input_order(cuda):
+    rr = QuantumReranker({"method": "swap_test"})
+    docs = [Document(str(i), t) for i, t in enumerate(["x", "y", "z"])]
+    assert rr.rerank("q", docs, 2) == [(docs[0], 0.5), (docs[1], 0.5)]
+
+
+def test_controller_dispatch(cuda):
+    ctl = RerankerController()
+    docs = [Document(str(i), t) for i, t in enumerate(["alpha", "beta", "gamma delta"])]
+    out = ctl.rerank("find the sponsor read", docs, top_k=2)
+    assert out["reranker_used"] == "quantum" and out["query"] == "find the sponsor read"
+    want = oq.quantum_rerank_strings("find the sponsor read", [d.content for d in docs], 2)
+    assert [docs.index(d) for d, _ in out["documents"]] == [i for i, _ in want]
+    assert ctl.rerank("hello", docs)["reranker_used"] == orr.dispatch("auto", "hello") == "classical"
+    assert ctl.rerank("hello", docs, reranker_type="quantum")["reranker_used"] == "quantum"
+    assert ctl.rerank("sponsor", docs, reranker_type="weird")["reranker_used"] == "classical"
+
+
+def test_config1_fixture_search_then_quantum_rerank(cuda, piers):
+    """FAISS top-20 over the reference's index, then quantum rerank of those 20 (both encodings)."""
+    from quantum_rag_b200 import api
+    x, labels = piers["vectors"], [str(s) for s in piers["labels"]]
+    q = x[:1]
+    _, ids = api.search_topk(q, x, 20, "l2")
+    ids = ids[0].cpu().tolist()
+    assert ids == piers["top20_ids"][0].tolist()
+    # (i) reference circuit on Document(content=label), n_qubits = 4
+    docs = [Document(str(i), labels[i]) for i in ids]
+    got = QuantumReranker().rerank(labels[0], docs, top_k=10)
+    want = oq.quantum_rerank_strings(labels[0], [labels[i] for i in ids], 10)
+    assert [docs.index(d) for d, _ in got] == [i for i, _ in want]
+    # (ii) amplitude encoding of the stored 1536-d embeddings, 11 qubits
+    docs = [Document(str(i), labels[i], metadata={"embedding": x[i]}) for i in ids]
+    rr = QuantumReranker({"encoding": "amplitude", "n_qubits": 11, "query_embedding": q[0]})
+    got = rr.rerank(labels[0], docs)
+    f = oq.amplitude_fidelity_batch(q, x[ids][None])[0]
+    assert [docs.index(d) for d, _ in got] == oq.stable_rank(f.tolist())
+    assert np.allclose([s for _, s in got], sorted(f.tolist(), reverse=True), rtol=1e-12)
+
+
+@pytest.mark.parametrize("method,mid", [("cosine", osr.METRIC_COSINE), ("ip", osr.METRIC_IP), ("l2", osr.METRIC_L2)])
+def test_classical_embedding_methods(cuda, method, mid):
+    rng = np.random.RandomState(3)
+    emb = rng.standard_normal((30, 64)).astype(np.float32)
+    emb[7] = emb[2]
+    table = {f"doc {i}": emb[i] for i in range(30)}
+    qv = rng.standard_normal(64).astype(np.float32)
+    table["the query"] = qv
+    rr = ClassicalReranker({"method": method, "embedder": lambda texts: np.stack([table[t] for t in texts])})
+    docs = [Document(str(i), f"doc {i}") for i in range(30)]
+    got = rr.rerank("the query", docs, top_k=12)
+    s, i = osr.exact_search(qv[None], emb, 12, mid)
+    assert [docs.index(d) for d, _ in got] == i[0].tolist()
+    sign = -1.0 if method == "l2" else 1.0
+    assert np.allclose([v for _, v in got], sign * s[0], rtol=1e-12, atol=1e-13)
+    assert len(rr.rerank("the query", docs, top_k=0)) == 30                      # classical.py:307: only if > 0
+    # embeddings carried by the documents instead of an embedder
+    docs_m = [Document(str(i), f"doc {i}", metadata={"embedding": emb[i]}) for i in range(30)]
+    rr2 = ClassicalReranker({"method": method, "query_embedding": qv})
+    assert [docs_m.index(d) for d, _ in rr2.rerank("the query", docs_m, 12)] == i[0].tolist()
