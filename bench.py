@@ -223,7 +223,7 @@ def run_b200(args):
                                        api._ptr(scores), api._ptr(pos), None, api._stream()))
 
     # spin-up (clocks, caches, lazy module load), then the W warm-up steps asked for
-    t_end = time.perf_counter() + 0.2
+    t_end = time.perf_counter() + (0.0 if args.no_spinup else 0.2)
     i = 0
     while time.perf_counter() < t_end:
         step(i); i += 1
@@ -246,8 +246,8 @@ def run_b200(args):
     hQ, hC = make_batch(SEED + 1000 * rank + 999)
     hQ, hC = hQ.pin_memory(), hC.pin_memory()
     pipe = api.HostRerankPipeline(NQ, C, D, TOPK, NQUBITS, chunks=8)
-    e2e_steps = max(3, min(args.steps, 50))
-    for _ in range(3):
+    e2e_steps = 1 if args.no_e2e else max(3, min(args.steps, 50))
+    for _ in range(0 if args.no_e2e else 3):
         pipe(hQ, hC)
     barrier()
     t0 = time.perf_counter()
@@ -286,9 +286,9 @@ def run_b200(args):
                     "api": "quantum_rag_b200.api.HostRerankPipeline (pinned host tensors in/out, 8 slices on 2 streams)",
                     "reranked_queries_per_s": e2e_value / C},
             "gpu_launches": args.steps,
-            "kernels": ["qrag::amp_fidelity_kernel<3,true> (1 launch per step)"],
+            "kernels": ["qrag::amp_stream_kernel<3,4> (1 launch per step; TMA bulk-copy ring + fused rank)"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "amp_fidelity_kernel<3,true>",
+                         "traffic": None, "kernel": "amp_stream_kernel<3,4>",
                          "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_score": BYTES_PER_SCORE,
                          "peak_source": peak_src},
             "clocks": clocks,
@@ -329,6 +329,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: a single untimed-quality e2e pass")
+    ap.add_argument("--no-spinup", action="store_true", help="profiling runs: skip the 0.2 s clock spin-up")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -16,7 +16,7 @@ from typing import Dict, List, Optional
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libqrag.so")
-SOURCES = ["lib.cu", "amp_fidelity.cu", "sv_kernels.cu", "search_exact.cu", "search_tc.cu"]
+SOURCES = ["lib.cu", "amp_fidelity.cu", "amp_stream.cu", "sv_kernels.cu", "search_exact.cu", "search_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",

@@ -296,6 +296,9 @@ static int check_amp_common(const float* Q, int nq, const float* cand, const flo
 }
 
 namespace qrag {
+int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, const int64_t* idx, int64_t C, int D,
+                   bool fused, double* out64, float* out32, int top_k, double* out_scores, int32_t* out_pos,
+                   int64_t* out_ids, cudaStream_t st, bool* handled);                          // amp_stream.cu
 int fmap_fidelity(const float* Q, int nq, const float* cand, const float* X, const int64_t* idx, int64_t C, int D,
                   int n_qubits, int layers, double* out64, float* out32, cudaStream_t st);   // sv_kernels.cu
 }
@@ -310,7 +313,11 @@ extern "C" int qrag_amp_fidelity(const float* Q, int nq, const float* cand, cons
     if (nq == 0 || C == 0) return QRAG_OK;
     if (layers > 0)
         return fmap_fidelity(Q, nq, cand, X, idx, C, D, n_qubits, layers, out64, out32, (cudaStream_t)stream);
-    AmpParams p{};
+    bool handled = false;
+    rc = amp_stream_try(Q, nq, cand, X, idx, C, D, false, out64, out32, 0, nullptr, nullptr, nullptr,
+                        (cudaStream_t)stream, &handled);
+    if (rc || handled) return rc;
+    AmpParams p{};           // rows that are not 16-byte aligned: plain load kernel
     p.Q = Q; p.cand = cand; p.X = X; p.idx = idx; p.nq = nq; p.C = C; p.D = D;
     p.out64 = out64; p.out32 = out32;
     return amp_fidelity_plain(p, (cudaStream_t)stream);
@@ -327,6 +334,10 @@ extern "C" int qrag_amp_rerank(const float* Q, int nq, const float* cand, const 
     QRAG_REQUIRE(top_k >= 1 && top_k <= C, QRAG_ERR_INVALID, "top_k=%d outside [1, C=%lld]", top_k, (long long)C);
     QRAG_REQUIRE(out_ids == nullptr || idx != nullptr, QRAG_ERR_INVALID, "out_ids needs idx");
     if (nq == 0) return QRAG_OK;
+    bool handled = false;
+    rc = amp_stream_try(Q, nq, cand, X, idx, C, D, true, nullptr, nullptr, top_k, out_scores, out_pos, out_ids,
+                        (cudaStream_t)stream, &handled);
+    if (rc || handled) return rc;
     AmpParams p{};
     p.Q = Q; p.cand = cand; p.X = X; p.idx = idx; p.nq = nq; p.C = C; p.D = D;
     p.top_k = top_k; p.out_scores = out_scores; p.out_pos = out_pos; p.out_ids = out_ids;

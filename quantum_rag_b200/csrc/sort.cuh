@@ -6,6 +6,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace qrag {
 
@@ -15,10 +16,12 @@ __device__ __forceinline__ bool pair_less(double ka, Tag ta, double kb, Tag tb) 
 }
 
 // In-place bitonic sort of P (power of two) pairs held in shared memory.
-// Must be called by every thread of the block; ends with a barrier.
+// Called by `nt` threads (ids 0..nt-1) that synchronise on barrier `bar_id` (0 = the whole
+// block via __syncthreads, otherwise a named barrier over exactly those nt threads);
+// ends with a barrier.
 template <typename Tag>
-__device__ void block_bitonic_sort(double* __restrict__ key, Tag* __restrict__ tag, int P) {
-    const int tid = threadIdx.x, nt = blockDim.x;
+__device__ void block_bitonic_sort(double* __restrict__ key, Tag* __restrict__ tag, int P, int tid, int nt,
+                                   int bar_id) {
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = tid; t < (P >> 1); t += nt) {
@@ -33,9 +36,15 @@ __device__ void block_bitonic_sort(double* __restrict__ key, Tag* __restrict__ t
                     tag[lo] = th; tag[hi] = tl;
                 }
             }
-            __syncthreads();
+            if (bar_id == 0) __syncthreads();
+            else named_bar_sync(bar_id, nt);
         }
     }
+}
+
+template <typename Tag>
+__device__ __forceinline__ void block_bitonic_sort(double* __restrict__ key, Tag* __restrict__ tag, int P) {
+    block_bitonic_sort<Tag>(key, tag, P, threadIdx.x, blockDim.x, 0);
 }
 
 template <typename Tag> struct TagPad;
