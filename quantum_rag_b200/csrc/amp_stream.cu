@@ -1,7 +1,7 @@
 // K2 (streaming form): amplitude-encoded fidelity with the candidate rows staged through a
 // shared-memory ring by the TMA bulk-copy engine.
 //
-//   one persistent CTA per SM = 1 producer warp + 8 consumer warps
+//   one persistent CTA per SM = 1 producer warp + 16 consumer warps
 //   producer : cp.async.bulk (SASS UBLKCP) of whole tiles (R candidate rows, plus the
 //              query row when the query changes) into a ring of S stages, completion
 //              signalled on mbarriers; up to S*R*D*4 bytes (~200 KB) in flight per SM
@@ -22,7 +22,7 @@
 
 namespace qrag {
 
-constexpr int AS_CWARPS = 8;
+constexpr int AS_CWARPS = 16;
 constexpr int AS_CONSUMERS = AS_CWARPS * 32;
 constexpr int AS_THREADS = AS_CONSUMERS + 32;
 constexpr int AS_MAX_STAGES = 8;
@@ -38,28 +38,31 @@ struct AmpStreamParams {
     int top_k; double* out_scores; int32_t* out_pos; int64_t* out_ids;
 };
 
-__device__ __forceinline__ double reduce8s(const double (&v)[8], int lane) {
-    // identical to amp_fidelity.cu::reduce8 (kept in sync so that both kernels agree bit for bit)
-    double w4[4], w2[2], w1;
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+// Transposed butterfly over the 2*RB per-lane partials v[2*r] = q.d of row r, v[2*r+1] = |d|^2 of
+// row r.  Halving steps exchange half of the values with the partner lane, so 2*RB values
+// cost (2*RB - 1) + (5 - log2(2*RB)) double shuffles instead of 5 * 2 * RB.  Afterwards every lane
+// holds the complete sum of value index (lane >> (5 - log2(2*RB))).  Every value goes through the
+// same balanced tree (fp add commutes), so a row's result does not depend on its slot.
+template <int NV>
+__device__ __forceinline__ double reduce_vals(const double (&v)[NV], int lane) {
+    static_assert(NV == 2 || NV == 4 || NV == 8, "2, 4 or 8 values");
+    double w[NV];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const double send = b4 ? v[i] : v[i + 4];
-        const double keep = b4 ? v[i + 4] : v[i];
-        w4[i] = keep + __shfl_xor_sync(FULL_MASK, send, 16);
-    }
+    for (int i = 0; i < NV; ++i) w[i] = v[i];
+    int off = 16;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const double send = b3 ? w4[i] : w4[i + 2];
-        const double keep = b3 ? w4[i + 2] : w4[i];
-        w2[i] = keep + __shfl_xor_sync(FULL_MASK, send, 8);
+    for (int n = NV; n > 1; n >>= 1, off >>= 1) {
+        const bool up = lane & off;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const double send = up ? w[i] : w[i + n / 2];
+            const double keep = up ? w[i + n / 2] : w[i];
+            w[i] = keep + __shfl_xor_sync(FULL_MASK, send, off);
+        }
     }
-    const double send = b2 ? w2[0] : w2[1];
-    const double keep = b2 ? w2[1] : w2[0];
-    w1 = keep + __shfl_xor_sync(FULL_MASK, send, 4);
-    w1 += __shfl_xor_sync(FULL_MASK, w1, 2);
-    w1 += __shfl_xor_sync(FULL_MASK, w1, 1);
-    return w1;
+    double r = w[0];
+    for (; off > 0; off >>= 1) r += __shfl_xor_sync(FULL_MASK, r, off);
+    return r;
 }
 
 __device__ __forceinline__ void fma4s(const float4& d, const double* q, double& dot, double& nrm) {
@@ -72,7 +75,7 @@ __device__ __forceinline__ void fma4s(const float4& d, const double* q, double& 
 
 // NCHUNK > 0: D == 128 * NCHUNK, query cached in registers.  NCHUNK == 0: any D % 4 == 0,
 // query converted once per query into shared memory.  RB = rows per consumer warp per tile
-// (tile height R = 8 * RB).
+// (tile height R = 16 * RB).
 template <int NCHUNK, int RB>
 __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStreamParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -112,12 +115,11 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
 
     if (warp == AS_CWARPS) {
         // ------------------------------------------------------------------ producer
-        int it = 0;
-        for (int64_t g = g0; g < g1; ++g, ++it) {
-            const int s = it % S;
-            const uint32_t par = (uint32_t)(it / S) & 1u;
-            const int64_t q = g / tpq;
-            const int ti = (int)(g - q * tpq);
+        int64_t q = g0 / tpq;
+        int ti = (int)(g0 - q * tpq);
+        int s = 0;
+        uint32_t par = 0;
+        for (int64_t g = g0; g < g1; ++g) {
             const int r0 = ti * R;
             const int nr = (int)((C - r0) < R ? (C - r0) : R);
             const bool newq = (g == g0) || (ti == 0);
@@ -140,6 +142,8 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
                 __syncwarp();
                 if (id >= 0) bulk_g2s(st + (size_t)lane * row_bytes, p.X + (size_t)id * D, row_bytes, &full[s]);
             }
+            if (++ti == tpq) { ti = 0; ++q; }
+            if (++s == S) { s = 0; par ^= 1u; }
         }
         return;
     }
@@ -148,12 +152,11 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
     double qreg[NCHUNK > 0 ? NCHUNK * 4 : 1];
     double nq2 = 0.0;
     const int D4 = D >> 2;
-    int it = 0;
-    for (int64_t g = g0; g < g1; ++g, ++it) {
-        const int s = it % S;
-        const uint32_t par = (uint32_t)(it / S) & 1u;
-        const int64_t q = g / tpq;
-        const int ti = (int)(g - q * tpq);
+    int64_t q = g0 / tpq;
+    int ti = (int)(g0 - q * tpq);
+    int s = 0;
+    uint32_t par = 0;
+    for (int64_t g = g0; g < g1; ++g) {
         const int r0 = ti * R;
         const int nr = (int)((C - r0) < R ? (C - r0) : R);
         const bool newq = (g == g0) || (ti == 0);
@@ -181,15 +184,15 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
             nq2 = warp_sum(part);
         }
 
-        // rows of this tile owned by the warp: slot i -> row (warp + ti) % 8 + 8 i
-        const int rbase = (warp + ti) & 7;
-        double acc[8];
+        // rows of this tile owned by the warp: slot i -> row (warp + ti) % 16 + 16 i
+        const int rbase = (warp + ti) & (AS_CWARPS - 1);
+        double acc[2 * RB];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.0;
+        for (int i = 0; i < 2 * RB; ++i) acc[i] = 0.0;
         const float4* rp[RB];
 #pragma unroll
         for (int i = 0; i < RB; ++i) {
-            const int rr = rbase + 8 * i;
+            const int rr = rbase + AS_CWARPS * i;
             rp[i] = reinterpret_cast<const float4*>(st + (size_t)(rr < nr ? rr : 0) * row_bytes);
         }
         if (NCHUNK > 0) {
@@ -206,16 +209,18 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
                 for (int i = 0; i < RB; ++i) fma4s(rp[i][j], qv, acc[2 * i], acc[2 * i + 1]);
             }
         }
-        const double tot = reduce8s(acc, lane);
-        const double nd2 = __shfl_down_sync(FULL_MASK, tot, 4);
+        // lane L ends with value index L / LPV: even index = q.d, odd = |d|^2 of row slot index / 2
+        constexpr int LPV = 32 / (2 * RB);
+        const double tot = reduce_vals<2 * RB>(acc, lane);
+        const double nd2 = __shfl_down_sync(FULL_MASK, tot, LPV);
         // all shared-memory reads of this stage are complete (their values were consumed above)
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
 
-        if ((lane & 7) == 0) {
-            const int i = lane >> 3;
-            const int rr = rbase + 8 * i;
-            if (i < RB && rr < nr) {
+        if ((lane & (2 * LPV - 1)) == 0) {
+            const int i = lane / (2 * LPV);
+            const int rr = rbase + AS_CWARPS * i;
+            if (rr < nr) {
                 const int64_t c = r0 + rr;
                 const double den = nq2 * nd2;
                 double f = den > 0.0 ? (tot * tot) / den : 0.0;
@@ -266,6 +271,8 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
             }
             named_bar_sync(AS_BAR, AS_CONSUMERS);              // sc[] is free for the next query
         }
+        if (++ti == tpq) { ti = 0; ++q; }
+        if (++s == S) { s = 0; par ^= 1u; }
     }
 }
 
@@ -293,10 +300,10 @@ int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, co
     p.Q = Q; p.cand = cand; p.X = X; p.idx = idx; p.nq = nq; p.C = C; p.D = D;
     p.out64 = out64; p.out32 = out32; p.top_k = top_k; p.out_scores = out_scores; p.out_pos = out_pos;
     p.out_ids = out_ids; p.fused = fused ? 1 : 0;
-    // tile height: 32 rows while a stage stays <= 64 KB, else 16, else 8
-    int rb = 4;
-    while (rb > 1 && (size_t)(8 * rb + 1) * D * 4 > 64 * 1024) rb >>= 1;
-    p.R = 8 * rb;
+    // tile height: 32 rows while a stage stays <= 64 KB, else 16
+    int rb = 2;
+    while (rb > 1 && (size_t)(AS_CWARPS * rb + 1) * D * 4 > 64 * 1024) rb >>= 1;
+    p.R = AS_CWARPS * rb;
     p.tpq = (int)ceil_div(C, p.R);
     p.stage_bytes = ((size_t)(p.R + 1) * D * 4 + 127) / 128 * 128;
     const bool nchunk_path = (D == 128 || D == 256 || D == 384 || D == 512);
@@ -319,17 +326,14 @@ int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, co
     *handled = true;
     if (nchunk_path) {
         switch (D / 128) {
-            case 1: return launch_stream<1, 4>(p, smem_bytes, grid, st);
-            case 2: return launch_stream<2, 4>(p, smem_bytes, grid, st);
-            case 3: return launch_stream<3, 4>(p, smem_bytes, grid, st);
-            default: return launch_stream<4, 4>(p, smem_bytes, grid, st);
+            case 1: return launch_stream<1, 2>(p, smem_bytes, grid, st);
+            case 2: return launch_stream<2, 2>(p, smem_bytes, grid, st);
+            case 3: return launch_stream<3, 2>(p, smem_bytes, grid, st);
+            default: return launch_stream<4, 2>(p, smem_bytes, grid, st);
         }
     }
-    switch (rb) {
-        case 4: return launch_stream<0, 4>(p, smem_bytes, grid, st);
-        case 2: return launch_stream<0, 2>(p, smem_bytes, grid, st);
-        default: return launch_stream<0, 1>(p, smem_bytes, grid, st);
-    }
+    if (rb == 2) return launch_stream<0, 2>(p, smem_bytes, grid, st);
+    return launch_stream<0, 1>(p, smem_bytes, grid, st);
 }
 
 }  // namespace qrag
