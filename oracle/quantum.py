@@ -228,8 +228,10 @@ def amplitude_fidelity_batch(Q: np.ndarray, cand: np.ndarray) -> np.ndarray:
     nq2 = np.einsum("qd,qd->q", Q64, Q64)
     for i in range(cand.shape[0]):
         c64 = cand[i].astype(np.float64)
-        qd = c64 @ Q64[i]
-        nd2 = np.einsum("cd,cd->c", c64, c64)
+        # row-wise pairwise sums (not a BLAS gemv): every row is reduced in the same order, so
+        # duplicate candidates get bit-identical scores and tie exactly, as they do in the reference
+        qd = (c64 * Q64[i]).sum(axis=1)
+        nd2 = (c64 * c64).sum(axis=1)
         den = nq2[i] * nd2
         with np.errstate(divide="ignore", invalid="ignore"):
             f = np.where(den > 0, qd * qd / np.where(den > 0, den, 1.0), 0.0)

@@ -1,48 +1,72 @@
 // K2 (streaming form): amplitude-encoded fidelity with the candidate rows staged through a
-// shared-memory ring by the TMA bulk-copy engine.
+// shared-memory ring by the TMA bulk-copy engine, and the per-query ranking taken off the
+// streaming path.
 //
-//   one persistent CTA per SM = 1 producer warp + 16 consumer warps
-//   producer : cp.async.bulk (SASS UBLKCP) of whole tiles (R candidate rows, plus the
-//              query row when the query changes) into a ring of S stages, completion
-//              signalled on mbarriers; up to S*R*D*4 bytes (~200 KB) in flight per SM
-//   consumers: wait on the stage's "full" barrier, read rows with conflict-free LDS.128,
-//              accumulate q.d and |d|^2 in fp64 against the query state cached in
-//              registers, transposed warp-shuffle reduction, release the stage
-//   fused    : when a query's last tile is done its C scores sit in shared memory and are
-//              ranked there ((score desc, position asc), quantum.py:70-76); only top_k
-//              (score, position) pairs leave the SM.
+//   one persistent CTA per SM, warp-specialised, no CTA-wide barrier after start-up:
+//   producer  (1 warp) : cp.async.bulk (SASS UBLKCP) of tiles of RB candidate rows into a ring
+//                        of S stages (~200 KB in flight per SM) and of each query row into one
+//                        of QS query slots; completion lands on mbarriers as transaction bytes
+//   converter (1 warp) : turns a query slot into fp64 once (and |q|^2), so that the consumers
+//                        never convert the query
+//   consumers (16 warps): warp w owns tiles w, w+16, ... of the CTA's tile sequence: waits for
+//                        its stage, reads the RB rows with conflict-free LDS.128, accumulates
+//                        q.d and |d|^2 in fp64 (transposed warp-shuffle reduction), releases the
+//                        stage, and drops (q.d, |q|^2 |d|^2) into the query's score buffer
+//   rankers   (2 warps) : fused mode only.  When all tiles of a query have reported, compute
+//                        F = (q.d)^2 / (|q|^2 |d|^2) and rank the query's C scores in shared
+//                        memory ((score desc, position asc), quantum.py:70-76); only top_k
+//                        (score, position) pairs leave the SM.  Score buffers are double-buffered,
+//                        so ranking query i overlaps streaming query i+1.
 //
 // HBM traffic = every candidate row exactly once; nothing else of size touches DRAM.
-// Per-row numerics follow amp_fidelity.cu (same lane->element map and reduction tree); every
-// score of a query is computed the same way in fused and unfused mode, so the two agree bit
-// for bit and duplicate candidates tie exactly.
+// Every score is computed by the same instruction sequence (same lane->element map, same
+// reduction tree) whichever slot its row sits in, so duplicate candidates tie exactly and the
+// fused and unfused forms agree bit for bit.
 #include "common.cuh"
 #include "sort.cuh"
 #include "tma.cuh"
 
+#include <stdlib.h>
+
 namespace qrag {
 
 constexpr int AS_CWARPS = 16;
-constexpr int AS_CONSUMERS = AS_CWARPS * 32;
-constexpr int AS_THREADS = AS_CONSUMERS + 32;
-constexpr int AS_MAX_STAGES = 8;
-constexpr int AS_BAR = 1;                 // named barrier id for the consumer warps
-constexpr int AS_RANK_SORT_MAX = 128;
+constexpr int AS_RWARPS = 2;
+constexpr int AS_RTHREADS = AS_RWARPS * 32;
+constexpr int AS_WARP_RANK = AS_CWARPS;                  // first ranker warp
+constexpr int AS_WARP_CONV = AS_CWARPS + AS_RWARPS;
+constexpr int AS_WARP_PROD = AS_WARP_CONV + 1;
+constexpr int AS_THREADS = (AS_WARP_PROD + 1) * 32;      // 640
+constexpr int AS_MAX_STAGES = 64;
+constexpr int AS_MAX_QSLOTS = 8;
+constexpr int AS_MAX_SBUFS = 8;
+constexpr int AS_BAR_RANK = 1;                           // named barrier of the ranker warps
+constexpr int AS_RANK_COUNT_MAX = 2 * AS_RTHREADS;       // rank-by-counting up to this many candidates
+constexpr int AS_BAR_BYTES = (2 * AS_MAX_STAGES + 2 * AS_MAX_QSLOTS + 2 * AS_MAX_SBUFS) * 8;   // 1280
+constexpr int AS_HDR_BYTES = 1280;
 
 struct AmpStreamParams {
     const float* Q; const float* cand; const float* X; const int64_t* idx;
     int nq; int64_t C; int D;
-    int R, tpq, stages, fused;
-    size_t stage_bytes;
+    int G;              // consumer warps per team; a team drains one tile of R = G * RB rows together
+    int R;              // rows per tile (one bulk copy, one pair of barriers)
+    int tpq;            // tiles per query = ceil(C / R)
+    int stages;         // S (a multiple of teams)
+    int teams;          // teams that take tiles = min(16 / G, S); tile t belongs to team t % teams
+    int qslots;         // QS
+    int nbuf;           // score buffers (fused): rankers may lag the stream by nbuf - 1 queries
+    int fused;
+    int P;              // next_pow2(C) (fused)
+    uint32_t stage_bytes, qslot_bytes;
     double* out64; float* out32;
     int top_k; double* out_scores; int32_t* out_pos; int64_t* out_ids;
 };
 
-// Transposed butterfly over the 2*RB per-lane partials v[2*r] = q.d of row r, v[2*r+1] = |d|^2 of
-// row r.  Halving steps exchange half of the values with the partner lane, so 2*RB values
-// cost (2*RB - 1) + (5 - log2(2*RB)) double shuffles instead of 5 * 2 * RB.  Afterwards every lane
-// holds the complete sum of value index (lane >> (5 - log2(2*RB))).  Every value goes through the
-// same balanced tree (fp add commutes), so a row's result does not depend on its slot.
+// Transposed butterfly over the NV = 2*RB per-lane partials v[2*r] = q.d of row r, v[2*r+1] = |d|^2
+// of row r.  Halving steps exchange half of the values with the partner lane, so NV values cost
+// (NV - 1) + (5 - log2 NV) double shuffles instead of 5 * NV.  Afterwards every lane holds the
+// complete sum of value index lane / (32 / NV).  Every value goes through the same balanced
+// tree (fp add commutes), so a row's result does not depend on its slot.
 template <int NV>
 __device__ __forceinline__ double reduce_vals(const double (&v)[NV], int lane) {
     static_assert(NV == 2 || NV == 4 || NV == 8, "2, 4 or 8 values");
@@ -73,35 +97,70 @@ __device__ __forceinline__ void fma4s(const float4& d, const double* q, double& 
     dot = fma(q[3], d3, dot); nrm = fma(d3, d3, nrm);
 }
 
-// NCHUNK > 0: D == 128 * NCHUNK, query cached in registers.  NCHUNK == 0: any D % 4 == 0,
-// query converted once per query into shared memory.  RB = rows per consumer warp per tile
-// (tile height R = 16 * RB).
+// score from the pair the consumers leave behind: den < 0 marks a padding candidate (idx < 0)
+__device__ __forceinline__ double fidelity_pair(double dot, double den) {
+    if (den < 0.0) return -pos_inf();
+    return den > 0.0 ? (dot * dot) / den : 0.0;
+}
+
+// bitonic sort of P (power of two) {key, tag-as-int64-bits} pairs laid out as double2, ascending
+// by (key, tag); nt threads on named barrier `bar`
+__device__ void bitonic_sort_aos(double2* a, int P, int tid, int nt, int bar) {
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (P >> 1); t += nt) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int hi = lo | j;
+                const double2 l = a[lo], h = a[hi];
+                const bool ascending = (lo & k) == 0;
+                const bool hi_first = pair_less<long long>(h.x, __double_as_longlong(h.y), l.x, __double_as_longlong(l.y));
+                if (hi_first == ascending) { a[lo] = h; a[hi] = l; }
+            }
+            named_bar_sync(bar, nt);
+        }
+    }
+}
+
+// NCHUNK > 0: D == 128 * NCHUNK, query cached in registers.  NCHUNK == 0: any D % 4 == 0, query read
+// from its fp64 slot in shared memory.  RB = candidate rows per tile (one consumer warp per tile).
 template <int NCHUNK, int RB>
 __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStreamParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + AS_MAX_STAGES;
-    unsigned char* ring = smem + 128;
-    const int D = p.D, R = p.R, S = p.stages;
+    uint64_t* qfull = empty + AS_MAX_STAGES;
+    uint64_t* qready = qfull + AS_MAX_QSLOTS;
+    uint64_t* sfull = qready + AS_MAX_QSLOTS;
+    uint64_t* sempty = sfull + AS_MAX_SBUFS;
+    const int D = p.D, S = p.stages, QS = p.qslots, tpq = p.tpq, P = p.P, NT = p.teams, NB = p.nbuf, G = p.G, R = p.R;
     const int64_t C = p.C;
-    double* qd = reinterpret_cast<double*>(ring + (size_t)S * p.stage_bytes);          // [D] (NCHUNK == 0 only)
-    double* sc = qd + (NCHUNK == 0 ? ((D + 1) & ~1) : 0);                               // [P] fused scores / keys
-    int P = 1;
-    while (P < C) P <<= 1;
-    int* stag = reinterpret_cast<int*>(sc + P);
+    const uint32_t row_bytes = (uint32_t)D * 4u;
+    // query slot: [D] fp32 (TMA destination) | [D] fp64 | |q|^2
+    unsigned char* qslot0 = smem + AS_HDR_BYTES;
+    const uint32_t qd_off = (row_bytes + 15u) & ~15u;
+    const uint32_t qn_off = qd_off + (uint32_t)D * 8u;
+    double2* sc = reinterpret_cast<double2*>(qslot0 + (size_t)QS * p.qslot_bytes);     // [NB][P] (fused)
+    unsigned char* ring = reinterpret_cast<unsigned char*>(sc + (p.fused ? (size_t)NB * P : 0));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], AS_CWARPS);
+            mbar_init(&empty[s], (uint32_t)G);
+        }
+        for (int s = 0; s < QS; ++s) {
+            mbar_init(&qfull[s], 1);
+            mbar_init(&qready[s], 1);
+        }
+        for (int s = 0; s < NB; ++s) {
+            mbar_init(&sfull[s], p.fused ? (uint32_t)(tpq * G) : 1u);
+            mbar_init(&sempty[s], AS_RWARPS);
         }
         fence_barrier_init();
     }
     __syncthreads();
 
-    // tile range of this CTA
-    const int tpq = p.tpq;
+    // tile range [g0, g1) of this CTA in the global sequence (query-major, tpq tiles per query)
     int64_t g0, g1;
     if (p.fused) {
         g0 = ((int64_t)blockIdx.x * p.nq / gridDim.x) * tpq;
@@ -111,168 +170,262 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
         g0 = (int64_t)blockIdx.x * T / gridDim.x;
         g1 = (int64_t)(blockIdx.x + 1) * T / gridDim.x;
     }
-    const uint32_t row_bytes = (uint32_t)D * 4u;
+    const int ntiles = (int)(g1 - g0);
+    if (ntiles <= 0) return;
+    const int64_t qfirst = g0 / tpq;
+    const int ti_first = (int)(g0 - qfirst * tpq);
+    const int nqueries = (int)((g1 - 1) / tpq - qfirst) + 1;
 
-    if (warp == AS_CWARPS) {
-        // ------------------------------------------------------------------ producer
-        int64_t q = g0 / tpq;
-        int ti = (int)(g0 - q * tpq);
-        int s = 0;
-        uint32_t par = 0;
-        for (int64_t g = g0; g < g1; ++g) {
+    if (warp == AS_WARP_PROD) {
+        // ---------------------------------------------------------------------- producer
+        int consumed = 0, cst = 0;          // tiles [0, consumed) are known to be released
+        uint32_t cpar = 0;
+        auto ensure_consumed = [&](int upto) {
+            while (consumed < upto) {
+                mbar_wait(&empty[cst], cpar);
+                ++consumed;
+                if (++cst == S) { cst = 0; cpar ^= 1u; }
+            }
+        };
+        int64_t q = qfirst;
+        int ti = ti_first, st = 0, qs = 0, slot = 0;
+        for (int it = 0; it < ntiles; ++it) {
+            if (it == 0 || ti == 0) {
+                // the slot's previous query (qs - QS) must be fully consumed: all tiles before
+                // the first tile of query qs - QS + 1
+                if (qs >= QS) ensure_consumed((qs - QS + 1) * tpq - ti_first);
+                // fused: the rankers must be done with query qs - NB before its score buffer is rewritten
+                if (p.fused && qs >= NB) mbar_wait(&sempty[qs % NB], ((uint32_t)(qs / NB) & 1u) ^ 1u);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&qfull[slot], row_bytes);
+                    bulk_g2s(qslot0 + (size_t)slot * p.qslot_bytes, p.Q + (size_t)q * D, row_bytes, &qfull[slot]);
+                }
+            }
+            if (it >= S) ensure_consumed(it - S + 1);
             const int r0 = ti * R;
             const int nr = (int)((C - r0) < R ? (C - r0) : R);
-            const bool newq = (g == g0) || (ti == 0);
-            unsigned char* st = ring + (size_t)s * p.stage_bytes;
-            mbar_wait(&empty[s], par ^ 1u);
+            unsigned char* dst = ring + (size_t)st * p.stage_bytes;
             if (p.cand) {
                 if (lane == 0) {
-                    mbar_arrive_expect_tx(&full[s], (uint32_t)nr * row_bytes + (newq ? row_bytes : 0u));
-                    if (newq) bulk_g2s(st + (size_t)R * row_bytes, p.Q + (size_t)q * D, row_bytes, &full[s]);
-                    bulk_g2s(st, p.cand + ((size_t)q * C + r0) * D, (uint32_t)nr * row_bytes, &full[s]);
+                    mbar_arrive_expect_tx(&full[st], (uint32_t)nr * row_bytes);
+                    bulk_g2s(dst, p.cand + ((size_t)q * C + r0) * D, (uint32_t)nr * row_bytes, &full[st]);
                 }
             } else {
-                int64_t id = -1;
-                if (lane < nr) id = p.idx[(size_t)q * C + r0 + lane];
-                const unsigned valid = __ballot_sync(FULL_MASK, id >= 0);
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full[s], (uint32_t)__popc(valid) * row_bytes + (newq ? row_bytes : 0u));
-                    if (newq) bulk_g2s(st + (size_t)R * row_bytes, p.Q + (size_t)q * D, row_bytes, &full[s]);
-                }
+                // R <= 64: two rows per lane at most
+                int64_t ida = -1, idb = -1;
+                if (lane < nr) ida = p.idx[(size_t)q * C + r0 + lane];
+                if (lane + 32 < nr) idb = p.idx[(size_t)q * C + r0 + lane + 32];
+                const int nvalid = __popc(__ballot_sync(FULL_MASK, ida >= 0)) + __popc(__ballot_sync(FULL_MASK, idb >= 0));
+                if (lane == 0) mbar_arrive_expect_tx(&full[st], (uint32_t)nvalid * row_bytes);
                 __syncwarp();
-                if (id >= 0) bulk_g2s(st + (size_t)lane * row_bytes, p.X + (size_t)id * D, row_bytes, &full[s]);
+                if (ida >= 0) bulk_g2s(dst + (size_t)lane * row_bytes, p.X + (size_t)ida * D, row_bytes, &full[st]);
+                if (idb >= 0) bulk_g2s(dst + (size_t)(lane + 32) * row_bytes, p.X + (size_t)idb * D, row_bytes, &full[st]);
             }
-            if (++ti == tpq) { ti = 0; ++q; }
-            if (++s == S) { s = 0; par ^= 1u; }
+            if (++st == S) st = 0;
+            if (++ti == tpq) {
+                ti = 0; ++q; ++qs;
+                if (++slot == QS) slot = 0;
+            }
         }
         return;
     }
 
-    // ---------------------------------------------------------------------- consumers
-    double qreg[NCHUNK > 0 ? NCHUNK * 4 : 1];
-    double nq2 = 0.0;
-    const int D4 = D >> 2;
-    int64_t q = g0 / tpq;
-    int ti = (int)(g0 - q * tpq);
-    int s = 0;
-    uint32_t par = 0;
-    for (int64_t g = g0; g < g1; ++g) {
-        const int r0 = ti * R;
-        const int nr = (int)((C - r0) < R ? (C - r0) : R);
-        const bool newq = (g == g0) || (ti == 0);
-        const unsigned char* st = ring + (size_t)s * p.stage_bytes;
-        mbar_wait(&full[s], par);
-
-        if (newq) {
-            const float* qslot = reinterpret_cast<const float*>(st + (size_t)R * row_bytes);
+    if (warp == AS_WARP_CONV) {
+        // --------------------------------------------------------------------- converter
+        int slot = 0;
+        uint32_t par = 0;
+        const int D4 = D >> 2;
+        for (int qs = 0; qs < nqueries; ++qs) {
+            unsigned char* sl = qslot0 + (size_t)slot * p.qslot_bytes;
+            const float4* qf = reinterpret_cast<const float4*>(sl);
+            double2* qd = reinterpret_cast<double2*>(sl + qd_off);
+            mbar_wait(&qfull[slot], par);
             double part = 0.0;
+            for (int j = lane; j < D4; j += 32) {
+                const float4 v = qf[j];
+                const double a = (double)v.x, b = (double)v.y, c = (double)v.z, d = (double)v.w;
+                qd[2 * j] = make_double2(a, b);
+                qd[2 * j + 1] = make_double2(c, d);
+                part = fma(a, a, part); part = fma(b, b, part); part = fma(c, c, part); part = fma(d, d, part);
+            }
+            part = warp_sum(part);
+            if (lane == 0) *reinterpret_cast<double*>(sl + qn_off) = part;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&qready[slot]);
+            if (++slot == QS) { slot = 0; par ^= 1u; }
+        }
+        return;
+    }
+
+    if (warp >= AS_WARP_RANK) {
+        // ----------------------------------------------------------------------- rankers
+        if (!p.fused) return;
+        const int rt = tid - AS_WARP_RANK * 32;
+        const int top_k = p.top_k;
+        for (int qs = 0; qs < nqueries; ++qs) {
+            const int buf = qs % NB;
+            const int64_t q = qfirst + qs;
+            double2* sb = sc + (size_t)buf * P;
+            mbar_wait(&sfull[buf], (uint32_t)(qs / NB) & 1u);
+            double* os = p.out_scores + (size_t)q * top_k;
+            int32_t* op = p.out_pos + (size_t)q * top_k;
+            int64_t* oi = p.out_ids ? p.out_ids + (size_t)q * top_k : nullptr;
+            if (C <= AS_RANK_COUNT_MAX) {
+                // rank by counting; thread rt owns candidates rt and rt + 64
+                const int c0 = rt, c1 = rt + AS_RTHREADS;
+                double s0 = 0.0, s1 = 0.0;
+                if (c0 < C) { const double2 v = sb[c0]; s0 = fidelity_pair(v.x, v.y); sb[c0].x = s0; }
+                if (c1 < C) { const double2 v = sb[c1]; s1 = fidelity_pair(v.x, v.y); sb[c1].x = s1; }
+                named_bar_sync(AS_BAR_RANK, AS_RTHREADS);
+                int k0 = 0, k1 = 0;
+                const int Ci = (int)C;
+#pragma unroll 4
+                for (int j = 0; j < Ci; ++j) {
+                    const double sj = sb[j].x;
+                    k0 += (sj > s0) || (sj == s0 && j < c0);
+                    k1 += (sj > s1) || (sj == s1 && j < c1);
+                }
+                if (c0 < C && k0 < top_k) {
+                    os[k0] = s0; op[k0] = c0;
+                    if (oi) oi[k0] = p.idx[(size_t)q * C + c0];
+                }
+                if (c1 < C && k1 < top_k) {
+                    os[k1] = s1; op[k1] = c1;
+                    if (oi) oi[k1] = p.idx[(size_t)q * C + c1];
+                }
+            } else {
+                for (int i = rt; i < P; i += AS_RTHREADS) {
+                    double key = pos_inf();
+                    long long tag = TagPad<long long>::value();
+                    if (i < C) {
+                        const double2 v = sb[i];
+                        key = -fidelity_pair(v.x, v.y);
+                        tag = i;
+                    }
+                    sb[i] = make_double2(key, __longlong_as_double(tag));
+                }
+                named_bar_sync(AS_BAR_RANK, AS_RTHREADS);
+                bitonic_sort_aos(sb, P, rt, AS_RTHREADS, AS_BAR_RANK);
+                for (int i = rt; i < top_k; i += AS_RTHREADS) {
+                    const double2 v = sb[i];
+                    const int pos = (int)__double_as_longlong(v.y);
+                    os[i] = -v.x;
+                    op[i] = pos;
+                    if (oi) oi[i] = p.idx[(size_t)q * C + pos];
+                }
+            }
+            __syncwarp();                                   // this warp's reads of sb are complete
+            if (lane == 0) mbar_arrive(&sempty[buf]);
+        }
+        return;
+    }
+
+    // ------------------------------------------------------------------------- consumers
+    double qreg[NCHUNK > 0 ? NCHUNK * 4 : 1];
+    const double* qd = nullptr;
+    double nq2 = 0.0;
+    int qs_cached = -1;
+    const int D4 = D >> 2;
+    constexpr int NV = 2 * RB;
+    constexpr int LPV = 32 / NV;
+
+    // Each stage is always drained by the same team (S % NT == 0), and a warp waits for the tile
+    // before it looks at the query slot, so no barrier is ever waited on more than one phase ahead.
+    const int team = warp / G, sub = warp - team * G;
+    if (team >= NT) return;
+    int64_t q = qfirst;
+    int ti = ti_first + team;
+    while (ti >= tpq) { ti -= tpq; ++q; }
+    int st = team;
+    uint32_t par = 0;
+
+    for (int it = team; it < ntiles; it += NT) {
+        const int qs = (int)(q - qfirst);
+        const int r0 = ti * R + sub * RB;                    // this warp's rows of the tile
+        const int64_t left = C - r0;
+        const int nr = left < 0 ? 0 : (left < RB ? (int)left : RB);
+        const unsigned char* src = ring + (size_t)st * p.stage_bytes + (size_t)sub * RB * row_bytes;
+        mbar_wait(&full[st], par);
+        if (qs != qs_cached) {
+            const int slot = qs % QS;
+            const unsigned char* sl = qslot0 + (size_t)slot * p.qslot_bytes;
+            mbar_wait(&qready[slot], (uint32_t)(qs / QS) & 1u);
+            qd = reinterpret_cast<const double*>(sl + qd_off);
+            nq2 = *reinterpret_cast<const double*>(sl + qn_off);
             if (NCHUNK > 0) {
 #pragma unroll
                 for (int t = 0; t < (NCHUNK > 0 ? NCHUNK : 0); ++t) {
-                    const float4 v = reinterpret_cast<const float4*>(qslot)[lane + 32 * t];
-                    qreg[4 * t + 0] = (double)v.x; qreg[4 * t + 1] = (double)v.y;
-                    qreg[4 * t + 2] = (double)v.z; qreg[4 * t + 3] = (double)v.w;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) part = fma(qreg[4 * t + e], qreg[4 * t + e], part);
+                    const double2 a = *reinterpret_cast<const double2*>(qd + 4 * (lane + 32 * t));
+                    const double2 b = *reinterpret_cast<const double2*>(qd + 4 * (lane + 32 * t) + 2);
+                    qreg[4 * t + 0] = a.x; qreg[4 * t + 1] = a.y; qreg[4 * t + 2] = b.x; qreg[4 * t + 3] = b.y;
                 }
-            } else {
-                named_bar_sync(AS_BAR, AS_CONSUMERS);          // everyone is done with the previous query's qd
-                for (int i = tid; i < D; i += AS_CONSUMERS) qd[i] = (double)qslot[i];
-                named_bar_sync(AS_BAR, AS_CONSUMERS);
-                for (int i = lane; i < D; i += 32) part = fma(qd[i], qd[i], part);
             }
-            nq2 = warp_sum(part);
+            qs_cached = qs;
         }
 
-        // rows of this tile owned by the warp: slot i -> row (warp + ti) % 16 + 16 i
-        const int rbase = (warp + ti) & (AS_CWARPS - 1);
-        double acc[2 * RB];
+        double acc[NV];
 #pragma unroll
-        for (int i = 0; i < 2 * RB; ++i) acc[i] = 0.0;
-        const float4* rp[RB];
-#pragma unroll
-        for (int i = 0; i < RB; ++i) {
-            const int rr = rbase + AS_CWARPS * i;
-            rp[i] = reinterpret_cast<const float4*>(st + (size_t)(rr < nr ? rr : 0) * row_bytes);
-        }
+        for (int i = 0; i < NV; ++i) acc[i] = 0.0;
         if (NCHUNK > 0) {
+            if (nr == RB) {
 #pragma unroll
-            for (int t = 0; t < (NCHUNK > 0 ? NCHUNK : 0); ++t)
+                for (int t = 0; t < (NCHUNK > 0 ? NCHUNK : 0); ++t) {
+                    float4 v[RB];
 #pragma unroll
-                for (int i = 0; i < RB; ++i) fma4s(rp[i][lane + 32 * t], &qreg[4 * t], acc[2 * i], acc[2 * i + 1]);
+                    for (int i = 0; i < RB; ++i)
+                        v[i] = reinterpret_cast<const float4*>(src + (size_t)i * row_bytes)[lane + 32 * t];
+#pragma unroll
+                    for (int i = 0; i < RB; ++i) fma4s(v[i], &qreg[4 * t], acc[2 * i], acc[2 * i + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < RB; ++i) {
+                    if (i < nr) {
+#pragma unroll
+                        for (int t = 0; t < (NCHUNK > 0 ? NCHUNK : 0); ++t)
+                            fma4s(reinterpret_cast<const float4*>(src + (size_t)i * row_bytes)[lane + 32 * t],
+                                  &qreg[4 * t], acc[2 * i], acc[2 * i + 1]);
+                    }
+                }
+            }
         } else {
             for (int j = lane; j < D4; j += 32) {
                 const double2 qa = *reinterpret_cast<const double2*>(qd + 4 * j);
                 const double2 qb = *reinterpret_cast<const double2*>(qd + 4 * j + 2);
                 const double qv[4] = {qa.x, qa.y, qb.x, qb.y};
 #pragma unroll
-                for (int i = 0; i < RB; ++i) fma4s(rp[i][j], qv, acc[2 * i], acc[2 * i + 1]);
+                for (int i = 0; i < RB; ++i)
+                    if (i < nr) fma4s(reinterpret_cast<const float4*>(src + (size_t)i * row_bytes)[j], qv, acc[2 * i],
+                                      acc[2 * i + 1]);
             }
         }
-        // lane L ends with value index L / LPV: even index = q.d, odd = |d|^2 of row slot index / 2
-        constexpr int LPV = 32 / (2 * RB);
-        const double tot = reduce_vals<2 * RB>(acc, lane);
+        // lane L ends with value index L / LPV: even index = q.d, odd = |d|^2 of row index / 2
+        const double tot = reduce_vals<NV>(acc, lane);
         const double nd2 = __shfl_down_sync(FULL_MASK, tot, LPV);
         // all shared-memory reads of this stage are complete (their values were consumed above)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+        if (lane == 0) mbar_arrive(&empty[st]);
 
-        if ((lane & (2 * LPV - 1)) == 0) {
-            const int i = lane / (2 * LPV);
-            const int rr = rbase + AS_CWARPS * i;
-            if (rr < nr) {
-                const int64_t c = r0 + rr;
-                const double den = nq2 * nd2;
-                double f = den > 0.0 ? (tot * tot) / den : 0.0;
-                if (p.idx && p.idx[(size_t)q * C + c] < 0) f = -pos_inf();
-                if (p.fused) {
-                    sc[c] = f;
-                } else {
-                    p.out64[(size_t)q * C + c] = f;
-                    if (p.out32) p.out32[(size_t)q * C + c] = (float)f;
-                }
-            }
+        const int i = lane / (2 * LPV);
+        const bool owner = (lane & (2 * LPV - 1)) == 0 && i < nr;
+        const int64_t c = r0 + i;
+        double den = nq2 * nd2;
+        if (owner && p.idx && p.idx[(size_t)q * C + c] < 0) den = -1.0;
+        if (p.fused) {
+            const int buf = qs % NB;           // free: the producer waited for the rankers before issuing this query
+            if (owner) sc[(size_t)buf * P + c] = make_double2(tot, den);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sfull[buf]);
+        } else if (owner) {
+            const double f = fidelity_pair(tot, den);
+            p.out64[(size_t)q * C + c] = f;
+            if (p.out32) p.out32[(size_t)q * C + c] = (float)f;
         }
 
-        if (p.fused && ti == tpq - 1) {
-            named_bar_sync(AS_BAR, AS_CONSUMERS);              // all C scores of query q are in sc[]
-            const int top_k = p.top_k;
-            double* os = p.out_scores + (size_t)q * top_k;
-            int32_t* op = p.out_pos + (size_t)q * top_k;
-            int64_t* oi = p.out_ids ? p.out_ids + (size_t)q * top_k : nullptr;
-            if (C <= AS_RANK_SORT_MAX) {
-                if (tid < C) {
-                    const double si = sc[tid];
-                    int rank = 0;
-                    for (int j = 0; j < (int)C; ++j) {
-                        const double sj = sc[j];
-                        rank += (sj > si) || (sj == si && j < tid);
-                    }
-                    if (rank < top_k) {
-                        os[rank] = si;
-                        op[rank] = tid;
-                        if (oi) oi[rank] = p.idx[(size_t)q * C + tid];
-                    }
-                }
-            } else {
-                for (int i = tid; i < P; i += AS_CONSUMERS) {
-                    const bool real = i < C;
-                    const double v = real ? sc[i] : 0.0;
-                    sc[i] = real ? -v : pos_inf();
-                    stag[i] = real ? i : TagPad<int>::value();
-                }
-                named_bar_sync(AS_BAR, AS_CONSUMERS);
-                block_bitonic_sort<int>(sc, stag, P, tid, AS_CONSUMERS, AS_BAR);
-                for (int i = tid; i < top_k; i += AS_CONSUMERS) {
-                    os[i] = -sc[i];
-                    op[i] = stag[i];
-                    if (oi) oi[i] = p.idx[(size_t)q * C + stag[i]];
-                }
-            }
-            named_bar_sync(AS_BAR, AS_CONSUMERS);              // sc[] is free for the next query
-        }
-        if (++ti == tpq) { ti = 0; ++q; }
-        if (++s == S) { s = 0; par ^= 1u; }
+        ti += NT;
+        while (ti >= tpq) { ti -= tpq; ++q; }
+        st += NT;
+        if (st >= S) { st -= S; par ^= 1u; }
     }
 }
 
@@ -285,6 +438,48 @@ static int launch_stream(const AmpStreamParams& p, size_t smem_bytes, int grid, 
     return QRAG_OK;
 }
 
+// Shared-memory plan for a given tile height; returns the number of stages (0 = does not fit).
+static int plan_stream(AmpStreamParams& p, int rb, int g, bool fused, size_t budget, size_t* smem_bytes) {
+    const int D = p.D;
+    p.G = g;
+    p.R = g * rb;
+    p.tpq = (int)ceil_div(p.C, p.R);
+    p.stage_bytes = (uint32_t)(((size_t)p.R * D * 4 + 127) / 128 * 128);
+    p.qslot_bytes = (uint32_t)((((size_t)D * 4 + 15) / 16 * 16 + (size_t)D * 8 + 16 + 127) / 128 * 128);
+    p.P = fused ? next_pow2(p.C) : 0;
+    // score buffers: enough that ranking never throttles the stream, within 32 KB (always >= 2)
+    p.nbuf = 2;
+    if (fused) {
+        int want = (int)((size_t)(192 * 1024) / p.stage_bytes / p.tpq) + 3;
+        if (want > AS_MAX_SBUFS) want = AS_MAX_SBUFS;
+        while (want > 2 && (size_t)want * p.P * 16 > 32 * 1024) --want;
+        p.nbuf = want;
+    }
+    const size_t scb = fused ? (size_t)p.nbuf * p.P * 16 : 0;
+    int qs = 3, stages = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const size_t fixed = AS_HDR_BYTES + (size_t)qs * p.qslot_bytes + scb;
+        if (fixed + 2 * (size_t)p.stage_bytes > budget) return 0;
+        stages = (int)((budget - fixed) / p.stage_bytes);
+        if (stages > AS_MAX_STAGES) stages = AS_MAX_STAGES;
+        // enough query slots that the ring, not the slots, bounds what is in flight
+        int want = stages / p.tpq + 2;
+        if (want > AS_MAX_QSLOTS) want = AS_MAX_QSLOTS;
+        if (want <= qs) break;
+        qs = want;
+    }
+    const size_t fixed = AS_HDR_BYTES + (size_t)qs * p.qslot_bytes + scb;
+    if (fixed + 2 * (size_t)p.stage_bytes > budget) return 0;
+    stages = (int)((budget - fixed) / p.stage_bytes);
+    if (stages > AS_MAX_STAGES) stages = AS_MAX_STAGES;
+    p.teams = stages < AS_CWARPS / g ? stages : AS_CWARPS / g;
+    stages -= stages % p.teams;
+    p.qslots = qs;
+    p.stages = stages;
+    *smem_bytes = fixed + (size_t)stages * p.stage_bytes;
+    return stages;
+}
+
 // Returns QRAG_OK and sets *handled = true if the streaming kernel took the job.
 int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, const int64_t* idx, int64_t C, int D,
                    bool fused, double* out64, float* out32, int top_k, double* out_scores, int32_t* out_pos,
@@ -292,7 +487,7 @@ int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, co
     *handled = false;
     const DeviceProps& dp = device_props();
     QRAG_REQUIRE(dp.ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
-    if (D % 4 != 0 || D > 4096) return QRAG_OK;
+    if (D % 4 != 0 || D > 8192) return QRAG_OK;
     if (((uintptr_t)Q | (uintptr_t)(cand ? cand : X)) % 16 != 0) return QRAG_OK;
     if (nq < 1 || C < 1) return QRAG_OK;
 
@@ -300,21 +495,25 @@ int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, co
     p.Q = Q; p.cand = cand; p.X = X; p.idx = idx; p.nq = nq; p.C = C; p.D = D;
     p.out64 = out64; p.out32 = out32; p.top_k = top_k; p.out_scores = out_scores; p.out_pos = out_pos;
     p.out_ids = out_ids; p.fused = fused ? 1 : 0;
-    // tile height: 32 rows while a stage stays <= 64 KB, else 16
-    int rb = 2;
-    while (rb > 1 && (size_t)(AS_CWARPS * rb + 1) * D * 4 > 64 * 1024) rb >>= 1;
-    p.R = AS_CWARPS * rb;
-    p.tpq = (int)ceil_div(C, p.R);
-    p.stage_bytes = ((size_t)(p.R + 1) * D * 4 + 127) / 128 * 128;
+
     const bool nchunk_path = (D == 128 || D == 256 || D == 384 || D == 512);
-    size_t fixed = 128 + (nchunk_path ? 0 : (size_t)((D + 1) & ~1) * 8);
-    if (fused) fixed += (size_t)next_pow2(C) * 12;
     const size_t budget = (size_t)dp.max_smem_optin;
-    if (fixed + 2 * p.stage_bytes > budget) return QRAG_OK;
-    int stages = (int)((budget - fixed) / p.stage_bytes);
-    if (stages > AS_MAX_STAGES) stages = AS_MAX_STAGES;
-    p.stages = stages;
-    const size_t smem_bytes = fixed + (size_t)stages * p.stage_bytes;
+    // rows per warp: 4 while a warp's slice stays <= 8 KB, else 2, else 1; team size: the widest
+    // tile (one bulk copy, one barrier pair) of <= 24 KB, so that >= 8 tiles are in flight per SM
+    int rb = 4;
+    while (rb > 1 && (size_t)rb * D * 4 > 8 * 1024) rb >>= 1;
+    int g = AS_CWARPS;
+    while (g > 1 && (size_t)g * rb * D * 4 > 24 * 1024) g >>= 1;
+    if (const char* e = getenv("QRAG_AMP_STREAM_RB")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) rb = v; }
+    if (const char* e = getenv("QRAG_AMP_STREAM_G")) { const int v = atoi(e); if (v >= 1 && v <= 16 && !(v & (v - 1))) g = v; }
+    size_t smem_bytes = 0;
+    while (plan_stream(p, rb, g, fused, budget, &smem_bytes) < 2) {
+        if (g > 1) g >>= 1;
+        else if (rb > 1 && !nchunk_path) rb >>= 1;
+        else return QRAG_OK;
+    }
+    // per-CTA tile counts are kept in 32 bits
+    if ((int64_t)p.tpq * nq / dp.sm_count > ((int64_t)1 << 30)) return QRAG_OK;
 
     int grid = dp.sm_count;
     if (fused) {
@@ -324,16 +523,22 @@ int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, co
         if (grid > T) grid = (int)T;
     }
     *handled = true;
-    if (nchunk_path) {
-        switch (D / 128) {
-            case 1: return launch_stream<1, 2>(p, smem_bytes, grid, st);
-            case 2: return launch_stream<2, 2>(p, smem_bytes, grid, st);
-            case 3: return launch_stream<3, 2>(p, smem_bytes, grid, st);
-            default: return launch_stream<4, 2>(p, smem_bytes, grid, st);
-        }
+    switch ((nchunk_path ? D / 128 : 0) * 8 + rb) {
+        case 0 * 8 + 4: return launch_stream<0, 4>(p, smem_bytes, grid, st);
+        case 0 * 8 + 2: return launch_stream<0, 2>(p, smem_bytes, grid, st);
+        case 0 * 8 + 1: return launch_stream<0, 1>(p, smem_bytes, grid, st);
+        case 1 * 8 + 4: return launch_stream<1, 4>(p, smem_bytes, grid, st);
+        case 1 * 8 + 2: return launch_stream<1, 2>(p, smem_bytes, grid, st);
+        case 2 * 8 + 4: return launch_stream<2, 4>(p, smem_bytes, grid, st);
+        case 2 * 8 + 2: return launch_stream<2, 2>(p, smem_bytes, grid, st);
+        case 3 * 8 + 4: return launch_stream<3, 4>(p, smem_bytes, grid, st);
+        case 3 * 8 + 2: return launch_stream<3, 2>(p, smem_bytes, grid, st);
+        case 4 * 8 + 4: return launch_stream<4, 4>(p, smem_bytes, grid, st);
+        case 4 * 8 + 2: return launch_stream<4, 2>(p, smem_bytes, grid, st);
+        default: break;
     }
-    if (rb == 2) return launch_stream<0, 2>(p, smem_bytes, grid, st);
-    return launch_stream<0, 1>(p, smem_bytes, grid, st);
+    *handled = false;        // (NCHUNK, RB) pair without an instantiation: the caller uses the plain kernel
+    return QRAG_OK;
 }
 
 }  // namespace qrag

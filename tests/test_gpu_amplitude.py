@@ -72,6 +72,37 @@ def test_fused_rerank_order_is_bit_exact(cuda, C, top_k):
     assert np.array_equal(srt.cpu().numpy(), scores.cpu().numpy())
 
 
+@pytest.mark.parametrize("nq,C,D,top_k", [(3000, 1, 128, 1), (2500, 3, 384, 2), (1500, 7, 256, 7), (700, 20, 512, 5),
+                                           (300, 150, 1024, 9), (40, 300, 1536, 300), (9, 2000, 64, 50),
+                                           (2, 1000, 4096, 10), (333, 100, 384, 10)])
+def test_fused_rerank_many_queries_all_shapes(cuda, nq, C, D, top_k):
+    """Exercises every pipeline regime of the streaming kernel: more queries in flight than query slots,
+    rings shorter than the warp count, ragged last tiles, both ranking algorithms."""
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(nq + C + D)
+    Q = rng.standard_normal((nq, D)).astype(np.float32)
+    cand = rng.standard_normal((nq, C, D)).astype(np.float32)
+    if C >= 3:
+        cand[:, 2] = cand[:, 0]
+    scores, pos, _ = api.quantum_rerank_batch(Q, cand=cand, top_k=top_k)
+    want = oq.amplitude_fidelity_batch(Q, cand)
+    order = oq.rank_rows(want, top_k)
+    assert np.array_equal(pos.cpu().numpy(), order)
+    assert np.allclose(scores.cpu().numpy(), np.take_along_axis(want, order, 1), rtol=REL, atol=1e-16)
+    full = api.amp_fidelity(Q, cand=cand)
+    assert np.allclose(full.cpu().numpy(), want, rtol=REL, atol=1e-16)
+    assert np.array_equal(np.take_along_axis(full.cpu().numpy(), order, 1), scores.cpu().numpy())
+
+
+def test_one_query_many_candidates_unfused(cuda):
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(5)
+    Q = rng.standard_normal((1, 384)).astype(np.float32)
+    cand = rng.standard_normal((1, 50001, 384)).astype(np.float32)
+    got = api.amp_fidelity(Q, cand=cand).cpu().numpy()
+    assert np.allclose(got, oq.amplitude_fidelity_batch(Q, cand), rtol=REL, atol=1e-16)
+
+
 def test_golden_amplitude_and_feature_map(cuda, kat):
     from quantum_rag_b200 import api
     for c in kat["oracle"]["amplitude"]:

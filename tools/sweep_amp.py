@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Tuning sweep for the streaming amplitude-rerank kernel (config 2 shape by default).
+
+    python tools/sweep_amp.py [--nq 1000 --C 100 --D 384 --k 10]
+
+Sets QRAG_AMP_STREAM_G / QRAG_AMP_STREAM_RB (debug overrides read by amp_stream.cu) and times
+qrag_amp_rerank with CUDA events over rotating input sets (larger than L2 in total).
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from quantum_rag_b200 import _lib, api  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nq", type=int, default=1000)
+    ap.add_argument("--C", type=int, default=100)
+    ap.add_argument("--D", type=int, default=384)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--configs", default="default,1x4,2x4,4x4,8x4,16x4,2x2,4x2,8x2,16x2")
+    a = ap.parse_args()
+    _lib.build()
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(7)
+    nsets = max(2, int(520e6 / (a.nq * a.C * a.D * 4)) + 1)
+    sets = [(torch.randn(a.nq, a.D, generator=g).cuda(), torch.randn(a.nq, a.C, a.D, generator=g).cuda())
+            for _ in range(nsets)]
+    scores = torch.empty((a.nq, a.k), dtype=torch.float64, device="cuda")
+    pos = torch.empty((a.nq, a.k), dtype=torch.int32, device="cuda")
+    nbytes = a.nq * a.C * a.D * 4
+
+    def step(i):
+        Q, c = sets[i % nsets]
+        _lib.check(lib.qrag_amp_rerank(api._ptr(Q), a.nq, api._ptr(c), None, None, a.C, a.D, api.qubits_for(a.D), a.k,
+                                       api._ptr(scores), api._ptr(pos), None, api._stream()))
+
+    ref = None
+    for cfg in a.configs.split(","):
+        os.environ.pop("QRAG_AMP_STREAM_G", None)
+        os.environ.pop("QRAG_AMP_STREAM_RB", None)
+        if cfg != "default":
+            gg, rb = cfg.split("x")
+            os.environ["QRAG_AMP_STREAM_G"] = gg
+            os.environ["QRAG_AMP_STREAM_RB"] = rb
+        step(0)
+        torch.cuda.synchronize()
+        cur = (scores.clone(), pos.clone())
+        if ref is None:
+            ref = cur
+        same = bool(torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1]))
+        for i in range(20):
+            step(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(a.steps):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / a.steps
+        print(f"GxRB={cfg:8s} {us:8.2f} us/launch  {nbytes / us / 1e3:8.1f} GB/s  same_as_first={same}", flush=True)
+
+
+if __name__ == "__main__":
+    main()
