@@ -53,6 +53,24 @@ int         qrag_version(void);
 int         qrag_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* ---------------------------------------------------------------------------
+ * Stream-overlap policy of the streaming kernels (process-wide, default SAFE).
+ * The kernels are launched with programmatic stream serialization so that back-to-back
+ * batches on one stream overlap instead of paying launch latency and tail drain per batch:
+ *   NONE           plain stream order.
+ *   SAFE           the next kernel's CTAs become resident early, but every global access
+ *                  waits for the previous kernel to complete (always correct).
+ *   INPUTS_STABLE  only the kernel's WRITES wait for the previous kernel; its input reads
+ *                  start as soon as an SM is free.  The caller promises that Q / cand / X /
+ *                  idx are not produced by the kernel immediately preceding it on the stream
+ *                  (copies and events are unaffected: only kernel -> kernel edges relax).
+ * ------------------------------------------------------------------------- */
+#define QRAG_OVERLAP_NONE          0
+#define QRAG_OVERLAP_SAFE          1
+#define QRAG_OVERLAP_INPUTS_STABLE 2
+int qrag_set_overlap(int mode);
+int qrag_get_overlap(void);
+
+/* ---------------------------------------------------------------------------
  * (1a) Reference circuit, exact statevector, complex128.
  * Replaces QuantumReranker._quantum_similarity + _vector_to_circuit
  * (quantum.py:108-167) for a whole batch in one launch.

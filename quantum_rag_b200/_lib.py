@@ -27,6 +27,8 @@ PROTOTYPES: Dict[str, tuple] = {
     "qrag_last_error": (c_char_p, []),
     "qrag_version": (c_int, []),
     "qrag_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "qrag_set_overlap": (c_int, [c_int]),
+    "qrag_get_overlap": (c_int, []),
     "qrag_sv_fidelity_angle": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                                        c_void_p, c_void_p]),
     "qrag_amp_fidelity": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,

@@ -58,6 +58,17 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+OVERLAP_NONE, OVERLAP_SAFE, OVERLAP_INPUTS_STABLE = 0, 1, 2
+
+
+def set_overlap(mode: int) -> int:
+    """Stream-overlap policy of the streaming kernels (include/qrag.h); returns the previous mode."""
+    lib = _lib.load()
+    old = lib.qrag_get_overlap()
+    _lib.check(lib.qrag_set_overlap(int(mode)))
+    return old
+
+
 def qubits_for(dim: int) -> int:
     """Smallest n with 2**n >= dim (amplitude encoding zero-pads to 2**n)."""
     return max(1, int(dim - 1).bit_length())

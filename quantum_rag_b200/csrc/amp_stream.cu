@@ -60,6 +60,7 @@ struct AmpStreamParams {
     uint32_t stage_bytes, qslot_bytes;
     double* out64; float* out32;
     int top_k; double* out_scores; int32_t* out_pos; int64_t* out_ids;
+    int overlap;        // QRAG_OVERLAP_*: where the kernel orders itself after the previous kernel on the stream
 };
 
 // Transposed butterfly over the NV = 2*RB per-lane partials v[2*r] = q.d of row r, v[2*r+1] = |d|^2
@@ -159,6 +160,13 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
         fence_barrier_init();
     }
     __syncthreads();
+    // Programmatic dependent launch: let the next kernel on the stream start filling SMs as this
+    // grid's CTAs retire.  QRAG_OVERLAP_SAFE orders every global access of this kernel after the
+    // previous kernel (only launch latency and this prologue overlap); QRAG_OVERLAP_INPUTS_STABLE
+    // orders only the writes, so streaming starts while the previous grid drains.
+    if (p.overlap != QRAG_OVERLAP_NONE && tid == 0) griddep_launch_dependents();
+    const bool wait_reads = p.overlap == QRAG_OVERLAP_SAFE;
+    const bool wait_writes = p.overlap == QRAG_OVERLAP_INPUTS_STABLE;
 
     // tile range [g0, g1) of this CTA in the global sequence (query-major, tpq tiles per query)
     int64_t g0, g1;
@@ -189,6 +197,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
         };
         int64_t q = qfirst;
         int ti = ti_first, st = 0, qs = 0, slot = 0;
+        if (wait_reads) griddep_wait();
         for (int it = 0; it < ntiles; ++it) {
             if (it == 0 || ti == 0) {
                 // the slot's previous query (qs - QS) must be fully consumed: all tiles before
@@ -262,6 +271,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
         if (!p.fused) return;
         const int rt = tid - AS_WARP_RANK * 32;
         const int top_k = p.top_k;
+        bool ordered = !wait_writes;
         for (int qs = 0; qs < nqueries; ++qs) {
             const int buf = qs % NB;
             const int64_t q = qfirst + qs;
@@ -270,6 +280,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
             double* os = p.out_scores + (size_t)q * top_k;
             int32_t* op = p.out_pos + (size_t)q * top_k;
             int64_t* oi = p.out_ids ? p.out_ids + (size_t)q * top_k : nullptr;
+            if (!ordered) { griddep_wait(); ordered = true; }       // first write of this thread
             if (C <= AS_RANK_COUNT_MAX) {
                 // rank by counting; thread rt owns candidates rt and rt + 64
                 const int c0 = rt, c1 = rt + AS_RTHREADS;
@@ -333,6 +344,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
     // before it looks at the query slot, so no barrier is ever waited on more than one phase ahead.
     const int team = warp / G, sub = warp - team * G;
     if (team >= NT) return;
+    bool ordered = !(wait_writes && !p.fused);
     int64_t q = qfirst;
     int ti = ti_first + team;
     while (ti >= tpq) { ti -= tpq; ++q; }
@@ -416,12 +428,14 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
             if (owner) sc[(size_t)buf * P + c] = make_double2(tot, den);
             __syncwarp();
             if (lane == 0) mbar_arrive(&sfull[buf]);
-        } else if (owner) {
-            const double f = fidelity_pair(tot, den);
-            p.out64[(size_t)q * C + c] = f;
-            if (p.out32) p.out32[(size_t)q * C + c] = (float)f;
+        } else {
+            if (!ordered) { griddep_wait(); ordered = true; }       // first write of this warp
+            if (owner) {
+                const double f = fidelity_pair(tot, den);
+                p.out64[(size_t)q * C + c] = f;
+                if (p.out32) p.out32[(size_t)q * C + c] = (float)f;
+            }
         }
-
         ti += NT;
         while (ti >= tpq) { ti -= tpq; ++q; }
         st += NT;
@@ -433,7 +447,17 @@ template <int NCHUNK, int RB>
 static int launch_stream(const AmpStreamParams& p, size_t smem_bytes, int grid, cudaStream_t st) {
     auto kern = amp_stream_kernel<NCHUNK, RB>;
     QRAG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    kern<<<grid, AS_THREADS, smem_bytes, st>>>(p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(AS_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p.overlap != QRAG_OVERLAP_NONE ? 1 : 0;
+    QRAG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
     QRAG_LAUNCH_CHECK("amp_stream_kernel");
     return QRAG_OK;
 }
@@ -495,6 +519,7 @@ int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, co
     p.Q = Q; p.cand = cand; p.X = X; p.idx = idx; p.nq = nq; p.C = C; p.D = D;
     p.out64 = out64; p.out32 = out32; p.top_k = top_k; p.out_scores = out_scores; p.out_pos = out_pos;
     p.out_ids = out_ids; p.fused = fused ? 1 : 0;
+    p.overlap = overlap_mode();
 
     const bool nchunk_path = (D == 128 || D == 256 || D == 384 || D == 512);
     const size_t budget = (size_t)dp.max_smem_optin;

@@ -45,6 +45,9 @@ struct DeviceProps {
 // cached per process for the current device; ok == false if no CUDA device
 const DeviceProps& device_props();
 
+// process-wide stream-overlap policy (qrag_set_overlap)
+int overlap_mode();
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int next_pow2(int64_t v) {
     int p = 1;

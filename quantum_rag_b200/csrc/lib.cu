@@ -1,6 +1,7 @@
 // libqrag.so: error state, device query, version.
 #include "common.cuh"
 
+#include <atomic>
 #include <mutex>
 
 namespace qrag {
@@ -8,6 +9,9 @@ namespace qrag {
 static thread_local char g_err[512] = "";
 
 char* err_buf() { return g_err; }
+
+static std::atomic<int> g_overlap{QRAG_OVERLAP_SAFE};
+int overlap_mode() { return g_overlap.load(std::memory_order_relaxed); }
 
 int set_error(int code, const char* fmt, ...) {
     va_list ap;
@@ -57,3 +61,12 @@ extern "C" int qrag_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     if (cc_minor) *cc_minor = d.cc_minor;
     return QRAG_OK;
 }
+
+extern "C" int qrag_set_overlap(int mode) {
+    QRAG_REQUIRE(mode >= QRAG_OVERLAP_NONE && mode <= QRAG_OVERLAP_INPUTS_STABLE, QRAG_ERR_INVALID,
+                 "overlap mode %d (expected QRAG_OVERLAP_NONE / _SAFE / _INPUTS_STABLE)", mode);
+    qrag::g_overlap.store(mode, std::memory_order_relaxed);
+    return QRAG_OK;
+}
+
+extern "C" int qrag_get_overlap(void) { return qrag::overlap_mode(); }

@@ -23,7 +23,8 @@ def main():
     ap.add_argument("--D", type=int, default=384)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--configs", default="default,1x4,2x4,4x4,8x4,16x4,2x2,4x2,8x2,16x2")
+    ap.add_argument("--configs", default="default,4x4,8x4,8x2")
+    ap.add_argument("--overlap", default="0,1,2")
     a = ap.parse_args()
     _lib.build()
     lib = _lib.load()
@@ -41,7 +42,8 @@ def main():
                                        api._ptr(scores), api._ptr(pos), None, api._stream()))
 
     ref = None
-    for cfg in a.configs.split(","):
+    for cfg, ov in [(c, int(o)) for c in a.configs.split(",") for o in a.overlap.split(",")]:
+        api.set_overlap(ov)
         os.environ.pop("QRAG_AMP_STREAM_G", None)
         os.environ.pop("QRAG_AMP_STREAM_RB", None)
         if cfg != "default":
@@ -64,7 +66,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / a.steps
-        print(f"GxRB={cfg:8s} {us:8.2f} us/launch  {nbytes / us / 1e3:8.1f} GB/s  same_as_first={same}", flush=True)
+        print(f"GxRB={cfg:8s} overlap={ov} {us:8.2f} us/launch  {nbytes / us / 1e3:8.1f} GB/s  same_as_first={same}", flush=True)
 
 
 if __name__ == "__main__":
