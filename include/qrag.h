@@ -141,11 +141,13 @@ int qrag_mock_embedding(const uint32_t* seeds, int64_t n, int n_qubits, double* 
  * reference, semantics follow faiss's API).  Exact: fp32 inputs, fp64
  * accumulation, order (best, id asc), ids = id_base + row, -1 padding if k > N.
  *
- *   qrag_search_topk       CUDA-core exact path (any nq; the checker for (2b)).
- *   qrag_search_topk_tc    tcgen05 path: bf16 GEMM + fused threshold filter,
- *                          exact fp64 rescore of the survivors, and a per-query
- *                          certificate that no discarded row can belong to the
- *                          top-k; returns QRAG_ERR_INEXACT if it cannot certify.
+ *   qrag_search_topk       CUDA-core exact path (any nq; the checker for the tensor-core path).
+ *   qrag_search_topk_tc    tcgen05 path: bf16 GEMM used as a filter with a proven error bound
+ *                          (bucket-maximum pass -> per-query threshold -> filter pass; the score
+ *                          matrix never leaves TMEM), exact fp64 rescoring of the survivors with the
+ *                          same code as the CUDA-core path, so scores and ids are bit-identical to
+ *                          qrag_search_topk.  status[q] != 0 flags a query whose candidate list
+ *                          overflowed (never silent): rerun those with qrag_search_topk.
  * ------------------------------------------------------------------------- */
 int qrag_search_workspace(int nq, int64_t N, int D, int k, size_t* bytes);
 int qrag_search_topk(const float* Q, int nq, const float* X, int64_t N, int D, int k,
@@ -153,13 +155,16 @@ int qrag_search_topk(const float* Q, int nq, const float* X, int64_t N, int D, i
                      double* out_scores, int64_t* out_ids,
                      void* workspace, size_t workspace_bytes, void* stream);
 
-/* bf16 shadow copy + squared norms of the corpus (built once per index). */
-int qrag_index_prepare(const float* X, int64_t N, int D,
-                       uint16_t* Xb /* [N, D] bf16 */, float* xnorm2 /* [N] */, void* stream);
-int qrag_search_tc_workspace(int nq, int64_t N, int D, int k, size_t* bytes);
-int qrag_search_topk_tc(const float* Q, int nq, const float* X, const uint16_t* Xb, const float* xnorm2,
+/* bf16 shadow of the corpus for one metric, built once per index (shard):
+ *   Xb [N, Kp] bf16 with Kp from qrag_index_prepared_dims (IP: x; cosine: x/|x|;
+ *   L2: [x, hi(|x|^2), lo(|x|^2)]), aux [4] floats (aux[0] = max |x|). */
+int qrag_index_prepared_dims(int D, int metric, int* Kp);
+int qrag_index_prepare(const float* X, int64_t N, int D, int metric,
+                       uint16_t* Xb, float* aux, void* stream);
+int qrag_search_tc_workspace(int nq, int64_t N, int D, int k, int metric, size_t* bytes);
+int qrag_search_topk_tc(const float* Q, int nq, const float* X, const uint16_t* Xb, const float* aux,
                         int64_t N, int D, int k, int metric, int64_t id_base,
-                        double* out_scores, int64_t* out_ids,
+                        double* out_scores, int64_t* out_ids, int32_t* status,
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------

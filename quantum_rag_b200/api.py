@@ -226,6 +226,72 @@ def search_topk(Q: ArrayLike, X: ArrayLike, k: int, metric="l2", id_base: int = 
     return scores, ids
 
 
+class FlatIndexTC:
+    """A flat index (shard) prepared for the tcgen05 search: fp32 rows plus their bf16 shadow.
+
+    ``search(Q, k)`` returns exactly what ``search_topk`` returns (same fp64 scores, same ids, same
+    order): the tensor cores only filter, survivors are rescored by the exact code.  Queries whose
+    candidate list overflowed are flagged by the kernel and rerun on the exact path here, so the
+    result never silently degrades.
+    """
+
+    def __init__(self, X: ArrayLike, metric="l2", id_base: int = 0):
+        self.X = _dev(X, torch.float32)
+        if self.X.dim() != 2:
+            raise ValueError("X must be [N, D]")
+        self.N, self.D = self.X.shape
+        self.metric = metric_id(metric)
+        self.id_base = int(id_base)
+        lib = _lib.load()
+        kp = ctypes.c_int(0)
+        _lib.check(lib.qrag_index_prepared_dims(self.D, self.metric, ctypes.byref(kp)))
+        self.Kp = kp.value
+        self.Xb = torch.empty((max(self.N, 1), self.Kp), dtype=torch.bfloat16, device=self.X.device)
+        self.aux = torch.empty(4, dtype=torch.float32, device=self.X.device)
+        _lib.check(lib.qrag_index_prepare(_ptr(self.X), self.N, self.D, self.metric, _ptr(self.Xb), _ptr(self.aux),
+                                          _stream()))
+        self._ws = None
+        self.last_fallback = 0          # queries the last search() had to rerun exactly
+
+    def _workspace(self, nq: int, k: int) -> torch.Tensor:
+        lib = _lib.load()
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.qrag_search_tc_workspace(nq, self.N, self.D, k, self.metric, ctypes.byref(nbytes)))
+        if self._ws is None or self._ws.numel() < nbytes.value:
+            self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.X.device)
+        return self._ws
+
+    def search_async(self, Q: ArrayLike, k: int):
+        """Enqueue the search; returns (Q, scores, ids, status) device tensors without synchronising."""
+        Qd = _dev(Q, torch.float32)
+        if Qd.dim() == 1:
+            Qd = Qd[None, :]
+        if Qd.shape[1] != self.D:
+            raise ValueError("Q [nq, D] must match the index dimension")
+        nq = Qd.shape[0]
+        lib = _lib.load()
+        ws = self._workspace(nq, k)
+        scores = torch.empty((nq, k), dtype=torch.float64, device=Qd.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=Qd.device)
+        status = torch.zeros(nq, dtype=torch.int32, device=Qd.device)
+        _lib.check(lib.qrag_search_topk_tc(_ptr(Qd), nq, _ptr(self.X), _ptr(self.Xb), _ptr(self.aux), self.N, self.D, k,
+                                           self.metric, self.id_base, _ptr(scores), _ptr(ids), _ptr(status), _ptr(ws),
+                                           ws.numel(), _stream()))
+        return Qd, scores, ids, status
+
+    def search(self, Q: ArrayLike, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.N == 0:
+            return search_topk(Q, self.X, k, self.metric, self.id_base)
+        Qd, scores, ids, status = self.search_async(Q, k)
+        flagged = torch.nonzero(status).flatten()          # synchronises; the certificate is never skipped
+        self.last_fallback = int(flagged.numel())
+        if self.last_fallback:
+            s2, i2 = search_topk(Qd[flagged], self.X, k, self.metric, self.id_base)
+            scores[flagged] = s2
+            ids[flagged] = i2
+        return scores, ids
+
+
 def topk_merge(scores: ArrayLike, ids: ArrayLike, k_out: int, metric="l2") -> Tuple[torch.Tensor, torch.Tensor]:
     """Merge per-shard lists [G, nq, k] into [nq, k_out] (id < 0 = padding)."""
     s = _dev(scores, torch.float64)

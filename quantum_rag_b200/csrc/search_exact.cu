@@ -13,13 +13,14 @@
 //   until one list per query remains.  The same kernel merges the per-shard lists
 //   after the NCCL all-gather (qrag_topk_merge).
 #include "common.cuh"
+#include "exact_score.cuh"
 #include "sort.cuh"
 
 namespace qrag {
 
-constexpr int SE_THREADS = 256;
-constexpr int SE_WARPS = SE_THREADS / 32;
-constexpr int SE_ROWS = 4;
+constexpr int SE_THREADS = XS_THREADS;
+constexpr int SE_WARPS = XS_WARPS;
+constexpr int SE_ROWS = XS_ROWS;
 constexpr int MERGE_MAX = 8192;          // pairs sorted at once by merge_lists_kernel (128 KB smem)
 constexpr long long TAG_PAD = 0x7fffffffffffffffLL;
 
@@ -29,30 +30,6 @@ struct ChunkParams {
     int chunk, kk, nchunks;
     double* ws_key; long long* ws_tag;    // [nq, nchunks, kk]
 };
-
-__device__ __forceinline__ double reduce4pairs(const double (&v)[8], int lane) {
-    // same transposed butterfly as amp_fidelity.cu::reduce8
-    double w4[4], w2[2], w1;
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const double send = b4 ? v[i] : v[i + 4];
-        const double keep = b4 ? v[i + 4] : v[i];
-        w4[i] = keep + __shfl_xor_sync(FULL_MASK, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const double send = b3 ? w4[i] : w4[i + 2];
-        const double keep = b3 ? w4[i + 2] : w4[i];
-        w2[i] = keep + __shfl_xor_sync(FULL_MASK, send, 8);
-    }
-    const double send = b2 ? w2[0] : w2[1];
-    const double keep = b2 ? w2[1] : w2[0];
-    w1 = keep + __shfl_xor_sync(FULL_MASK, send, 4);
-    w1 += __shfl_xor_sync(FULL_MASK, w1, 2);
-    w1 += __shfl_xor_sync(FULL_MASK, w1, 1);
-    return w1;
-}
 
 template <bool VEC>
 __global__ void __launch_bounds__(SE_THREADS) search_chunk_kernel(const ChunkParams p) {
@@ -71,19 +48,7 @@ __global__ void __launch_bounds__(SE_THREADS) search_chunk_kernel(const ChunkPar
     const bool l2 = p.metric == QRAG_METRIC_L2;
 
     for (int q = blockIdx.y; q < p.nq; q += gridDim.y) {
-        const float* qrow = p.Q + (size_t)q * D;
-        double part = 0.0;
-        for (int i = tid; i < D; i += SE_THREADS) {
-            const double v = (double)qrow[i];
-            qs[i] = v;
-            part = fma(v, v, part);
-        }
-        part = warp_sum(part);
-        if (lane == 0) red[warp] = part;
-        __syncthreads();
-        double nq2 = 0.0;
-#pragma unroll
-        for (int w = 0; w < SE_WARPS; ++w) nq2 += red[w];
+        const double nq2 = xs_stage_query(p.Q + (size_t)q * D, D, qs, red);
 
         for (int r0 = warp * SE_ROWS; r0 < P; r0 += SE_WARPS * SE_ROWS) {
             if (r0 >= rows) {                                   // padding slots of the sort
@@ -96,62 +61,12 @@ __global__ void __launch_bounds__(SE_THREADS) search_chunk_kernel(const ChunkPar
                 const int r = (r0 + i < rows) ? r0 + i : r0;
                 rp[i] = p.X + (size_t)(row0 + r) * D;
             }
-            double acc[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = 0.0;
-            if (VEC) {
-                const int D4 = D >> 2;
-#pragma unroll 2
-                for (int j = lane; j < D4; j += 32) {
-                    float4 v[SE_ROWS];
-#pragma unroll
-                    for (int i = 0; i < SE_ROWS; ++i) v[i] = ldg_stream(reinterpret_cast<const float4*>(rp[i]) + j);
-                    const double2 qa = *reinterpret_cast<const double2*>(qs + 4 * j);
-                    const double2 qb = *reinterpret_cast<const double2*>(qs + 4 * j + 2);
-                    const double qv[4] = {qa.x, qa.y, qb.x, qb.y};
-#pragma unroll
-                    for (int i = 0; i < SE_ROWS; ++i) {
-                        const double d[4] = {(double)v[i].x, (double)v[i].y, (double)v[i].z, (double)v[i].w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (l2) {
-                                const double t = qv[e] - d[e];
-                                acc[2 * i] = fma(t, t, acc[2 * i]);
-                            } else {
-                                acc[2 * i] = fma(qv[e], d[e], acc[2 * i]);
-                                acc[2 * i + 1] = fma(d[e], d[e], acc[2 * i + 1]);
-                            }
-                        }
-                    }
-                }
-            } else {
-                for (int j = lane; j < D; j += 32) {
-                    const double qv = qs[j];
-#pragma unroll
-                    for (int i = 0; i < SE_ROWS; ++i) {
-                        const double d = (double)__ldg(rp[i] + j);
-                        if (l2) {
-                            const double t = qv - d;
-                            acc[2 * i] = fma(t, t, acc[2 * i]);
-                        } else {
-                            acc[2 * i] = fma(qv, d, acc[2 * i]);
-                            acc[2 * i + 1] = fma(d, d, acc[2 * i + 1]);
-                        }
-                    }
-                }
-            }
-            const double tot = reduce4pairs(acc, lane);
-            const double nd2 = __shfl_down_sync(FULL_MASK, tot, 4);
+            double nd2;
+            const double tot = xs_score4<VEC>(rp, qs, D, l2, lane, nd2);
             if ((lane & 7) == 0) {
                 const int i = lane >> 3, r = r0 + i;
                 if (r < rows) {
-                    double kv;
-                    if (l2) kv = tot;
-                    else if (p.metric == QRAG_METRIC_IP) kv = -tot;
-                    else {
-                        const double den = nq2 * nd2;
-                        kv = den > 0.0 ? -(tot / sqrt(den)) : -0.0;
-                    }
+                    const double kv = xs_key(p.metric, tot, nd2, nq2);
                     key[r] = kv;
                     tag[r] = p.id_base + row0 + r;
                 } else if (r < P) {

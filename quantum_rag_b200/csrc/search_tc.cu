@@ -1,13 +1,710 @@
-// placeholder until the tcgen05 path lands (replaced in a later commit)
+// K3 / K4: brute-force search over a flat index on the 5th-generation tensor cores, with results
+// identical to the exact CUDA-core search (search_exact.cu).
+//
+// The index is the faiss IndexFlat* the ingest tool writes (store_in_faiss.py:99-109); `.search` is
+// never called by the reference, so the contract is faiss's API made canonical: fp32 inputs, fp64
+// accumulation, order (best score, smaller id).
+//
+// A bf16 tensor-core product cannot give fp32-exact order, so the GEMM is used as a FILTER with a
+// proven error bound, and only the survivors are scored exactly:
+//
+//   prepare (once per index)  Xb = bf16 shadow of the corpus, shaped so that every metric is a plain
+//                             inner product: IP: x; cosine: x/|x|; L2: [x, hi(|x|^2), lo(|x|^2)]
+//                             against [2q, -1, -1], i.e. s' = 2 q.x - |x|^2 (descending = nearer).
+//   pass 1  sim_gemm<BUCKET>  S = Qb Xb^T over every `sample`-th 256-document tile; the epilogue keeps
+//                             only the maximum of each 32-document bucket.
+//   tau     per query, m_k = k-th largest bucket maximum.  At least k documents have approximate
+//           score >= m_k, so the exact k-th best is >= m_k - eps and every member of the exact
+//           top-k has approximate score >= tau = m_k - 2 eps  (eps = bound on |approx - exact|).
+//   pass 2  sim_gemm<FILTER>  S over all tiles; the epilogue compares each 32-score chunk's maximum
+//                             with tau and appends the (score, row) pairs >= tau to the query's list.
+//                             S itself never leaves TMEM.
+//   final   per query: a_k = k-th best approximate score of the list; candidates = entries
+//           >= a_k - 2 eps (a superset of the exact top-k, typically k + a few hundred); exact fp64
+//           rescoring with the code of the CUDA-core path (exact_score.cuh), sort by (score, id).
+//   status  a query whose list overflowed is flagged (never silent); the caller reruns it exactly.
+//
+// sim_gemm: one persistent CTA per SM, warp-specialised.  Warp 0 = TMA producer (the query tile
+// A = 128 x K stays resident in shared memory, document tiles B = 256 x 64 stream through a ring),
+// warp 1 = MMA issuer (tcgen05.mma, M=128 N=256 K=16, fp32 accumulators in TMEM, two accumulator
+// buffers of 256 columns so that the epilogue of tile i overlaps the MMAs of tile i+1), warp 2 =
+// TMEM allocator, warps 4-7 = epilogue (tcgen05.ld 32x32b: one thread per query row).
 #include "common.cuh"
+#include "exact_score.cuh"
+#include "sort.cuh"
+#include "tma.cuh"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace qrag {
+
+constexpr int TC_BM = 128;            // queries per tile (UMMA M)
+constexpr int TC_BN = 256;            // documents per tile (UMMA N)
+constexpr int TC_BK = 64;             // K elements per shared-memory chunk (128 B rows, SWIZZLE_128B)
+constexpr int TC_UK = 16;             // K per tcgen05.mma (bf16)
+constexpr int TC_THREADS = 256;
+constexpr int TC_A_CHUNK = TC_BM * TC_BK * 2;     // 16 KB
+constexpr int TC_B_STAGE = TC_BN * TC_BK * 2;     // 32 KB
+constexpr int TC_BUCKET = 32;         // documents per bucket maximum (one tcgen05.ld chunk)
+constexpr int TC_CAP = 16384;         // survivor list capacity per query
+constexpr int TC_MAX_CAND = 4096;     // exact-rescore capacity per query
+constexpr int TC_MAX_STAGES = 6;
+constexpr int TC_MODE_BUCKET = 0, TC_MODE_FILTER = 1;
+
+struct TcGemmParams {
+    int kchunks;            // ceil(Kp / 64)
+    int ksteps_last;        // tcgen05.mma K-steps in the last chunk (1..4)
+    int stages;             // ring depth
+    int a_resident;         // 1: the query tile (all K chunks) stays in shared memory; 0: its chunks stream with B
+    int stage_bytes;        // 32 KB (B chunk) or 48 KB (B chunk + A chunk)
+    int groups;             // query groups (of 128) in this launch
+    int group0;             // first query group of this launch
+    int nq;                 // total queries
+    int64_t N;              // documents
+    int ntiles;             // ceil(N / 256)
+    int sample;             // pass 1 visits tiles 0, sample, 2*sample, ...
+    int nbuckets;           // buckets per query in pass 1 = nsample_tiles * 8
+    const float* tau;       // [nq] (filter)
+    float* bmax;            // [nq, nbuckets] (bucket)
+    unsigned int* cnt;      // [nq] (filter)
+    float2* surv;           // [nq, TC_CAP] (score, row as int bits) (filter)
+};
+
+// ------------------------------------------------------------------ PTX wrappers (tcgen05 / TMA)
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile with 128-byte swizzled rows: 8-row groups are 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float neg_inf_f() { return __int_as_float(0xff800000); }
+
+// ------------------------------------------------------------------------------- the GEMM
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcGemmParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* sA = smem;                                             // [kchunks][128 rows][128 B]
+    unsigned char* sB = sA + (p.a_resident ? (size_t)p.kchunks * TC_A_CHUNK : 0);   // [stages]{[256 rows][128 B], A chunk}
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * p.stage_bytes);
+    uint64_t* a_full = bars;
+    uint64_t* full = bars + 1;
+    uint64_t* empty = full + TC_MAX_STAGES;
+    uint64_t* acc_full = empty + TC_MAX_STAGES;       // [2]
+    uint64_t* acc_empty = acc_full + 2;               // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = p.stages, KC = p.kchunks;
+
+    if (tid == 0) {
+        mbar_init(a_full, 1);
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // work of this CTA: query group g, tiles u0, u0 + cpg, ... (pass 1: of the sampled tiles)
+    const int g = blockIdx.x % p.groups;
+    const int u0 = blockIdx.x / p.groups;
+    const int cpg = gridDim.x / p.groups;
+    const int step = MODE == TC_MODE_BUCKET ? p.sample : 1;
+    const int nunits = (p.ntiles + step - 1) / step;          // tiles this pass visits
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ TMA producer
+            if (p.a_resident) {
+                mbar_arrive_expect_tx(a_full, (uint32_t)KC * TC_A_CHUNK);
+                for (int kc = 0; kc < KC; ++kc)
+                    tma_load_2d(sA + (size_t)kc * TC_A_CHUNK, &mapA, a_full, kc * TC_BK, (p.group0 + g) * TC_BM);
+            }
+            int s = 0;
+            uint32_t par = 0;
+            for (int u = u0; u < nunits; u += cpg) {
+                const int tile = u * step;
+                for (int kc = 0; kc < KC; ++kc) {
+                    mbar_wait(&empty[s], par ^ 1u);
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)p.stage_bytes);
+                    tma_load_2d(sB + (size_t)s * p.stage_bytes, &mapB, &full[s], kc * TC_BK, tile * TC_BN);
+                    if (!p.a_resident)
+                        tma_load_2d(sB + (size_t)s * p.stage_bytes + TC_B_STAGE, &mapA, &full[s], kc * TC_BK,
+                                    (p.group0 + g) * TC_BM);
+                    if (++s == S) { s = 0; par ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // -------------------------------------------------------------- MMA issuer
+            // instruction descriptor: D fp32, A/B bf16, both K-major, N = 256, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                                   ((uint32_t)(TC_BM >> 4) << 24);
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+            if (p.a_resident) mbar_wait(a_full, 0);
+            int s = 0;
+            uint32_t par = 0;
+            int n = 0;
+            for (int u = u0; u < nunits; u += cpg, ++n) {
+                const int buf = n & 1;
+                mbar_wait(&acc_empty[buf], (((uint32_t)n >> 1) & 1u) ^ 1u);      // epilogue drained this buffer
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)buf * TC_BN;
+                for (int kc = 0; kc < KC; ++kc) {
+                    mbar_wait(&full[s], par);
+                    tc_fence_after();
+                    const int ks = (kc == KC - 1) ? p.ksteps_last : TC_BK / TC_UK;
+                    for (int k = 0; k < ks; ++k) {
+                        const uint32_t bs = b0 + (uint32_t)s * (uint32_t)p.stage_bytes;
+                        const uint32_t as = p.a_resident ? a0 + (uint32_t)kc * TC_A_CHUNK : bs + TC_B_STAGE;
+                        const uint64_t ad = umma_desc_sw128(as + (uint32_t)k * TC_UK * 2);
+                        const uint64_t bd = umma_desc_sw128(bs + (uint32_t)k * TC_UK * 2);
+                        umma_bf16(d, ad, bd, idesc, (kc | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);                  // frees the stage when these MMAs have read it
+                    if (++s == S) { s = 0; par ^= 1u; }
+                }
+                umma_commit(&acc_full[buf]);                 // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue
+        const int ew = warp - 4;                              // == warp % 4: TMEM lanes 32*ew .. 32*ew+31
+        const int row = ew * 32 + lane;
+        const int q = (p.group0 + g) * TC_BM + row;
+        const bool qvalid = q < p.nq;
+        float tau = __int_as_float(0x7f800000);               // +inf: rows beyond nq never emit
+        if (MODE == TC_MODE_FILTER && qvalid) tau = p.tau[q];
+        int n = 0;
+        for (int u = u0; u < nunits; u += cpg, ++n) {
+            const int buf = n & 1;
+            const int tile = u * step;
+            const int64_t doc0 = (int64_t)tile * TC_BN;
+            const bool ragged = doc0 + TC_BN > p.N;
+            mbar_wait(&acc_full[buf], ((uint32_t)n >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * TC_BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(t0 + (uint32_t)c0, r);
+                tmem_ld_wait();
+                if (ragged) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (doc0 + c0 + j >= p.N) r[j] = 0xff800000u;             // -inf: rows past the end
+                }
+                float m = __uint_as_float(r[0]);
+#pragma unroll
+                for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+                if (MODE == TC_MODE_BUCKET) {
+                    if (qvalid) p.bmax[(size_t)q * p.nbuckets + (size_t)u * (TC_BN / TC_BUCKET) + (c0 >> 5)] = m;
+                } else if (m >= tau) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = __uint_as_float(r[j]);
+                        if (v >= tau && doc0 + c0 + j < p.N) {
+                            const unsigned int pos = atomicAdd(&p.cnt[q], 1u);
+                            if (pos < (unsigned)TC_CAP)
+                                p.surv[(size_t)q * TC_CAP + pos] = make_float2(v, __int_as_float((int)(doc0 + c0 + j)));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------- operand preparation
+// one warp per corpus row: |x|^2 in fp64, then the bf16 shadow row for the metric
+__global__ void __launch_bounds__(256) index_prepare_kernel(const float* __restrict__ X, int64_t N, int D, int Kp, int metric,
+                                                            __nv_bfloat16* __restrict__ Xb, float* __restrict__ aux) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= N) return;
+    const float* x = X + (size_t)row * D;
+    double part = 0.0;
+    for (int j = lane; j < D; j += 32) { const double v = (double)x[j]; part = fma(v, v, part); }
+    const double n2 = warp_sum(part);
+    const double nrm = sqrt(n2);
+    __nv_bfloat16* o = Xb + (size_t)row * Kp;
+    for (int j = lane; j < Kp; j += 32) {
+        float v = 0.f;
+        if (j < D) {
+            v = x[j];
+            if (metric == QRAG_METRIC_COSINE) v = nrm > 0.0 ? (float)((double)v / nrm) : 0.f;
+        } else if (metric == QRAG_METRIC_L2 && j < D + 2) {
+            const float n2f = (float)n2;
+            const float hi = __bfloat162float(__float2bfloat16_rn(n2f));
+            v = (j == D) ? hi : (n2f - hi);
+        }
+        o[j] = __float2bfloat16_rn(v);
+    }
+    if (lane == 0) {
+        const float up = __double2float_ru(nrm);                 // max |x| (rounded up); floats >= 0 order like ints
+        atomicMax(reinterpret_cast<int*>(aux), __float_as_int(up));
+    }
+}
+
+// one warp per query row: bf16 query operand for the metric, |q| rounded up
+__global__ void __launch_bounds__(256) query_prepare_kernel(const float* __restrict__ Q, int nq, int nq_pad, int D, int Kp,
+                                                            int metric, __nv_bfloat16* __restrict__ Qb,
+                                                            float* __restrict__ qnorm) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= nq_pad) return;
+    __nv_bfloat16* o = Qb + (size_t)row * Kp;
+    if (row >= nq) {
+        for (int j = lane; j < Kp; j += 32) o[j] = __float2bfloat16_rn(0.f);
+        return;
+    }
+    const float* x = Q + (size_t)row * D;
+    double part = 0.0;
+    for (int j = lane; j < Kp; j += 32) {
+        float v = 0.f;
+        if (j < D) {
+            v = x[j];
+            part = fma((double)v, (double)v, part);
+            if (metric == QRAG_METRIC_L2) v *= 2.f;              // exact in bf16: bf16(2q) == 2 bf16(q)
+        } else if (metric == QRAG_METRIC_L2 && j < D + 2) {
+            v = -1.f;
+        }
+        o[j] = __float2bfloat16_rn(v);
+    }
+    part = warp_sum(part);
+    if (lane == 0) qnorm[row] = __double2float_ru(sqrt(part));
+}
+
+// Bound on |approximate - exact| in the units of the approximate score, per unit of |q| (a) and
+// absolute (b): eps = a |q| + b.  bf16 rounding of both operands (2^-9 each, plus the cross term),
+// fp32 accumulation of Kp exact products inside the tensor core (Kp * 2^-22, generous), Cauchy-Schwarz.
+__device__ __forceinline__ float tc_eps(int metric, int Kp, float qn, float xmax) {
+    const float c = 0.00390625f + 0.0000153f + (float)Kp * 2.4e-7f;
+    float e;
+    if (metric == QRAG_METRIC_IP) e = c * qn * xmax;
+    else if (metric == QRAG_METRIC_COSINE) e = c * qn * 1.0000002f;
+    else e = 2.f * c * qn * xmax + 3.1e-5f * xmax * xmax;        // + hi/lo split of |x|^2 (2^-15, generous)
+    return e * 1.0001f + 1e-30f;
+}
+
+// per query: tau = (k-th largest bucket maximum) - 2 eps, rounded down
+__global__ void __launch_bounds__(256) tau_kernel(const float* __restrict__ bmax, int nbuckets, int k, int metric, int Kp,
+                                                  const float* __restrict__ qnorm, const float* __restrict__ aux,
+                                                  float* __restrict__ tau, float* __restrict__ eps) {
+    extern __shared__ float sk[];
+    const int q = blockIdx.x;
+    int P = 1;
+    while (P < nbuckets) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += blockDim.x)
+        sk[i] = i < nbuckets ? -bmax[(size_t)q * nbuckets + i] : __int_as_float(0x7f800000);
+    __syncthreads();
+    for (int kk = 2; kk <= P; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int hi = lo | j;
+                const float a = sk[lo], b = sk[hi];
+                const bool asc = (lo & kk) == 0;
+                if ((b < a) == asc) { sk[lo] = b; sk[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        const float e = tc_eps(metric, Kp, qnorm[q], aux[0]);
+        eps[q] = e;
+        float t = neg_inf_f();
+        if (nbuckets >= k) {
+            const float mk = -sk[k - 1];
+            t = mk - 2.f * e;
+            t = t - fabsf(t) * 2.4e-7f - 1e-37f;                  // the subtraction above rounds to nearest: step down
+        }
+        tau[q] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------- final stage
+struct TcFinalParams {
+    const float* Q; const float* X; int nq; int64_t N; int D; int k; int metric; int64_t id_base;
+    const unsigned int* cnt; const float2* surv; const float* eps;
+    double* out_scores; int64_t* out_ids; int32_t* status;
+};
+
+template <typename K, typename T>
+__device__ void bitonic_sort_kt(K* key, T* tag, int P) {
+    for (int kk = 2; kk <= P; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int hi = lo | j;
+                const K kl = key[lo], kh = key[hi];
+                const T tl = tag[lo], th = tag[hi];
+                const bool asc = (lo & kk) == 0;
+                const bool hi_first = (kh < kl) || (kh == kl && th < tl);
+                if (hi_first == asc) { key[lo] = kh; key[hi] = kl; tag[lo] = th; tag[hi] = tl; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int D = p.D, Dpad = (D + 3) & ~3;
+    double* qs = reinterpret_cast<double*>(smem_raw);
+    double* red = qs + Dpad;
+    double* ckey = red + XS_WARPS;                                         // [TC_MAX_CAND]
+    long long* ctag = reinterpret_cast<long long*>(ckey + TC_MAX_CAND);    // [TC_MAX_CAND]
+    float* skey = reinterpret_cast<float*>(ctag + TC_MAX_CAND);            // [TC_CAP]
+    int* stag = reinterpret_cast<int*>(skey + TC_CAP);                     // [TC_CAP]
+    __shared__ int s_m;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = blockIdx.x;
+    const int k = p.k;
+    const bool l2 = p.metric == QRAG_METRIC_L2;
+
+    const unsigned int total = p.cnt[q];
+    int n = total < (unsigned)TC_CAP ? (int)total : TC_CAP;
+    int bad = total > (unsigned)TC_CAP ? 1 : 0;
+    int P = 1;
+    while (P < n) P <<= 1;
+    for (int i = tid; i < P; i += XS_THREADS) {
+        float kv = __int_as_float(0x7f800000);
+        int tv = 0x7fffffff;
+        if (i < n) {
+            const float2 e = p.surv[(size_t)q * TC_CAP + i];
+            kv = -e.x;
+            tv = __float_as_int(e.y);
+        }
+        skey[i] = kv;
+        stag[i] = tv;
+    }
+    if (tid == 0) s_m = 0;
+    __syncthreads();
+    bitonic_sort_kt<float, int>(skey, stag, P);
+    // candidates: approximate score >= a_k - 2 eps (a prefix of the sorted list)
+    float thr = neg_inf_f();
+    if (n >= k) {
+        const float ak = -skey[k - 1];
+        thr = ak - 2.f * p.eps[q];
+        thr = thr - fabsf(thr) * 2.4e-7f - 1e-37f;
+    }
+    int local = 0;
+    for (int i = tid; i < n; i += XS_THREADS) local += (-skey[i] >= thr) ? 1 : 0;
+    local = __reduce_add_sync(FULL_MASK, local);
+    if (lane == 0 && local) atomicAdd(&s_m, local);
+    const double nq2 = xs_stage_query(p.Q + (size_t)q * D, D, qs, red);     // ends with __syncthreads()
+    int m = s_m;
+    if (m > TC_MAX_CAND) { m = TC_MAX_CAND; bad = 1; }
+    int P2 = 1;
+    while (P2 < m) P2 <<= 1;
+    for (int r0 = warp * XS_ROWS; r0 < P2; r0 += XS_WARPS * XS_ROWS) {
+        if (r0 >= m) {
+            if (lane < XS_ROWS && r0 + lane < P2) { ckey[r0 + lane] = pos_inf(); ctag[r0 + lane] = 0x7fffffffffffffffLL; }
+            continue;
+        }
+        const float* rp[XS_ROWS];
+#pragma unroll
+        for (int i = 0; i < XS_ROWS; ++i) {
+            const int r = (r0 + i < m) ? r0 + i : r0;
+            rp[i] = p.X + (size_t)stag[r] * D;
+        }
+        double nd2;
+        const double tot = xs_score4<VEC>(rp, qs, D, l2, lane, nd2);
+        if ((lane & 7) == 0) {
+            const int i = lane >> 3, r = r0 + i;
+            if (r < m) {
+                ckey[r] = xs_key(p.metric, tot, nd2, nq2);
+                ctag[r] = p.id_base + stag[r];
+            } else if (r < P2) {
+                ckey[r] = pos_inf();
+                ctag[r] = 0x7fffffffffffffffLL;
+            }
+        }
+    }
+    __syncthreads();
+    bitonic_sort_kt<double, long long>(ckey, ctag, P2);
+    for (int i = tid; i < k; i += XS_THREADS) {
+        double kv = pos_inf();
+        long long tv = 0x7fffffffffffffffLL;
+        if (i < m) { kv = ckey[i]; tv = ctag[i]; }
+        if (tv == 0x7fffffffffffffffLL) { tv = -1; kv = l2 ? pos_inf() : -pos_inf(); }
+        else if (!l2) kv = -kv;
+        p.out_scores[(size_t)q * k + i] = kv;
+        p.out_ids[(size_t)q * k + i] = tv;
+    }
+    // fewer than k candidates is only legitimate when the whole shard is shorter than k
+    if (m < k && (int64_t)m < p.N) bad = 1;
+    if (tid == 0) p.status[q] = bad;
+}
+
+// --------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// [rows, Kp] bf16 row-major, box = 64 x box_rows, 128-byte swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int Kp, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    QRAG_REQUIRE(fn != nullptr, QRAG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)Kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    QRAG_REQUIRE(r == CUDA_SUCCESS, QRAG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld Kp=%d", (int)r,
+                 (long long)rows, Kp);
+    return QRAG_OK;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int tc_kp(int D, int metric) { return (int)align_up((size_t)D + (metric == QRAG_METRIC_L2 ? 2 : 0), 16); }
+
+struct TcPlan {
+    int Kp, kchunks, ksteps_last, stages, a_resident, stage_bytes, nq_pad, groups, ntiles, sample, nsample_tiles, nbuckets;
+    size_t smem_gemm, off_qb, off_qnorm, off_bmax, off_tau, off_eps, off_cnt, off_surv, total;
+};
+
+static int tc_plan(int nq, int64_t N, int D, int k, int metric, TcPlan* pl) {
+    QRAG_REQUIRE(nq >= 0 && N >= 0 && D > 0, QRAG_ERR_INVALID, "bad sizes nq=%d N=%lld D=%d", nq, (long long)N, D);
+    QRAG_REQUIRE(metric >= 0 && metric <= 2, QRAG_ERR_INVALID, "unknown metric %d", metric);
+    QRAG_REQUIRE(k >= 1 && k <= 2048, QRAG_ERR_UNSUPPORTED, "tensor-core search supports 1 <= k <= 2048 (got %d)", k);
+    QRAG_REQUIRE(N < ((int64_t)1 << 31) - TC_BN, QRAG_ERR_UNSUPPORTED, "shard too large (N=%lld)", (long long)N);
+    pl->Kp = tc_kp(D, metric);
+    pl->kchunks = (pl->Kp + TC_BK - 1) / TC_BK;
+    pl->ksteps_last = (pl->Kp - (pl->kchunks - 1) * TC_BK) / TC_UK;
+    // the query tile stays resident when that still leaves a 3-deep ring for the document chunks;
+    // otherwise (long rows) its chunks travel through the ring next to them
+    const size_t a_bytes = (size_t)pl->kchunks * TC_A_CHUNK;
+    const size_t budget = (size_t)device_props().max_smem_optin;
+    pl->a_resident = (1024 + 256 + a_bytes + 3 * (size_t)TC_B_STAGE <= budget) ? 1 : 0;
+    pl->stage_bytes = pl->a_resident ? TC_B_STAGE : TC_B_STAGE + TC_A_CHUNK;
+    const size_t fixed = 1024 + 256 + (pl->a_resident ? a_bytes : 0);
+    int stages = (int)((budget - fixed) / pl->stage_bytes);
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    QRAG_REQUIRE(stages >= 2, QRAG_ERR_UNSUPPORTED, "not enough shared memory for the tensor-core search");
+    pl->stages = stages;
+    pl->smem_gemm = fixed + (size_t)stages * pl->stage_bytes;
+    pl->nq_pad = (int)align_up((size_t)(nq > 0 ? nq : 1), TC_BM);
+    pl->groups = pl->nq_pad / TC_BM;
+    pl->ntiles = (int)ceil_div(N > 0 ? N : 1, TC_BN);
+    // pass 1 samples every `sample`-th tile: survivors ~ sample * k per query, kept well under TC_CAP,
+    // and the sample must hold many more buckets than k for the bound to be tight
+    int sample = TC_CAP / (4 * k);
+    if (sample > 16) sample = 16;
+    const int64_t by_buckets = N / ((int64_t)256 * k);
+    if (sample > by_buckets) sample = (int)by_buckets;
+    if (sample < 1) sample = 1;
+    pl->sample = sample;
+    pl->nsample_tiles = (pl->ntiles + sample - 1) / sample;
+    pl->nbuckets = pl->nsample_tiles * (TC_BN / TC_BUCKET);
+    QRAG_REQUIRE(pl->nbuckets <= 32768, QRAG_ERR_UNSUPPORTED, "shard too large for one pass (N=%lld): split it",
+                 (long long)N);
+    size_t off = 0;
+    pl->off_qb = off; off = align_up(off + (size_t)pl->nq_pad * pl->Kp * 2, 256);
+    pl->off_qnorm = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
+    pl->off_bmax = off; off = align_up(off + (size_t)pl->nq_pad * pl->nbuckets * 4, 256);
+    pl->off_tau = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
+    pl->off_eps = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
+    pl->off_cnt = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
+    pl->off_surv = off; off = align_up(off + (size_t)pl->nq_pad * TC_CAP * 8, 256);
+    pl->total = off + 256;
+    return QRAG_OK;
+}
+
+}  // namespace qrag
+
 using namespace qrag;
-extern "C" int qrag_index_prepare(const float*, int64_t, int, uint16_t*, float*, void*) {
-    return set_error(QRAG_ERR_UNSUPPORTED, "tcgen05 search path not built yet");
+
+extern "C" int qrag_index_prepared_dims(int D, int metric, int* Kp) {
+    QRAG_REQUIRE(Kp != nullptr && D > 0 && metric >= 0 && metric <= 2, QRAG_ERR_INVALID, "bad arguments");
+    *Kp = tc_kp(D, metric);
+    return QRAG_OK;
 }
-extern "C" int qrag_search_tc_workspace(int, int64_t, int, int, size_t*) {
-    return set_error(QRAG_ERR_UNSUPPORTED, "tcgen05 search path not built yet");
+
+extern "C" int qrag_index_prepare(const float* X, int64_t N, int D, int metric, uint16_t* Xb, float* aux, void* stream) {
+    QRAG_REQUIRE(Xb && aux && (X || N == 0), QRAG_ERR_INVALID, "null pointer argument");
+    QRAG_REQUIRE(N >= 0 && D > 0 && metric >= 0 && metric <= 2, QRAG_ERR_INVALID, "bad arguments");
+    QRAG_REQUIRE(device_props().ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
+    cudaStream_t st = (cudaStream_t)stream;
+    QRAG_CUDA_CHECK(cudaMemsetAsync(aux, 0, 4 * sizeof(float), st));
+    if (N == 0) return QRAG_OK;
+    const int Kp = tc_kp(D, metric);
+    index_prepare_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(X, N, D, Kp, metric, reinterpret_cast<__nv_bfloat16*>(Xb),
+                                                                  aux);
+    QRAG_LAUNCH_CHECK("index_prepare_kernel");
+    return QRAG_OK;
 }
-extern "C" int qrag_search_topk_tc(const float*, int, const float*, const uint16_t*, const float*, int64_t, int, int,
-                                   int, int64_t, double*, int64_t*, void*, size_t, void*) {
-    return set_error(QRAG_ERR_UNSUPPORTED, "tcgen05 search path not built yet");
+
+extern "C" int qrag_search_tc_workspace(int nq, int64_t N, int D, int k, int metric, size_t* bytes) {
+    QRAG_REQUIRE(bytes != nullptr, QRAG_ERR_INVALID, "bytes is null");
+    QRAG_REQUIRE(device_props().ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
+    TcPlan pl;
+    int rc = tc_plan(nq, N, D, k, metric, &pl);
+    if (rc) return rc;
+    *bytes = pl.total;
+    return QRAG_OK;
+}
+
+template <int MODE>
+static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcGemmParams& gp, size_t smem, int grid,
+                       cudaStream_t st) {
+    auto kern = sim_gemm_kernel<MODE>;
+    QRAG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, TC_THREADS, smem, st>>>(mapA, mapB, gp);
+    QRAG_LAUNCH_CHECK("sim_gemm_kernel");
+    return QRAG_OK;
+}
+
+extern "C" int qrag_search_topk_tc(const float* Q, int nq, const float* X, const uint16_t* Xb, const float* aux, int64_t N,
+                                   int D, int k, int metric, int64_t id_base, double* out_scores, int64_t* out_ids,
+                                   int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+    QRAG_REQUIRE(Q && X && Xb && aux && out_scores && out_ids && status, QRAG_ERR_INVALID, "null pointer argument");
+    const DeviceProps& dp = device_props();
+    QRAG_REQUIRE(dp.ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
+    QRAG_REQUIRE(dp.cc_major == 10, QRAG_ERR_UNSUPPORTED, "tcgen05 search needs compute capability 10.x (got %d.%d)",
+                 dp.cc_major, dp.cc_minor);
+    TcPlan pl;
+    int rc = tc_plan(nq, N, D, k, metric, &pl);
+    if (rc) return rc;
+    QRAG_REQUIRE(N >= 1, QRAG_ERR_INVALID, "empty shard: use qrag_search_topk");
+    if (nq == 0) return QRAG_OK;
+    QRAG_REQUIRE(workspace != nullptr && workspace_bytes >= pl.total, QRAG_ERR_WORKSPACE,
+                 "workspace too small: need %zu bytes, got %zu", pl.total, workspace_bytes);
+    QRAG_REQUIRE((uintptr_t)Xb % 16 == 0, QRAG_ERR_INVALID, "Xb must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* ws = reinterpret_cast<unsigned char*>(align_up((size_t)workspace, 256));
+    __nv_bfloat16* Qb = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_qb);
+    float* qnorm = reinterpret_cast<float*>(ws + pl.off_qnorm);
+    float* bmax = reinterpret_cast<float*>(ws + pl.off_bmax);
+    float* tau = reinterpret_cast<float*>(ws + pl.off_tau);
+    float* eps = reinterpret_cast<float*>(ws + pl.off_eps);
+    unsigned int* cnt = reinterpret_cast<unsigned int*>(ws + pl.off_cnt);
+    float2* surv = reinterpret_cast<float2*>(ws + pl.off_surv);
+
+    query_prepare_kernel<<<(unsigned)ceil_div(pl.nq_pad, 8), 256, 0, st>>>(Q, nq, pl.nq_pad, D, pl.Kp, metric, Qb, qnorm);
+    QRAG_LAUNCH_CHECK("query_prepare_kernel");
+    QRAG_CUDA_CHECK(cudaMemsetAsync(cnt, 0, (size_t)pl.nq_pad * 4, st));
+
+    CUtensorMap mapA, mapB;
+    rc = make_map(&mapA, Qb, pl.nq_pad, pl.Kp, TC_BM);
+    if (rc) return rc;
+    rc = make_map(&mapB, Xb, N, pl.Kp, TC_BN);
+    if (rc) return rc;
+
+    TcGemmParams gp{};
+    gp.kchunks = pl.kchunks; gp.ksteps_last = pl.ksteps_last; gp.stages = pl.stages;
+    gp.a_resident = pl.a_resident; gp.stage_bytes = pl.stage_bytes;
+    gp.nq = nq; gp.N = N; gp.ntiles = pl.ntiles; gp.sample = pl.sample; gp.nbuckets = pl.nbuckets;
+    gp.tau = tau; gp.bmax = bmax; gp.cnt = cnt; gp.surv = surv;
+
+    const int sms = dp.sm_count;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int units = pass == 0 ? pl.nsample_tiles : pl.ntiles;
+        for (int g0 = 0; g0 < pl.groups; g0 += sms) {
+            const int groups = pl.groups - g0 < sms ? pl.groups - g0 : sms;
+            int cpg = sms / groups;
+            if (cpg > units) cpg = units;
+            gp.groups = groups;
+            gp.group0 = g0;
+            rc = pass == 0 ? launch_gemm<TC_MODE_BUCKET>(mapA, mapB, gp, pl.smem_gemm, groups * cpg, st)
+                           : launch_gemm<TC_MODE_FILTER>(mapA, mapB, gp, pl.smem_gemm, groups * cpg, st);
+            if (rc) return rc;
+        }
+        if (pass == 0) {
+            const size_t smem = (size_t)next_pow2(pl.nbuckets) * sizeof(float);
+            if (smem > 48 * 1024)
+                QRAG_CUDA_CHECK(cudaFuncSetAttribute(tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tau_kernel<<<nq, 256, smem, st>>>(bmax, pl.nbuckets, k, metric, pl.Kp, qnorm, aux, tau, eps);
+            QRAG_LAUNCH_CHECK("tau_kernel");
+        }
+    }
+
+    TcFinalParams fp{Q, X, nq, N, D, k, metric, id_base, cnt, surv, eps, out_scores, out_ids, status};
+    const int Dpad = (D + 3) & ~3;
+    const size_t smem = (size_t)(Dpad + XS_WARPS) * 8 + (size_t)TC_MAX_CAND * 16 + (size_t)TC_CAP * 8;
+    QRAG_REQUIRE(smem <= (size_t)dp.max_smem_optin, QRAG_ERR_UNSUPPORTED, "D=%d too large for the rescoring stage", D);
+    const bool vec = (D % 4 == 0) && ((uintptr_t)X % 16 == 0);
+    if (vec) {
+        QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_final_kernel<true><<<nq, XS_THREADS, smem, st>>>(fp);
+    } else {
+        QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_final_kernel<false><<<nq, XS_THREADS, smem, st>>>(fp);
+    }
+    QRAG_LAUNCH_CHECK("tc_final_kernel");
+    return QRAG_OK;
 }

@@ -1,0 +1,111 @@
+"""K3/K4 parity: the tcgen05 search returns exactly what the exact CUDA-core search and the oracle return."""
+import numpy as np
+import pytest
+
+from oracle import search as osr
+
+pytestmark = pytest.mark.gpu
+
+METRICS = [("ip", osr.METRIC_IP), ("l2", osr.METRIC_L2), ("cosine", osr.METRIC_COSINE)]
+
+
+def _compare_with_exact(api, Q, X, k, name, id_base=0, allow_fallback=False):
+    import torch
+    index = api.FlatIndexTC(X, name, id_base=id_base)
+    s, i = index.search(Q, k)
+    if not allow_fallback:
+        assert index.last_fallback == 0, f"{index.last_fallback} queries fell back to the exact path"
+    es, ei = api.search_topk(Q, X, k, name, id_base=id_base)
+    assert torch.equal(i, ei), name
+    assert torch.equal(s, es), name                     # bit-identical fp64 scores (same scoring code)
+    return index
+
+
+@pytest.mark.parametrize("name,mid", METRICS)
+@pytest.mark.parametrize("nq,N,D,k", [(5, 3000, 64, 10), (130, 20000, 384, 100), (1, 70000, 384, 100),
+                                      (300, 66000, 128, 37), (64, 50000, 96, 1000), (7, 9000, 40, 7),
+                                      (33, 30011, 1536, 20)])
+def test_tc_search_equals_exact_search(cuda, name, mid, nq, N, D, k):
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(nq + N + D + k)
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Q = rng.standard_normal((nq, D)).astype(np.float32)
+    X[17] = X[3]
+    X[N - 1] = X[3]                                     # duplicates far apart: exact ties, id order decides
+    Q[0] = X[3]
+    _compare_with_exact(api, Q, X, k, name, id_base=12345)
+
+
+@pytest.mark.parametrize("name,mid", METRICS)
+def test_tc_search_matches_oracle_unit_rows(cuda, name, mid):
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(3)
+    X = rng.standard_normal((12000, 384)).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    Q = rng.standard_normal((20, 384)).astype(np.float32)
+    Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    index = api.FlatIndexTC(X, name)
+    s, i = index.search(Q, 50)
+    rs, ri = osr.exact_search(Q, X, 50, mid)
+    assert np.array_equal(i.cpu().numpy(), ri)
+    assert np.allclose(s.cpu().numpy(), rs, rtol=1e-12, atol=1e-13)
+
+
+def test_tc_search_on_reference_fixture(cuda, piers, kat):
+    """Config 1 through the tensor-core path: the reference's own index, every row as the query."""
+    from quantum_rag_b200 import api
+    x = piers["vectors"]
+    index = api.FlatIndexTC(x, "l2")
+    s, i = index.search(x, 20)
+    assert np.array_equal(i.cpu().numpy(), piers["top20_ids"])
+    assert i[0].cpu().tolist() == kat["survey"]["fixture_top20_row0"]
+    assert np.allclose(s.cpu().numpy(), piers["top20_dist"], rtol=1e-12, atol=1e-13)
+
+
+def test_tc_search_scaled_and_clustered_data(cuda):
+    """Norm spread and heavy clustering stress the error bound and the survivor lists."""
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(9)
+    centers = rng.standard_normal((8, 128)).astype(np.float32)
+    X = (centers[rng.randint(0, 8, 40000)] + 0.05 * rng.standard_normal((40000, 128))).astype(np.float32)
+    X *= rng.uniform(0.1, 30.0, size=(40000, 1)).astype(np.float32)
+    Q = (centers[rng.randint(0, 8, 50)] + 0.05 * rng.standard_normal((50, 128))).astype(np.float32)
+    for name, _ in METRICS:
+        _compare_with_exact(api, Q, X, 64, name, allow_fallback=True)
+
+
+def test_tc_search_k_larger_than_shard(cuda):
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(1)
+    X = rng.standard_normal((40, 32)).astype(np.float32)
+    Q = rng.standard_normal((3, 32)).astype(np.float32)
+    _compare_with_exact(api, Q, X, 64, "ip")
+
+
+def test_config3_full_size_properties(cuda):
+    """BASELINE config 3 (1M x 384 unit rows, top-100) through size-independent properties."""
+    import torch
+    from quantum_rag_b200 import api
+    g = torch.Generator(device="cuda").manual_seed(1234 + 3)
+    N, D, nq, k = 1_000_000, 384, 256, 100
+    X = torch.nn.functional.normalize(torch.randn(N, D, generator=g, device="cuda"), dim=1)
+    Q = torch.nn.functional.normalize(torch.randn(nq, D, generator=g, device="cuda"), dim=1)
+    planted = torch.arange(nq, device="cuda") * 3001 + 7
+    X[planted] = Q                                       # every query has itself in the corpus
+    X[planted + 1] = Q                                   # ... twice: exact tie, smaller id first
+    index = api.FlatIndexTC(X, "cosine")
+    s, i = index.search(Q, k)
+    assert index.last_fallback == 0
+    assert torch.equal(i[:, 0], planted) and torch.equal(i[:, 1], planted + 1)
+    assert torch.all(s[:, 0] == s[:, 1]) and torch.allclose(s[:, 0], torch.ones_like(s[:, 0]), atol=1e-6)
+    assert torch.all(s[:, :-1] >= s[:, 1:])              # sorted
+    # a subset of queries against the exact CUDA-core search: identical ids and bits
+    sub = torch.arange(0, nq, 37, device="cuda")
+    es, ei = api.search_topk(Q[sub], X, k, "cosine")
+    assert torch.equal(i[sub], ei) and torch.equal(s[sub], es)
+    # sharding: merging two half-corpus searches reproduces the full search
+    h = N // 2
+    a = api.FlatIndexTC(X[:h], "cosine", id_base=0).search(Q, k)
+    b = api.FlatIndexTC(X[h:], "cosine", id_base=h).search(Q, k)
+    ms, mi = api.topk_merge(torch.stack([a[0], b[0]]), torch.stack([a[1], b[1]]), k, "cosine")
+    assert torch.equal(mi, i) and torch.equal(ms, s)
