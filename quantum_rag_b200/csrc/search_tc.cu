@@ -48,7 +48,8 @@ constexpr int TC_A_CHUNK = TC_BM * TC_BK * 2;     // 16 KB
 constexpr int TC_B_STAGE = TC_BN * TC_BK * 2;     // 32 KB
 constexpr int TC_BUCKET = 32;         // documents per bucket maximum (one tcgen05.ld chunk)
 constexpr int TC_CAP = 16384;         // survivor list capacity per query
-constexpr int TC_MAX_CAND = 4096;     // exact-rescore capacity per query
+constexpr int TC_MAX_CAND = 8192;     // largest exact-rescore capacity per query
+constexpr int TC_MAX_SEGS = 160;      // survivor-list segments per query (one per CTA of the query's group)
 constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_MODE_BUCKET = 0, TC_MODE_FILTER = 1;
 
@@ -67,8 +68,9 @@ struct TcGemmParams {
     int nbuckets;           // buckets per query in pass 1 = nsample_tiles * 8
     const float* tau;       // [nq] (filter)
     float* bmax;            // [nq, nbuckets] (bucket)
-    unsigned int* cnt;      // [nq] (filter)
-    float2* surv;           // [nq, TC_CAP] (score, row as int bits) (filter)
+    int seg_cap;            // survivor slots per (query, CTA) segment = TC_CAP / CTAs per group
+    unsigned int* cnt;      // [nq, TC_MAX_SEGS] survivors found per segment, may exceed seg_cap (filter)
+    float2* surv;           // [nq, TC_CAP] (score, row as int bits), segment s at s * seg_cap (filter)
 };
 
 // ------------------------------------------------------------------ PTX wrappers (tcgen05 / TMA)
@@ -223,6 +225,9 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const bool qvalid = q < p.nq;
         float tau = __int_as_float(0x7f800000);               // +inf: rows beyond nq never emit
         if (MODE == TC_MODE_FILTER && qvalid) tau = p.tau[q];
+        // this thread is the only writer of segment u0 of query q: no atomics on the hot path
+        float2* seg = p.surv + (size_t)(qvalid ? q : 0) * TC_CAP + (size_t)u0 * p.seg_cap;
+        unsigned int found = 0;
         int n = 0;
         for (int u = u0; u < nunits; u += cpg, ++n) {
             const int buf = n & 1;
@@ -252,9 +257,8 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     for (int j = 0; j < 32; ++j) {
                         const float v = __uint_as_float(r[j]);
                         if (v >= tau && doc0 + c0 + j < p.N) {
-                            const unsigned int pos = atomicAdd(&p.cnt[q], 1u);
-                            if (pos < (unsigned)TC_CAP)
-                                p.surv[(size_t)q * TC_CAP + pos] = make_float2(v, __int_as_float((int)(doc0 + c0 + j)));
+                            if (found < (unsigned)p.seg_cap) seg[found] = make_float2(v, __int_as_float((int)(doc0 + c0 + j)));
+                            ++found;
                         }
                     }
                 }
@@ -263,6 +267,7 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
+        if (MODE == TC_MODE_FILTER && qvalid) p.cnt[(size_t)q * TC_MAX_SEGS + u0] = found;
     }
     tc_fence_before();
     __syncthreads();
@@ -382,7 +387,8 @@ __global__ void __launch_bounds__(256) tau_kernel(const float* __restrict__ bmax
 
 // ---------------------------------------------------------------------------------- final stage
 struct TcFinalParams {
-    const float* Q; const float* X; int nq; int64_t N; int D; int k; int metric; int64_t id_base;
+    const float* Q; const float* X; int q0; int nq; int64_t N; int D; int k; int metric; int64_t id_base;
+    int nseg, seg_cap, cand_cap;
     const unsigned int* cnt; const float2* surv; const float* eps;
     double* out_scores; int64_t* out_ids; int32_t* status;
 };
@@ -405,55 +411,95 @@ __device__ void bitonic_sort_kt(K* key, T* tag, int P) {
     }
 }
 
+// order-preserving map float -> uint32 (larger float <-> larger integer) and back
+__device__ __forceinline__ uint32_t f2sortable(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float sortable2f(uint32_t u) {
+    return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
+// One CTA per query: k-th best approximate score by radix select over the query's survivor
+// segments, candidates = survivors >= a_k - 2 eps, exact rescoring, sort by (score, id).
 template <bool VEC>
 __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = p.D, Dpad = (D + 3) & ~3;
     double* qs = reinterpret_cast<double*>(smem_raw);
     double* red = qs + Dpad;
-    double* ckey = red + XS_WARPS;                                         // [TC_MAX_CAND]
-    long long* ctag = reinterpret_cast<long long*>(ckey + TC_MAX_CAND);    // [TC_MAX_CAND]
-    float* skey = reinterpret_cast<float*>(ctag + TC_MAX_CAND);            // [TC_CAP]
-    int* stag = reinterpret_cast<int*>(skey + TC_CAP);                     // [TC_CAP]
-    __shared__ int s_m;
+    double* ckey = red + XS_WARPS;                                          // [cand_cap]
+    long long* ctag = reinterpret_cast<long long*>(ckey + p.cand_cap);      // [cand_cap]
+    int* cand = reinterpret_cast<int*>(ctag + p.cand_cap);                  // [cand_cap] corpus rows
+    int* hist = cand + p.cand_cap;                                          // [256]
+    int* seg_n = hist + 256;                                                // [nseg]
+    __shared__ int s_m, s_n, s_bad;
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_remaining;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int q = blockIdx.x;
+    const int q = p.q0 + blockIdx.x;
     const int k = p.k;
     const bool l2 = p.metric == QRAG_METRIC_L2;
+    const float2* sv = p.surv + (size_t)q * TC_CAP;
 
-    const unsigned int total = p.cnt[q];
-    int n = total < (unsigned)TC_CAP ? (int)total : TC_CAP;
-    int bad = total > (unsigned)TC_CAP ? 1 : 0;
-    int P = 1;
-    while (P < n) P <<= 1;
-    for (int i = tid; i < P; i += XS_THREADS) {
-        float kv = __int_as_float(0x7f800000);
-        int tv = 0x7fffffff;
-        if (i < n) {
-            const float2 e = p.surv[(size_t)q * TC_CAP + i];
-            kv = -e.x;
-            tv = __float_as_int(e.y);
-        }
-        skey[i] = kv;
-        stag[i] = tv;
-    }
-    if (tid == 0) s_m = 0;
+    if (tid == 0) { s_m = 0; s_n = 0; s_bad = 0; s_prefix = 0; s_remaining = k; }
     __syncthreads();
-    bitonic_sort_kt<float, int>(skey, stag, P);
-    // candidates: approximate score >= a_k - 2 eps (a prefix of the sorted list)
+    for (int sgi = tid; sgi < p.nseg; sgi += XS_THREADS) {
+        const unsigned int c = p.cnt[(size_t)q * TC_MAX_SEGS + sgi];
+        const int c2 = c < (unsigned)p.seg_cap ? (int)c : p.seg_cap;
+        seg_n[sgi] = c2;
+        if (c > (unsigned)p.seg_cap) s_bad = 1;
+        atomicAdd(&s_n, c2);
+    }
+    __syncthreads();
+    const int n = s_n;
+
     float thr = neg_inf_f();
     if (n >= k) {
-        const float ak = -skey[k - 1];
+        // radix select (4 x 8 bits, most significant first) of the k-th largest approximate score
+        for (int pass = 3; pass >= 0; --pass) {
+            for (int i = tid; i < 256; i += XS_THREADS) hist[i] = 0;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            const uint32_t mask = pass == 3 ? 0u : (0xffffffffu << (8 * (pass + 1)));
+            for (int sgi = warp; sgi < p.nseg; sgi += XS_WARPS) {
+                const float2* sp = sv + (size_t)sgi * p.seg_cap;
+                for (int i = lane; i < seg_n[sgi]; i += 32) {
+                    const uint32_t u = f2sortable(sp[i].x);
+                    if ((u & mask) == prefix) atomicAdd(&hist[(u >> (8 * pass)) & 255u], 1);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int remaining = s_remaining, d = 255;
+                for (; d > 0; --d) {
+                    if (hist[d] >= remaining) break;
+                    remaining -= hist[d];
+                }
+                s_remaining = remaining;
+                s_prefix = prefix | ((uint32_t)d << (8 * pass));
+            }
+            __syncthreads();
+        }
+        const float ak = sortable2f(s_prefix);
         thr = ak - 2.f * p.eps[q];
         thr = thr - fabsf(thr) * 2.4e-7f - 1e-37f;
     }
-    int local = 0;
-    for (int i = tid; i < n; i += XS_THREADS) local += (-skey[i] >= thr) ? 1 : 0;
-    local = __reduce_add_sync(FULL_MASK, local);
-    if (lane == 0 && local) atomicAdd(&s_m, local);
+    // candidates (any order: the final sort is a total order on (score, id))
+    for (int sgi = warp; sgi < p.nseg; sgi += XS_WARPS) {
+        const float2* sp = sv + (size_t)sgi * p.seg_cap;
+        for (int i = lane; i < seg_n[sgi]; i += 32) {
+            const float2 e = sp[i];
+            if (e.x >= thr) {
+                const int pos = atomicAdd(&s_m, 1);
+                if (pos < p.cand_cap) cand[pos] = __float_as_int(e.y);
+            }
+        }
+    }
     const double nq2 = xs_stage_query(p.Q + (size_t)q * D, D, qs, red);     // ends with __syncthreads()
     int m = s_m;
-    if (m > TC_MAX_CAND) { m = TC_MAX_CAND; bad = 1; }
+    int bad = s_bad;
+    if (m > p.cand_cap) { m = p.cand_cap; bad = 1; }
     int P2 = 1;
     while (P2 < m) P2 <<= 1;
     for (int r0 = warp * XS_ROWS; r0 < P2; r0 += XS_WARPS * XS_ROWS) {
@@ -465,7 +511,7 @@ __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParam
 #pragma unroll
         for (int i = 0; i < XS_ROWS; ++i) {
             const int r = (r0 + i < m) ? r0 + i : r0;
-            rp[i] = p.X + (size_t)stag[r] * D;
+            rp[i] = p.X + (size_t)cand[r] * D;
         }
         double nd2;
         const double tot = xs_score4<VEC>(rp, qs, D, l2, lane, nd2);
@@ -473,7 +519,7 @@ __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParam
             const int i = lane >> 3, r = r0 + i;
             if (r < m) {
                 ckey[r] = xs_key(p.metric, tot, nd2, nq2);
-                ctag[r] = p.id_base + stag[r];
+                ctag[r] = p.id_base + cand[r];
             } else if (r < P2) {
                 ckey[r] = pos_inf();
                 ctag[r] = 0x7fffffffffffffffLL;
@@ -579,7 +625,7 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, TcPlan* pl) {
     pl->off_bmax = off; off = align_up(off + (size_t)pl->nq_pad * pl->nbuckets * 4, 256);
     pl->off_tau = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
     pl->off_eps = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
-    pl->off_cnt = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
+    pl->off_cnt = off; off = align_up(off + (size_t)pl->nq_pad * TC_MAX_SEGS * 4, 256);
     pl->off_surv = off; off = align_up(off + (size_t)pl->nq_pad * TC_CAP * 8, 256);
     pl->total = off + 256;
     return QRAG_OK;
@@ -657,7 +703,6 @@ extern "C" int qrag_search_topk_tc(const float* Q, int nq, const float* X, const
 
     query_prepare_kernel<<<(unsigned)ceil_div(pl.nq_pad, 8), 256, 0, st>>>(Q, nq, pl.nq_pad, D, pl.Kp, metric, Qb, qnorm);
     QRAG_LAUNCH_CHECK("query_prepare_kernel");
-    QRAG_CUDA_CHECK(cudaMemsetAsync(cnt, 0, (size_t)pl.nq_pad * 4, st));
 
     CUtensorMap mapA, mapB;
     rc = make_map(&mapA, Qb, pl.nq_pad, pl.Kp, TC_BM);
@@ -671,7 +716,13 @@ extern "C" int qrag_search_topk_tc(const float* Q, int nq, const float* X, const
     gp.nq = nq; gp.N = N; gp.ntiles = pl.ntiles; gp.sample = pl.sample; gp.nbuckets = pl.nbuckets;
     gp.tau = tau; gp.bmax = bmax; gp.cnt = cnt; gp.surv = surv;
 
-    const int sms = dp.sm_count;
+    const int sms = dp.sm_count < TC_MAX_SEGS ? dp.sm_count : TC_MAX_SEGS;
+    const int Dpad = (D + 3) & ~3;
+    int cand_cap = next_pow2(2 * (int64_t)k + 512);
+    if (cand_cap > TC_MAX_CAND) cand_cap = TC_MAX_CAND;
+    const size_t smem_final = (size_t)(Dpad + XS_WARPS) * 8 + (size_t)cand_cap * 20 + 256 * 4 + TC_MAX_SEGS * 4;
+    QRAG_REQUIRE(smem_final <= (size_t)dp.max_smem_optin, QRAG_ERR_UNSUPPORTED, "D=%d too large for the rescoring stage", D);
+    const bool vec = (D % 4 == 0) && ((uintptr_t)X % 16 == 0);
     for (int pass = 0; pass < 2; ++pass) {
         const int units = pass == 0 ? pl.nsample_tiles : pl.ntiles;
         for (int g0 = 0; g0 < pl.groups; g0 += sms) {
@@ -680,9 +731,26 @@ extern "C" int qrag_search_topk_tc(const float* Q, int nq, const float* X, const
             if (cpg > units) cpg = units;
             gp.groups = groups;
             gp.group0 = g0;
+            gp.seg_cap = TC_CAP / cpg;
             rc = pass == 0 ? launch_gemm<TC_MODE_BUCKET>(mapA, mapB, gp, pl.smem_gemm, groups * cpg, st)
                            : launch_gemm<TC_MODE_FILTER>(mapA, mapB, gp, pl.smem_gemm, groups * cpg, st);
             if (rc) return rc;
+            if (pass == 1) {
+                const int q0 = g0 * TC_BM;
+                const int q1 = (g0 + groups) * TC_BM < nq ? (g0 + groups) * TC_BM : nq;
+                TcFinalParams fp{Q, X, q0, nq, N, D, k, metric, id_base, cpg, gp.seg_cap, cand_cap,
+                                 cnt, surv, eps, out_scores, out_ids, status};
+                if (vec) {
+                    QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)smem_final));
+                    tc_final_kernel<true><<<q1 - q0, XS_THREADS, smem_final, st>>>(fp);
+                } else {
+                    QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)smem_final));
+                    tc_final_kernel<false><<<q1 - q0, XS_THREADS, smem_final, st>>>(fp);
+                }
+                QRAG_LAUNCH_CHECK("tc_final_kernel");
+            }
         }
         if (pass == 0) {
             const size_t smem = (size_t)next_pow2(pl.nbuckets) * sizeof(float);
@@ -692,19 +760,5 @@ extern "C" int qrag_search_topk_tc(const float* Q, int nq, const float* X, const
             QRAG_LAUNCH_CHECK("tau_kernel");
         }
     }
-
-    TcFinalParams fp{Q, X, nq, N, D, k, metric, id_base, cnt, surv, eps, out_scores, out_ids, status};
-    const int Dpad = (D + 3) & ~3;
-    const size_t smem = (size_t)(Dpad + XS_WARPS) * 8 + (size_t)TC_MAX_CAND * 16 + (size_t)TC_CAP * 8;
-    QRAG_REQUIRE(smem <= (size_t)dp.max_smem_optin, QRAG_ERR_UNSUPPORTED, "D=%d too large for the rescoring stage", D);
-    const bool vec = (D % 4 == 0) && ((uintptr_t)X % 16 == 0);
-    if (vec) {
-        QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_final_kernel<true><<<nq, XS_THREADS, smem, st>>>(fp);
-    } else {
-        QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_final_kernel<false><<<nq, XS_THREADS, smem, st>>>(fp);
-    }
-    QRAG_LAUNCH_CHECK("tc_final_kernel");
     return QRAG_OK;
 }
