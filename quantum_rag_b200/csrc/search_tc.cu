@@ -43,13 +43,16 @@ constexpr int TC_BM = 128;            // queries per tile (UMMA M)
 constexpr int TC_BN = 256;            // documents per tile (UMMA N)
 constexpr int TC_BK = 64;             // K elements per shared-memory chunk (128 B rows, SWIZZLE_128B)
 constexpr int TC_UK = 16;             // K per tcgen05.mma (bf16)
-constexpr int TC_THREADS = 256;
+constexpr int TC_EPI_WARPS = 16;       // four per TMEM lane quarter: each takes a quarter of the tile's columns
+constexpr int TC_EPI_SPLIT = TC_EPI_WARPS / 4;
+constexpr int TC_EPI_COLS = TC_BN / TC_EPI_SPLIT;
+constexpr int TC_THREADS = (4 + TC_EPI_WARPS) * 32;
 constexpr int TC_A_CHUNK = TC_BM * TC_BK * 2;     // 16 KB
 constexpr int TC_B_STAGE = TC_BN * TC_BK * 2;     // 32 KB
 constexpr int TC_BUCKET = 32;         // documents per bucket maximum (one tcgen05.ld chunk)
 constexpr int TC_CAP = 16384;         // survivor list capacity per query
 constexpr int TC_MAX_CAND = 8192;     // largest exact-rescore capacity per query
-constexpr int TC_MAX_SEGS = 160;      // survivor-list segments per query (one per CTA of the query's group)
+constexpr int TC_MAX_SEGS = 640;      // survivor-list segments per query (TC_EPI_SPLIT per CTA of the query's group)
 constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_MODE_BUCKET = 0, TC_MODE_FILTER = 1;
 
@@ -145,7 +148,7 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (tid == 0) {
         mbar_init(a_full, 1);
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], TC_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -219,14 +222,15 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue
-        const int ew = warp - 4;                              // == warp % 4: TMEM lanes 32*ew .. 32*ew+31
+        const int ew = warp & 3;                              // TMEM lanes 32*ew .. 32*ew+31 (fixed by warp % 4)
+        const int half = (warp - 4) >> 2;                      // columns [TC_EPI_COLS*half, +TC_EPI_COLS)
         const int row = ew * 32 + lane;
         const int q = (p.group0 + g) * TC_BM + row;
         const bool qvalid = q < p.nq;
         float tau = __int_as_float(0x7f800000);               // +inf: rows beyond nq never emit
-        if (MODE == TC_MODE_FILTER && qvalid) tau = p.tau[q];
+        if (MODE == TC_MODE_FILTER && qvalid) tau = fmaxf(p.tau[q], -3.0e38f);   // -inf (rows past the end) never passes
         // this thread is the only writer of segment u0 of query q: no atomics on the hot path
-        float2* seg = p.surv + (size_t)(qvalid ? q : 0) * TC_CAP + (size_t)u0 * p.seg_cap;
+        float2* seg = p.surv + (size_t)(qvalid ? q : 0) * TC_CAP + (size_t)(TC_EPI_SPLIT * u0 + half) * p.seg_cap;
         unsigned int found = 0;
         int n = 0;
         for (int u = u0; u < nunits; u += cpg, ++n) {
@@ -236,27 +240,33 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const bool ragged = doc0 + TC_BN > p.N;
             mbar_wait(&acc_full[buf], ((uint32_t)n >> 1) & 1u);
             tc_fence_after();
-            const uint32_t t0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * TC_BN;
-#pragma unroll 1
-            for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+            const uint32_t t0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * TC_BN + (uint32_t)half * TC_EPI_COLS;
+#pragma unroll
+            for (int cc = 0; cc < TC_EPI_COLS / 32; ++cc) {
                 uint32_t r[32];
-                tmem_ld32(t0 + (uint32_t)c0, r);
+                tmem_ld32(t0 + (uint32_t)cc * 32, r);
                 tmem_ld_wait();
+                const int c0 = half * TC_EPI_COLS + cc * 32;
                 if (ragged) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (doc0 + c0 + j >= p.N) r[j] = 0xff800000u;             // -inf: rows past the end
                 }
-                float m = __uint_as_float(r[0]);
+                float t[16];
 #pragma unroll
-                for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+                for (int j = 0; j < 16; ++j) t[j] = fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 16]));
+#pragma unroll
+                for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+                    for (int j = 0; j < w; ++j) t[j] = fmaxf(t[j], t[j + w]);
+                const float m = t[0];
                 if (MODE == TC_MODE_BUCKET) {
                     if (qvalid) p.bmax[(size_t)q * p.nbuckets + (size_t)u * (TC_BN / TC_BUCKET) + (c0 >> 5)] = m;
                 } else if (m >= tau) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float v = __uint_as_float(r[j]);
-                        if (v >= tau && doc0 + c0 + j < p.N) {
+                        if (v >= tau) {
                             if (found < (unsigned)p.seg_cap) seg[found] = make_float2(v, __int_as_float((int)(doc0 + c0 + j)));
                             ++found;
                         }
@@ -267,7 +277,7 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        if (MODE == TC_MODE_FILTER && qvalid) p.cnt[(size_t)q * TC_MAX_SEGS + u0] = found;
+        if (MODE == TC_MODE_FILTER && qvalid) p.cnt[(size_t)q * TC_MAX_SEGS + TC_EPI_SPLIT * u0 + half] = found;
     }
     tc_fence_before();
     __syncthreads();
@@ -716,7 +726,7 @@ extern "C" int qrag_search_topk_tc(const float* Q, int nq, const float* X, const
     gp.nq = nq; gp.N = N; gp.ntiles = pl.ntiles; gp.sample = pl.sample; gp.nbuckets = pl.nbuckets;
     gp.tau = tau; gp.bmax = bmax; gp.cnt = cnt; gp.surv = surv;
 
-    const int sms = dp.sm_count < TC_MAX_SEGS ? dp.sm_count : TC_MAX_SEGS;
+    const int sms = dp.sm_count < TC_MAX_SEGS / TC_EPI_SPLIT ? dp.sm_count : TC_MAX_SEGS / TC_EPI_SPLIT;
     const int Dpad = (D + 3) & ~3;
     int cand_cap = next_pow2(2 * (int64_t)k + 512);
     if (cand_cap > TC_MAX_CAND) cand_cap = TC_MAX_CAND;
@@ -731,14 +741,14 @@ extern "C" int qrag_search_topk_tc(const float* Q, int nq, const float* X, const
             if (cpg > units) cpg = units;
             gp.groups = groups;
             gp.group0 = g0;
-            gp.seg_cap = TC_CAP / cpg;
+            gp.seg_cap = TC_CAP / (TC_EPI_SPLIT * cpg);
             rc = pass == 0 ? launch_gemm<TC_MODE_BUCKET>(mapA, mapB, gp, pl.smem_gemm, groups * cpg, st)
                            : launch_gemm<TC_MODE_FILTER>(mapA, mapB, gp, pl.smem_gemm, groups * cpg, st);
             if (rc) return rc;
             if (pass == 1) {
                 const int q0 = g0 * TC_BM;
                 const int q1 = (g0 + groups) * TC_BM < nq ? (g0 + groups) * TC_BM : nq;
-                TcFinalParams fp{Q, X, q0, nq, N, D, k, metric, id_base, cpg, gp.seg_cap, cand_cap,
+                TcFinalParams fp{Q, X, q0, nq, N, D, k, metric, id_base, TC_EPI_SPLIT * cpg, gp.seg_cap, cand_cap,
                                  cnt, surv, eps, out_scores, out_ids, status};
                 if (vec) {
                     QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
