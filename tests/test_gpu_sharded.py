@@ -1,0 +1,63 @@
+"""Config 4 path on the GPU: search -> merge -> owner-computes quantum rerank, for 1 and for G shards.
+
+One GPU is enough to check what matters for the multi-GPU claim: with the CUDA engine the G-shard
+result (shards searched one after another on the same device, exchange steps emulated with
+stack/max) is bit-identical to the 1-shard result.  The real NCCL exchange is covered by
+tools/sharded_check.py under torchrun and by tests/test_sharded_gloo.py on CPU.
+"""
+import numpy as np
+import pytest
+
+from oracle import quantum as oq
+from oracle import search as osr
+
+pytestmark = pytest.mark.gpu
+
+
+def _emulated(X, Q, G, k1, k2, metric):
+    import torch
+    from quantum_rag_b200.sharded import CudaEngine, shard_bounds
+    n = X.shape[0]
+    engines = []
+    for r in range(G):
+        lo, hi = shard_bounds(n, G, r)
+        engines.append((lo, hi, CudaEngine(X[lo:hi], metric, lo)))
+    lists = [e.search(Q, k1) for _, _, e in engines]
+    gs = torch.stack([s for s, _ in lists])
+    gi = torch.stack([i for _, i in lists])
+    ss, si = engines[0][2].merge(gs, gi, k1)
+    f = None
+    for lo, hi, e in engines:
+        own = (si >= lo) & (si < hi)
+        local = torch.where(own, si - lo, torch.full_like(si, -1))
+        fr = e.fidelity_rows(Q, local)
+        f = fr if f is None else torch.maximum(f, fr)
+    pos, top = engines[0][2].sort_scores(f, k2)
+    return top, torch.gather(si, 1, pos.long()), ss, si
+
+
+@pytest.mark.parametrize("metric", ["cosine", "l2", "ip"])
+def test_sharded_path_matches_oracle_and_single_shard(cuda, metric):
+    import torch
+    from quantum_rag_b200.sharded import ShardedSearchRerank
+    rng = np.random.RandomState(4)
+    n, d, nq, k1, k2 = 30000, 384, 12, 200, 10
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((nq, d)).astype(np.float32)
+    X[n - 2] = X[1]
+    X[n // 2 + 5] = X[1]
+    Q[0] = X[1]
+    Xd, Qd = torch.from_numpy(X).cuda(), torch.from_numpy(Q).cuda()
+    res = ShardedSearchRerank(Xd, n, metric)(Qd, k1, k2)                 # world size 1, CUDA engine
+    # oracle: exact search, then amplitude fidelity of the found rows, stable order
+    mid = {"cosine": osr.METRIC_COSINE, "l2": osr.METRIC_L2, "ip": osr.METRIC_IP}[metric]
+    rs, ri = osr.exact_search(Q, X, k1, mid)
+    assert np.array_equal(res.search_ids.cpu().numpy(), ri)
+    f = oq.amplitude_fidelity_batch(Q, X[ri])
+    order = oq.rank_rows(f, k2)
+    assert np.array_equal(res.ids.cpu().numpy(), np.take_along_axis(ri, order, 1))
+    assert np.allclose(res.scores.cpu().numpy(), np.take_along_axis(f, order, 1), rtol=1e-12, atol=1e-16)
+    for G in (2, 3, 8):
+        top, ids, ss, si = _emulated(Xd, Qd, G, k1, k2, metric)
+        assert torch.equal(si, res.search_ids) and torch.equal(ss, res.search_scores), f"G={G}"
+        assert torch.equal(ids, res.ids) and torch.equal(top, res.scores), f"G={G}"

@@ -1,0 +1,124 @@
+"""Multi-rank logic of the sharded search + rerank on CPU: world_size 2 and 3 over gloo.
+
+The exchange steps (row partition, id_base, packed all-gather, merge, owner-computes rerank,
+all-reduce(MAX), final stable sort) run for real over ``torch.distributed``; the per-rank compute is
+the NumPy oracle plugged in as the engine (the CUDA engine is exercised by tests/test_gpu_sharded.py).
+The G-rank result must equal the 1-rank result bit for bit, ties included.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import quantum as oq
+from oracle import search as osr
+from quantum_rag_b200.sharded import ShardedSearchRerank, shard_bounds
+
+
+class OracleEngine:
+    """CPU stand-in for CudaEngine: every per-row number depends on that row only (no BLAS blocking)."""
+
+    def __init__(self, X_shard, metric, id_base):
+        self.X = np.asarray(X_shard, dtype=np.float32)
+        self.metric, self.id_base = metric, id_base
+
+    def _scores(self, Q):
+        Q64, X64 = np.asarray(Q, np.float32).astype(np.float64), self.X.astype(np.float64)
+        out = np.empty((Q64.shape[0], X64.shape[0]))
+        for i, q in enumerate(Q64):
+            if self.metric == osr.METRIC_L2:
+                out[i] = ((X64 - q) ** 2).sum(axis=1)
+            else:
+                ip = (X64 * q).sum(axis=1)
+                if self.metric == osr.METRIC_COSINE:
+                    den = (q * q).sum() * (X64 * X64).sum(axis=1)
+                    ip = np.where(den > 0, ip / np.sqrt(np.where(den > 0, den, 1.0)), 0.0)
+                out[i] = ip
+        return out
+
+    def search(self, Q, k):
+        s, i = osr.topk_from_scores(self._scores(Q.numpy()), k, self.metric, self.id_base)
+        return torch.from_numpy(np.ascontiguousarray(s)), torch.from_numpy(np.ascontiguousarray(i))
+
+    def merge(self, scores, ids, k_out):
+        s, i = osr.merge_topk(scores.numpy(), ids.numpy(), k_out, self.metric)
+        return torch.from_numpy(np.ascontiguousarray(s)), torch.from_numpy(np.ascontiguousarray(i))
+
+    def fidelity_rows(self, Q, local_idx):
+        idx = local_idx.numpy()
+        rows = self.X[np.maximum(idx, 0)] if self.X.shape[0] else np.zeros(idx.shape + (Q.shape[1],), np.float32)
+        f = oq.amplitude_fidelity_batch(Q.numpy(), rows)
+        return torch.from_numpy(np.where(idx < 0, -np.inf, f))
+
+    def sort_scores(self, scores, k):
+        order = oq.rank_rows(scores.numpy(), k)
+        return torch.from_numpy(order.astype(np.int32)), torch.from_numpy(np.take_along_axis(scores.numpy(), order, 1))
+
+
+def _data(n, d, nq, seed=0):
+    rng = np.random.RandomState(seed)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((nq, d)).astype(np.float32)
+    X[n - 2] = X[1]                 # duplicates in different shards: exact ties, global id decides
+    X[n // 2] = X[1]
+    Q[0] = X[1]
+    return X, Q
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, d, nq, k1, k2, metric, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        X, Q = _data(n, d, nq)
+        lo, hi = shard_bounds(n, world, rank)
+        eng = OracleEngine(X[lo:hi], metric, lo)
+        res = ShardedSearchRerank(torch.from_numpy(X[lo:hi]), n, metric, engine=eng)(torch.from_numpy(Q), k1, k2)
+        out[rank] = (res.scores.numpy(), res.ids.numpy(), res.search_scores.numpy(), res.search_ids.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def _single(n, d, nq, k1, k2, metric):
+    X, Q = _data(n, d, nq)
+    eng = OracleEngine(X, metric, 0)
+    res = ShardedSearchRerank(torch.from_numpy(X), n, metric, engine=eng)(torch.from_numpy(Q), k1, k2)
+    return res.scores.numpy(), res.ids.numpy(), res.search_scores.numpy(), res.search_ids.numpy()
+
+
+def test_shard_bounds_partition():
+    for n in (0, 1, 7, 10, 1000003):
+        for world in (1, 2, 3, 8):
+            b = [shard_bounds(n, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("world,metric,n,k1,k2", [(2, osr.METRIC_COSINE, 301, 40, 7), (3, osr.METRIC_L2, 100, 50, 10),
+                                                  (2, osr.METRIC_IP, 9, 16, 16)])
+def test_sharded_equals_single_rank(world, metric, n, k1, k2):
+    d, nq = 24, 5
+    want = _single(n, d, nq, k1, k2, metric)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), n, d, nq, k1, k2, metric, out), nprocs=world, join=True)
+    assert len(out) == world
+    for rank in range(world):
+        got = out[rank]
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b), f"rank {rank} differs from the single-rank result"
+    # and against the plain oracle search on the whole corpus
+    X, Q = _data(n, d, nq)
+    rs, ri = osr.topk_from_scores(OracleEngine(X, metric, 0)._scores(Q), k1, metric)
+    assert np.array_equal(want[3], ri)
