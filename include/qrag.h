@@ -167,6 +167,25 @@ int qrag_search_topk_tc(const float* Q, int nq, const float* X, const uint16_t* 
                         double* out_scores, int64_t* out_ids, int32_t* status,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same search split at its two exchange points, for a corpus sharded over G GPUs (the
+ * all-gathers in between are the caller's: quantum_rag_b200/sharded.py issues them with NCCL).
+ * Thresholds come from ALL shards, so every shard filters and rescores only ~ (k + margin) / G
+ * candidates and the work scales with 1/G.  The workspace carries state between the phases.
+ *   begin   bm_top [nq, k]: this shard's k largest sampled bucket maxima
+ *   filter  bm_top_all [G, nq, k] (all-gathered) -> tau; ap_top [nq, k]: this shard's k best
+ *           approximate scores.  aux[0] must hold the maximum |x| over ALL shards.
+ *   finish  ap_top_all [G, nq, k] (all-gathered) -> exact, sorted list of this shard's members of
+ *           the global top-k (ids -1 padded); merge the G lists with qrag_topk_merge. */
+int qrag_search_tc_begin(const float* Q, int nq, const uint16_t* Xb, int64_t N, int D, int k, int metric,
+                         float* bm_top, void* workspace, size_t workspace_bytes, void* stream);
+int qrag_search_tc_filter(int nq, const uint16_t* Xb, const float* aux, int64_t N, int D, int k, int metric,
+                          const float* bm_top_all, int G, float* ap_top,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int qrag_search_tc_finish(const float* Q, int nq, const float* X, int64_t N, int D, int k, int metric,
+                          int64_t id_base, const float* ap_top_all, int G,
+                          double* out_scores, int64_t* out_ids, int32_t* status,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------
  * (3) Merge of per-shard top-k lists after the all-gather: scores/ids
  * [G, nq, k] -> [nq, k_out] in the canonical order; id < 0 is padding.

@@ -279,6 +279,56 @@ class FlatIndexTC:
                                            ws.numel(), _stream()))
         return Qd, scores, ids, status
 
+    # ---- the search split at its two exchange points (corpus sharded over G GPUs) ----
+    def tc_begin(self, Q: ArrayLike, k: int) -> torch.Tensor:
+        """Phase 1: returns bm_top [nq, k] fp32, this shard's k largest sampled bucket maxima."""
+        Qd = _dev(Q, torch.float32)
+        if Qd.dim() == 1:
+            Qd = Qd[None, :]
+        nq = Qd.shape[0]
+        ws = self._workspace(nq, k)
+        bm_top = torch.empty((nq, k), dtype=torch.float32, device=Qd.device)
+        _lib.check(_lib.load().qrag_search_tc_begin(_ptr(Qd), nq, _ptr(self.Xb), self.N, self.D, k, self.metric,
+                                                    _ptr(bm_top), _ptr(ws), ws.numel(), _stream()))
+        self._phase = (Qd, k, ws)
+        return bm_top
+
+    def tc_filter(self, bm_top_all: torch.Tensor) -> torch.Tensor:
+        """Phase 2: bm_top_all [G, nq, k] from every shard -> ap_top [nq, k], this shard's k best approximate scores."""
+        Qd, k, ws = self._phase
+        nq = Qd.shape[0]
+        bm = bm_top_all.contiguous()
+        ap_top = torch.empty((nq, k), dtype=torch.float32, device=Qd.device)
+        _lib.check(_lib.load().qrag_search_tc_filter(nq, _ptr(self.Xb), _ptr(self.aux), self.N, self.D, k, self.metric,
+                                                     _ptr(bm), bm.shape[0], _ptr(ap_top), _ptr(ws), ws.numel(),
+                                                     _stream()))
+        return ap_top
+
+    def tc_finish(self, ap_top_all: torch.Tensor):
+        """Phase 3: ap_top_all [G, nq, k] -> (scores, ids, status): this shard's exact, sorted members of the
+        global top-k (ids -1 padded); status != 0 flags a query this shard could not certify."""
+        Qd, k, ws = self._phase
+        nq = Qd.shape[0]
+        ap = ap_top_all.contiguous()
+        scores = torch.empty((nq, k), dtype=torch.float64, device=Qd.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=Qd.device)
+        status = torch.zeros(nq, dtype=torch.int32, device=Qd.device)
+        _lib.check(_lib.load().qrag_search_tc_finish(_ptr(Qd), nq, _ptr(self.X), self.N, self.D, k, self.metric,
+                                                     self.id_base, _ptr(ap), ap.shape[0], _ptr(scores), _ptr(ids),
+                                                     _ptr(status), _ptr(ws), ws.numel(), _stream()))
+        self._phase = None
+        return scores, ids, status
+
+    def search_sharded(self, Q: ArrayLike, k: int, all_gather):
+        """This shard's part of a search over G shards: ``all_gather(t)`` must return ``[G, *t.shape]``.
+
+        Thresholds are global, so the shard filters and rescores only ~ (k + margin) / G rows.
+        ``self.aux[0]`` must already hold the maximum |x| over all shards (see sharded.py).
+        """
+        bm_all = all_gather(self.tc_begin(Q, k))
+        ap_all = all_gather(self.tc_filter(bm_all))
+        return self.tc_finish(ap_all)
+
     def search(self, Q: ArrayLike, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         if self.N == 0:
             return search_topk(Q, self.X, k, self.metric, self.id_base)

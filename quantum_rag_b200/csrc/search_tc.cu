@@ -359,46 +359,126 @@ __device__ __forceinline__ float tc_eps(int metric, int Kp, float qn, float xmax
     return e * 1.0001f + 1e-30f;
 }
 
-// per query: tau = (k-th largest bucket maximum) - 2 eps, rounded down
-__global__ void __launch_bounds__(256) tau_kernel(const float* __restrict__ bmax, int nbuckets, int k, int metric, int Kp,
-                                                  const float* __restrict__ qnorm, const float* __restrict__ aux,
-                                                  float* __restrict__ tau, float* __restrict__ eps) {
-    extern __shared__ float sk[];
-    const int q = blockIdx.x;
-    int P = 1;
-    while (P < nbuckets) P <<= 1;
-    for (int i = threadIdx.x; i < P; i += blockDim.x)
-        sk[i] = i < nbuckets ? -bmax[(size_t)q * nbuckets + i] : __int_as_float(0x7f800000);
+// order-preserving map float -> uint32 (larger float <-> larger integer) and back
+__device__ __forceinline__ uint32_t f2sortable(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float sortable2f(uint32_t u) {
+    return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
+struct RadixSel { int hist[256]; uint32_t prefix; int remaining; int count; };     // lives in shared memory
+
+// k-th largest (1-based) of the values `for_each` enumerates (each thread its own part; the
+// enumeration must be repeatable and hold at least k values).  Radix select, 4 x 8 bits.
+template <class ForEach>
+__device__ float block_kth_largest(RadixSel& rs, int k, ForEach for_each) {
+    if (threadIdx.x == 0) { rs.prefix = 0; rs.remaining = k; }
     __syncthreads();
-    for (int kk = 2; kk <= P; kk <<= 1) {
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
-                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int hi = lo | j;
-                const float a = sk[lo], b = sk[hi];
-                const bool asc = (lo & kk) == 0;
-                if ((b < a) == asc) { sk[lo] = b; sk[hi] = a; }
+    for (int pass = 3; pass >= 0; --pass) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) rs.hist[i] = 0;
+        __syncthreads();
+        const uint32_t prefix = rs.prefix;
+        const uint32_t mask = pass == 3 ? 0u : (0xffffffffu << (8 * (pass + 1)));
+        for_each([&](float v) {
+            const uint32_t u = f2sortable(v);
+            if ((u & mask) == prefix) atomicAdd(&rs.hist[(u >> (8 * pass)) & 255u], 1);
+        });
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int remaining = rs.remaining, d = 255;
+            for (; d > 0; --d) {
+                if (rs.hist[d] >= remaining) break;
+                remaining -= rs.hist[d];
             }
-            __syncthreads();
+            rs.remaining = remaining;
+            rs.prefix = prefix | ((uint32_t)d << (8 * pass));
         }
+        __syncthreads();
     }
+    return sortable2f(rs.prefix);
+}
+
+// out[0..k) = the k largest enumerated values as a multiset (any order), -inf padded when fewer exist
+template <class ForEach>
+__device__ void block_topk_values(RadixSel& rs, int k, int total, ForEach for_each, float* __restrict__ out) {
+    float t = neg_inf_f();
+    if (total >= k) t = block_kth_largest(rs, k, for_each);
+    if (threadIdx.x == 0) rs.count = 0;
+    __syncthreads();
+    const bool all = total < k;
+    for_each([&](float v) {
+        if (all || v > t) {
+            const int pos = atomicAdd(&rs.count, 1);
+            if (pos < k) out[pos] = v;
+        }
+    });
+    __syncthreads();
+    for (int i = rs.count + threadIdx.x; i < k; i += blockDim.x) out[i] = t;       // ties with the k-th / padding
+}
+
+// per query: the k largest bucket maxima of this shard -> bm_top [nq, k]
+__global__ void __launch_bounds__(256) bucket_topk_kernel(const float* __restrict__ bmax, int nbuckets, int k,
+                                                          float* __restrict__ bm_top) {
+    __shared__ RadixSel rs;
+    const int q = blockIdx.x;
+    const float* row = bmax + (size_t)q * nbuckets;
+    auto fe = [&](auto f) { for (int i = threadIdx.x; i < nbuckets; i += blockDim.x) f(row[i]); };
+    block_topk_values(rs, k, nbuckets, fe, bm_top + (size_t)q * k);
+}
+
+// per query: m_k = k-th largest bucket maximum over all G shards' lists; tau = m_k - 2 eps, rounded down
+__global__ void __launch_bounds__(256) tau_union_kernel(const float* __restrict__ bm_top_all, int G, int nq, int k, int metric,
+                                                        int Kp, const float* __restrict__ qnorm, const float* __restrict__ aux,
+                                                        float* __restrict__ tau, float* __restrict__ eps) {
+    __shared__ RadixSel rs;
+    const int q = blockIdx.x;
+    auto fe = [&](auto f) {
+        for (int i = threadIdx.x; i < G * k; i += blockDim.x) f(bm_top_all[((size_t)(i / k) * nq + q) * k + (i % k)]);
+    };
+    const float mk = block_kth_largest(rs, k, fe);
     if (threadIdx.x == 0) {
         const float e = tc_eps(metric, Kp, qnorm[q], aux[0]);
         eps[q] = e;
-        float t = neg_inf_f();
-        if (nbuckets >= k) {
-            const float mk = -sk[k - 1];
-            t = mk - 2.f * e;
-            t = t - fabsf(t) * 2.4e-7f - 1e-37f;                  // the subtraction above rounds to nearest: step down
-        }
+        float t = mk - 2.f * e;                                   // -inf stays -inf (fewer than k buckets)
+        t = t - fabsf(t) * 2.4e-7f - 1e-37f;                      // the subtraction above rounds to nearest: step down
         tau[q] = t;
     }
+}
+
+// per query: the k largest approximate scores among this shard's survivors -> ap_top [nq, k]
+__global__ void __launch_bounds__(256) surv_topk_kernel(const unsigned int* __restrict__ cnt, const float2* __restrict__ surv,
+                                                        int q0, int nseg, int seg_cap, int k, float* __restrict__ ap_top) {
+    __shared__ RadixSel rs;
+    __shared__ int seg_n[TC_MAX_SEGS];
+    __shared__ int s_n;
+    const int q = q0 + blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int sgi = threadIdx.x; sgi < nseg; sgi += blockDim.x) {
+        const unsigned int c = cnt[(size_t)q * TC_MAX_SEGS + sgi];
+        const int c2 = c < (unsigned)seg_cap ? (int)c : seg_cap;
+        seg_n[sgi] = c2;
+        atomicAdd(&s_n, c2);
+    }
+    __syncthreads();
+    const float2* sv = surv + (size_t)q * TC_CAP;
+    auto fe = [&](auto f) {
+        for (int sgi = warp; sgi < nseg; sgi += nwarps) {
+            const float2* sp = sv + (size_t)sgi * seg_cap;
+            for (int i = lane; i < seg_n[sgi]; i += 32) f(sp[i].x);
+        }
+    };
+    block_topk_values(rs, k, s_n, fe, ap_top + (size_t)q * k);
 }
 
 // ---------------------------------------------------------------------------------- final stage
 struct TcFinalParams {
     const float* Q; const float* X; int q0; int nq; int64_t N; int D; int k; int metric; int64_t id_base;
     int nseg, seg_cap, cand_cap;
+    int G; const float* ap_top_all;          // [G, nq, k] the k best approximate scores of every shard
     const unsigned int* cnt; const float2* surv; const float* eps;
     double* out_scores; int64_t* out_ids; int32_t* status;
 };
@@ -421,17 +501,8 @@ __device__ void bitonic_sort_kt(K* key, T* tag, int P) {
     }
 }
 
-// order-preserving map float -> uint32 (larger float <-> larger integer) and back
-__device__ __forceinline__ uint32_t f2sortable(float f) {
-    const uint32_t b = __float_as_uint(f);
-    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
-}
-__device__ __forceinline__ float sortable2f(uint32_t u) {
-    return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xffffffffu));
-}
-
-// One CTA per query: k-th best approximate score by radix select over the query's survivor
-// segments, candidates = survivors >= a_k - 2 eps, exact rescoring, sort by (score, id).
+// One CTA per query: a_k = k-th best approximate score over all shards (from their top-k lists),
+// candidates = this shard's survivors >= a_k - 2 eps, exact rescoring, sort by (score, id).
 template <bool VEC>
 __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -441,60 +512,28 @@ __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParam
     double* ckey = red + XS_WARPS;                                          // [cand_cap]
     long long* ctag = reinterpret_cast<long long*>(ckey + p.cand_cap);      // [cand_cap]
     int* cand = reinterpret_cast<int*>(ctag + p.cand_cap);                  // [cand_cap] corpus rows
-    int* hist = cand + p.cand_cap;                                          // [256]
-    int* seg_n = hist + 256;                                                // [nseg]
-    __shared__ int s_m, s_n, s_bad;
-    __shared__ uint32_t s_prefix;
-    __shared__ int s_remaining;
+    int* seg_n = cand + p.cand_cap;                                         // [nseg]
+    __shared__ RadixSel rs;
+    __shared__ int s_m, s_bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = p.q0 + blockIdx.x;
     const int k = p.k;
     const bool l2 = p.metric == QRAG_METRIC_L2;
     const float2* sv = p.surv + (size_t)q * TC_CAP;
 
-    if (tid == 0) { s_m = 0; s_n = 0; s_bad = 0; s_prefix = 0; s_remaining = k; }
+    if (tid == 0) { s_m = 0; s_bad = 0; }
     __syncthreads();
     for (int sgi = tid; sgi < p.nseg; sgi += XS_THREADS) {
         const unsigned int c = p.cnt[(size_t)q * TC_MAX_SEGS + sgi];
-        const int c2 = c < (unsigned)p.seg_cap ? (int)c : p.seg_cap;
-        seg_n[sgi] = c2;
+        seg_n[sgi] = c < (unsigned)p.seg_cap ? (int)c : p.seg_cap;
         if (c > (unsigned)p.seg_cap) s_bad = 1;
-        atomicAdd(&s_n, c2);
     }
-    __syncthreads();
-    const int n = s_n;
-
-    float thr = neg_inf_f();
-    if (n >= k) {
-        // radix select (4 x 8 bits, most significant first) of the k-th largest approximate score
-        for (int pass = 3; pass >= 0; --pass) {
-            for (int i = tid; i < 256; i += XS_THREADS) hist[i] = 0;
-            __syncthreads();
-            const uint32_t prefix = s_prefix;
-            const uint32_t mask = pass == 3 ? 0u : (0xffffffffu << (8 * (pass + 1)));
-            for (int sgi = warp; sgi < p.nseg; sgi += XS_WARPS) {
-                const float2* sp = sv + (size_t)sgi * p.seg_cap;
-                for (int i = lane; i < seg_n[sgi]; i += 32) {
-                    const uint32_t u = f2sortable(sp[i].x);
-                    if ((u & mask) == prefix) atomicAdd(&hist[(u >> (8 * pass)) & 255u], 1);
-                }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                int remaining = s_remaining, d = 255;
-                for (; d > 0; --d) {
-                    if (hist[d] >= remaining) break;
-                    remaining -= hist[d];
-                }
-                s_remaining = remaining;
-                s_prefix = prefix | ((uint32_t)d << (8 * pass));
-            }
-            __syncthreads();
-        }
-        const float ak = sortable2f(s_prefix);
-        thr = ak - 2.f * p.eps[q];
-        thr = thr - fabsf(thr) * 2.4e-7f - 1e-37f;
-    }
+    auto fe = [&](auto f) {
+        for (int i = tid; i < p.G * k; i += XS_THREADS) f(p.ap_top_all[((size_t)(i / k) * p.nq + q) * k + (i % k)]);
+    };
+    const float ak = block_kth_largest(rs, k, fe);                          // starts and ends with __syncthreads()
+    float thr = ak - 2.f * p.eps[q];                                        // -inf stays -inf
+    thr = thr - fabsf(thr) * 2.4e-7f - 1e-37f;
     // candidates (any order: the final sort is a total order on (score, id))
     for (int sgi = warp; sgi < p.nseg; sgi += XS_WARPS) {
         const float2* sp = sv + (size_t)sgi * p.seg_cap;
@@ -547,8 +586,6 @@ __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParam
         p.out_scores[(size_t)q * k + i] = kv;
         p.out_ids[(size_t)q * k + i] = tv;
     }
-    // fewer than k candidates is only legitimate when the whole shard is shorter than k
-    if (m < k && (int64_t)m < p.N) bad = 1;
     if (tid == 0) p.status[q] = bad;
 }
 
@@ -591,7 +628,9 @@ static int tc_kp(int D, int metric) { return (int)align_up((size_t)D + (metric =
 
 struct TcPlan {
     int Kp, kchunks, ksteps_last, stages, a_resident, stage_bytes, nq_pad, groups, ntiles, sample, nsample_tiles, nbuckets;
-    size_t smem_gemm, off_qb, off_qnorm, off_bmax, off_tau, off_eps, off_cnt, off_surv, total;
+    int cand_cap;
+    size_t smem_gemm, smem_final;
+    size_t off_qb, off_qnorm, off_bmax, off_tau, off_eps, off_cnt, off_surv, off_bmtop, off_aptop, total;
 };
 
 static int tc_plan(int nq, int64_t N, int D, int k, int metric, TcPlan* pl) {
@@ -599,13 +638,17 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, TcPlan* pl) {
     QRAG_REQUIRE(metric >= 0 && metric <= 2, QRAG_ERR_INVALID, "unknown metric %d", metric);
     QRAG_REQUIRE(k >= 1 && k <= 2048, QRAG_ERR_UNSUPPORTED, "tensor-core search supports 1 <= k <= 2048 (got %d)", k);
     QRAG_REQUIRE(N < ((int64_t)1 << 31) - TC_BN, QRAG_ERR_UNSUPPORTED, "shard too large (N=%lld)", (long long)N);
+    const DeviceProps& dp = device_props();
+    QRAG_REQUIRE(dp.ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
+    QRAG_REQUIRE(dp.cc_major == 10, QRAG_ERR_UNSUPPORTED, "tcgen05 search needs compute capability 10.x (got %d.%d)",
+                 dp.cc_major, dp.cc_minor);
     pl->Kp = tc_kp(D, metric);
     pl->kchunks = (pl->Kp + TC_BK - 1) / TC_BK;
     pl->ksteps_last = (pl->Kp - (pl->kchunks - 1) * TC_BK) / TC_UK;
     // the query tile stays resident when that still leaves a 3-deep ring for the document chunks;
     // otherwise (long rows) its chunks travel through the ring next to them
     const size_t a_bytes = (size_t)pl->kchunks * TC_A_CHUNK;
-    const size_t budget = (size_t)device_props().max_smem_optin;
+    const size_t budget = (size_t)dp.max_smem_optin;
     pl->a_resident = (1024 + 256 + a_bytes + 3 * (size_t)TC_B_STAGE <= budget) ? 1 : 0;
     pl->stage_bytes = pl->a_resident ? TC_B_STAGE : TC_B_STAGE + TC_A_CHUNK;
     const size_t fixed = 1024 + 256 + (pl->a_resident ? a_bytes : 0);
@@ -627,8 +670,12 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, TcPlan* pl) {
     pl->sample = sample;
     pl->nsample_tiles = (pl->ntiles + sample - 1) / sample;
     pl->nbuckets = pl->nsample_tiles * (TC_BN / TC_BUCKET);
-    QRAG_REQUIRE(pl->nbuckets <= 32768, QRAG_ERR_UNSUPPORTED, "shard too large for one pass (N=%lld): split it",
-                 (long long)N);
+    int cand_cap = next_pow2(2 * (int64_t)k + 512);
+    if (cand_cap > TC_MAX_CAND) cand_cap = TC_MAX_CAND;
+    pl->cand_cap = cand_cap;
+    const int Dpad = (D + 3) & ~3;
+    pl->smem_final = (size_t)(Dpad + XS_WARPS) * 8 + (size_t)cand_cap * 20 + TC_MAX_SEGS * 4;
+    QRAG_REQUIRE(pl->smem_final <= budget, QRAG_ERR_UNSUPPORTED, "D=%d too large for the rescoring stage", D);
     size_t off = 0;
     pl->off_qb = off; off = align_up(off + (size_t)pl->nq_pad * pl->Kp * 2, 256);
     pl->off_qnorm = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
@@ -637,7 +684,84 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, TcPlan* pl) {
     pl->off_eps = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
     pl->off_cnt = off; off = align_up(off + (size_t)pl->nq_pad * TC_MAX_SEGS * 4, 256);
     pl->off_surv = off; off = align_up(off + (size_t)pl->nq_pad * TC_CAP * 8, 256);
+    pl->off_bmtop = off; off = align_up(off + (size_t)pl->nq_pad * k * 4, 256);
+    pl->off_aptop = off; off = align_up(off + (size_t)pl->nq_pad * k * 4, 256);
     pl->total = off + 256;
+    return QRAG_OK;
+}
+
+// workspace carved the same way by every phase of one search (the phases share state through it)
+struct TcWs {
+    TcPlan pl;
+    __nv_bfloat16* Qb; float* qnorm; float* bmax; float* tau; float* eps; unsigned int* cnt; float2* surv;
+    float* bmtop; float* aptop;
+};
+
+static int tc_ws(int nq, int64_t N, int D, int k, int metric, void* workspace, size_t workspace_bytes, TcWs* w) {
+    int rc = tc_plan(nq, N, D, k, metric, &w->pl);
+    if (rc) return rc;
+    QRAG_REQUIRE(N >= 1, QRAG_ERR_INVALID, "empty shard: nothing to search");
+    QRAG_REQUIRE(workspace != nullptr && workspace_bytes >= w->pl.total, QRAG_ERR_WORKSPACE,
+                 "workspace too small: need %zu bytes, got %zu", w->pl.total, workspace_bytes);
+    unsigned char* ws = reinterpret_cast<unsigned char*>(align_up((size_t)workspace, 256));
+    const TcPlan& pl = w->pl;
+    w->Qb = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_qb);
+    w->qnorm = reinterpret_cast<float*>(ws + pl.off_qnorm);
+    w->bmax = reinterpret_cast<float*>(ws + pl.off_bmax);
+    w->tau = reinterpret_cast<float*>(ws + pl.off_tau);
+    w->eps = reinterpret_cast<float*>(ws + pl.off_eps);
+    w->cnt = reinterpret_cast<unsigned int*>(ws + pl.off_cnt);
+    w->surv = reinterpret_cast<float2*>(ws + pl.off_surv);
+    w->bmtop = reinterpret_cast<float*>(ws + pl.off_bmtop);
+    w->aptop = reinterpret_cast<float*>(ws + pl.off_aptop);
+    return QRAG_OK;
+}
+
+template <int MODE>
+static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcGemmParams& gp, size_t smem, int grid,
+                       cudaStream_t st) {
+    auto kern = sim_gemm_kernel<MODE>;
+    QRAG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, TC_THREADS, smem, st>>>(mapA, mapB, gp);
+    QRAG_LAUNCH_CHECK("sim_gemm_kernel");
+    return QRAG_OK;
+}
+
+static int tc_sms() {
+    const int n = device_props().sm_count;
+    return n < TC_MAX_SEGS / TC_EPI_SPLIT ? n : TC_MAX_SEGS / TC_EPI_SPLIT;
+}
+
+// One GEMM pass over the shard for every query group; `after` runs once per launch (query range).
+template <int MODE, class After>
+static int tc_gemm_pass(const TcWs& w, int nq, int64_t N, const uint16_t* Xb, cudaStream_t st, After after) {
+    const TcPlan& pl = w.pl;
+    CUtensorMap mapA, mapB;
+    int rc = make_map(&mapA, w.Qb, pl.nq_pad, pl.Kp, TC_BM);
+    if (rc) return rc;
+    rc = make_map(&mapB, Xb, N, pl.Kp, TC_BN);
+    if (rc) return rc;
+    TcGemmParams gp{};
+    gp.kchunks = pl.kchunks; gp.ksteps_last = pl.ksteps_last; gp.stages = pl.stages;
+    gp.a_resident = pl.a_resident; gp.stage_bytes = pl.stage_bytes;
+    gp.nq = nq; gp.N = N; gp.ntiles = pl.ntiles; gp.sample = pl.sample; gp.nbuckets = pl.nbuckets;
+    gp.tau = w.tau; gp.bmax = w.bmax; gp.cnt = w.cnt; gp.surv = w.surv;
+    const int sms = tc_sms();
+    const int units = MODE == TC_MODE_BUCKET ? pl.nsample_tiles : pl.ntiles;
+    for (int g0 = 0; g0 < pl.groups; g0 += sms) {
+        const int groups = pl.groups - g0 < sms ? pl.groups - g0 : sms;
+        int cpg = sms / groups;
+        if (cpg > units) cpg = units;
+        gp.groups = groups;
+        gp.group0 = g0;
+        gp.seg_cap = TC_CAP / (TC_EPI_SPLIT * cpg);
+        rc = launch_gemm<MODE>(mapA, mapB, gp, pl.smem_gemm, groups * cpg, st);
+        if (rc) return rc;
+        const int q0 = g0 * TC_BM;
+        const int q1 = (g0 + groups) * TC_BM < nq ? (g0 + groups) * TC_BM : nq;
+        rc = after(q0, q1, TC_EPI_SPLIT * cpg, gp.seg_cap);
+        if (rc) return rc;
+    }
     return QRAG_OK;
 }
 
@@ -667,7 +791,6 @@ extern "C" int qrag_index_prepare(const float* X, int64_t N, int D, int metric, 
 
 extern "C" int qrag_search_tc_workspace(int nq, int64_t N, int D, int k, int metric, size_t* bytes) {
     QRAG_REQUIRE(bytes != nullptr, QRAG_ERR_INVALID, "bytes is null");
-    QRAG_REQUIRE(device_props().ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
     TcPlan pl;
     int rc = tc_plan(nq, N, D, k, metric, &pl);
     if (rc) return rc;
@@ -675,100 +798,93 @@ extern "C" int qrag_search_tc_workspace(int nq, int64_t N, int D, int k, int met
     return QRAG_OK;
 }
 
-template <int MODE>
-static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcGemmParams& gp, size_t smem, int grid,
-                       cudaStream_t st) {
-    auto kern = sim_gemm_kernel<MODE>;
-    QRAG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TC_THREADS, smem, st>>>(mapA, mapB, gp);
-    QRAG_LAUNCH_CHECK("sim_gemm_kernel");
+// phase 1: operands, sampled bucket-maximum GEMM, the shard's k largest bucket maxima
+extern "C" int qrag_search_tc_begin(const float* Q, int nq, const uint16_t* Xb, int64_t N, int D, int k, int metric,
+                                    float* bm_top, void* workspace, size_t workspace_bytes, void* stream) {
+    QRAG_REQUIRE(Q && Xb && bm_top, QRAG_ERR_INVALID, "null pointer argument");
+    QRAG_REQUIRE((uintptr_t)Xb % 16 == 0, QRAG_ERR_INVALID, "Xb must be 16-byte aligned");
+    if (nq == 0) return QRAG_OK;
+    TcWs w;
+    int rc = tc_ws(nq, N, D, k, metric, workspace, workspace_bytes, &w);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const TcPlan& pl = w.pl;
+    query_prepare_kernel<<<(unsigned)ceil_div(pl.nq_pad, 8), 256, 0, st>>>(Q, nq, pl.nq_pad, D, pl.Kp, metric, w.Qb, w.qnorm);
+    QRAG_LAUNCH_CHECK("query_prepare_kernel");
+    rc = tc_gemm_pass<TC_MODE_BUCKET>(w, nq, N, Xb, st, [](int, int, int, int) { return QRAG_OK; });
+    if (rc) return rc;
+    bucket_topk_kernel<<<nq, 256, 0, st>>>(w.bmax, pl.nbuckets, k, bm_top);
+    QRAG_LAUNCH_CHECK("bucket_topk_kernel");
     return QRAG_OK;
 }
 
+// phase 2: threshold from all shards' bucket maxima, filter GEMM, the shard's k best approximate scores
+extern "C" int qrag_search_tc_filter(int nq, const uint16_t* Xb, const float* aux, int64_t N, int D, int k, int metric,
+                                     const float* bm_top_all, int G, float* ap_top, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    QRAG_REQUIRE(Xb && aux && bm_top_all && ap_top && G >= 1, QRAG_ERR_INVALID, "bad argument");
+    if (nq == 0) return QRAG_OK;
+    TcWs w;
+    int rc = tc_ws(nq, N, D, k, metric, workspace, workspace_bytes, &w);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    tau_union_kernel<<<nq, 256, 0, st>>>(bm_top_all, G, nq, k, metric, w.pl.Kp, w.qnorm, aux, w.tau, w.eps);
+    QRAG_LAUNCH_CHECK("tau_union_kernel");
+    return tc_gemm_pass<TC_MODE_FILTER>(w, nq, N, Xb, st, [&](int q0, int q1, int nseg, int seg_cap) {
+        surv_topk_kernel<<<q1 - q0, 256, 0, st>>>(w.cnt, w.surv, q0, nseg, seg_cap, k, ap_top);
+        QRAG_LAUNCH_CHECK("surv_topk_kernel");
+        return QRAG_OK;
+    });
+}
+
+// phase 3: candidates against the global k-th best approximate score, exact rescoring, sorted shard list
+extern "C" int qrag_search_tc_finish(const float* Q, int nq, const float* X, int64_t N, int D, int k, int metric,
+                                     int64_t id_base, const float* ap_top_all, int G, double* out_scores, int64_t* out_ids,
+                                     int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+    QRAG_REQUIRE(Q && X && ap_top_all && out_scores && out_ids && status && G >= 1, QRAG_ERR_INVALID, "bad argument");
+    if (nq == 0) return QRAG_OK;
+    TcWs w;
+    int rc = tc_ws(nq, N, D, k, metric, workspace, workspace_bytes, &w);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const TcPlan& pl = w.pl;
+    const bool vec = (D % 4 == 0) && ((uintptr_t)X % 16 == 0);
+    const int sms = tc_sms();
+    for (int g0 = 0; g0 < pl.groups; g0 += sms) {              // same launch partition as the filter pass
+        const int groups = pl.groups - g0 < sms ? pl.groups - g0 : sms;
+        int cpg = sms / groups;
+        if (cpg > pl.ntiles) cpg = pl.ntiles;
+        const int q0 = g0 * TC_BM;
+        const int q1 = (g0 + groups) * TC_BM < nq ? (g0 + groups) * TC_BM : nq;
+        TcFinalParams fp{Q, X, q0, nq, N, D, k, metric, id_base, TC_EPI_SPLIT * cpg, TC_CAP / (TC_EPI_SPLIT * cpg),
+                         pl.cand_cap, G, ap_top_all, w.cnt, w.surv, w.eps, out_scores, out_ids, status};
+        if (vec) {
+            QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)pl.smem_final));
+            tc_final_kernel<true><<<q1 - q0, XS_THREADS, pl.smem_final, st>>>(fp);
+        } else {
+            QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)pl.smem_final));
+            tc_final_kernel<false><<<q1 - q0, XS_THREADS, pl.smem_final, st>>>(fp);
+        }
+        QRAG_LAUNCH_CHECK("tc_final_kernel");
+    }
+    return QRAG_OK;
+}
+
+// single shard: the three phases back to back, exchanging through the workspace
 extern "C" int qrag_search_topk_tc(const float* Q, int nq, const float* X, const uint16_t* Xb, const float* aux, int64_t N,
                                    int D, int k, int metric, int64_t id_base, double* out_scores, int64_t* out_ids,
                                    int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
     QRAG_REQUIRE(Q && X && Xb && aux && out_scores && out_ids && status, QRAG_ERR_INVALID, "null pointer argument");
-    const DeviceProps& dp = device_props();
-    QRAG_REQUIRE(dp.ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
-    QRAG_REQUIRE(dp.cc_major == 10, QRAG_ERR_UNSUPPORTED, "tcgen05 search needs compute capability 10.x (got %d.%d)",
-                 dp.cc_major, dp.cc_minor);
-    TcPlan pl;
-    int rc = tc_plan(nq, N, D, k, metric, &pl);
-    if (rc) return rc;
-    QRAG_REQUIRE(N >= 1, QRAG_ERR_INVALID, "empty shard: use qrag_search_topk");
     if (nq == 0) return QRAG_OK;
-    QRAG_REQUIRE(workspace != nullptr && workspace_bytes >= pl.total, QRAG_ERR_WORKSPACE,
-                 "workspace too small: need %zu bytes, got %zu", pl.total, workspace_bytes);
-    QRAG_REQUIRE((uintptr_t)Xb % 16 == 0, QRAG_ERR_INVALID, "Xb must be 16-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
-    unsigned char* ws = reinterpret_cast<unsigned char*>(align_up((size_t)workspace, 256));
-    __nv_bfloat16* Qb = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_qb);
-    float* qnorm = reinterpret_cast<float*>(ws + pl.off_qnorm);
-    float* bmax = reinterpret_cast<float*>(ws + pl.off_bmax);
-    float* tau = reinterpret_cast<float*>(ws + pl.off_tau);
-    float* eps = reinterpret_cast<float*>(ws + pl.off_eps);
-    unsigned int* cnt = reinterpret_cast<unsigned int*>(ws + pl.off_cnt);
-    float2* surv = reinterpret_cast<float2*>(ws + pl.off_surv);
-
-    query_prepare_kernel<<<(unsigned)ceil_div(pl.nq_pad, 8), 256, 0, st>>>(Q, nq, pl.nq_pad, D, pl.Kp, metric, Qb, qnorm);
-    QRAG_LAUNCH_CHECK("query_prepare_kernel");
-
-    CUtensorMap mapA, mapB;
-    rc = make_map(&mapA, Qb, pl.nq_pad, pl.Kp, TC_BM);
+    TcWs w;
+    int rc = tc_ws(nq, N, D, k, metric, workspace, workspace_bytes, &w);
     if (rc) return rc;
-    rc = make_map(&mapB, Xb, N, pl.Kp, TC_BN);
+    rc = qrag_search_tc_begin(Q, nq, Xb, N, D, k, metric, w.bmtop, workspace, workspace_bytes, stream);
     if (rc) return rc;
-
-    TcGemmParams gp{};
-    gp.kchunks = pl.kchunks; gp.ksteps_last = pl.ksteps_last; gp.stages = pl.stages;
-    gp.a_resident = pl.a_resident; gp.stage_bytes = pl.stage_bytes;
-    gp.nq = nq; gp.N = N; gp.ntiles = pl.ntiles; gp.sample = pl.sample; gp.nbuckets = pl.nbuckets;
-    gp.tau = tau; gp.bmax = bmax; gp.cnt = cnt; gp.surv = surv;
-
-    const int sms = dp.sm_count < TC_MAX_SEGS / TC_EPI_SPLIT ? dp.sm_count : TC_MAX_SEGS / TC_EPI_SPLIT;
-    const int Dpad = (D + 3) & ~3;
-    int cand_cap = next_pow2(2 * (int64_t)k + 512);
-    if (cand_cap > TC_MAX_CAND) cand_cap = TC_MAX_CAND;
-    const size_t smem_final = (size_t)(Dpad + XS_WARPS) * 8 + (size_t)cand_cap * 20 + 256 * 4 + TC_MAX_SEGS * 4;
-    QRAG_REQUIRE(smem_final <= (size_t)dp.max_smem_optin, QRAG_ERR_UNSUPPORTED, "D=%d too large for the rescoring stage", D);
-    const bool vec = (D % 4 == 0) && ((uintptr_t)X % 16 == 0);
-    for (int pass = 0; pass < 2; ++pass) {
-        const int units = pass == 0 ? pl.nsample_tiles : pl.ntiles;
-        for (int g0 = 0; g0 < pl.groups; g0 += sms) {
-            const int groups = pl.groups - g0 < sms ? pl.groups - g0 : sms;
-            int cpg = sms / groups;
-            if (cpg > units) cpg = units;
-            gp.groups = groups;
-            gp.group0 = g0;
-            gp.seg_cap = TC_CAP / (TC_EPI_SPLIT * cpg);
-            rc = pass == 0 ? launch_gemm<TC_MODE_BUCKET>(mapA, mapB, gp, pl.smem_gemm, groups * cpg, st)
-                           : launch_gemm<TC_MODE_FILTER>(mapA, mapB, gp, pl.smem_gemm, groups * cpg, st);
-            if (rc) return rc;
-            if (pass == 1) {
-                const int q0 = g0 * TC_BM;
-                const int q1 = (g0 + groups) * TC_BM < nq ? (g0 + groups) * TC_BM : nq;
-                TcFinalParams fp{Q, X, q0, nq, N, D, k, metric, id_base, TC_EPI_SPLIT * cpg, gp.seg_cap, cand_cap,
-                                 cnt, surv, eps, out_scores, out_ids, status};
-                if (vec) {
-                    QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         (int)smem_final));
-                    tc_final_kernel<true><<<q1 - q0, XS_THREADS, smem_final, st>>>(fp);
-                } else {
-                    QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         (int)smem_final));
-                    tc_final_kernel<false><<<q1 - q0, XS_THREADS, smem_final, st>>>(fp);
-                }
-                QRAG_LAUNCH_CHECK("tc_final_kernel");
-            }
-        }
-        if (pass == 0) {
-            const size_t smem = (size_t)next_pow2(pl.nbuckets) * sizeof(float);
-            if (smem > 48 * 1024)
-                QRAG_CUDA_CHECK(cudaFuncSetAttribute(tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            tau_kernel<<<nq, 256, smem, st>>>(bmax, pl.nbuckets, k, metric, pl.Kp, qnorm, aux, tau, eps);
-            QRAG_LAUNCH_CHECK("tau_kernel");
-        }
-    }
-    return QRAG_OK;
+    rc = qrag_search_tc_filter(nq, Xb, aux, N, D, k, metric, w.bmtop, 1, w.aptop, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    return qrag_search_tc_finish(Q, nq, X, N, D, k, metric, id_base, w.aptop, 1, out_scores, out_ids, status, workspace,
+                                 workspace_bytes, stream);
 }

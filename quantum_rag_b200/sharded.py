@@ -5,7 +5,9 @@ this is the multi-GPU form BASELINE.json's config 4 asks for:
 
     corpus rows   contiguous row partition, rank g owns rows [lo_g, hi_g); global id = lo_g + row
     queries       replicated on every rank
-    search        per shard: tcgen05 filter GEMM + exact rescoring (FlatIndexTC), top-k1
+    search        per shard: tcgen05 filter GEMM + exact rescoring (FlatIndexTC); the filter
+                  thresholds are global (two [nq, k1] fp32 all-gathers between the phases), so a
+                  shard rescores only its ~1/G share of the global top-k1
     exchange 1    ONE all-gather of the per-shard lists, [nq, k1] x (fp64 score, int64 id)
     merge         every rank merges the G lists to the global top-k1 (same kernel as the
                   single-GPU merge, so the order is the canonical (score, id) order)
@@ -52,6 +54,14 @@ class CudaEngine:
     def search(self, Q, k):
         return self.index.search(Q, k)
 
+    def sync_corpus_bound(self, all_reduce_max):
+        """The filter's error bound uses max |x| over the WHOLE corpus: reduce it once per index."""
+        all_reduce_max(self.index.aux[:1])
+
+    def search_sharded(self, Q, k, all_gather):
+        """This shard's members of the global top-k (thresholds exchanged through ``all_gather``)."""
+        return self.index.search_sharded(Q, k, all_gather)
+
     def merge(self, scores, ids, k_out):
         return self.api.topk_merge(scores, ids, k_out, self.metric)
 
@@ -85,6 +95,8 @@ class ShardedSearchRerank:
             raise ValueError(f"rank {self.rank} owns rows [{self.lo}, {self.hi}) but got {X_shard.shape[0]} rows")
         self.metric = metric
         self.engine = engine if engine is not None else CudaEngine(X_shard, metric, self.lo)
+        if hasattr(self.engine, "sync_corpus_bound"):
+            self.engine.sync_corpus_bound(self._all_reduce_max)
 
     # ------------------------------------------------------------------ exchange steps
     def _all_gather(self, t: torch.Tensor) -> torch.Tensor:
@@ -102,8 +114,24 @@ class ShardedSearchRerank:
 
     # ------------------------------------------------------------------------- the path
     def search(self, Q, k1: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Global top-k1 (identical on every rank): per-shard search, one all-gather, merge."""
-        s, i = self.engine.search(Q, k1)
+        """Global top-k1 (identical on every rank): per-shard search, all-gather of the lists, merge.
+
+        With the CUDA engine and G > 1 the shards also exchange their filter thresholds (two [nq, k1]
+        fp32 all-gathers inside the search), so that each shard rescores only its ~1/G share of the
+        global list; any query a shard could not certify makes every rank rerun it exactly.
+        """
+        if self.world > 1 and hasattr(self.engine, "search_sharded"):
+            s, i, status = self.engine.search_sharded(Q, k1, self._all_gather)
+            bad = self._all_reduce_max(status.clone())
+            flagged = torch.nonzero(bad).flatten()
+            if flagged.numel():                                   # identical on every rank after the reduce
+                from . import api
+                Qd = Q if isinstance(Q, torch.Tensor) else torch.as_tensor(Q)
+                s2, i2 = api.search_topk(Qd.to(s.device)[flagged], self.engine.index.X, k1, self.metric, self.lo)
+                s[flagged] = s2
+                i[flagged] = i2
+        else:
+            s, i = self.engine.search(Q, k1)
         # one collective for both arrays: scores and ids are both 8 bytes wide
         packed = torch.stack([s.view(torch.int64), i], dim=0)                 # [2, nq, k1]
         gathered = self._all_gather(packed)                                   # [G, 2, nq, k1]

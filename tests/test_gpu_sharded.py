@@ -14,7 +14,7 @@ from oracle import search as osr
 pytestmark = pytest.mark.gpu
 
 
-def _emulated(X, Q, G, k1, k2, metric):
+def _emulated(X, Q, G, k1, k2, metric, phased):
     import torch
     from quantum_rag_b200.sharded import CudaEngine, shard_bounds
     n = X.shape[0]
@@ -22,7 +22,20 @@ def _emulated(X, Q, G, k1, k2, metric):
     for r in range(G):
         lo, hi = shard_bounds(n, G, r)
         engines.append((lo, hi, CudaEngine(X[lo:hi], metric, lo)))
-    lists = [e.search(Q, k1) for _, _, e in engines]
+    if phased:
+        # the three phases of every shard with the exchanges emulated by stack (what NCCL does under torchrun)
+        xmax = torch.stack([e.index.aux[:1] for _, _, e in engines]).max()
+        for _, _, e in engines:
+            e.index.aux[:1] = xmax
+        bm_all = torch.stack([e.index.tc_begin(Q, k1) for _, _, e in engines])
+        ap_all = torch.stack([e.index.tc_filter(bm_all) for _, _, e in engines])
+        lists = []
+        for _, _, e in engines:
+            s, i, status = e.index.tc_finish(ap_all)
+            assert int(status.count_nonzero()) == 0
+            lists.append((s, i))
+    else:
+        lists = [e.search(Q, k1) for _, _, e in engines]
     gs = torch.stack([s for s, _ in lists])
     gi = torch.stack([i for _, i in lists])
     ss, si = engines[0][2].merge(gs, gi, k1)
@@ -57,7 +70,7 @@ def test_sharded_path_matches_oracle_and_single_shard(cuda, metric):
     order = oq.rank_rows(f, k2)
     assert np.array_equal(res.ids.cpu().numpy(), np.take_along_axis(ri, order, 1))
     assert np.allclose(res.scores.cpu().numpy(), np.take_along_axis(f, order, 1), rtol=1e-12, atol=1e-16)
-    for G in (2, 3, 8):
-        top, ids, ss, si = _emulated(Xd, Qd, G, k1, k2, metric)
-        assert torch.equal(si, res.search_ids) and torch.equal(ss, res.search_scores), f"G={G}"
-        assert torch.equal(ids, res.ids) and torch.equal(top, res.scores), f"G={G}"
+    for G, phased in ((2, False), (2, True), (3, True), (8, True)):
+        top, ids, ss, si = _emulated(Xd, Qd, G, k1, k2, metric, phased)
+        assert torch.equal(si, res.search_ids) and torch.equal(ss, res.search_scores), f"G={G} phased={phased}"
+        assert torch.equal(ids, res.ids) and torch.equal(top, res.scores), f"G={G} phased={phased}"
