@@ -110,28 +110,33 @@ __global__ void __launch_bounds__(256) merge_lists_kernel(const MergeParams p) {
     const int l0 = gi * p.group;
     const int nl = (p.nlists - l0) < p.group ? (p.nlists - l0) : p.group;
     const int total = nl * p.kin;
-    int P = 1;
-    while (P < total) P <<= 1;
     double* key = reinterpret_cast<double*>(smem_raw);
     long long* tag = reinterpret_cast<long long*>(key + p.pmax);
     const bool l2 = p.metric == QRAG_METRIC_L2;
+    __shared__ int s_cnt;
     for (int q = blockIdx.y; q < p.nq; q += gridDim.y) {
-        for (int i = threadIdx.x; i < P; i += blockDim.x) {
-            double kv = pos_inf();
-            long long tv = TAG_PAD;
-            if (i < total) {
-                const int l = l0 + i / p.kin, e = i % p.kin;
-                const size_t off = (size_t)l * p.stride_l + (size_t)q * p.stride_q + e;
-                kv = p.in_key[off];
-                tv = p.in_tag[off];
-                if (p.raw_scores) {
-                    if (tv < 0) { kv = pos_inf(); tv = TAG_PAD; }
-                    else if (!l2) kv = -kv;
-                }
+        // compact: padding entries (short shards, per-shard lists of a sharded search) are dropped before
+        // the sort, so the sort size follows the number of real entries, not G * k
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int l = l0 + i / p.kin, e = i % p.kin;
+            const size_t off = (size_t)l * p.stride_l + (size_t)q * p.stride_q + e;
+            double kv = p.in_key[off];
+            const long long tv = p.in_tag[off];
+            const bool pad = p.raw_scores ? tv < 0 : tv == TAG_PAD;
+            if (!pad) {
+                if (p.raw_scores && !l2) kv = -kv;
+                const int pos = atomicAdd(&s_cnt, 1);
+                key[pos] = kv;
+                tag[pos] = tv;
             }
-            key[i] = kv;
-            tag[i] = tv;
         }
+        __syncthreads();
+        const int real = s_cnt;
+        int P = 1;
+        while (P < real) P <<= 1;
+        for (int i = real + threadIdx.x; i < P; i += blockDim.x) { key[i] = pos_inf(); tag[i] = TAG_PAD; }
         __syncthreads();
         block_bitonic_sort<long long>(key, tag, P);
         double* ok = p.out_key + ((size_t)q * ngroups + gi) * p.kout;

@@ -94,9 +94,24 @@ class ShardedSearchRerank:
         if X_shard.shape[0] != self.hi - self.lo:
             raise ValueError(f"rank {self.rank} owns rows [{self.lo}, {self.hi}) but got {X_shard.shape[0]} rows")
         self.metric = metric
+        self.profile = None          # set to {} to collect per-stage CUDA-event timings (ms) of the next call
+        self._marks = []
         self.engine = engine if engine is not None else CudaEngine(X_shard, metric, self.lo)
         if hasattr(self.engine, "sync_corpus_bound"):
             self.engine.sync_corpus_bound(self._all_reduce_max)
+
+    def _mark(self, name: str) -> None:
+        if self.profile is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._marks.append((name, ev))
+
+    def _flush_marks(self) -> None:
+        if self.profile is not None and self._marks:
+            torch.cuda.synchronize()
+            for (_, a), (name, b) in zip(self._marks[:-1], self._marks[1:]):
+                self.profile[name] = self.profile.get(name, 0.0) + a.elapsed_time(b)
+            self._marks = []
 
     # ------------------------------------------------------------------ exchange steps
     def _all_gather(self, t: torch.Tensor) -> torch.Tensor:
@@ -120,10 +135,13 @@ class ShardedSearchRerank:
         fp32 all-gathers inside the search), so that each shard rescores only its ~1/G share of the
         global list; any query a shard could not certify makes every rank rerun it exactly.
         """
+        self._mark("start")
         if self.world > 1 and hasattr(self.engine, "search_sharded"):
             s, i, status = self.engine.search_sharded(Q, k1, self._all_gather)
+            self._mark("search_phases")
             bad = self._all_reduce_max(status.clone())
             flagged = torch.nonzero(bad).flatten()
+            self._mark("status_sync")
             if flagged.numel():                                   # identical on every rank after the reduce
                 from . import api
                 Qd = Q if isinstance(Q, torch.Tensor) else torch.as_tensor(Q)
@@ -132,21 +150,30 @@ class ShardedSearchRerank:
                 i[flagged] = i2
         else:
             s, i = self.engine.search(Q, k1)
+            self._mark("search_phases")
         # one collective for both arrays: scores and ids are both 8 bytes wide
         packed = torch.stack([s.view(torch.int64), i], dim=0)                 # [2, nq, k1]
         gathered = self._all_gather(packed)                                   # [G, 2, nq, k1]
         gs = gathered[:, 0].contiguous().view(torch.float64)
         gi = gathered[:, 1].contiguous()
-        return self.engine.merge(gs, gi, k1)
+        self._mark("gather_lists")
+        out = self.engine.merge(gs, gi, k1)
+        self._mark("merge")
+        return out
 
     def rerank(self, Q, search_ids: torch.Tensor, k2: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """Amplitude-fidelity rerank of the merged list: owner computes, all-reduce(MAX), stable top-k2."""
         own = (search_ids >= self.lo) & (search_ids < self.hi)
         local = torch.where(own, search_ids - self.lo, torch.full_like(search_ids, -1))
+        self._mark("ownership")
         f = self.engine.fidelity_rows(Q, local)                                # -inf where not owned / padding
+        self._mark("rerank_fidelity")
         f = self._all_reduce_max(f)
+        self._mark("allreduce_fidelity")
         pos, top = self.engine.sort_scores(f, k2)
         ids = torch.gather(search_ids, 1, pos.long())
+        self._mark("final_sort")
+        self._flush_marks()
         return top, ids
 
     def __call__(self, Q, k1: int = 1000, k2: int = 10) -> ShardedResult:

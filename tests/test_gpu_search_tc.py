@@ -109,3 +109,23 @@ def test_config3_full_size_properties(cuda):
     b = api.FlatIndexTC(X[h:], "cosine", id_base=h).search(Q, k)
     ms, mi = api.topk_merge(torch.stack([a[0], b[0]]), torch.stack([a[1], b[1]]), k, "cosine")
     assert torch.equal(mi, i) and torch.equal(ms, s)
+
+
+def test_flat_index_file_roundtrip_and_search(cuda, piers, tmp_path):
+    """(f)1: an IxF2 file as the reference's ingest tool writes it -> searchable device index, faiss-style (D, I)."""
+    from quantum_rag_b200 import index as qidx
+    x = piers["vectors"]
+    path = tmp_path / "piers.faiss"
+    path.write_bytes(qidx.dump_ixf(x, qidx.FAISS_METRIC_L2))
+    labels = [f"row{i}" for i in range(x.shape[0])]
+    import pickle
+    (tmp_path / "piers.pkl").write_bytes(pickle.dumps(labels))
+    idx = qidx.FlatIndex.read(str(path), str(tmp_path / "piers.pkl"))
+    assert (idx.d, idx.ntotal, idx.metric) == (1536, 119, "l2")
+    D, I = idx.search(x[:5], 20)
+    assert np.array_equal(I.cpu().numpy(), piers["top20_ids"][:5])
+    assert np.allclose(D.cpu().numpy(), piers["top20_dist"][:5], rtol=1e-12, atol=1e-13)
+    _, names = idx.search_labels(x[:1], 3)
+    assert names[0] == [labels[i] for i in piers["top20_ids"][0, :3]]
+    idx.write(str(tmp_path / "again.faiss"))
+    assert (tmp_path / "again.faiss").read_bytes() == path.read_bytes()

@@ -136,3 +136,31 @@ def test_no_cpu_fallback_without_cuda():
         QuantumReranker().rerank("query", [Document("a", "x")])
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         RerankerController().rerank("sponsor ad", [Document("a", "x")], reranker_type="quantum")
+
+
+def test_ixf_parse_dump_roundtrip_and_fixture_header(piers):
+    from oracle import search as osr
+    from quantum_rag_b200 import index as qidx
+    x = piers["vectors"]
+    buf = qidx.dump_ixf(x, qidx.FAISS_METRIC_L2)
+    assert buf == osr.write_ixf(x, 1)                      # product writer == oracle writer
+    assert len(buf) == 731181                              # the size of the reference's fixture file
+    y, metric = qidx.parse_ixf(buf)
+    assert metric == 1 and np.array_equal(y, x)
+    y2, metric2 = qidx.parse_ixf(qidx.dump_ixf(x[:3], qidx.FAISS_METRIC_IP))
+    assert metric2 == 0 and np.array_equal(y2, x[:3])
+    with pytest.raises(ValueError):
+        qidx.parse_ixf(b"IxF2" + buf[4:40])
+    with pytest.raises(ValueError):
+        qidx.parse_ixf(b"IVFx" + buf[4:])
+
+
+def test_metadata_sidecar_only_plain_lists(tmp_path):
+    import pickle
+    from quantum_rag_b200 import index as qidx
+    p = tmp_path / "meta.pkl"
+    p.write_bytes(pickle.dumps(["show/a", "show/b"]))
+    assert qidx.load_metadata(str(p)) == ["show/a", "show/b"]
+    p.write_bytes(pickle.dumps(np.arange(3)))              # needs a global -> refused, never executed
+    with pytest.raises(pickle.UnpicklingError):
+        qidx.load_metadata(str(p))
