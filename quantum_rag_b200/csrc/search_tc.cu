@@ -36,6 +36,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace qrag {
 
@@ -53,7 +54,7 @@ constexpr int TC_BUCKET = 32;         // documents per bucket maximum (one tcgen
 constexpr int TC_CAP = 16384;         // survivor list capacity per query
 constexpr int TC_MAX_CAND = 8192;     // largest exact-rescore capacity per query
 constexpr int TC_MAX_SEGS = 640;      // survivor-list segments per query (TC_EPI_SPLIT per CTA of the query's group)
-constexpr int TC_MAX_STAGES = 6;
+constexpr int TC_MAX_STAGES = 10;
 constexpr int TC_MODE_BUCKET = 0, TC_MODE_FILTER = 1;
 
 struct TcGemmParams {
@@ -122,12 +123,66 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// ---- cta_group::2 forms (a CTA pair = one cluster of 2; rank 0 is the leader and issues the MMAs)
+constexpr uint32_t TC_PEER_MASK = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address: rank 0's copy
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(rank)
+        : "memory");
+}
+// TMA load whose completion bytes are counted on the LEADER's barrier (same offset in rank 0)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & TC_PEER_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair when the MMAs issued so far are done
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float neg_inf_f() { return __int_as_float(0xff800000); }
 
 // ------------------------------------------------------------------------------- the GEMM
-template <int MODE>
+// CG == 1: one CTA computes 128 queries x 256 documents per tile.  CG == 2: a CTA pair computes 256 queries x 256
+// documents per tile with tcgen05.mma.cta_group::2: each CTA keeps its own 128 query rows resident and loads HALF of
+// every document tile (128 rows); the pair's tensor cores read both halves.  Per SM that halves the L2->SM bytes per
+// flop and doubles the MMA work each in-flight stage feeds, which is what the single-CTA mainloop waits on.
+template <int MODE, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcGemmParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -144,23 +199,32 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = p.stages, KC = p.kchunks;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;      // position in the CTA pair; 0 issues the MMAs
+    constexpr int B_ROWS = TC_BN / CG;                            // document rows this CTA loads per tile
 
     if (tid == 0) {
-        mbar_init(a_full, 1);
-        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], TC_EPI_WARPS); }
+        // full / a_full / acc_empty are only used in the leader: both CTAs' producers and epilogues report there
+        mbar_init(a_full, CG);
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], CG); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], CG * TC_EPI_WARPS); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == 2) {
+        if (CG == 2) tmem_alloc_pair(tmem_slot, 512);
+        else tmem_alloc(tmem_slot, 512);
+    }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();                              // the peer's barriers exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // work of this CTA: query group g, tiles u0, u0 + cpg, ... (pass 1: of the sampled tiles)
-    const int g = blockIdx.x % p.groups;
-    const int u0 = blockIdx.x / p.groups;
-    const int cpg = gridDim.x / p.groups;
+    // work of this CTA (pair): query group g, tiles u0, u0 + cpg, ... (pass 1: of the sampled tiles)
+    const int unit_id = blockIdx.x / CG;                          // CTA (CG 1) or pair (CG 2) index
+    const int ugroups = p.groups / CG;                            // query groups are handled CG at a time
+    const int g = (unit_id % ugroups) * CG + (int)rank;
+    const int u0 = unit_id / ugroups;
+    const int cpg = (gridDim.x / CG) / ugroups;
     const int step = MODE == TC_MODE_BUCKET ? p.sample : 1;
     const int nunits = (p.ntiles + step - 1) / step;          // tiles this pass visits
 
@@ -168,9 +232,16 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (lane == 0) {
             // ------------------------------------------------------------ TMA producer
             if (p.a_resident) {
-                mbar_arrive_expect_tx(a_full, (uint32_t)KC * TC_A_CHUNK);
-                for (int kc = 0; kc < KC; ++kc)
-                    tma_load_2d(sA + (size_t)kc * TC_A_CHUNK, &mapA, a_full, kc * TC_BK, (p.group0 + g) * TC_BM);
+                if (CG == 2) {
+                    if (rank == 0) mbar_arrive_expect_tx(a_full, (uint32_t)KC * TC_A_CHUNK * 2);
+                    else mbar_arrive_cta(a_full, 0);
+                    for (int kc = 0; kc < KC; ++kc)
+                        tma_load_2d_pair(sA + (size_t)kc * TC_A_CHUNK, &mapA, a_full, kc * TC_BK, (p.group0 + g) * TC_BM);
+                } else {
+                    mbar_arrive_expect_tx(a_full, (uint32_t)KC * TC_A_CHUNK);
+                    for (int kc = 0; kc < KC; ++kc)
+                        tma_load_2d(sA + (size_t)kc * TC_A_CHUNK, &mapA, a_full, kc * TC_BK, (p.group0 + g) * TC_BM);
+                }
             }
             int s = 0;
             uint32_t par = 0;
@@ -178,23 +249,32 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const int tile = u * step;
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&empty[s], par ^ 1u);
-                    mbar_arrive_expect_tx(&full[s], (uint32_t)p.stage_bytes);
-                    tma_load_2d(sB + (size_t)s * p.stage_bytes, &mapB, &full[s], kc * TC_BK, tile * TC_BN);
-                    if (!p.a_resident)
-                        tma_load_2d(sB + (size_t)s * p.stage_bytes + TC_B_STAGE, &mapA, &full[s], kc * TC_BK,
-                                    (p.group0 + g) * TC_BM);
+                    if (CG == 2) {
+                        // both halves of the tile report their bytes to the leader's barrier
+                        if (rank == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)p.stage_bytes * 2);
+                        else mbar_arrive_cta(&full[s], 0);
+                        tma_load_2d_pair(sB + (size_t)s * p.stage_bytes, &mapB, &full[s], kc * TC_BK,
+                                         tile * TC_BN + (int)rank * B_ROWS);
+                    } else {
+                        mbar_arrive_expect_tx(&full[s], (uint32_t)p.stage_bytes);
+                        tma_load_2d(sB + (size_t)s * p.stage_bytes, &mapB, &full[s], kc * TC_BK, tile * TC_BN);
+                        if (!p.a_resident)
+                            tma_load_2d(sB + (size_t)s * p.stage_bytes + TC_B_STAGE, &mapA, &full[s], kc * TC_BK,
+                                        (p.group0 + g) * TC_BM);
+                    }
                     if (++s == S) { s = 0; par ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
             // -------------------------------------------------------------- MMA issuer
-            // instruction descriptor: D fp32, A/B bf16, both K-major, N = 256, M = 128
+            // instruction descriptor: D fp32, A/B bf16, both K-major, N = 256, M = 128 (256 across a pair)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
-                                   ((uint32_t)(TC_BM >> 4) << 24);
+                                   ((uint32_t)((TC_BM * CG) >> 4) << 24);
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
             if (p.a_resident) mbar_wait(a_full, 0);
+            const uint32_t b_bytes = (uint32_t)B_ROWS * TC_BK * 2;               // this CTA's share of a document chunk
             int s = 0;
             uint32_t par = 0;
             int n = 0;
@@ -209,15 +289,19 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     const int ks = (kc == KC - 1) ? p.ksteps_last : TC_BK / TC_UK;
                     for (int k = 0; k < ks; ++k) {
                         const uint32_t bs = b0 + (uint32_t)s * (uint32_t)p.stage_bytes;
-                        const uint32_t as = p.a_resident ? a0 + (uint32_t)kc * TC_A_CHUNK : bs + TC_B_STAGE;
+                        const uint32_t as = p.a_resident ? a0 + (uint32_t)kc * TC_A_CHUNK : bs + b_bytes;
                         const uint64_t ad = umma_desc_sw128(as + (uint32_t)k * TC_UK * 2);
                         const uint64_t bd = umma_desc_sw128(bs + (uint32_t)k * TC_UK * 2);
-                        umma_bf16(d, ad, bd, idesc, (kc | k) != 0 ? 1u : 0u);
+                        if (CG == 2) umma_bf16_pair(d, ad, bd, idesc, (kc | k) != 0 ? 1u : 0u);
+                        else umma_bf16(d, ad, bd, idesc, (kc | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty[s]);                  // frees the stage when these MMAs have read it
+                    // frees the stage (in both CTAs of a pair) when these MMAs have read it
+                    if (CG == 2) umma_commit_pair(&empty[s]);
+                    else umma_commit(&empty[s]);
                     if (++s == S) { s = 0; par ^= 1u; }
                 }
-                umma_commit(&acc_full[buf]);                 // accumulator complete
+                if (CG == 2) umma_commit_pair(&acc_full[buf]);                   // accumulator complete
+                else umma_commit(&acc_full[buf]);
             }
         }
     } else if (warp >= 4) {
@@ -275,15 +359,20 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cta(&acc_empty[buf], 0);                // the leader issues the next MMAs
+                else mbar_arrive(&acc_empty[buf]);
+            }
         }
         if (MODE == TC_MODE_FILTER && qvalid) p.cnt[(size_t)q * TC_MAX_SEGS + TC_EPI_SPLIT * u0 + half] = found;
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();                              // neither CTA leaves while the other may still signal it
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (CG == 2) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -627,7 +716,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static int tc_kp(int D, int metric) { return (int)align_up((size_t)D + (metric == QRAG_METRIC_L2 ? 2 : 0), 16); }
 
 struct TcPlan {
-    int Kp, kchunks, ksteps_last, stages, a_resident, stage_bytes, nq_pad, groups, ntiles, sample, nsample_tiles, nbuckets;
+    int Kp, kchunks, ksteps_last, stages, a_resident, stage_bytes, cg, nq_pad, groups, ntiles, sample, nsample_tiles, nbuckets;
     int cand_cap;
     size_t smem_gemm, smem_final;
     size_t off_qb, off_qnorm, off_bmax, off_tau, off_eps, off_cnt, off_surv, off_bmtop, off_aptop, total;
@@ -650,14 +739,16 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, TcPlan* pl) {
     const size_t a_bytes = (size_t)pl->kchunks * TC_A_CHUNK;
     const size_t budget = (size_t)dp.max_smem_optin;
     pl->a_resident = (1024 + 256 + a_bytes + 3 * (size_t)TC_B_STAGE <= budget) ? 1 : 0;
-    pl->stage_bytes = pl->a_resident ? TC_B_STAGE : TC_B_STAGE + TC_A_CHUNK;
+    // CTA pairs (cta_group::2) whenever there are at least two query groups and the query tile is resident
+    pl->cg = (pl->a_resident && nq > TC_BM && !getenv("QRAG_TC_NO_PAIR")) ? 2 : 1;
+    pl->stage_bytes = pl->a_resident ? TC_B_STAGE / pl->cg : TC_B_STAGE + TC_A_CHUNK;
     const size_t fixed = 1024 + 256 + (pl->a_resident ? a_bytes : 0);
     int stages = (int)((budget - fixed) / pl->stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     QRAG_REQUIRE(stages >= 2, QRAG_ERR_UNSUPPORTED, "not enough shared memory for the tensor-core search");
     pl->stages = stages;
     pl->smem_gemm = fixed + (size_t)stages * pl->stage_bytes;
-    pl->nq_pad = (int)align_up((size_t)(nq > 0 ? nq : 1), TC_BM);
+    pl->nq_pad = (int)align_up((size_t)(nq > 0 ? nq : 1), (size_t)TC_BM * pl->cg);
     pl->groups = pl->nq_pad / TC_BM;
     pl->ntiles = (int)ceil_div(N > 0 ? N : 1, TC_BN);
     // pass 1 samples every `sample`-th tile: survivors ~ sample * k per query, kept well under TC_CAP,
@@ -717,19 +808,45 @@ static int tc_ws(int nq, int64_t N, int D, int k, int metric, void* workspace, s
     return QRAG_OK;
 }
 
-template <int MODE>
+template <int MODE, int CG>
 static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcGemmParams& gp, size_t smem, int grid,
                        cudaStream_t st) {
-    auto kern = sim_gemm_kernel<MODE>;
+    auto kern = sim_gemm_kernel<MODE, CG>;
     QRAG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TC_THREADS, smem, st>>>(mapA, mapB, gp);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CG > 1 ? 1 : 0;
+    QRAG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mapA, mapB, gp));
     QRAG_LAUNCH_CHECK("sim_gemm_kernel");
     return QRAG_OK;
 }
 
-static int tc_sms() {
-    const int n = device_props().sm_count;
-    return n < TC_MAX_SEGS / TC_EPI_SPLIT ? n : TC_MAX_SEGS / TC_EPI_SPLIT;
+// How the query groups [g0, g0 + groups) of one launch share the SMs: `groups` groups (a multiple of cg), each
+// visited by `cpg` CTAs (pairs), i.e. cpg * TC_EPI_SPLIT survivor segments per query.
+struct TcLaunch { int g0, groups, cpg; };
+
+static int tc_sm_units(int cg) {
+    int n = device_props().sm_count / cg;
+    const int cap = TC_MAX_SEGS / TC_EPI_SPLIT;
+    return n < cap ? n : cap;
+}
+
+static TcLaunch tc_launch_at(const TcPlan& pl, int g0, int units) {
+    const int su = tc_sm_units(pl.cg);                       // CTAs (cg 1) or pairs (cg 2) available
+    int ug = (pl.groups - g0) / pl.cg;                       // group units left
+    if (ug > su) ug = su;
+    int cpg = su / ug;
+    if (cpg > units) cpg = units;
+    return TcLaunch{g0, ug * pl.cg, cpg};
 }
 
 // One GEMM pass over the shard for every query group; `after` runs once per launch (query range).
@@ -739,28 +856,30 @@ static int tc_gemm_pass(const TcWs& w, int nq, int64_t N, const uint16_t* Xb, cu
     CUtensorMap mapA, mapB;
     int rc = make_map(&mapA, w.Qb, pl.nq_pad, pl.Kp, TC_BM);
     if (rc) return rc;
-    rc = make_map(&mapB, Xb, N, pl.Kp, TC_BN);
+    rc = make_map(&mapB, Xb, N, pl.Kp, TC_BN / pl.cg);
     if (rc) return rc;
     TcGemmParams gp{};
     gp.kchunks = pl.kchunks; gp.ksteps_last = pl.ksteps_last; gp.stages = pl.stages;
     gp.a_resident = pl.a_resident; gp.stage_bytes = pl.stage_bytes;
     gp.nq = nq; gp.N = N; gp.ntiles = pl.ntiles; gp.sample = pl.sample; gp.nbuckets = pl.nbuckets;
     gp.tau = w.tau; gp.bmax = w.bmax; gp.cnt = w.cnt; gp.surv = w.surv;
-    const int sms = tc_sms();
     const int units = MODE == TC_MODE_BUCKET ? pl.nsample_tiles : pl.ntiles;
-    for (int g0 = 0; g0 < pl.groups; g0 += sms) {
-        const int groups = pl.groups - g0 < sms ? pl.groups - g0 : sms;
-        int cpg = sms / groups;
-        if (cpg > units) cpg = units;
-        gp.groups = groups;
-        gp.group0 = g0;
-        gp.seg_cap = TC_CAP / (TC_EPI_SPLIT * cpg);
-        rc = launch_gemm<MODE>(mapA, mapB, gp, pl.smem_gemm, groups * cpg, st);
+    for (int g0 = 0; g0 < pl.groups;) {
+        const TcLaunch L = tc_launch_at(pl, g0, units);
+        gp.groups = L.groups;
+        gp.group0 = L.g0;
+        gp.seg_cap = TC_CAP / (TC_EPI_SPLIT * L.cpg);
+        const int grid = L.groups * L.cpg;
+        rc = pl.cg == 2 ? launch_gemm<MODE, 2>(mapA, mapB, gp, pl.smem_gemm, grid, st)
+                        : launch_gemm<MODE, 1>(mapA, mapB, gp, pl.smem_gemm, grid, st);
         if (rc) return rc;
         const int q0 = g0 * TC_BM;
-        const int q1 = (g0 + groups) * TC_BM < nq ? (g0 + groups) * TC_BM : nq;
-        rc = after(q0, q1, TC_EPI_SPLIT * cpg, gp.seg_cap);
-        if (rc) return rc;
+        const int q1 = (g0 + L.groups) * TC_BM < nq ? (g0 + L.groups) * TC_BM : nq;
+        if (q1 > q0) {
+            rc = after(q0, q1, TC_EPI_SPLIT * L.cpg, gp.seg_cap);
+            if (rc) return rc;
+        }
+        g0 += L.groups;
     }
     return QRAG_OK;
 }
@@ -849,14 +968,13 @@ extern "C" int qrag_search_tc_finish(const float* Q, int nq, const float* X, int
     cudaStream_t st = (cudaStream_t)stream;
     const TcPlan& pl = w.pl;
     const bool vec = (D % 4 == 0) && ((uintptr_t)X % 16 == 0);
-    const int sms = tc_sms();
-    for (int g0 = 0; g0 < pl.groups; g0 += sms) {              // same launch partition as the filter pass
-        const int groups = pl.groups - g0 < sms ? pl.groups - g0 : sms;
-        int cpg = sms / groups;
-        if (cpg > pl.ntiles) cpg = pl.ntiles;
+    for (int g0 = 0; g0 < pl.groups;) {                        // same launch partition as the filter pass
+        const TcLaunch L = tc_launch_at(pl, g0, pl.ntiles);
         const int q0 = g0 * TC_BM;
-        const int q1 = (g0 + groups) * TC_BM < nq ? (g0 + groups) * TC_BM : nq;
-        TcFinalParams fp{Q, X, q0, nq, N, D, k, metric, id_base, TC_EPI_SPLIT * cpg, TC_CAP / (TC_EPI_SPLIT * cpg),
+        const int q1 = (g0 + L.groups) * TC_BM < nq ? (g0 + L.groups) * TC_BM : nq;
+        g0 += L.groups;
+        if (q1 <= q0) continue;
+        TcFinalParams fp{Q, X, q0, nq, N, D, k, metric, id_base, TC_EPI_SPLIT * L.cpg, TC_CAP / (TC_EPI_SPLIT * L.cpg),
                          pl.cand_cap, G, ap_top_all, w.cnt, w.surv, w.eps, out_scores, out_ids, status};
         if (vec) {
             QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
