@@ -28,6 +28,7 @@ METRIC = "query-candidate scores/sec"
 UNIT = "scores/s"
 BYTES_PER_SCORE = 4 * D + 4 * D / C + TOPK * 12 / C      # candidate row + amortised query + amortised outputs
 L2_BYTES = 126 * 2**20
+NCU_DRAM_BYTES_PER_LAUNCH = 155.188736e6 + 3.671296e6     # one ncu --set full capture of the timed kernel (profiles/)
 
 
 def workload_config(n_gpus):
@@ -391,12 +392,16 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "api": "quantum_rag_b200.api.HostRerankPipeline (pinned host tensors in/out, 8 slices on 2 streams)",
+                    "h2d_gbs": h2d_bytes * e2e_steps / (e2e_ms * 1e-3) / 1e9,
+                    "note": "bound by the host-to-device copy of the fp32 candidates (PCIe), not by the kernel",
                     "reranked_queries_per_s": e2e_value / C},
             "gpu_launches": args.steps,
             "kernels": ["qrag::amp_stream_kernel<3,4> (1 launch per step; TMA bulk-copy ring, warp-specialised "
                         "producer / converter / 16 consumers / 2 rankers, fused rank)"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "amp_stream_kernel<3,4>",
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full, profiles/r01_amp_stream_key_metrics.csv "
+                         "(dram__bytes_read.sum 155.19 MB + dram__bytes_write.sum 3.67 MB per launch)",
+                         "kernel": "amp_stream_kernel<3,4>",
                          "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_score": BYTES_PER_SCORE,
                          "peak_source": peak_src},
             "clocks": clocks,
