@@ -212,7 +212,7 @@ def bench_sharded(world, rank, steps=5):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
     h = hashlib.sha256()
-    for x in (res.ids, res.scores, res.search_ids):
+    for x in (res.ids, res.scores):
         h.update(x.cpu().numpy().tobytes())
     out = {"workload": "config 4: 10,000,000 docs x 384-d row-sharded, 1024 queries, per-shard top-1000 -> NCCL "
                        "all-gather -> merge -> quantum rerank (9 qubits) -> top-10", "n_gpus": world, "scaling": "strong",

@@ -161,7 +161,7 @@ int qrag_search_topk(const float* Q, int nq, const float* X, int64_t N, int D, i
 int qrag_index_prepared_dims(int D, int metric, int* Kp);
 int qrag_index_prepare(const float* X, int64_t N, int D, int metric,
                        uint16_t* Xb, float* aux, void* stream);
-int qrag_search_tc_workspace(int nq, int64_t N, int D, int k, int metric, size_t* bytes);
+int qrag_search_tc_workspace(int nq, int64_t N, int D, int k, int metric, int shards, size_t* bytes);
 int qrag_search_topk_tc(const float* Q, int nq, const float* X, const uint16_t* Xb, const float* aux,
                         int64_t N, int D, int k, int metric, int64_t id_base,
                         double* out_scores, int64_t* out_ids, int32_t* status,
@@ -171,12 +171,15 @@ int qrag_search_topk_tc(const float* Q, int nq, const float* X, const uint16_t* 
  * all-gathers in between are the caller's: quantum_rag_b200/sharded.py issues them with NCCL).
  * Thresholds come from ALL shards, so every shard filters and rescores only ~ (k + margin) / G
  * candidates and the work scales with 1/G.  The workspace carries state between the phases.
+ *   (`shards` = G sizes the sample and the workspace: the same value in the workspace query and every phase;
+ *    qrag_search_topk_tc is the G = 1 composition)
  *   begin   bm_top [nq, k]: this shard's k largest sampled bucket maxima
  *   filter  bm_top_all [G, nq, k] (all-gathered) -> tau; ap_top [nq, k]: this shard's k best
  *           approximate scores.  aux[0] must hold the maximum |x| over ALL shards.
  *   finish  ap_top_all [G, nq, k] (all-gathered) -> exact, sorted list of this shard's members of
  *           the global top-k (ids -1 padded); merge the G lists with qrag_topk_merge. */
 int qrag_search_tc_begin(const float* Q, int nq, const uint16_t* Xb, int64_t N, int D, int k, int metric,
+                         int shards /* = G of the later phases */,
                          float* bm_top, void* workspace, size_t workspace_bytes, void* stream);
 int qrag_search_tc_filter(int nq, const uint16_t* Xb, const float* aux, int64_t N, int D, int k, int metric,
                           const float* bm_top_all, int G, float* ap_top,

@@ -42,10 +42,10 @@ PROTOTYPES: Dict[str, tuple] = {
                                  c_void_p, c_void_p, c_size_t, c_void_p]),
     "qrag_index_prepared_dims": (c_int, [c_int, c_int, POINTER(c_int)]),
     "qrag_index_prepare": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "qrag_search_tc_workspace": (c_int, [c_int, c_int64, c_int, c_int, c_int, POINTER(c_size_t)]),
+    "qrag_search_tc_workspace": (c_int, [c_int, c_int64, c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "qrag_search_topk_tc": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                     c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "qrag_search_tc_begin": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
+    "qrag_search_tc_begin": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                      c_size_t, c_void_p]),
     "qrag_search_tc_filter": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int,
                                       c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -253,10 +253,10 @@ class FlatIndexTC:
         self._ws = None
         self.last_fallback = 0          # queries the last search() had to rerun exactly
 
-    def _workspace(self, nq: int, k: int) -> torch.Tensor:
+    def _workspace(self, nq: int, k: int, shards: int = 1) -> torch.Tensor:
         lib = _lib.load()
         nbytes = ctypes.c_size_t(0)
-        _lib.check(lib.qrag_search_tc_workspace(nq, self.N, self.D, k, self.metric, ctypes.byref(nbytes)))
+        _lib.check(lib.qrag_search_tc_workspace(nq, self.N, self.D, k, self.metric, shards, ctypes.byref(nbytes)))
         if self._ws is None or self._ws.numel() < nbytes.value:
             self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.X.device)
         return self._ws
@@ -280,24 +280,26 @@ class FlatIndexTC:
         return Qd, scores, ids, status
 
     # ---- the search split at its two exchange points (corpus sharded over G GPUs) ----
-    def tc_begin(self, Q: ArrayLike, k: int) -> torch.Tensor:
-        """Phase 1: returns bm_top [nq, k] fp32, this shard's k largest sampled bucket maxima."""
+    def tc_begin(self, Q: ArrayLike, k: int, shards: int) -> torch.Tensor:
+        """Phase 1 of a search over ``shards`` shards: bm_top [nq, k] fp32, this shard's k largest sampled bucket maxima."""
         Qd = _dev(Q, torch.float32)
         if Qd.dim() == 1:
             Qd = Qd[None, :]
         nq = Qd.shape[0]
-        ws = self._workspace(nq, k)
+        ws = self._workspace(nq, k, shards)
         bm_top = torch.empty((nq, k), dtype=torch.float32, device=Qd.device)
-        _lib.check(_lib.load().qrag_search_tc_begin(_ptr(Qd), nq, _ptr(self.Xb), self.N, self.D, k, self.metric,
+        _lib.check(_lib.load().qrag_search_tc_begin(_ptr(Qd), nq, _ptr(self.Xb), self.N, self.D, k, self.metric, shards,
                                                     _ptr(bm_top), _ptr(ws), ws.numel(), _stream()))
-        self._phase = (Qd, k, ws)
+        self._phase = (Qd, k, ws, shards)
         return bm_top
 
     def tc_filter(self, bm_top_all: torch.Tensor) -> torch.Tensor:
         """Phase 2: bm_top_all [G, nq, k] from every shard -> ap_top [nq, k], this shard's k best approximate scores."""
-        Qd, k, ws = self._phase
+        Qd, k, ws, shards = self._phase
         nq = Qd.shape[0]
         bm = bm_top_all.contiguous()
+        if bm.shape[0] != shards:
+            raise ValueError("bm_top_all must hold one list per shard")
         ap_top = torch.empty((nq, k), dtype=torch.float32, device=Qd.device)
         _lib.check(_lib.load().qrag_search_tc_filter(nq, _ptr(self.Xb), _ptr(self.aux), self.N, self.D, k, self.metric,
                                                      _ptr(bm), bm.shape[0], _ptr(ap_top), _ptr(ws), ws.numel(),
@@ -307,7 +309,7 @@ class FlatIndexTC:
     def tc_finish(self, ap_top_all: torch.Tensor):
         """Phase 3: ap_top_all [G, nq, k] -> (scores, ids, status): this shard's exact, sorted members of the
         global top-k (ids -1 padded); status != 0 flags a query this shard could not certify."""
-        Qd, k, ws = self._phase
+        Qd, k, ws, shards = self._phase
         nq = Qd.shape[0]
         ap = ap_top_all.contiguous()
         scores = torch.empty((nq, k), dtype=torch.float64, device=Qd.device)
@@ -319,13 +321,13 @@ class FlatIndexTC:
         self._phase = None
         return scores, ids, status
 
-    def search_sharded(self, Q: ArrayLike, k: int, all_gather):
+    def search_sharded(self, Q: ArrayLike, k: int, all_gather, shards: int):
         """This shard's part of a search over G shards: ``all_gather(t)`` must return ``[G, *t.shape]``.
 
         Thresholds are global, so the shard filters and rescores only ~ (k + margin) / G rows.
         ``self.aux[0]`` must already hold the maximum |x| over all shards (see sharded.py).
         """
-        bm_all = all_gather(self.tc_begin(Q, k))
+        bm_all = all_gather(self.tc_begin(Q, k, shards))
         ap_all = all_gather(self.tc_filter(bm_all))
         return self.tc_finish(ap_all)
 

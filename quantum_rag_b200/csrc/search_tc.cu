@@ -722,7 +722,7 @@ struct TcPlan {
     size_t off_qb, off_qnorm, off_bmax, off_tau, off_eps, off_cnt, off_surv, off_bmtop, off_aptop, total;
 };
 
-static int tc_plan(int nq, int64_t N, int D, int k, int metric, TcPlan* pl) {
+static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPlan* pl) {
     QRAG_REQUIRE(nq >= 0 && N >= 0 && D > 0, QRAG_ERR_INVALID, "bad sizes nq=%d N=%lld D=%d", nq, (long long)N, D);
     QRAG_REQUIRE(metric >= 0 && metric <= 2, QRAG_ERR_INVALID, "unknown metric %d", metric);
     QRAG_REQUIRE(k >= 1 && k <= 2048, QRAG_ERR_UNSUPPORTED, "tensor-core search supports 1 <= k <= 2048 (got %d)", k);
@@ -753,13 +753,17 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, TcPlan* pl) {
     pl->ntiles = (int)ceil_div(N > 0 ? N : 1, TC_BN);
     // pass 1 samples every `sample`-th tile: survivors ~ sample * k per query, kept well under TC_CAP,
     // and the sample must hold many more buckets than k for the bound to be tight
-    int sample = TC_CAP / (4 * k);
-    if (sample > 16) sample = 16;
-    const int64_t by_buckets = N / ((int64_t)256 * k);
-    if (sample > by_buckets) sample = (int)by_buckets;
+    // (the threshold comes from the union of all shards' samples, so a shard of a G-way search samples G x less)
+    QRAG_REQUIRE(shards >= 1 && shards <= 1024, QRAG_ERR_INVALID, "shards=%d", shards);
+    int64_t sample = (int64_t)TC_CAP * shards / (4 * (int64_t)k);
+    if (sample > 64) sample = 64;
+    if (sample > 16 * (int64_t)shards) sample = 16 * (int64_t)shards;
+    const int64_t by_buckets = N * shards / ((int64_t)256 * k);
+    if (sample > by_buckets) sample = by_buckets;
     if (sample < 1) sample = 1;
-    pl->sample = sample;
-    pl->nsample_tiles = (pl->ntiles + sample - 1) / sample;
+    pl->sample = (int)sample;
+    const int sample_i = (int)sample;
+    pl->nsample_tiles = (pl->ntiles + sample_i - 1) / sample_i;
     pl->nbuckets = pl->nsample_tiles * (TC_BN / TC_BUCKET);
     int cand_cap = next_pow2(2 * (int64_t)k + 512);
     if (cand_cap > TC_MAX_CAND) cand_cap = TC_MAX_CAND;
@@ -788,8 +792,8 @@ struct TcWs {
     float* bmtop; float* aptop;
 };
 
-static int tc_ws(int nq, int64_t N, int D, int k, int metric, void* workspace, size_t workspace_bytes, TcWs* w) {
-    int rc = tc_plan(nq, N, D, k, metric, &w->pl);
+static int tc_ws(int nq, int64_t N, int D, int k, int metric, int shards, void* workspace, size_t workspace_bytes, TcWs* w) {
+    int rc = tc_plan(nq, N, D, k, metric, shards, &w->pl);
     if (rc) return rc;
     QRAG_REQUIRE(N >= 1, QRAG_ERR_INVALID, "empty shard: nothing to search");
     QRAG_REQUIRE(workspace != nullptr && workspace_bytes >= w->pl.total, QRAG_ERR_WORKSPACE,
@@ -908,10 +912,10 @@ extern "C" int qrag_index_prepare(const float* X, int64_t N, int D, int metric, 
     return QRAG_OK;
 }
 
-extern "C" int qrag_search_tc_workspace(int nq, int64_t N, int D, int k, int metric, size_t* bytes) {
+extern "C" int qrag_search_tc_workspace(int nq, int64_t N, int D, int k, int metric, int shards, size_t* bytes) {
     QRAG_REQUIRE(bytes != nullptr, QRAG_ERR_INVALID, "bytes is null");
     TcPlan pl;
-    int rc = tc_plan(nq, N, D, k, metric, &pl);
+    int rc = tc_plan(nq, N, D, k, metric, shards, &pl);
     if (rc) return rc;
     *bytes = pl.total;
     return QRAG_OK;
@@ -919,12 +923,12 @@ extern "C" int qrag_search_tc_workspace(int nq, int64_t N, int D, int k, int met
 
 // phase 1: operands, sampled bucket-maximum GEMM, the shard's k largest bucket maxima
 extern "C" int qrag_search_tc_begin(const float* Q, int nq, const uint16_t* Xb, int64_t N, int D, int k, int metric,
-                                    float* bm_top, void* workspace, size_t workspace_bytes, void* stream) {
+                                    int shards, float* bm_top, void* workspace, size_t workspace_bytes, void* stream) {
     QRAG_REQUIRE(Q && Xb && bm_top, QRAG_ERR_INVALID, "null pointer argument");
     QRAG_REQUIRE((uintptr_t)Xb % 16 == 0, QRAG_ERR_INVALID, "Xb must be 16-byte aligned");
     if (nq == 0) return QRAG_OK;
     TcWs w;
-    int rc = tc_ws(nq, N, D, k, metric, workspace, workspace_bytes, &w);
+    int rc = tc_ws(nq, N, D, k, metric, shards, workspace, workspace_bytes, &w);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const TcPlan& pl = w.pl;
@@ -944,7 +948,7 @@ extern "C" int qrag_search_tc_filter(int nq, const uint16_t* Xb, const float* au
     QRAG_REQUIRE(Xb && aux && bm_top_all && ap_top && G >= 1, QRAG_ERR_INVALID, "bad argument");
     if (nq == 0) return QRAG_OK;
     TcWs w;
-    int rc = tc_ws(nq, N, D, k, metric, workspace, workspace_bytes, &w);
+    int rc = tc_ws(nq, N, D, k, metric, G, workspace, workspace_bytes, &w);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     tau_union_kernel<<<nq, 256, 0, st>>>(bm_top_all, G, nq, k, metric, w.pl.Kp, w.qnorm, aux, w.tau, w.eps);
@@ -963,7 +967,7 @@ extern "C" int qrag_search_tc_finish(const float* Q, int nq, const float* X, int
     QRAG_REQUIRE(Q && X && ap_top_all && out_scores && out_ids && status && G >= 1, QRAG_ERR_INVALID, "bad argument");
     if (nq == 0) return QRAG_OK;
     TcWs w;
-    int rc = tc_ws(nq, N, D, k, metric, workspace, workspace_bytes, &w);
+    int rc = tc_ws(nq, N, D, k, metric, G, workspace, workspace_bytes, &w);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const TcPlan& pl = w.pl;
@@ -997,9 +1001,9 @@ extern "C" int qrag_search_topk_tc(const float* Q, int nq, const float* X, const
     QRAG_REQUIRE(Q && X && Xb && aux && out_scores && out_ids && status, QRAG_ERR_INVALID, "null pointer argument");
     if (nq == 0) return QRAG_OK;
     TcWs w;
-    int rc = tc_ws(nq, N, D, k, metric, workspace, workspace_bytes, &w);
+    int rc = tc_ws(nq, N, D, k, metric, 1, workspace, workspace_bytes, &w);
     if (rc) return rc;
-    rc = qrag_search_tc_begin(Q, nq, Xb, N, D, k, metric, w.bmtop, workspace, workspace_bytes, stream);
+    rc = qrag_search_tc_begin(Q, nq, Xb, N, D, k, metric, 1, w.bmtop, workspace, workspace_bytes, stream);
     if (rc) return rc;
     rc = qrag_search_tc_filter(nq, Xb, aux, N, D, k, metric, w.bmtop, 1, w.aptop, workspace, workspace_bytes, stream);
     if (rc) return rc;

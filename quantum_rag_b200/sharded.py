@@ -58,9 +58,9 @@ class CudaEngine:
         """The filter's error bound uses max |x| over the WHOLE corpus: reduce it once per index."""
         all_reduce_max(self.index.aux[:1])
 
-    def search_sharded(self, Q, k, all_gather):
+    def search_sharded(self, Q, k, all_gather, shards):
         """This shard's members of the global top-k (thresholds exchanged through ``all_gather``)."""
-        return self.index.search_sharded(Q, k, all_gather)
+        return self.index.search_sharded(Q, k, all_gather, shards)
 
     def merge(self, scores, ids, k_out):
         return self.api.topk_merge(scores, ids, k_out, self.metric)
@@ -135,9 +135,8 @@ class ShardedSearchRerank:
         fp32 all-gathers inside the search), so that each shard rescores only its ~1/G share of the
         global list; any query a shard could not certify makes every rank rerun it exactly.
         """
-        self._mark("start")
         if self.world > 1 and hasattr(self.engine, "search_sharded"):
-            s, i, status = self.engine.search_sharded(Q, k1, self._all_gather)
+            s, i, status = self.engine.search_sharded(Q, k1, self._all_gather, self.world)
             self._mark("search_phases")
             bad = self._all_reduce_max(status.clone())
             flagged = torch.nonzero(bad).flatten()
@@ -176,7 +175,85 @@ class ShardedSearchRerank:
         self._flush_marks()
         return top, ids
 
-    def __call__(self, Q, k1: int = 1000, k2: int = 10) -> ShardedResult:
+    def _all_to_all(self, t: torch.Tensor) -> torch.Tensor:
+        """t [G, ...]: slice g goes to rank g; returns [G, ...] with slice g received from rank g."""
+        out = torch.empty_like(t)
+        dist.all_to_all_single(out, t.contiguous(), group=self.group)
+        return out
+
+    def _owner_pipeline(self, Q, k1: int, k2: int) -> Optional[ShardedResult]:
+        """G > 1: everything after the shard search is partitioned BY QUERY, so it scales with 1/G too.
+
+        Each rank scores the fidelity of its own list entries (its rows, no communication), then one
+        all-to-all sends (search score, id, fidelity) of query q to the rank owning q; the owner merges the
+        G lists into the global top-k1 order, ranks by (fidelity desc, position asc) and keeps k2; one small
+        all-gather returns the [nq, k2] result to every rank.  Lists are cut to the longest valid prefix found
+        on any rank before they travel.  Returns None if some query could not be certified (caller falls back).
+        """
+        dev_lists = self.engine.search_sharded(Q, k1, self._all_gather, self.world) \
+            if hasattr(self.engine, "search_sharded") else self.engine.search(Q, k1) + (None,)
+        s, i, status = dev_lists
+        self._mark("search_phases")
+        nq = s.shape[0]
+        valid = (i >= 0).sum(dim=1).max().to(torch.int64).reshape(1)
+        flag = status.max().to(torch.int64).reshape(1) if status is not None else torch.zeros_like(valid)
+        meta = self._all_reduce_max(torch.cat([flag, valid]))
+        flagged, max_valid = (int(v) for v in meta.cpu().tolist())          # the one host sync of the path
+        self._mark("status_sync")
+        if flagged:
+            return None
+        kk = max(1, min(k1, -(-max_valid // 32) * 32))
+        s, i = s[:, :kk].contiguous(), i[:, :kk].contiguous()
+        own = i >= 0
+        f = self.engine.fidelity_rows(Q, torch.where(own, i - self.lo, torch.full_like(i, -1)))
+        self._mark("rerank_fidelity")
+        # pack [nq_pad, 3, kk] int64 (score bits, id, fidelity bits), queries padded to a multiple of G
+        per = -(-nq // self.world)
+        pack = torch.full((per * self.world, 3, kk), -1, dtype=torch.int64, device=s.device)
+        pack[:nq, 0], pack[:nq, 1], pack[:nq, 2] = s.view(torch.int64), i, f.view(torch.int64)
+        recv = self._all_to_all(pack.view(self.world, per, 3, kk))           # [G (source shard), per, 3, kk]
+        self._mark("all_to_all")
+        gs = recv[:, :, 0].contiguous().view(torch.float64)
+        gi = recv[:, :, 1].contiguous()
+        gf = recv[:, :, 2].contiguous().view(torch.float64)
+        # carry the source slot through the merge in the low 20 bits of the tag: ids are unique, so the order
+        # (score, id << 20 | slot) is the canonical (score, id) order
+        slot = (torch.arange(self.world, device=s.device)[:, None, None] * kk +
+                torch.arange(kk, device=s.device)[None, None, :]).expand(self.world, per, kk)
+        tagged = torch.where(gi >= 0, (gi << 20) | slot, gi)
+        k_m = min(k1, self.world * kk)
+        ms, mt = self.engine.merge(gs, tagged, k_m)
+        mi = torch.where(mt >= 0, mt >> 20, mt)
+        src = torch.where(mt >= 0, mt & 0xFFFFF, torch.zeros_like(mt))
+        f_all = gf.permute(1, 0, 2).reshape(per, self.world * kk)
+        mf = torch.gather(f_all, 1, src)
+        mf = torch.where(mt >= 0, mf, torch.full_like(mf, float("-inf")))
+        self._mark("merge")
+        k2 = min(k2, k_m)
+        pos, top = self.engine.sort_scores(mf, k2)
+        ids = torch.gather(mi, 1, pos.long())
+        out = self._all_gather(torch.stack([top.view(torch.int64), ids], dim=0))          # [G, 2, per, k2]
+        top_all = out[:, 0].reshape(self.world * per, k2)[:nq].contiguous().view(torch.float64)
+        ids_all = out[:, 1].reshape(self.world * per, k2)[:nq].contiguous()
+        self._mark("final_sort")
+        self._flush_marks()
+        return ShardedResult(top_all, ids_all, None, None)
+
+    def __call__(self, Q, k1: int = 1000, k2: int = 10, return_search_lists: bool = False) -> ShardedResult:
+        """Top-k2 by amplitude fidelity among the global top-k1 of the search (identical on every rank).
+
+        ``return_search_lists`` also materialises the merged [nq, k1] search lists on every rank (the
+        all-gather form of the path); without it, G > 1 takes the query-partitioned form.
+        """
+        if self.n_total >= (1 << 40):
+            raise ValueError("corpus too large: ids must stay below 2**40")
+        self._mark("start")
+        if self.world > 1 and not return_search_lists:
+            res = self._owner_pipeline(Q, k1, k2)
+            if res is not None:
+                return res
+            self._marks = []
+            self._mark("start")
         ss, si = self.search(Q, k1)
         top, ids = self.rerank(Q, si, min(k2, k1))
         return ShardedResult(top, ids, ss, si)

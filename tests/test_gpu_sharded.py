@@ -27,7 +27,7 @@ def _emulated(X, Q, G, k1, k2, metric, phased):
         xmax = torch.stack([e.index.aux[:1] for _, _, e in engines]).max()
         for _, _, e in engines:
             e.index.aux[:1] = xmax
-        bm_all = torch.stack([e.index.tc_begin(Q, k1) for _, _, e in engines])
+        bm_all = torch.stack([e.index.tc_begin(Q, k1, G) for _, _, e in engines])
         ap_all = torch.stack([e.index.tc_filter(bm_all) for _, _, e in engines])
         lists = []
         for _, _, e in engines:

@@ -82,8 +82,12 @@ def _worker(rank, world, port, n, d, nq, k1, k2, metric, out):
         X, Q = _data(n, d, nq)
         lo, hi = shard_bounds(n, world, rank)
         eng = OracleEngine(X[lo:hi], metric, lo)
-        res = ShardedSearchRerank(torch.from_numpy(X[lo:hi]), n, metric, engine=eng)(torch.from_numpy(Q), k1, k2)
-        out[rank] = (res.scores.numpy(), res.ids.numpy(), res.search_scores.numpy(), res.search_ids.numpy())
+        path = ShardedSearchRerank(torch.from_numpy(X[lo:hi]), n, metric, engine=eng)
+        own = path(torch.from_numpy(Q), k1, k2)                                   # query-partitioned form (all-to-all)
+        assert own.search_ids is None
+        res = path(torch.from_numpy(Q), k1, k2, return_search_lists=True)         # all-gather form
+        out[rank] = (own.scores.numpy(), own.ids.numpy(), res.scores.numpy(), res.ids.numpy(),
+                     res.search_scores.numpy(), res.search_ids.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -92,7 +96,8 @@ def _single(n, d, nq, k1, k2, metric):
     X, Q = _data(n, d, nq)
     eng = OracleEngine(X, metric, 0)
     res = ShardedSearchRerank(torch.from_numpy(X), n, metric, engine=eng)(torch.from_numpy(Q), k1, k2)
-    return res.scores.numpy(), res.ids.numpy(), res.search_scores.numpy(), res.search_ids.numpy()
+    return (res.scores.numpy(), res.ids.numpy(), res.scores.numpy(), res.ids.numpy(),
+            res.search_scores.numpy(), res.search_ids.numpy())
 
 
 def test_shard_bounds_partition():
@@ -106,7 +111,7 @@ def test_shard_bounds_partition():
 
 
 @pytest.mark.parametrize("world,metric,n,k1,k2", [(2, osr.METRIC_COSINE, 301, 40, 7), (3, osr.METRIC_L2, 100, 50, 10),
-                                                  (2, osr.METRIC_IP, 9, 16, 16)])
+                                                  (2, osr.METRIC_IP, 9, 16, 16), (4, osr.METRIC_COSINE, 257, 33, 5)])
 def test_sharded_equals_single_rank(world, metric, n, k1, k2):
     d, nq = 24, 5
     want = _single(n, d, nq, k1, k2, metric)
@@ -121,4 +126,4 @@ def test_sharded_equals_single_rank(world, metric, n, k1, k2):
     # and against the plain oracle search on the whole corpus
     X, Q = _data(n, d, nq)
     rs, ri = osr.topk_from_scores(OracleEngine(X, metric, 0)._scores(Q), k1, metric)
-    assert np.array_equal(want[3], ri)
+    assert np.array_equal(want[5], ri)

@@ -80,7 +80,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     h = hashlib.sha256()
-    for x in (res.ids, res.scores, res.search_ids, res.search_scores):
+    for x in (res.ids, res.scores):
         h.update(x.cpu().numpy().tobytes())
     if rank == 0:
         ms = float(t[0])
