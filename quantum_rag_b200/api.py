@@ -407,3 +407,39 @@ class HostRerankPipeline:
         for s in self.streams:
             s.synchronize()
         return self.hS, self.hP
+
+
+class HostIdRerankPipeline:
+    """End-to-end rerank of candidates named by ID against a corpus resident on the GPU.
+
+    This is the serving shape behind a retrieval step (faiss-style ids in, reranked ids out): per call
+    the host sends the queries [nq, D] fp32 and the candidate ids [nq, C] int64 from pinned memory, the
+    kernel gathers the rows by TMA from the resident corpus, and (score, id) top-k come back to pinned
+    host memory.  ``__call__`` returns after everything has landed on the host.
+    """
+
+    def __init__(self, X: ArrayLike, nq: int, C: int, top_k: int, n_qubits: Optional[int] = None):
+        self.X = _dev(X, torch.float32)
+        dev = self.X.device
+        self.nq, self.C, self.D, self.k = nq, C, self.X.shape[1], top_k
+        self.n = qubits_for(self.D) if n_qubits is None else n_qubits
+        self.dQ = torch.empty((nq, self.D), dtype=torch.float32, device=dev)
+        self.dI = torch.empty((nq, C), dtype=torch.int64, device=dev)
+        self.dS = torch.empty((nq, top_k), dtype=torch.float64, device=dev)
+        self.dP = torch.empty((nq, top_k), dtype=torch.int32, device=dev)
+        self.dO = torch.empty((nq, top_k), dtype=torch.int64, device=dev)
+        self.hS = torch.empty((nq, top_k), dtype=torch.float64).pin_memory()
+        self.hO = torch.empty((nq, top_k), dtype=torch.int64).pin_memory()
+        self.h2d_bytes = nq * self.D * 4 + nq * C * 8
+        self.d2h_bytes = nq * top_k * 16
+
+    def __call__(self, Q_host: torch.Tensor, idx_host: torch.Tensor):
+        lib = _lib.load()
+        self.dQ.copy_(Q_host, non_blocking=True)
+        self.dI.copy_(idx_host, non_blocking=True)
+        _lib.check(lib.qrag_amp_rerank(_ptr(self.dQ), self.nq, None, _ptr(self.X), _ptr(self.dI), self.C, self.D, self.n,
+                                       self.k, _ptr(self.dS), _ptr(self.dP), _ptr(self.dO), _stream()))
+        self.hS.copy_(self.dS, non_blocking=True)
+        self.hO.copy_(self.dO, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.hS, self.hO
