@@ -518,15 +518,24 @@ __global__ void __launch_bounds__(256) bucket_topk_kernel(const float* __restric
 }
 
 // per query: m_k = k-th largest bucket maximum over all G shards' lists; tau = m_k - 2 eps, rounded down
+// (single shard: bm_top_all == nullptr and the k-th largest is taken straight from this shard's bucket maxima)
 __global__ void __launch_bounds__(256) tau_union_kernel(const float* __restrict__ bm_top_all, int G, int nq, int k, int metric,
                                                         int Kp, const float* __restrict__ qnorm, const float* __restrict__ aux,
+                                                        const float* __restrict__ bmax, int nbuckets,
                                                         float* __restrict__ tau, float* __restrict__ eps) {
     __shared__ RadixSel rs;
     const int q = blockIdx.x;
-    auto fe = [&](auto f) {
-        for (int i = threadIdx.x; i < G * k; i += blockDim.x) f(bm_top_all[((size_t)(i / k) * nq + q) * k + (i % k)]);
-    };
-    const float mk = block_kth_largest(rs, k, fe);
+    float mk = neg_inf_f();
+    if (bm_top_all != nullptr) {
+        auto fe = [&](auto f) {
+            for (int i = threadIdx.x; i < G * k; i += blockDim.x) f(bm_top_all[((size_t)(i / k) * nq + q) * k + (i % k)]);
+        };
+        mk = block_kth_largest(rs, k, fe);
+    } else if (nbuckets >= k) {
+        const float* row = bmax + (size_t)q * nbuckets;
+        auto fe = [&](auto f) { for (int i = threadIdx.x; i < nbuckets; i += blockDim.x) f(row[i]); };
+        mk = block_kth_largest(rs, k, fe);
+    }
     if (threadIdx.x == 0) {
         const float e = tc_eps(metric, Kp, qnorm[q], aux[0]);
         eps[q] = e;
@@ -617,10 +626,32 @@ __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParam
         seg_n[sgi] = c < (unsigned)p.seg_cap ? (int)c : p.seg_cap;
         if (c > (unsigned)p.seg_cap) s_bad = 1;
     }
-    auto fe = [&](auto f) {
-        for (int i = tid; i < p.G * k; i += XS_THREADS) f(p.ap_top_all[((size_t)(i / k) * p.nq + q) * k + (i % k)]);
-    };
-    const float ak = block_kth_largest(rs, k, fe);                          // starts and ends with __syncthreads()
+    float ak = neg_inf_f();
+    if (p.ap_top_all != nullptr) {
+        auto fe = [&](auto f) {
+            for (int i = tid; i < p.G * k; i += XS_THREADS) f(p.ap_top_all[((size_t)(i / k) * p.nq + q) * k + (i % k)]);
+        };
+        ak = block_kth_largest(rs, k, fe);                                  // starts and ends with __syncthreads()
+    } else {
+        // single shard: the k-th best approximate score straight from this query's survivor segments
+        __shared__ int s_total;
+        if (tid == 0) s_total = 0;
+        __syncthreads();
+        int mine = 0;
+        for (int sgi = tid; sgi < p.nseg; sgi += XS_THREADS) mine += seg_n[sgi];
+        if (mine) atomicAdd(&s_total, mine);
+        __syncthreads();
+        if (s_total >= k) {
+            auto fe = [&](auto f) {
+                for (int sgi = warp; sgi < p.nseg; sgi += XS_WARPS) {
+                    const float2* sp = sv + (size_t)sgi * p.seg_cap;
+                    for (int i = lane; i < seg_n[sgi]; i += 32) f(sp[i].x);
+                }
+            };
+            ak = block_kth_largest(rs, k, fe);
+        }
+        __syncthreads();
+    }
     float thr = ak - 2.f * p.eps[q];                                        // -inf stays -inf
     thr = thr - fabsf(thr) * 2.4e-7f - 1e-37f;
     // candidates (any order: the final sort is a total order on (score, id))
@@ -924,7 +955,7 @@ extern "C" int qrag_search_tc_workspace(int nq, int64_t N, int D, int k, int met
 // phase 1: operands, sampled bucket-maximum GEMM, the shard's k largest bucket maxima
 extern "C" int qrag_search_tc_begin(const float* Q, int nq, const uint16_t* Xb, int64_t N, int D, int k, int metric,
                                     int shards, float* bm_top, void* workspace, size_t workspace_bytes, void* stream) {
-    QRAG_REQUIRE(Q && Xb && bm_top, QRAG_ERR_INVALID, "null pointer argument");
+    QRAG_REQUIRE(Q && Xb && (bm_top || shards == 1), QRAG_ERR_INVALID, "null pointer argument");
     QRAG_REQUIRE((uintptr_t)Xb % 16 == 0, QRAG_ERR_INVALID, "Xb must be 16-byte aligned");
     if (nq == 0) return QRAG_OK;
     TcWs w;
@@ -936,8 +967,10 @@ extern "C" int qrag_search_tc_begin(const float* Q, int nq, const uint16_t* Xb, 
     QRAG_LAUNCH_CHECK("query_prepare_kernel");
     rc = tc_gemm_pass<TC_MODE_BUCKET>(w, nq, N, Xb, st, [](int, int, int, int) { return QRAG_OK; });
     if (rc) return rc;
-    bucket_topk_kernel<<<nq, 256, 0, st>>>(w.bmax, pl.nbuckets, k, bm_top);
-    QRAG_LAUNCH_CHECK("bucket_topk_kernel");
+    if (bm_top != nullptr) {                                   // single shard: the threshold kernel reads bmax itself
+        bucket_topk_kernel<<<nq, 256, 0, st>>>(w.bmax, pl.nbuckets, k, bm_top);
+        QRAG_LAUNCH_CHECK("bucket_topk_kernel");
+    }
     return QRAG_OK;
 }
 
@@ -945,15 +978,17 @@ extern "C" int qrag_search_tc_begin(const float* Q, int nq, const uint16_t* Xb, 
 extern "C" int qrag_search_tc_filter(int nq, const uint16_t* Xb, const float* aux, int64_t N, int D, int k, int metric,
                                      const float* bm_top_all, int G, float* ap_top, void* workspace, size_t workspace_bytes,
                                      void* stream) {
-    QRAG_REQUIRE(Xb && aux && bm_top_all && ap_top && G >= 1, QRAG_ERR_INVALID, "bad argument");
+    QRAG_REQUIRE(Xb && aux && G >= 1 && (bm_top_all || G == 1) && (ap_top || G == 1), QRAG_ERR_INVALID, "bad argument");
     if (nq == 0) return QRAG_OK;
     TcWs w;
     int rc = tc_ws(nq, N, D, k, metric, G, workspace, workspace_bytes, &w);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    tau_union_kernel<<<nq, 256, 0, st>>>(bm_top_all, G, nq, k, metric, w.pl.Kp, w.qnorm, aux, w.tau, w.eps);
+    tau_union_kernel<<<nq, 256, 0, st>>>(bm_top_all, G, nq, k, metric, w.pl.Kp, w.qnorm, aux, w.bmax, w.pl.nbuckets, w.tau,
+                                         w.eps);
     QRAG_LAUNCH_CHECK("tau_union_kernel");
     return tc_gemm_pass<TC_MODE_FILTER>(w, nq, N, Xb, st, [&](int q0, int q1, int nseg, int seg_cap) {
+        if (ap_top == nullptr) return (int)QRAG_OK;            // single shard: the final stage selects by itself
         surv_topk_kernel<<<q1 - q0, 256, 0, st>>>(w.cnt, w.surv, q0, nseg, seg_cap, k, ap_top);
         QRAG_LAUNCH_CHECK("surv_topk_kernel");
         return QRAG_OK;
@@ -964,7 +999,8 @@ extern "C" int qrag_search_tc_filter(int nq, const uint16_t* Xb, const float* au
 extern "C" int qrag_search_tc_finish(const float* Q, int nq, const float* X, int64_t N, int D, int k, int metric,
                                      int64_t id_base, const float* ap_top_all, int G, double* out_scores, int64_t* out_ids,
                                      int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
-    QRAG_REQUIRE(Q && X && ap_top_all && out_scores && out_ids && status && G >= 1, QRAG_ERR_INVALID, "bad argument");
+    QRAG_REQUIRE(Q && X && out_scores && out_ids && status && G >= 1 && (ap_top_all || G == 1), QRAG_ERR_INVALID,
+                 "bad argument");
     if (nq == 0) return QRAG_OK;
     TcWs w;
     int rc = tc_ws(nq, N, D, k, metric, G, workspace, workspace_bytes, &w);
@@ -1003,10 +1039,10 @@ extern "C" int qrag_search_topk_tc(const float* Q, int nq, const float* X, const
     TcWs w;
     int rc = tc_ws(nq, N, D, k, metric, 1, workspace, workspace_bytes, &w);
     if (rc) return rc;
-    rc = qrag_search_tc_begin(Q, nq, Xb, N, D, k, metric, 1, w.bmtop, workspace, workspace_bytes, stream);
+    rc = qrag_search_tc_begin(Q, nq, Xb, N, D, k, metric, 1, nullptr, workspace, workspace_bytes, stream);
     if (rc) return rc;
-    rc = qrag_search_tc_filter(nq, Xb, aux, N, D, k, metric, w.bmtop, 1, w.aptop, workspace, workspace_bytes, stream);
+    rc = qrag_search_tc_filter(nq, Xb, aux, N, D, k, metric, nullptr, 1, nullptr, workspace, workspace_bytes, stream);
     if (rc) return rc;
-    return qrag_search_tc_finish(Q, nq, X, N, D, k, metric, id_base, w.aptop, 1, out_scores, out_ids, status, workspace,
+    return qrag_search_tc_finish(Q, nq, X, N, D, k, metric, id_base, nullptr, 1, out_scores, out_ids, status, workspace,
                                  workspace_bytes, stream);
 }
