@@ -411,12 +411,13 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
                                       acc[2 * i + 1]);
             }
         }
+        // every shared-memory read of this stage has completed (its value went through an FMA above), so the
+        // stage goes back to the producer before the reduction, not after it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
         // lane L ends with value index L / LPV: even index = q.d, odd = |d|^2 of row index / 2
         const double tot = reduce_vals<NV>(acc, lane);
         const double nd2 = __shfl_down_sync(FULL_MASK, tot, LPV);
-        // all shared-memory reads of this stage are complete (their values were consumed above)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
 
         const int i = lane / (2 * LPV);
         const bool owner = (lane & (2 * LPV - 1)) == 0 && i < nr;

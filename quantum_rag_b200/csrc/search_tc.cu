@@ -51,7 +51,8 @@ constexpr int TC_THREADS = (4 + TC_EPI_WARPS) * 32;
 constexpr int TC_A_CHUNK = TC_BM * TC_BK * 2;     // 16 KB
 constexpr int TC_B_STAGE = TC_BN * TC_BK * 2;     // 32 KB
 constexpr int TC_BUCKET = 32;         // documents per bucket maximum (one tcgen05.ld chunk)
-constexpr int TC_CAP = 16384;         // survivor list capacity per query
+constexpr int TC_CAP_MIN = 16384;     // survivor list capacity per query: 64 k rounded up to a power of two,
+constexpr int TC_CAP_MAX = 131072;    // within these bounds (TcPlan::cap)
 constexpr int TC_MAX_CAND = 8192;     // largest exact-rescore capacity per query
 constexpr int TC_MAX_SEGS = 640;      // survivor-list segments per query (TC_EPI_SPLIT per CTA of the query's group)
 constexpr int TC_MAX_STAGES = 10;
@@ -72,9 +73,10 @@ struct TcGemmParams {
     int nbuckets;           // buckets per query in pass 1 = nsample_tiles * 8
     const float* tau;       // [nq] (filter)
     float* bmax;            // [nq, nbuckets] (bucket)
-    int seg_cap;            // survivor slots per (query, CTA) segment = TC_CAP / CTAs per group
+    int cap;                // survivor slots per query
+    int seg_cap;            // survivor slots per (query, CTA, column quarter) segment
     unsigned int* cnt;      // [nq, TC_MAX_SEGS] survivors found per segment, may exceed seg_cap (filter)
-    float2* surv;           // [nq, TC_CAP] (score, row as int bits), segment s at s * seg_cap (filter)
+    float2* surv;           // [nq, cap] (score, row as int bits), segment s at s * seg_cap (filter)
 };
 
 // ------------------------------------------------------------------ PTX wrappers (tcgen05 / TMA)
@@ -314,7 +316,7 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         float tau = __int_as_float(0x7f800000);               // +inf: rows beyond nq never emit
         if (MODE == TC_MODE_FILTER && qvalid) tau = fmaxf(p.tau[q], -3.0e38f);   // -inf (rows past the end) never passes
         // this thread is the only writer of segment u0 of query q: no atomics on the hot path
-        float2* seg = p.surv + (size_t)(qvalid ? q : 0) * TC_CAP + (size_t)(TC_EPI_SPLIT * u0 + half) * p.seg_cap;
+        float2* seg = p.surv + (size_t)(qvalid ? q : 0) * p.cap + (size_t)(TC_EPI_SPLIT * u0 + half) * p.seg_cap;
         unsigned int found = 0;
         int n = 0;
         for (int u = u0; u < nunits; u += cpg, ++n) {
@@ -547,7 +549,8 @@ __global__ void __launch_bounds__(256) tau_union_kernel(const float* __restrict_
 
 // per query: the k largest approximate scores among this shard's survivors -> ap_top [nq, k]
 __global__ void __launch_bounds__(256) surv_topk_kernel(const unsigned int* __restrict__ cnt, const float2* __restrict__ surv,
-                                                        int q0, int nseg, int seg_cap, int k, float* __restrict__ ap_top) {
+                                                        int q0, int nseg, int seg_cap, int cap, int k,
+                                                        float* __restrict__ ap_top) {
     __shared__ RadixSel rs;
     __shared__ int seg_n[TC_MAX_SEGS];
     __shared__ int s_n;
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(256) surv_topk_kernel(const unsigned int* __re
         atomicAdd(&s_n, c2);
     }
     __syncthreads();
-    const float2* sv = surv + (size_t)q * TC_CAP;
+    const float2* sv = surv + (size_t)q * cap;
     auto fe = [&](auto f) {
         for (int sgi = warp; sgi < nseg; sgi += nwarps) {
             const float2* sp = sv + (size_t)sgi * seg_cap;
@@ -575,7 +578,7 @@ __global__ void __launch_bounds__(256) surv_topk_kernel(const unsigned int* __re
 // ---------------------------------------------------------------------------------- final stage
 struct TcFinalParams {
     const float* Q; const float* X; int q0; int nq; int64_t N; int D; int k; int metric; int64_t id_base;
-    int nseg, seg_cap, cand_cap;
+    int nseg, seg_cap, cap, cand_cap;
     int G; const float* ap_top_all;          // [G, nq, k] the k best approximate scores of every shard
     const unsigned int* cnt; const float2* surv; const float* eps;
     double* out_scores; int64_t* out_ids; int32_t* status;
@@ -617,7 +620,7 @@ __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParam
     const int q = p.q0 + blockIdx.x;
     const int k = p.k;
     const bool l2 = p.metric == QRAG_METRIC_L2;
-    const float2* sv = p.surv + (size_t)q * TC_CAP;
+    const float2* sv = p.surv + (size_t)q * p.cap;
 
     if (tid == 0) { s_m = 0; s_bad = 0; }
     __syncthreads();
@@ -748,7 +751,7 @@ static int tc_kp(int D, int metric) { return (int)align_up((size_t)D + (metric =
 
 struct TcPlan {
     int Kp, kchunks, ksteps_last, stages, a_resident, stage_bytes, cg, nq_pad, groups, ntiles, sample, nsample_tiles, nbuckets;
-    int cand_cap;
+    int cand_cap, cap;
     size_t smem_gemm, smem_final;
     size_t off_qb, off_qnorm, off_bmax, off_tau, off_eps, off_cnt, off_surv, off_bmtop, off_aptop, total;
 };
@@ -782,11 +785,14 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPl
     pl->nq_pad = (int)align_up((size_t)(nq > 0 ? nq : 1), (size_t)TC_BM * pl->cg);
     pl->groups = pl->nq_pad / TC_BM;
     pl->ntiles = (int)ceil_div(N > 0 ? N : 1, TC_BN);
-    // pass 1 samples every `sample`-th tile: survivors ~ sample * k per query, kept well under TC_CAP,
+    int cap = TC_CAP_MIN;
+    while (cap < 64 * k && cap < TC_CAP_MAX) cap <<= 1;
+    pl->cap = cap;
+    // pass 1 samples every `sample`-th tile: survivors ~ sample * k per query, kept well under the capacity,
     // and the sample must hold many more buckets than k for the bound to be tight
     // (the threshold comes from the union of all shards' samples, so a shard of a G-way search samples G x less)
     QRAG_REQUIRE(shards >= 1 && shards <= 1024, QRAG_ERR_INVALID, "shards=%d", shards);
-    int64_t sample = (int64_t)TC_CAP * shards / (4 * (int64_t)k);
+    int64_t sample = (int64_t)cap * shards / (4 * (int64_t)k);
     if (sample > 64) sample = 64;
     if (sample > 16 * (int64_t)shards) sample = 16 * (int64_t)shards;
     const int64_t by_buckets = N * shards / ((int64_t)256 * k);
@@ -809,7 +815,7 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPl
     pl->off_tau = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
     pl->off_eps = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
     pl->off_cnt = off; off = align_up(off + (size_t)pl->nq_pad * TC_MAX_SEGS * 4, 256);
-    pl->off_surv = off; off = align_up(off + (size_t)pl->nq_pad * TC_CAP * 8, 256);
+    pl->off_surv = off; off = align_up(off + (size_t)pl->nq_pad * cap * 8, 256);
     pl->off_bmtop = off; off = align_up(off + (size_t)pl->nq_pad * k * 4, 256);
     pl->off_aptop = off; off = align_up(off + (size_t)pl->nq_pad * k * 4, 256);
     pl->total = off + 256;
@@ -903,7 +909,8 @@ static int tc_gemm_pass(const TcWs& w, int nq, int64_t N, const uint16_t* Xb, cu
         const TcLaunch L = tc_launch_at(pl, g0, units);
         gp.groups = L.groups;
         gp.group0 = L.g0;
-        gp.seg_cap = TC_CAP / (TC_EPI_SPLIT * L.cpg);
+        gp.cap = pl.cap;
+        gp.seg_cap = pl.cap / (TC_EPI_SPLIT * L.cpg);
         const int grid = L.groups * L.cpg;
         rc = pl.cg == 2 ? launch_gemm<MODE, 2>(mapA, mapB, gp, pl.smem_gemm, grid, st)
                         : launch_gemm<MODE, 1>(mapA, mapB, gp, pl.smem_gemm, grid, st);
@@ -989,7 +996,7 @@ extern "C" int qrag_search_tc_filter(int nq, const uint16_t* Xb, const float* au
     QRAG_LAUNCH_CHECK("tau_union_kernel");
     return tc_gemm_pass<TC_MODE_FILTER>(w, nq, N, Xb, st, [&](int q0, int q1, int nseg, int seg_cap) {
         if (ap_top == nullptr) return (int)QRAG_OK;            // single shard: the final stage selects by itself
-        surv_topk_kernel<<<q1 - q0, 256, 0, st>>>(w.cnt, w.surv, q0, nseg, seg_cap, k, ap_top);
+        surv_topk_kernel<<<q1 - q0, 256, 0, st>>>(w.cnt, w.surv, q0, nseg, seg_cap, w.pl.cap, k, ap_top);
         QRAG_LAUNCH_CHECK("surv_topk_kernel");
         return QRAG_OK;
     });
@@ -1014,8 +1021,8 @@ extern "C" int qrag_search_tc_finish(const float* Q, int nq, const float* X, int
         const int q1 = (g0 + L.groups) * TC_BM < nq ? (g0 + L.groups) * TC_BM : nq;
         g0 += L.groups;
         if (q1 <= q0) continue;
-        TcFinalParams fp{Q, X, q0, nq, N, D, k, metric, id_base, TC_EPI_SPLIT * L.cpg, TC_CAP / (TC_EPI_SPLIT * L.cpg),
-                         pl.cand_cap, G, ap_top_all, w.cnt, w.surv, w.eps, out_scores, out_ids, status};
+        TcFinalParams fp{Q, X, q0, nq, N, D, k, metric, id_base, TC_EPI_SPLIT * L.cpg, pl.cap / (TC_EPI_SPLIT * L.cpg),
+                         pl.cap, pl.cand_cap, G, ap_top_all, w.cnt, w.surv, w.eps, out_scores, out_ids, status};
         if (vec) {
             QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)pl.smem_final));

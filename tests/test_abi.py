@@ -58,3 +58,19 @@ def test_fails_loudly_without_device(libqrag):
     assert rc == -2 and b"no CPU fallback" in libqrag.qrag_last_error()
     sm = ctypes.c_int(0)
     assert libqrag.qrag_device_info(ctypes.byref(sm), None, None) == -2
+
+
+def test_tensor_core_search_argument_validation(libqrag):
+    """Bad arguments of the tcgen05 entry points are rejected on the host, before any CUDA work."""
+    import ctypes
+    kp = ctypes.c_int(0)
+    assert libqrag.qrag_index_prepared_dims(384, 1, ctypes.byref(kp)) == 0 and kp.value == 400   # L2: D + 2 -> mult of 16
+    assert libqrag.qrag_index_prepared_dims(384, 2, ctypes.byref(kp)) == 0 and kp.value == 384
+    assert libqrag.qrag_index_prepared_dims(10, 0, ctypes.byref(kp)) == 0 and kp.value == 16
+    assert libqrag.qrag_index_prepared_dims(384, 9, ctypes.byref(kp)) == -1
+    assert libqrag.qrag_set_overlap(5) == -1 and libqrag.qrag_get_overlap() in (0, 1, 2)
+    nbytes = ctypes.c_size_t(0)
+    rc = libqrag.qrag_search_tc_workspace(4, 1000, 64, 5000, 0, 1, ctypes.byref(nbytes))
+    assert rc in (-3, -2)                                  # k too large (or no device: still an error, never a fallback)
+    rc = libqrag.qrag_search_topk_tc(None, 1, None, None, None, 10, 8, 1, 0, 0, None, None, None, None, 0, None)
+    assert rc == -1 and b"null" in libqrag.qrag_last_error()

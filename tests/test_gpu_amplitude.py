@@ -166,3 +166,33 @@ def test_config2_full_size_properties(cuda):
     rows = [0, 499, 999]
     want = oq.amplitude_fidelity_batch(Q[rows].cpu().numpy(), cand[rows].cpu().numpy())
     assert np.allclose(full[rows].cpu().numpy(), want, rtol=REL)
+
+
+def test_overlap_policies_give_identical_results_back_to_back(cuda):
+    """Programmatic dependent launch: consecutive launches on one stream overlap, results must not change."""
+    import torch
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(21)
+    batches = [(torch.from_numpy(rng.standard_normal((600, 384)).astype(np.float32)).cuda(),
+                torch.from_numpy(rng.standard_normal((600, 100, 384)).astype(np.float32)).cuda()) for _ in range(3)]
+    results = {}
+    old = api.set_overlap(api.OVERLAP_SAFE)
+    try:
+        for mode in (api.OVERLAP_NONE, api.OVERLAP_SAFE, api.OVERLAP_INPUTS_STABLE):
+            api.set_overlap(mode)
+            outs = []
+            for rep in range(4):                         # 12 launches back to back, no host sync in between
+                for Q, cand in batches:
+                    outs.append(api.quantum_rerank_batch(Q, cand=cand, top_k=10)[:2])
+            torch.cuda.synchronize()
+            results[mode] = outs
+    finally:
+        api.set_overlap(old)
+    base = results[api.OVERLAP_NONE]
+    for mode, outs in results.items():
+        for (s, p), (bs, bp) in zip(outs, base):
+            assert torch.equal(s, bs) and torch.equal(p, bp), f"overlap mode {mode}"
+    want = oq.rank_rows(oq.amplitude_fidelity_batch(batches[0][0].cpu().numpy(), batches[0][1].cpu().numpy()), 10)
+    assert np.array_equal(base[0][1].cpu().numpy(), want)
+    with pytest.raises(Exception):
+        api.set_overlap(7)
