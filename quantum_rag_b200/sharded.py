@@ -195,14 +195,14 @@ class ShardedSearchRerank:
         s, i, status = dev_lists
         self._mark("search_phases")
         nq = s.shape[0]
+        # Lists travel cut to kk entries.  A shard holds ~ k1 / G members of the global top-k1; kk leaves 2x that
+        # plus 64, and the cut is VERIFIED at the end of the call (one host sync, after everything is queued): if
+        # any shard had more valid entries than kk, or flagged a query, the caller reruns the all-gather form.
+        kk = k1 if status is None else max(1, min(k1, -(-(2 * k1 // self.world + 64) // 32) * 32))
         valid = (i >= 0).sum(dim=1).max().to(torch.int64).reshape(1)
         flag = status.max().to(torch.int64).reshape(1) if status is not None else torch.zeros_like(valid)
         meta = self._all_reduce_max(torch.cat([flag, valid]))
-        flagged, max_valid = (int(v) for v in meta.cpu().tolist())          # the one host sync of the path
-        self._mark("status_sync")
-        if flagged:
-            return None
-        kk = max(1, min(k1, -(-max_valid // 32) * 32))
+        self._mark("status_reduce")
         s, i = s[:, :kk].contiguous(), i[:, :kk].contiguous()
         own = i >= 0
         f = self.engine.fidelity_rows(Q, torch.where(own, i - self.lo, torch.full_like(i, -1)))
@@ -236,7 +236,10 @@ class ShardedSearchRerank:
         top_all = out[:, 0].reshape(self.world * per, k2)[:nq].contiguous().view(torch.float64)
         ids_all = out[:, 1].reshape(self.world * per, k2)[:nq].contiguous()
         self._mark("final_sort")
+        flagged, max_valid = (int(v) for v in meta.cpu().tolist())          # the one host sync of the path
         self._flush_marks()
+        if flagged or max_valid > kk:
+            return None
         return ShardedResult(top_all, ids_all, None, None)
 
     def __call__(self, Q, k1: int = 1000, k2: int = 10, return_search_lists: bool = False) -> ShardedResult:
