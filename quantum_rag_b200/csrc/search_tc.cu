@@ -327,12 +327,8 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             mbar_wait(&acc_full[buf], ((uint32_t)n >> 1) & 1u);
             tc_fence_after();
             const uint32_t t0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * TC_BN + (uint32_t)half * TC_EPI_COLS;
-#pragma unroll
-            for (int cc = 0; cc < TC_EPI_COLS / 32; ++cc) {
-                uint32_t r[32];
-                tmem_ld32(t0 + (uint32_t)cc * 32, r);
-                tmem_ld_wait();
-                const int c0 = half * TC_EPI_COLS + cc * 32;
+            // one 32-column chunk of this thread's row: bucket maximum, or threshold test and survivor append
+            auto process = [&](uint32_t (&r)[32], const int c0) {
                 if (ragged) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
@@ -358,6 +354,15 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         }
                     }
                 }
+            };
+            static_assert(TC_EPI_COLS == 64, "the epilogue below issues both of a warp's chunk loads up front");
+            {
+                uint32_t ra[32], rb[32];
+                tmem_ld32(t0, ra);
+                tmem_ld32(t0 + 32, rb);
+                tmem_ld_wait();
+                process(ra, half * TC_EPI_COLS);
+                process(rb, half * TC_EPI_COLS + 32);
             }
             tc_fence_before();
             __syncwarp();
