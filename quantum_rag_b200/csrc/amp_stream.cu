@@ -513,6 +513,11 @@ int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, co
     const DeviceProps& dp = device_props();
     QRAG_REQUIRE(dp.ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
     if (D % 4 != 0 || D > 8192) return QRAG_OK;
+    if (getenv("QRAG_AMP_STREAM_OFF")) return QRAG_OK;          // tuning: force the plain-load kernel
+    // Gathered candidates (X + idx) are one 4*D-byte bulk copy per row; the copy engine's per-operation cost
+    // caps that form at ~2.5 TB/s for 1.5 KB rows, while the plain-load kernel (12 x 16 B loads in flight per
+    // lane) reaches 3.2 - 4.1 TB/s on the same input.  The streaming kernel keeps the dense form.
+    if (cand == nullptr && !getenv("QRAG_AMP_STREAM_GATHER")) return QRAG_OK;
     if (((uintptr_t)Q | (uintptr_t)(cand ? cand : X)) % 16 != 0) return QRAG_OK;
     if (nq < 1 || C < 1) return QRAG_OK;
 

@@ -29,8 +29,12 @@ def test_amp_fidelity_dense(cuda, D, C):
         assert float(got[2, 1]) == pytest.approx(1.0, abs=1e-14)
 
 
-def test_amp_fidelity_gather_and_padding_ids(cuda):
+@pytest.mark.parametrize("stream_kernel", [False, True])
+def test_amp_fidelity_gather_and_padding_ids(cuda, monkeypatch, stream_kernel):
+    """Gathered candidates: the plain-load kernel by default, the TMA streaming kernel when forced."""
     from quantum_rag_b200 import api
+    if stream_kernel:
+        monkeypatch.setenv("QRAG_AMP_STREAM_GATHER", "1")
     rng = np.random.RandomState(11)
     X = rng.standard_normal((300, 384)).astype(np.float32)
     Q = rng.standard_normal((6, 384)).astype(np.float32)

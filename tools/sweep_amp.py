@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--configs", default="default,4x4,8x4,8x2")
     ap.add_argument("--overlap", default="0,1,2")
+    ap.add_argument("--gather", action="store_true", help="candidates named by random ids into a resident corpus")
     a = ap.parse_args()
     _lib.build()
     lib = _lib.load()
@@ -36,8 +37,17 @@ def main():
     pos = torch.empty((a.nq, a.k), dtype=torch.int32, device="cuda")
     nbytes = a.nq * a.C * a.D * 4
 
+    if a.gather:
+        os.environ["QRAG_AMP_STREAM_GATHER"] = "1"        # the sweep is about the streaming kernel
+    corpus = torch.cat([c.view(-1, a.D) for _, c in sets], dim=0) if a.gather else None
+    idxs = [torch.randint(0, corpus.shape[0], (a.nq, a.C), generator=g).cuda() for _ in range(nsets)] if a.gather else None
+
     def step(i):
         Q, c = sets[i % nsets]
+        if a.gather:
+            _lib.check(lib.qrag_amp_rerank(api._ptr(Q), a.nq, None, api._ptr(corpus), api._ptr(idxs[i % nsets]), a.C, a.D,
+                                           api.qubits_for(a.D), a.k, api._ptr(scores), api._ptr(pos), None, api._stream()))
+            return
         _lib.check(lib.qrag_amp_rerank(api._ptr(Q), a.nq, api._ptr(c), None, None, a.C, a.D, api.qubits_for(a.D), a.k,
                                        api._ptr(scores), api._ptr(pos), None, api._stream()))
 
