@@ -73,6 +73,7 @@ struct TcGemmParams {
     int nbuckets;           // buckets per query in pass 1 = nsample_tiles * 8
     const float* tau;       // [nq] (filter)
     float* bmax;            // [nq, nbuckets] (bucket)
+    int debug_skip;         // TUNING ONLY
     int cap;                // survivor slots per query
     int seg_cap;            // survivor slots per (query, CTA, column quarter) segment
     unsigned int* cnt;      // [nq, TC_MAX_SEGS] survivors found per segment, may exceed seg_cap (filter)
@@ -175,6 +176,15 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, 
         : "memory");
 }
 
+// one lane of a converged warp; keeps the surrounding control flow warp-uniform, so that descriptors and barrier
+// addresses stay in uniform registers (a branch on lane == 0 makes the compiler wrap every tcgen05 / TMA
+// instruction in a per-lane loop of ~25 instructions, more than the 128 cycles an MMA lasts)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float neg_inf_f() { return __int_as_float(0xff800000); }
@@ -269,14 +279,21 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
-            // -------------------------------------------------------------- MMA issuer
+        if (rank == 0) {
+            // ------------------------------- MMA issuer: the whole warp runs the loop, one elected lane issues
             // instruction descriptor: D fp32, A/B bf16, both K-major, N = 256, M = 128 (256 across a pair)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
                                    ((uint32_t)((TC_BM * CG) >> 4) << 24);
-            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-            if (p.a_resident) mbar_wait(a_full, 0);
+            // The issuing thread has 128 cycles per MMA: descriptors are built once and advanced by adding the
+            // byte offset (>> 4) to their address field, the four K-steps of a chunk are unrolled.
+            const uint64_t adesc0 = umma_desc_sw128(smem_u32(sA)), bdesc0 = umma_desc_sw128(smem_u32(sB));
             const uint32_t b_bytes = (uint32_t)B_ROWS * TC_BK * 2;               // this CTA's share of a document chunk
+            const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
+            const uint32_t a_step16 = p.a_resident ? (uint32_t)TC_A_CHUNK >> 4 : 0u;      // per k-chunk
+            const uint64_t a_base = p.a_resident ? adesc0 : bdesc0 + (b_bytes >> 4);      // streamed A sits behind B
+            const uint32_t a_stage16 = p.a_resident ? 0u : stage16;
+            const int ks_last = p.ksteps_last;
+            if (p.a_resident) mbar_wait(a_full, 0);
             int s = 0;
             uint32_t par = 0;
             int n = 0;
@@ -285,25 +302,41 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 mbar_wait(&acc_empty[buf], (((uint32_t)n >> 1) & 1u) ^ 1u);      // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)buf * TC_BN;
+                uint32_t accumulate = 0;
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&full[s], par);
                     tc_fence_after();
-                    const int ks = (kc == KC - 1) ? p.ksteps_last : TC_BK / TC_UK;
-                    for (int k = 0; k < ks; ++k) {
-                        const uint32_t bs = b0 + (uint32_t)s * (uint32_t)p.stage_bytes;
-                        const uint32_t as = p.a_resident ? a0 + (uint32_t)kc * TC_A_CHUNK : bs + b_bytes;
-                        const uint64_t ad = umma_desc_sw128(as + (uint32_t)k * TC_UK * 2);
-                        const uint64_t bd = umma_desc_sw128(bs + (uint32_t)k * TC_UK * 2);
-                        if (CG == 2) umma_bf16_pair(d, ad, bd, idesc, (kc | k) != 0 ? 1u : 0u);
-                        else umma_bf16(d, ad, bd, idesc, (kc | k) != 0 ? 1u : 0u);
+                    const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)s * stage16);
+                    const uint64_t ad = a_base + (uint64_t)((uint32_t)kc * a_step16 + (uint32_t)s * a_stage16);
+                    const int ks = (kc == KC - 1) ? ks_last : TC_BK / TC_UK;
+                    if (elect_one()) {
+                        if (ks == TC_BK / TC_UK) {
+#pragma unroll
+                            for (int k = 0; k < TC_BK / TC_UK; ++k) {
+                                const uint64_t off = (uint64_t)(k * TC_UK * 2 >> 4);
+                                if (CG == 2) umma_bf16_pair(d, ad + off, bd + off, idesc, k == 0 ? accumulate : 1u);
+                                else umma_bf16(d, ad + off, bd + off, idesc, k == 0 ? accumulate : 1u);
+                            }
+                        } else {
+                            for (int k = 0; k < ks; ++k) {
+                                const uint64_t off = (uint64_t)(k * TC_UK * 2 >> 4);
+                                if (CG == 2) umma_bf16_pair(d, ad + off, bd + off, idesc, k == 0 ? accumulate : 1u);
+                                else umma_bf16(d, ad + off, bd + off, idesc, k == 0 ? accumulate : 1u);
+                            }
+                        }
+                        // frees the stage (in both CTAs of a pair) when these MMAs have read it
+                        if (CG == 2) umma_commit_pair(&empty[s]);
+                        else umma_commit(&empty[s]);
                     }
-                    // frees the stage (in both CTAs of a pair) when these MMAs have read it
-                    if (CG == 2) umma_commit_pair(&empty[s]);
-                    else umma_commit(&empty[s]);
+                    __syncwarp();
+                    accumulate = 1;
                     if (++s == S) { s = 0; par ^= 1u; }
                 }
-                if (CG == 2) umma_commit_pair(&acc_full[buf]);                   // accumulator complete
-                else umma_commit(&acc_full[buf]);
+                __syncwarp();
+                if (elect_one()) {
+                    if (CG == 2) umma_commit_pair(&acc_full[buf]);               // accumulator complete
+                    else umma_commit(&acc_full[buf]);
+                }
             }
         }
     } else if (warp >= 4) {
@@ -329,6 +362,7 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const uint32_t t0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * TC_BN + (uint32_t)half * TC_EPI_COLS;
             // one 32-column chunk of this thread's row: bucket maximum, or threshold test and survivor append
             auto process = [&](uint32_t (&r)[32], const int c0) {
+                if (p.debug_skip == 3) { if ((r[0] ^ r[31]) == 0x12345u) found += 1; return; }
                 if (ragged) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
@@ -342,6 +376,7 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < w; ++j) t[j] = fmaxf(t[j], t[j + w]);
                 const float m = t[0];
+                if (p.debug_skip == 4) { if (m == 1234.5f) found += 1; return; }
                 if (MODE == TC_MODE_BUCKET) {
                     if (qvalid) p.bmax[(size_t)q * p.nbuckets + (size_t)u * (TC_BN / TC_BUCKET) + (c0 >> 5)] = m;
                 } else if (m >= tau) {
@@ -356,7 +391,7 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 }
             };
             static_assert(TC_EPI_COLS == 64, "the epilogue below issues both of a warp's chunk loads up front");
-            {
+            if (p.debug_skip != 1) {
                 uint32_t ra[32], rb[32];
                 tmem_ld32(t0, ra);
                 tmem_ld32(t0 + 32, rb);
@@ -909,6 +944,7 @@ static int tc_gemm_pass(const TcWs& w, int nq, int64_t N, const uint16_t* Xb, cu
     gp.a_resident = pl.a_resident; gp.stage_bytes = pl.stage_bytes;
     gp.nq = nq; gp.N = N; gp.ntiles = pl.ntiles; gp.sample = pl.sample; gp.nbuckets = pl.nbuckets;
     gp.tau = w.tau; gp.bmax = w.bmax; gp.cnt = w.cnt; gp.surv = w.surv;
+    if (const char* e = getenv("QRAG_TC_DEBUG_SKIP")) gp.debug_skip = atoi(e);
     const int units = MODE == TC_MODE_BUCKET ? pl.nsample_tiles : pl.ntiles;
     for (int g0 = 0; g0 < pl.groups;) {
         const TcLaunch L = tc_launch_at(pl, g0, units);
