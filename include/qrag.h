@@ -106,6 +106,14 @@ int qrag_amp_fidelity(const float* Q, int nq,
                       int64_t C, int D, int n_qubits, int layers,
                       double* out64, float* out32, void* stream);
 
+/* Kernel choice for layers >= 1 (process-wide, default AUTO).  AUTO runs the warp-per-state
+ * register kernel where it applies (n_qubits == 10) and the shared-memory kernel elsewhere;
+ * GENERIC forces the shared-memory kernel (A/B timing and cross-checks; results agree to
+ * rounding, ~1e-15 relative). */
+#define QRAG_FMAP_AUTO    0
+#define QRAG_FMAP_GENERIC 1
+int qrag_set_fmap_kernel(int mode);
+
 /* ---------------------------------------------------------------------------
  * (1c) Fused amplitude-encoded rerank: score + stable descending sort + top_k
  * in one launch.  Replaces QuantumReranker.rerank (quantum.py:44-78) at tensor

@@ -16,7 +16,7 @@ from typing import Dict, List, Optional
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libqrag.so")
-SOURCES = ["lib.cu", "amp_fidelity.cu", "amp_stream.cu", "sv_kernels.cu", "search_exact.cu", "search_tc.cu"]
+SOURCES = ["lib.cu", "amp_fidelity.cu", "amp_stream.cu", "sv_kernels.cu", "fmap_warp.cu", "search_exact.cu", "search_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -29,6 +29,7 @@ PROTOTYPES: Dict[str, tuple] = {
     "qrag_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "qrag_set_overlap": (c_int, [c_int]),
     "qrag_get_overlap": (c_int, []),
+    "qrag_set_fmap_kernel": (c_int, [c_int]),
     "qrag_sv_fidelity_angle": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                                        c_void_p, c_void_p]),
     "qrag_amp_fidelity": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,

@@ -69,6 +69,14 @@ def set_overlap(mode: int) -> int:
     return old
 
 
+FMAP_AUTO, FMAP_GENERIC = 0, 1
+
+
+def set_fmap_kernel(mode: int) -> None:
+    """Feature-map kernel choice (include/qrag.h): FMAP_AUTO or FMAP_GENERIC (shared-memory kernel everywhere)."""
+    _lib.check(_lib.load().qrag_set_fmap_kernel(int(mode)))
+
+
 def qubits_for(dim: int) -> int:
     """Smallest n with 2**n >= dim (amplitude encoding zero-pads to 2**n)."""
     return max(1, int(dim - 1).bit_length())

@@ -47,6 +47,8 @@ const DeviceProps& device_props();
 
 // process-wide stream-overlap policy (qrag_set_overlap)
 int overlap_mode();
+// process-wide choice of the feature-map kernel (qrag_set_fmap_kernel)
+int fmap_kernel_mode();
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int next_pow2(int64_t v) {

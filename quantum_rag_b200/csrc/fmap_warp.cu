@@ -1,0 +1,417 @@
+// K1b: amplitude-encoded state followed by L feature-map layers at n = 10 qubits
+// (BASELINE config 5: 1024-d embeddings), one WARP per state, complex128.
+//
+// What it replaces: the per-pair `_vector_to_circuit` + two statevector runs of
+// /root/reference/src/reranker/quantum.py:108-167, with the amplitude-encoded
+// start state quantum.py:156 names and the layer block repeated (builder-defined,
+// SURVEY.md section 8d config 5; oracle: oracle/quantum.py feature_map_state).
+//
+// Why a second kernel beside sv_cta_kernel: that one keeps the state in shared
+// memory and makes four radix-8 round trips per layer with a CTA barrier after
+// each, applying RY and RZ as a general complex 2x2 per qubit.  Here
+//   * a lane holds 32 of the 1024 amplitudes in REGISTERS; five qubits are
+//     local to the lane, so a layer is two passes (qubits 0-4, then 5-9) with one
+//     warp-synchronous transpose through shared memory between them - no CTA
+//     barrier on the path;
+//   * the layer is regrouped as [all RY][all RZ] (gates on different qubits
+//     commute): RY is a REAL rotation (4 flops per amplitude instead of 8) and
+//     the ten RZ collapse into one diagonal, applied as two 32-entry phase tables
+//     (one complex multiply per amplitude and pass);
+//   * the first pass of the first layer works on the real amplitude vector;
+//   * the CX chain of layer l is folded into the shared-memory read of layer l+1
+//     (new[y] = old[y ^ (y << 1)]), and the chain of the LAST layer is dropped on
+//     both sides of the overlap (the same permutation of both states);
+//   * the query state is evolved once per (query, chunk of candidates) by warp 0
+//     while the other warps already evolve their first candidate.
+// Shared-memory layout of a state: element x lives at (x >> 5) * 33 + (x & 31) (16-byte units;
+// one unit of padding per 32), which makes the pass-A accesses (lane = high five bits), the
+// pass-B accesses (lane = low five bits) and the CX gather all bank-conflict free AND gives every
+// access a lane-dependent base plus a compile-time offset (no address registers).
+//
+// Bound: the FP64 pipe (64 FMA/clk/SM).  Per state and layer: 10 RY x 4 + 2 diagonals x 4
+// = 48 FP64 instructions per amplitude, i.e. 1 536 per lane; HBM traffic is the 4 KB row.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace qrag {
+
+namespace {
+
+constexpr int FW_N = 10;
+constexpr int FW_DIM = 1 << FW_N;
+constexpr int FW_ST = FW_DIM + 32;                          // state stride: rows of 32 amplitudes + 1 of padding
+
+struct FmapWarpParams {
+    const float* Q; const float* cand; const float* X; const int64_t* idx;
+    int64_t C; int D; int nq; int layers;
+    int64_t chunk; int chunks_per_q; int64_t units;
+    double* out; float* out32;
+};
+
+struct FwGate { double c, s, cp, sp; };                      // RY half-angle cos/sin, RZ half-angle cos/sin
+
+__host__ __device__ constexpr int fw_pxor5(int x) {          // CX chain on five bits: y_k = x_0 ^ ... ^ x_k
+    x ^= x << 1; x ^= x << 2; x ^= x << 4;
+    return x & 31;
+}
+__host__ __device__ constexpr int fw_parity5(int x) { return (x ^ (x >> 1) ^ (x >> 2) ^ (x >> 3) ^ (x >> 4)) & 1; }
+
+// RY on the five qubits that are bits of the register index.
+// FAST: RY = c * [[1, -t], [t, 1]], t = tan(half angle); the factor c goes into the phase table, so a
+// complex pair costs 4 FMAs instead of 8 flops.  Used when every |t| <= 1 (|a| <= 1/2), else the direct form.
+template <bool FAST>
+__device__ __forceinline__ void fw_ry5(double2 (&a)[32], const FwGate* __restrict__ g, const double* __restrict__ tn) {
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        if (FAST) {
+            const double t = tn[b];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (j & (1 << b)) continue;
+                const int k = j | (1 << b);
+                const double2 a0 = a[j], a1 = a[k];
+                a[j].x = fma(-t, a1.x, a0.x);
+                a[j].y = fma(-t, a1.y, a0.y);
+                a[k].x = fma(t, a0.x, a1.x);
+                a[k].y = fma(t, a0.y, a1.y);
+            }
+        } else {
+            const double c = g[b].c, s = g[b].s;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (j & (1 << b)) continue;
+                const int k = j | (1 << b);
+                const double2 a0 = a[j], a1 = a[k];
+                a[j].x = fma(-s, a1.x, c * a0.x);
+                a[j].y = fma(-s, a1.y, c * a0.y);
+                a[k].x = fma(s, a0.x, c * a1.x);
+                a[k].y = fma(s, a0.y, c * a1.y);
+            }
+        }
+    }
+}
+
+template <bool FAST>
+__device__ __forceinline__ void fw_ry5_real(double (&r)[32], const FwGate* __restrict__ g,
+                                            const double* __restrict__ tn) {
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        const double t = tn[b], c = g[b].c, s = g[b].s;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (j & (1 << b)) continue;
+            const int k = j | (1 << b);
+            const double a0 = r[j], a1 = r[k];
+            if (FAST) {
+                r[j] = fma(-t, a1, a0);
+                r[k] = fma(t, a0, a1);
+            } else {
+                r[j] = fma(-s, a1, c * a0);
+                r[k] = fma(s, a0, c * a1);
+            }
+        }
+    }
+}
+
+// Phase table of five RZ gates: entry j = prod_b (bit b of j ? e^{+i phi_b/2} : e^{-i phi_b/2}),
+// times the RY scale prod_b c_b in the FAST form.
+template <bool FAST>
+__device__ __forceinline__ double2 fw_phase(const FwGate* __restrict__ g, int j) {
+    double2 p = make_double2(1.0, 0.0);
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        const double cr = g[b].cp;
+        const double ci = ((j >> b) & 1) ? g[b].sp : -g[b].sp;
+        const double nx = p.x * cr - p.y * ci;
+        const double ny = p.x * ci + p.y * cr;
+        p.x = nx; p.y = ny;
+    }
+    if (FAST) {
+        const double sc = g[0].c * g[1].c * g[2].c * g[3].c * g[4].c;
+        p.x *= sc; p.y *= sc;
+    }
+    return p;
+}
+
+__device__ __forceinline__ void fw_diag(double2 (&a)[32], const double2* __restrict__ tab) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const double2 p = tab[j], v = a[j];
+        a[j].x = v.x * p.x - v.y * p.y;
+        a[j].y = fma(v.x, p.y, v.y * p.x);
+    }
+}
+
+// The layers.  Qubits 0-4 are the low five bits of the basis index x, qubits 5-9 the high five.
+//   layout A: a lane holds one value of the high bits (its "row") and all 32 low values in registers;
+//   layout B: a lane holds one value of the low bits (its "column") and all 32 high values.
+// A pass rotates the five qubits that are register bits and applies their half of the RZ diagonal.
+// Even layers run A then B, odd layers B then A, so there is ONE transpose through shared memory
+// per layer; the CX chain between layers (new[y] = old[x], y = prefix-xor of x) never touches
+// shared memory:
+//   after a B pass (column l, registers = high bits h): y_lo = pxor5(l) is a new column label,
+//   y_hi = pxor5(h) ^ (parity(l) ? 31 : 0) a register renaming plus, on odd-parity lanes, a reversal;
+//   after an A pass (row h, registers = low bits l): y_lo = pxor5(l) is a renaming, and y_hi =
+//   pxor5(h) ^ (parity(l) ? 31 : 0) means the odd-parity registers belong to the row of lane ^ 1:
+//   one __shfl_xor of 16 amplitudes.
+// Ends in layout B (layers odd) or A (layers even); the same for both states of an overlap.
+template <bool FAST>
+__device__ __forceinline__ void fw_layers(double (&r)[32], double2 (&a)[32], int layers, double2* __restrict__ st,
+                                          const FwGate* __restrict__ gates, const double* __restrict__ tn,
+                                          double2* __restrict__ tab) {
+    const int lane = threadIdx.x & 31;
+    const bool odd_lane = __popc(lane) & 1;
+    const int lcol = fw_pxor5(lane);                         // column label after a B-side CX
+    int hrow = lane;                                         // row label (changes after an A-side CX)
+    // ---- layer 0, pass A on the REAL amplitudes
+    tab[lane] = fw_phase<FAST>(gates, lane);
+    tab[32 + lane] = fw_phase<FAST>(gates + 5, lane);
+    __syncwarp();
+    fw_ry5_real<FAST>(r, gates, tn);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const double2 p = tab[j];
+        a[j].x = r[j] * p.x;
+        a[j].y = r[j] * p.y;
+    }
+    for (int layer = 0;; layer += 2) {
+        const FwGate* g = gates + layer * FW_N;
+        const double* t = tn + layer * FW_N;
+        // ================= even layer: A then B
+        if (layer > 0) {
+            tab[lane] = fw_phase<FAST>(g, lane);
+            tab[32 + lane] = fw_phase<FAST>(g + 5, lane);
+            __syncwarp();
+            fw_ry5<FAST>(a, g, t);
+            fw_diag(a, tab);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[hrow * 33 + j] = a[j];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = st[j * 33 + lane];
+        fw_ry5<FAST>(a, g + 5, t + 5);
+        fw_diag(a, tab + 32);
+        __syncwarp();                                        // reads of st and tab are complete
+        if (layer + 1 == layers) break;                      // the last CX chain is dropped (same on both states)
+        {   // B-side CX chain, in registers
+            double2 b[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) b[fw_pxor5(j)] = a[j];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                a[j].x = odd_lane ? b[31 - j].x : b[j].x;
+                a[j].y = odd_lane ? b[31 - j].y : b[j].y;
+                a[31 - j].x = odd_lane ? b[j].x : b[31 - j].x;
+                a[31 - j].y = odd_lane ? b[j].y : b[31 - j].y;
+            }
+        }
+        // ================= odd layer: B then A
+        g += FW_N; t += FW_N;
+        tab[lane] = fw_phase<FAST>(g, lane);
+        tab[32 + lane] = fw_phase<FAST>(g + 5, lane);
+        __syncwarp();
+        fw_ry5<FAST>(a, g + 5, t + 5);
+        fw_diag(a, tab + 32);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[j * 33 + lcol] = a[j];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = st[lane * 33 + j];
+        fw_ry5<FAST>(a, g, t);
+        fw_diag(a, tab);
+        __syncwarp();
+        if (layer + 2 == layers) break;
+        {   // A-side CX chain: odd-parity registers come from lane ^ 1, then the renaming
+            double2 b[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                double2 v = a[j];
+                if (fw_parity5(j)) {
+                    v.x = __shfl_xor_sync(FULL_MASK, v.x, 1);
+                    v.y = __shfl_xor_sync(FULL_MASK, v.y, 1);
+                }
+                b[fw_pxor5(j)] = v;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = b[j];
+        }
+        hrow = lcol;                                         // pxor5(lane)
+    }
+}
+
+// Evolves one fp32 row into the state after `layers` blocks WITHOUT the last CX chain, in the
+// final register layout of fw_layers.  Returns |row| == 0.  smem regions are private to the warp.
+__device__ __forceinline__ bool fw_evolve(const float* __restrict__ row, int D, int layers, double2 (&a)[32],
+                                       double2* __restrict__ st, FwGate* __restrict__ gates,
+                                       double* __restrict__ tn, double2* __restrict__ tab) {
+    const int lane = threadIdx.x & 31;
+    float* stage = reinterpret_cast<float*>(st);             // aliases the state buffer until the first transpose
+    // ---- row -> padded staging (coalesced; 4 floats of padding per 32), |row|^2 in fp64
+    double n2 = 0.0;
+    const bool vec = ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+    if (vec) {
+#pragma unroll
+        for (int r = 0; r < FW_DIM / 128; ++r) {
+            const int m = lane + 32 * r;                     // float4 index
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * m < D) v = ldg_stream(reinterpret_cast<const float4*>(row) + m);
+            n2 = fma((double)v.x, (double)v.x, n2); n2 = fma((double)v.y, (double)v.y, n2);
+            n2 = fma((double)v.z, (double)v.z, n2); n2 = fma((double)v.w, (double)v.w, n2);
+            *reinterpret_cast<float4*>(stage + 4 * m + (m >> 3) * 4) = v;
+        }
+    } else {
+        for (int i = lane; i < FW_DIM; i += 32) {
+            const float v = i < D ? row[i] : 0.f;
+            n2 = fma((double)v, (double)v, n2);
+            stage[i + (i >> 5) * 4] = v;
+        }
+    }
+    n2 = warp_sum(n2);
+    const double nrm = sqrt(n2);
+    const bool zero = !(nrm > 0.0);
+    const double inv = zero ? 1.0 : 1.0 / nrm;              // one division per state; x * inv is within 1 ulp of x / nrm
+    __syncwarp();
+    // ---- gate parameters: layer l, qubit i takes a = x^[(l*n + i) % D]  (quantum.py:160-161: ry(a pi), rz(a pi/2))
+    bool small = true;
+    for (int t = lane; t < layers * FW_N; t += 32) {
+        const int comp = t % D;
+        const double an = (double)stage[comp + (comp >> 5) * 4] * inv;
+        FwGate g;
+        sincospi(0.5 * an, &g.s, &g.c);
+        sincospi(0.25 * an, &g.sp, &g.cp);
+        gates[t] = g;
+        tn[t] = g.s / g.c;
+        small = small && (fabs(an) <= 0.5);
+    }
+    const bool fast = __all_sync(FULL_MASK, small);
+    // ---- my 32 real amplitudes: basis index (lane << 5) | j
+    double r[32];
+    {
+        const float4* src = reinterpret_cast<const float4*>(stage + lane * 36);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float4 v = src[u];
+            r[4 * u + 0] = (double)v.x * inv;
+            r[4 * u + 1] = (double)v.y * inv;
+            r[4 * u + 2] = (double)v.z * inv;
+            r[4 * u + 3] = (double)v.w * inv;
+        }
+    }
+    __syncwarp();                                            // gates visible; staging fully consumed
+    if (fast) fw_layers<true>(r, a, layers, st, gates, tn, tab);
+    else      fw_layers<false>(r, a, layers, st, gates, tn, tab);
+    return zero;
+}
+
+// One CTA = W warps; a unit = (query, chunk of its candidates).  Item 0 of a unit is the query
+// itself, item t >= 1 candidate t-1; warp w takes items w, w + W, ...  Warp 0 evolves the query
+// state while the others already evolve their first candidate.
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) fmap_warp_kernel(const FmapWarpParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double2* qstate = reinterpret_cast<double2*>(smem_raw);
+    double2* st = qstate + FW_ST + (size_t)warp * FW_ST;
+    double2* tab = qstate + FW_ST + (size_t)W * FW_ST + warp * 64;
+    FwGate* gates = reinterpret_cast<FwGate*>(qstate + FW_ST + (size_t)W * (FW_ST + 64)) + warp * p.layers * FW_N;
+    double* tn = reinterpret_cast<double*>(reinterpret_cast<FwGate*>(qstate + FW_ST + (size_t)W * (FW_ST + 64)) +
+                                           (size_t)W * p.layers * FW_N) + warp * p.layers * FW_N;
+    __shared__ int q_zero;
+
+    double2 a[32];
+    for (int64_t u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const int64_t qi = u / p.chunks_per_q;
+        const int64_t c0 = (u % p.chunks_per_q) * p.chunk;
+        int64_t cnt = p.C - c0;
+        if (cnt > p.chunk) cnt = p.chunk;
+        bool first = true;
+        for (int64_t t = warp; t <= cnt; t += W) {
+            const int64_t j = qi * p.C + c0 + (t - 1);
+            const float* row;
+            bool missing = false;
+            if (t == 0) {
+                row = p.Q + qi * p.D;
+            } else if (p.cand) {
+                row = p.cand + (size_t)j * p.D;
+            } else {
+                const int64_t id = p.idx[j];
+                missing = id < 0;
+                row = p.X + (size_t)(missing ? 0 : id) * p.D;
+            }
+            const bool zero = fw_evolve(row, p.D, p.layers, a, st, gates, tn, tab);
+            if (t == 0) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) qstate[k * 33 + lane] = a[k];
+                if (lane == 0) q_zero = zero;
+            }
+            if (first) {
+                __syncthreads();                             // query state of this unit is in place
+                first = false;
+            }
+            if (t > 0) {
+                double re = 0.0, im = 0.0;                   // <psi_d | psi_q> = sum conj(d) q
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const double2 q = qstate[k * 33 + lane], d = a[k];
+                    re = fma(d.x, q.x, re); re = fma(d.y, q.y, re);
+                    im = fma(d.x, q.y, im); im = fma(-d.y, q.x, im);
+                }
+                re = warp_sum(re);
+                im = warp_sum(im);
+                if (lane == 0) {
+                    double f = re * re + im * im;
+                    if (q_zero || zero) f = 0.0;
+                    if (missing) f = -__longlong_as_double(0x7ff0000000000000LL);
+                    p.out[j] = f;
+                    if (p.out32) p.out32[j] = (float)f;
+                }
+            }
+        }
+        if (first) __syncthreads();                          // warps without an item still join the barrier
+        __syncthreads();                                     // everyone is done with qstate before the next unit
+    }
+}
+
+}  // namespace
+
+size_t fmap_warp_smem(int W, int layers) {
+    return (size_t)(1 + W) * FW_ST * sizeof(double2) + (size_t)W * 64 * sizeof(double2) +
+           (size_t)W * layers * FW_N * (sizeof(FwGate) + sizeof(double));
+}
+
+// Returns QRAG_OK and sets *handled when the shape is served by this kernel (n = 10).
+int fmap_warp_try(const float* Q, int nq, const float* cand, const float* X, const int64_t* idx, int64_t C, int D,
+                  int n_qubits, int layers, double* out64, float* out32, cudaStream_t st, bool* handled) {
+    *handled = false;
+    if (n_qubits != FW_N || layers < 1 || D < 1 || D > FW_DIM) return QRAG_OK;
+    const DeviceProps& dp = device_props();
+    QRAG_REQUIRE(dp.ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
+    // 11 warps (168 registers, a few spilled bytes) or 8 warps (255 registers): QRAG_FMAP_WARPS=8 selects the latter
+    static const int want_w = [] { const char* e = getenv("QRAG_FMAP_WARPS"); return e ? atoi(e) : 11; }();
+    int W = want_w <= 8 ? (want_w < 1 ? 1 : want_w) : 11;
+    while (W > 1 && fmap_warp_smem(W, layers) + 64 > (size_t)dp.max_smem_optin) --W;
+    if (fmap_warp_smem(W, layers) + 64 > (size_t)dp.max_smem_optin) return QRAG_OK;    // layers too deep: generic kernel
+    FmapWarpParams p{};
+    p.Q = Q; p.cand = cand; p.X = X; p.idx = idx; p.C = C; p.D = D; p.nq = nq; p.layers = layers;
+    p.out = out64; p.out32 = out32;
+    // a unit should fill at least one round of the CTA (query + W-1 candidates); prefer >= 2 units per SM
+    int64_t cpq = ceil_div(2 * (int64_t)dp.sm_count, nq);
+    const int64_t max_cpq = ceil_div(C, W > 1 ? W - 1 : 1);
+    if (cpq > max_cpq) cpq = max_cpq;
+    if (cpq < 1) cpq = 1;
+    p.chunk = ceil_div(C, cpq);
+    p.chunks_per_q = (int)ceil_div(C, p.chunk);
+    p.units = (int64_t)nq * p.chunks_per_q;
+    const int64_t grid = p.units < dp.sm_count ? p.units : dp.sm_count;
+    const size_t smem = fmap_warp_smem(W, layers);
+    auto kern = W <= 8 ? fmap_warp_kernel<256> : fmap_warp_kernel<352>;
+    QRAG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, W * 32, smem, st>>>(p);
+    QRAG_LAUNCH_CHECK("fmap_warp_kernel");
+    *handled = true;
+    return QRAG_OK;
+}
+
+}  // namespace qrag

@@ -12,6 +12,8 @@ char* err_buf() { return g_err; }
 
 static std::atomic<int> g_overlap{QRAG_OVERLAP_SAFE};
 int overlap_mode() { return g_overlap.load(std::memory_order_relaxed); }
+static std::atomic<int> g_fmap_kernel{QRAG_FMAP_AUTO};
+int fmap_kernel_mode() { return g_fmap_kernel.load(std::memory_order_relaxed); }
 
 int set_error(int code, const char* fmt, ...) {
     va_list ap;
@@ -70,3 +72,10 @@ extern "C" int qrag_set_overlap(int mode) {
 }
 
 extern "C" int qrag_get_overlap(void) { return qrag::overlap_mode(); }
+
+extern "C" int qrag_set_fmap_kernel(int mode) {
+    QRAG_REQUIRE(mode == QRAG_FMAP_AUTO || mode == QRAG_FMAP_GENERIC, QRAG_ERR_INVALID,
+                 "feature-map kernel mode %d (expected QRAG_FMAP_AUTO / QRAG_FMAP_GENERIC)", mode);
+    qrag::g_fmap_kernel.store(mode, std::memory_order_relaxed);
+    return QRAG_OK;
+}

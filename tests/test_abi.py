@@ -69,6 +69,7 @@ def test_tensor_core_search_argument_validation(libqrag):
     assert libqrag.qrag_index_prepared_dims(10, 0, ctypes.byref(kp)) == 0 and kp.value == 16
     assert libqrag.qrag_index_prepared_dims(384, 9, ctypes.byref(kp)) == -1
     assert libqrag.qrag_set_overlap(5) == -1 and libqrag.qrag_get_overlap() in (0, 1, 2)
+    assert libqrag.qrag_set_fmap_kernel(7) == -1 and libqrag.qrag_set_fmap_kernel(0) == 0
     nbytes = ctypes.c_size_t(0)
     rc = libqrag.qrag_search_tc_workspace(4, 1000, 64, 5000, 0, 1, ctypes.byref(nbytes))
     assert rc in (-3, -2)                                  # k too large (or no device: still an error, never a fallback)

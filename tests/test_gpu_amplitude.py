@@ -135,6 +135,61 @@ def test_feature_map_layers_match_oracle(cuda, D, n, layers):
     assert got[1, 1] == 0.0 and got[0, 2] == pytest.approx(1.0, abs=1e-12)
 
 
+@pytest.mark.parametrize("D,layers", [(1024, 1), (1024, 4), (1000, 3), (515, 2), (7, 5), (1022, 9)])
+def test_feature_map_warp_kernel_n10(cuda, D, layers):
+    """n = 10 runs the warp-per-state register kernel: vs the oracle, and vs the shared-memory kernel."""
+    import torch
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(D + layers)
+    nq, C = 3, 29                                        # more items than warps in a CTA, ragged last round
+    Q = rng.standard_normal((nq, D)).astype(np.float32)
+    cand = rng.standard_normal((nq, C, D)).astype(np.float32)
+    cand[1, 1] = 0.0
+    cand[0, 2] = Q[0]
+    cand[2, 28] = cand[2, 5]                             # exact tie
+    got = api.amp_fidelity(Q, cand=cand, n_qubits=10, layers=layers).cpu().numpy()
+    sel = [(i, j) for i in range(nq) for j in (0, 1, 2, 5, 11, 28)]
+    for i, j in sel:
+        want = oq.feature_map_fidelity(Q[i], cand[i, j], 10, layers)
+        assert got[i, j] == pytest.approx(want, rel=1e-11, abs=1e-15), (i, j)
+    assert got[1, 1] == 0.0 and got[0, 2] == pytest.approx(1.0, abs=1e-12) and got[2, 28] == got[2, 5]
+    api.set_fmap_kernel(api.FMAP_GENERIC)
+    try:
+        ref = api.amp_fidelity(Q, cand=cand, n_qubits=10, layers=layers).cpu().numpy()
+    finally:
+        api.set_fmap_kernel(api.FMAP_AUTO)
+    assert np.allclose(got, ref, rtol=1e-11, atol=1e-15)
+    # gathered rows with a padding id and a zero query
+    X = cand.reshape(-1, D)
+    idx = torch.from_numpy(rng.randint(0, X.shape[0], size=(nq, 40)))
+    idx[1, 7] = -1
+    Qz = Q.copy()
+    Qz[2] = 0.0
+    g = api.amp_fidelity(Qz, X=X, idx=idx, n_qubits=10, layers=layers).cpu().numpy()
+    assert g[1, 7] == -np.inf and np.all(g[2] == 0.0)
+    for j in (0, 39):
+        want = oq.feature_map_fidelity(Q[0], X[int(idx[0, j])], 10, layers)
+        assert g[0, j] == pytest.approx(want, rel=1e-11, abs=1e-15)
+
+
+def test_feature_map_warp_kernel_many_units(cuda):
+    """Enough queries that CTAs loop over several units, and a chunked query (nq small, C large)."""
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(77)
+    for nq, C in ((400, 3), (1, 700)):
+        Q = rng.standard_normal((nq, 1024)).astype(np.float32)
+        cand = rng.standard_normal((nq, C, 1024)).astype(np.float32)
+        got = api.amp_fidelity(Q, cand=cand, n_qubits=10, layers=2).cpu().numpy()
+        api.set_fmap_kernel(api.FMAP_GENERIC)
+        try:
+            ref = api.amp_fidelity(Q, cand=cand, n_qubits=10, layers=2).cpu().numpy()
+        finally:
+            api.set_fmap_kernel(api.FMAP_AUTO)
+        assert np.allclose(got, ref, rtol=1e-11, atol=1e-15)
+        for i, j in ((0, 0), (nq - 1, C - 1)):
+            assert got[i, j] == pytest.approx(oq.feature_map_fidelity(Q[i], cand[i, j], 10, 2), rel=1e-11, abs=1e-15)
+
+
 def test_too_few_qubits_is_an_error(cuda):
     from quantum_rag_b200 import api
     from quantum_rag_b200._lib import QragError
