@@ -182,6 +182,45 @@ def bench_search(api, peaks, steps=20):
     return out
 
 
+def bench_feature_map(api, steps=3):
+    """BASELINE config 5 on one GPU: 4096 queries x 1000 candidates x 1024-d, 10 qubits, amplitude state followed
+    by L = 4 feature-map layers (builder-defined), complex128.  Bound: the FP64 pipe, not HBM."""
+    import numpy as np
+    import torch
+    from oracle import quantum as oq
+    nq, C, dim, n, L = 4096, 1000, 1024, 10, 4
+    g = torch.Generator(device="cuda").manual_seed(1234 + 5)
+    Q = torch.randn(nq, dim, generator=g, device="cuda")
+    cand = torch.randn(nq, C, dim, generator=g, device="cuda")            # 16.8 GB, resident
+    out = api.amp_fidelity(Q, cand=cand, n_qubits=n, layers=L)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = api.amp_fidelity(Q, cand=cand, n_qubits=n, layers=L)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    pairs = [(0, 0), (17, 999), (4095, 500)]                              # spot parity against the oracle (CPU, 3 pairs)
+    want = np.array([oq.feature_map_fidelity(Q[i].cpu().numpy(), cand[i, j].cpu().numpy(), n, L) for i, j in pairs])
+    got = np.array([float(out[i, j]) for i, j in pairs])
+    rate = nq * C / (ms * 1e-3)
+    fp64_instr = 3.7e3 * 32                                               # measured FP64 thread-instructions per state (ncu)
+    fp64_peak = 148 * 64 * 1.965e9                                        # 64 FP64 FMA lanes per clock per SM
+    res = {"workload": "config 5: 4096 queries x 1000 candidates x 1024-d, 10 qubits, amplitude state + 4 feature-map "
+                       "layers, complex128 statevector", "ms_per_batch": ms, "scores_per_s": rate,
+           "parity_vs_oracle_rel_err": float(np.max(np.abs(got / want - 1.0))),
+           "roofline": {"bound": "fp64 pipe", "achieved_fp64_inst_per_s": rate * fp64_instr, "peak": fp64_peak,
+                        "frac": rate * fp64_instr / fp64_peak,
+                        "hbm_gbs": rate * 4 * dim / 1e9,
+                        "note": "3.7e3 FP64 warp instructions per state (profiles/r01_fmap_warp_*); HBM traffic is the "
+                                "4 KB candidate row, far from the HBM roofline"},
+           "kernels": ["qrag::fmap_warp_kernel<256> (warp per state, 32 amplitudes per lane in registers)"]}
+    del cand, Q
+    torch.cuda.empty_cache()
+    return res
+
+
 def bench_sharded(world, rank, steps=5):
     """BASELINE config 4: 10M x 384 docs row-sharded over the ranks, top-1000 per shard -> NCCL all-gather ->
     merge -> amplitude-encoded quantum rerank -> top-10.  Strong scaling: the corpus is fixed, time is max over ranks."""
@@ -432,6 +471,7 @@ def run_b200(args):
             line["sharded_search_rerank"] = sharded
         if world == 1 and not args.no_extra:
             line["search"] = bench_search(api, peaks)
+            line["feature_map"] = bench_feature_map(api)
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             Qn, cn = host_sets0
@@ -470,7 +510,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: a single untimed-quality e2e pass")
-    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (configs 3 and 4)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (configs 3, 4 and 5)")
     ap.add_argument("--no-spinup", action="store_true", help="profiling runs: skip the 0.2 s clock spin-up")
     args = ap.parse_args()
     if args.impl == "reference":

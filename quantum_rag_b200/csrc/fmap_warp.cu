@@ -8,30 +8,32 @@
 //
 // Why a second kernel beside sv_cta_kernel: that one keeps the state in shared
 // memory and makes four radix-8 round trips per layer with a CTA barrier after
-// each, applying RY and RZ as a general complex 2x2 per qubit.  Here
+// each, applying RY and RZ as a general complex 2x2 per qubit (80 flops per
+// amplitude and layer).  Here
 //   * a lane holds 32 of the 1024 amplitudes in REGISTERS; five qubits are
-//     local to the lane, so a layer is two passes (qubits 0-4, then 5-9) with one
-//     warp-synchronous transpose through shared memory between them - no CTA
-//     barrier on the path;
+//     register-index bits, so a layer is two passes (qubits 0-4 and 5-9) with ONE
+//     warp-synchronous transpose through shared memory between them (even layers
+//     run 0-4 first, odd layers 5-9 first) - no CTA barrier on the path;
 //   * the layer is regrouped as [all RY][all RZ] (gates on different qubits
-//     commute): RY is a REAL rotation (4 flops per amplitude instead of 8) and
-//     the ten RZ collapse into one diagonal, applied as two 32-entry phase tables
-//     (one complex multiply per amplitude and pass);
-//   * the first pass of the first layer works on the real amplitude vector;
-//   * the CX chain of layer l is folded into the shared-memory read of layer l+1
-//     (new[y] = old[y ^ (y << 1)]), and the chain of the LAST layer is dropped on
-//     both sides of the overlap (the same permutation of both states);
+//     commute).  RY = c [[1, -t], [t, 1]] is a scaled real rotation: 2 FMAs per
+//     amplitude, the product of the c's goes into the phase table (used when every
+//     |t| <= 1, i.e. every |x^_i| <= 1/2; otherwise the direct 4-flop form).  The
+//     ten RZ collapse into one diagonal per layer = table[register index] x
+//     constant[lane], one table load and 8 flops per amplitude;
+//   * layer 0 stays real until its diagonal;
+//   * the CX chain between layers is a register renaming plus, per side, either a
+//     conditional register reversal or one 16-amplitude __shfl_xor with lane ^ 1
+//     (see fw_layers); the chain of the LAST layer is dropped on both sides of the
+//     overlap (the same permutation of both states);
 //   * the query state is evolved once per (query, chunk of candidates) by warp 0
 //     while the other warps already evolve their first candidate.
-// Shared-memory layout of a state: element x lives at (x >> 5) * 33 + (x & 31) (16-byte units;
-// one unit of padding per 32), which makes the pass-A accesses (lane = high five bits), the
-// pass-B accesses (lane = low five bits) and the CX gather all bank-conflict free AND gives every
-// access a lane-dependent base plus a compile-time offset (no address registers).
+// Shared-memory layout of a state: element (row, col) at row * 33 + col (one unit of padding per
+// 32): row-wise and column-wise accesses are bank-conflict free and every access is a
+// lane-dependent base plus a compile-time offset (no address registers).
 //
-// Bound: the FP64 pipe (64 FMA/clk/SM).  Per state and layer: 10 RY x 4 + 2 diagonals x 4
-// = 48 FP64 instructions per amplitude, i.e. 1 536 per lane; HBM traffic is the 4 KB row.
-#include <stdlib.h>
-
+// Bound: the FP64 pipe (64 FMA/clk/SM).  Per state and layer 10 x 2 + 8 = 28 FP64 instructions
+// per amplitude (896 per lane); measured 3.7e3 FP64 warp instructions per state at L = 4 against
+// 6.2e3 for the direct form; HBM traffic is the 4 KB row.  ncu: profiles/r01_fmap_warp_*.
 #include "common.cuh"
 
 namespace qrag {
@@ -134,21 +136,27 @@ __device__ __forceinline__ double2 fw_phase(const FwGate* __restrict__ g, int j)
     return p;
 }
 
-__device__ __forceinline__ void fw_diag(double2 (&a)[32], const double2* __restrict__ tab) {
+// a[j] *= tab[j] * cst: the RZ diagonal of a whole layer, split as (uniform table over the register
+// index) x (per-lane constant for the lane's own row / column).
+__device__ __forceinline__ void fw_diag(double2 (&a)[32], const double2* __restrict__ tab, const double2 cst) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         const double2 p = tab[j], v = a[j];
-        a[j].x = v.x * p.x - v.y * p.y;
-        a[j].y = fma(v.x, p.y, v.y * p.x);
+        const double wx = p.x * cst.x - p.y * cst.y;
+        const double wy = fma(p.x, cst.y, p.y * cst.x);
+        a[j].x = v.x * wx - v.y * wy;
+        a[j].y = fma(v.x, wy, v.y * wx);
     }
 }
 
 // The layers.  Qubits 0-4 are the low five bits of the basis index x, qubits 5-9 the high five.
 //   layout A: a lane holds one value of the high bits (its "row") and all 32 low values in registers;
 //   layout B: a lane holds one value of the low bits (its "column") and all 32 high values.
-// A pass rotates the five qubits that are register bits and applies their half of the RZ diagonal.
-// Even layers run A then B, odd layers B then A, so there is ONE transpose through shared memory
-// per layer; the CX chain between layers (new[y] = old[x], y = prefix-xor of x) never touches
+// A pass rotates the five qubits that are register bits.  Even layers run A then B, odd layers B
+// then A, so there is ONE transpose through shared memory per layer, and the layer's RZ diagonal
+// is applied once, after the second pass (it commutes with the RY of the other five qubits):
+// table[register index] x constant[lane's own row or column].  Layer 0 stays REAL until that
+// diagonal.  The CX chain between layers (new[y] = old[x], y = prefix-xor of x) never touches
 // shared memory:
 //   after a B pass (column l, registers = high bits h): y_lo = pxor5(l) is a new column label,
 //   y_hi = pxor5(h) ^ (parity(l) ? 31 : 0) a register renaming plus, on odd-parity lanes, a reversal;
@@ -164,37 +172,27 @@ __device__ __forceinline__ void fw_layers(double (&r)[32], double2 (&a)[32], int
     const bool odd_lane = __popc(lane) & 1;
     const int lcol = fw_pxor5(lane);                         // column label after a B-side CX
     int hrow = lane;                                         // row label (changes after an A-side CX)
-    // ---- layer 0, pass A on the REAL amplitudes
-    tab[lane] = fw_phase<FAST>(gates, lane);
-    tab[32 + lane] = fw_phase<FAST>(gates + 5, lane);
-    __syncwarp();
-    fw_ry5_real<FAST>(r, gates, tn);
+    // ---- layer 0 on the REAL amplitudes: A, transpose, B, then the diagonal makes them complex
+    {
+        tab[lane] = fw_phase<FAST>(gates + 5, lane);
+        const double2 cst = fw_phase<FAST>(gates, lane);
+        fw_ry5_real<FAST>(r, gates, tn);
+        double* sr = reinterpret_cast<double*>(st);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const double2 p = tab[j];
-        a[j].x = r[j] * p.x;
-        a[j].y = r[j] * p.y;
-    }
-    for (int layer = 0;; layer += 2) {
-        const FwGate* g = gates + layer * FW_N;
-        const double* t = tn + layer * FW_N;
-        // ================= even layer: A then B
-        if (layer > 0) {
-            tab[lane] = fw_phase<FAST>(g, lane);
-            tab[32 + lane] = fw_phase<FAST>(g + 5, lane);
-            __syncwarp();
-            fw_ry5<FAST>(a, g, t);
-            fw_diag(a, tab);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) st[hrow * 33 + j] = a[j];
+        for (int j = 0; j < 32; ++j) sr[lane * 33 + j] = r[j];
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) a[j] = st[j * 33 + lane];
-        fw_ry5<FAST>(a, g + 5, t + 5);
-        fw_diag(a, tab + 32);
-        __syncwarp();                                        // reads of st and tab are complete
-        if (layer + 1 == layers) break;                      // the last CX chain is dropped (same on both states)
+        for (int j = 0; j < 32; ++j) r[j] = sr[j * 33 + lane];
+        fw_ry5_real<FAST>(r, gates + 5, tn + 5);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const double2 p = tab[j];
+            a[j].x = r[j] * (p.x * cst.x - p.y * cst.y);
+            a[j].y = r[j] * fma(p.x, cst.y, p.y * cst.x);
+        }
+        __syncwarp();
+    }
+    for (int layer = 1; layer < layers; layer += 2) {
         {   // B-side CX chain, in registers
             double2 b[32];
 #pragma unroll
@@ -208,21 +206,20 @@ __device__ __forceinline__ void fw_layers(double (&r)[32], double2 (&a)[32], int
             }
         }
         // ================= odd layer: B then A
-        g += FW_N; t += FW_N;
+        const FwGate* g = gates + layer * FW_N;
+        const double* t = tn + layer * FW_N;
         tab[lane] = fw_phase<FAST>(g, lane);
-        tab[32 + lane] = fw_phase<FAST>(g + 5, lane);
-        __syncwarp();
+        double2 cst = fw_phase<FAST>(g + 5, lane);
         fw_ry5<FAST>(a, g + 5, t + 5);
-        fw_diag(a, tab + 32);
 #pragma unroll
         for (int j = 0; j < 32; ++j) st[j * 33 + lcol] = a[j];
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 32; ++j) a[j] = st[lane * 33 + j];
         fw_ry5<FAST>(a, g, t);
-        fw_diag(a, tab);
-        __syncwarp();
-        if (layer + 2 == layers) break;
+        fw_diag(a, tab, cst);
+        __syncwarp();                                        // reads of st and tab are complete
+        if (layer + 1 == layers) break;                      // the last CX chain is dropped (same on both states)
         {   // A-side CX chain: odd-parity registers come from lane ^ 1, then the renaming
             double2 b[32];
 #pragma unroll
@@ -238,6 +235,19 @@ __device__ __forceinline__ void fw_layers(double (&r)[32], double2 (&a)[32], int
             for (int j = 0; j < 32; ++j) a[j] = b[j];
         }
         hrow = lcol;                                         // pxor5(lane)
+        // ================= even layer: A then B
+        g += FW_N; t += FW_N;
+        tab[lane] = fw_phase<FAST>(g + 5, lane);
+        cst = fw_phase<FAST>(g, lane);
+        fw_ry5<FAST>(a, g, t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[hrow * 33 + j] = a[j];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = st[j * 33 + lane];
+        fw_ry5<FAST>(a, g + 5, t + 5);
+        fw_diag(a, tab, cst);
+        __syncwarp();
     }
 }
 
@@ -248,8 +258,7 @@ __device__ __forceinline__ bool fw_evolve(const float* __restrict__ row, int D, 
                                        double* __restrict__ tn, double2* __restrict__ tab) {
     const int lane = threadIdx.x & 31;
     float* stage = reinterpret_cast<float*>(st);             // aliases the state buffer until the first transpose
-    // ---- row -> padded staging (coalesced; 4 floats of padding per 32), |row|^2 in fp64
-    double n2 = 0.0;
+    // ---- row -> padded staging (coalesced; 4 floats of padding per 32)
     const bool vec = ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
     if (vec) {
 #pragma unroll
@@ -257,22 +266,32 @@ __device__ __forceinline__ bool fw_evolve(const float* __restrict__ row, int D, 
             const int m = lane + 32 * r;                     // float4 index
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (4 * m < D) v = ldg_stream(reinterpret_cast<const float4*>(row) + m);
-            n2 = fma((double)v.x, (double)v.x, n2); n2 = fma((double)v.y, (double)v.y, n2);
-            n2 = fma((double)v.z, (double)v.z, n2); n2 = fma((double)v.w, (double)v.w, n2);
             *reinterpret_cast<float4*>(stage + 4 * m + (m >> 3) * 4) = v;
         }
     } else {
-        for (int i = lane; i < FW_DIM; i += 32) {
-            const float v = i < D ? row[i] : 0.f;
-            n2 = fma((double)v, (double)v, n2);
-            stage[i + (i >> 5) * 4] = v;
+        for (int i = lane; i < FW_DIM; i += 32) stage[i + (i >> 5) * 4] = i < D ? row[i] : 0.f;
+    }
+    __syncwarp();
+    // ---- my 32 real amplitudes (basis index (lane << 5) | j), |row|^2 in fp64
+    double r[32];
+    double n2 = 0.0;
+    {
+        const float4* src = reinterpret_cast<const float4*>(stage + lane * 36);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float4 v = src[u];
+            r[4 * u + 0] = (double)v.x; r[4 * u + 1] = (double)v.y;
+            r[4 * u + 2] = (double)v.z; r[4 * u + 3] = (double)v.w;
         }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) n2 = fma(r[j], r[j], n2);
     }
     n2 = warp_sum(n2);
     const double nrm = sqrt(n2);
     const bool zero = !(nrm > 0.0);
     const double inv = zero ? 1.0 : 1.0 / nrm;              // one division per state; x * inv is within 1 ulp of x / nrm
-    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] *= inv;
     // ---- gate parameters: layer l, qubit i takes a = x^[(l*n + i) % D]  (quantum.py:160-161: ry(a pi), rz(a pi/2))
     bool small = true;
     for (int t = lane; t < layers * FW_N; t += 32) {
@@ -286,19 +305,6 @@ __device__ __forceinline__ bool fw_evolve(const float* __restrict__ row, int D, 
         small = small && (fabs(an) <= 0.5);
     }
     const bool fast = __all_sync(FULL_MASK, small);
-    // ---- my 32 real amplitudes: basis index (lane << 5) | j
-    double r[32];
-    {
-        const float4* src = reinterpret_cast<const float4*>(stage + lane * 36);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const float4 v = src[u];
-            r[4 * u + 0] = (double)v.x * inv;
-            r[4 * u + 1] = (double)v.y * inv;
-            r[4 * u + 2] = (double)v.z * inv;
-            r[4 * u + 3] = (double)v.w * inv;
-        }
-    }
     __syncwarp();                                            // gates visible; staging fully consumed
     if (fast) fw_layers<true>(r, a, layers, st, gates, tn, tab);
     else      fw_layers<false>(r, a, layers, st, gates, tn, tab);
@@ -314,9 +320,9 @@ __global__ void __launch_bounds__(MAXT, 1) fmap_warp_kernel(const FmapWarpParams
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double2* qstate = reinterpret_cast<double2*>(smem_raw);
     double2* st = qstate + FW_ST + (size_t)warp * FW_ST;
-    double2* tab = qstate + FW_ST + (size_t)W * FW_ST + warp * 64;
-    FwGate* gates = reinterpret_cast<FwGate*>(qstate + FW_ST + (size_t)W * (FW_ST + 64)) + warp * p.layers * FW_N;
-    double* tn = reinterpret_cast<double*>(reinterpret_cast<FwGate*>(qstate + FW_ST + (size_t)W * (FW_ST + 64)) +
+    double2* tab = qstate + FW_ST + (size_t)W * FW_ST + warp * 32;
+    FwGate* gates = reinterpret_cast<FwGate*>(qstate + FW_ST + (size_t)W * (FW_ST + 32)) + warp * p.layers * FW_N;
+    double* tn = reinterpret_cast<double*>(reinterpret_cast<FwGate*>(qstate + FW_ST + (size_t)W * (FW_ST + 32)) +
                                            (size_t)W * p.layers * FW_N) + warp * p.layers * FW_N;
     __shared__ int q_zero;
 
@@ -377,7 +383,7 @@ __global__ void __launch_bounds__(MAXT, 1) fmap_warp_kernel(const FmapWarpParams
 }  // namespace
 
 size_t fmap_warp_smem(int W, int layers) {
-    return (size_t)(1 + W) * FW_ST * sizeof(double2) + (size_t)W * 64 * sizeof(double2) +
+    return (size_t)(1 + W) * FW_ST * sizeof(double2) + (size_t)W * 32 * sizeof(double2) +
            (size_t)W * layers * FW_N * (sizeof(FwGate) + sizeof(double));
 }
 
@@ -388,9 +394,9 @@ int fmap_warp_try(const float* Q, int nq, const float* cand, const float* X, con
     if (n_qubits != FW_N || layers < 1 || D < 1 || D > FW_DIM) return QRAG_OK;
     const DeviceProps& dp = device_props();
     QRAG_REQUIRE(dp.ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
-    // 11 warps (168 registers, a few spilled bytes) or 8 warps (255 registers): QRAG_FMAP_WARPS=8 selects the latter
-    static const int want_w = [] { const char* e = getenv("QRAG_FMAP_WARPS"); return e ? atoi(e) : 11; }();
-    int W = want_w <= 8 ? (want_w < 1 ? 1 : want_w) : 11;
+    // 8 warps = 2 per scheduler at 255 registers.  Measured on B200 (512 x 1000 x 1024, L = 4): 7.9e7 scores/s;
+    // 11 warps at 168 registers 6.6e7 (spills, unbalanced schedulers); the 168-register build at 8 warps 6.2e7.
+    int W = 8;
     while (W > 1 && fmap_warp_smem(W, layers) + 64 > (size_t)dp.max_smem_optin) --W;
     if (fmap_warp_smem(W, layers) + 64 > (size_t)dp.max_smem_optin) return QRAG_OK;    // layers too deep: generic kernel
     FmapWarpParams p{};
@@ -406,7 +412,7 @@ int fmap_warp_try(const float* Q, int nq, const float* cand, const float* X, con
     p.units = (int64_t)nq * p.chunks_per_q;
     const int64_t grid = p.units < dp.sm_count ? p.units : dp.sm_count;
     const size_t smem = fmap_warp_smem(W, layers);
-    auto kern = W <= 8 ? fmap_warp_kernel<256> : fmap_warp_kernel<352>;
+    auto kern = fmap_warp_kernel<256>;
     QRAG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, W * 32, smem, st>>>(p);
     QRAG_LAUNCH_CHECK("fmap_warp_kernel");
