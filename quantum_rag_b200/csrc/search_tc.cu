@@ -651,9 +651,8 @@ __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParam
     double* qs = reinterpret_cast<double*>(smem_raw);
     double* red = qs + Dpad;
     double* ckey = red + XS_WARPS;                                          // [cand_cap]
-    long long* ctag = reinterpret_cast<long long*>(ckey + p.cand_cap);      // [cand_cap]
-    int* cand = reinterpret_cast<int*>(ctag + p.cand_cap);                  // [cand_cap] corpus rows
-    int* seg_n = cand + p.cand_cap;                                         // [nseg]
+    int* cand = reinterpret_cast<int*>(ckey + p.cand_cap);                  // [cand_cap] corpus rows = the sort tags
+    int* seg_n = cand + p.cand_cap;                                         // [nseg]   (12 B per candidate)
     __shared__ RadixSel rs;
     __shared__ int s_m, s_bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -716,7 +715,7 @@ __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParam
     while (P2 < m) P2 <<= 1;
     for (int r0 = warp * XS_ROWS; r0 < P2; r0 += XS_WARPS * XS_ROWS) {
         if (r0 >= m) {
-            if (lane < XS_ROWS && r0 + lane < P2) { ckey[r0 + lane] = pos_inf(); ctag[r0 + lane] = 0x7fffffffffffffffLL; }
+            if (lane < XS_ROWS && r0 + lane < P2) { ckey[r0 + lane] = pos_inf(); cand[r0 + lane] = 0x7fffffff; }
             continue;
         }
         const float* rp[XS_ROWS];
@@ -727,23 +726,23 @@ __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParam
         }
         double nd2;
         const double tot = xs_score4<VEC>(rp, qs, D, l2, lane, nd2);
+        __syncwarp();                                                       // every lane has read its cand[] entries
         if ((lane & 7) == 0) {
             const int i = lane >> 3, r = r0 + i;
             if (r < m) {
-                ckey[r] = xs_key(p.metric, tot, nd2, nq2);
-                ctag[r] = p.id_base + cand[r];
+                ckey[r] = xs_key(p.metric, tot, nd2, nq2);                  // the tag stays the row: id = id_base + row
             } else if (r < P2) {
                 ckey[r] = pos_inf();
-                ctag[r] = 0x7fffffffffffffffLL;
+                cand[r] = 0x7fffffff;
             }
         }
     }
     __syncthreads();
-    bitonic_sort_kt<double, long long>(ckey, ctag, P2);
+    bitonic_sort_kt<double, int>(ckey, cand, P2);
     for (int i = tid; i < k; i += XS_THREADS) {
         double kv = pos_inf();
         long long tv = 0x7fffffffffffffffLL;
-        if (i < m) { kv = ckey[i]; tv = ctag[i]; }
+        if (i < m && cand[i] != 0x7fffffff) { kv = ckey[i]; tv = p.id_base + cand[i]; }
         if (tv == 0x7fffffffffffffffLL) { tv = -1; kv = l2 ? pos_inf() : -pos_inf(); }
         else if (!l2) kv = -kv;
         p.out_scores[(size_t)q * k + i] = kv;
@@ -842,11 +841,18 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPl
     const int sample_i = (int)sample;
     pl->nsample_tiles = (pl->ntiles + sample_i - 1) / sample_i;
     pl->nbuckets = pl->nsample_tiles * (TC_BN / TC_BUCKET);
+    // rescoring candidates per query: k + the 2-eps margin; a shard of a G-way search expects (k + margin) / G of
+    // them, so its lists (and the shared memory that bounds the resident CTAs) are sized for 4x that share -- a
+    // shard that holds more flags the query (status) and the caller reruns it exactly
     int cand_cap = next_pow2(2 * (int64_t)k + 512);
+    if (shards > 1) {
+        const int share = next_pow2(4 * (int64_t)k / shards + 512);
+        if (share < cand_cap) cand_cap = share;
+    }
     if (cand_cap > TC_MAX_CAND) cand_cap = TC_MAX_CAND;
     pl->cand_cap = cand_cap;
     const int Dpad = (D + 3) & ~3;
-    pl->smem_final = (size_t)(Dpad + XS_WARPS) * 8 + (size_t)cand_cap * 20 + TC_MAX_SEGS * 4;
+    pl->smem_final = (size_t)(Dpad + XS_WARPS) * 8 + (size_t)cand_cap * 12 + TC_MAX_SEGS * 4;
     QRAG_REQUIRE(pl->smem_final <= budget, QRAG_ERR_UNSUPPORTED, "D=%d too large for the rescoring stage", D);
     size_t off = 0;
     pl->off_qb = off; off = align_up(off + (size_t)pl->nq_pad * pl->Kp * 2, 256);

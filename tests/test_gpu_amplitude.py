@@ -227,6 +227,44 @@ def test_config2_full_size_properties(cuda):
     assert np.allclose(full[rows].cpu().numpy(), want, rtol=REL)
 
 
+def test_config5_full_size_properties(cuda):
+    """BASELINE config 5 (4096 queries x 1000 candidates x 1024-d, 10 qubits, 4 feature-map layers): 4.1M scores,
+    candidates named by ids into a resident corpus (the dense form would be 16.8 GB), size-independent properties."""
+    import torch
+    from quantum_rag_b200 import api
+    g = torch.Generator(device="cuda").manual_seed(1234 + 5)
+    nq, C, D, N, L = 4096, 1000, 1024, 50_000, 4
+    X = torch.randn(N, D, generator=g, device="cuda")
+    qrow = torch.randint(0, N, (nq,), generator=g, device="cuda")
+    Q = X[qrow].clone()                                      # every query is a corpus row
+    idx = torch.randint(0, N, (nq, C), generator=g, device="cuda")
+    idx[:, 17] = qrow                                        # planted self-match
+    idx[:, 900] = idx[:, 3]                                  # planted duplicate
+    idx[5, 10] = -1                                          # padding id
+    F = api.amp_fidelity(Q, X=X, idx=idx, n_qubits=10, layers=L)
+    assert F.shape == (nq, C)
+    assert torch.allclose(F[:, 17], torch.ones(nq, dtype=torch.float64, device="cuda"), atol=1e-12)   # |<psi|psi>|^2 = 1
+    assert torch.equal(F[:, 900], F[:, 3])                   # same row -> bit-identical score
+    assert float(F[5, 10]) == float("-inf")
+    fin = F[torch.isfinite(F)]
+    assert float(fin.min()) >= 0.0 and float(fin.max()) <= 1.0 + 1e-12
+    # symmetry: F(q, d) = F(d, q), evaluated by swapping the roles for one column
+    d_rows = idx[:, 1]
+    Fsw = api.amp_fidelity(X[d_rows].contiguous(), X=X, idx=qrow[:, None].contiguous(), n_qubits=10, layers=L)
+    assert torch.allclose(Fsw[:, 0], F[:, 1], rtol=1e-10, atol=1e-18)
+    # scale invariance of state preparation and angles (power-of-two scaling is exact in fp32)
+    F2 = api.amp_fidelity(Q[:64] * 8.0, X=X * 0.25, idx=idx[:64], n_qubits=10, layers=L)
+    assert torch.allclose(F2[torch.isfinite(F2)], F[:64][torch.isfinite(F[:64])], rtol=1e-10, atol=1e-18)
+    # rerank of the full lists: sorted, stable, the self-match first
+    scores, pos, ids = api.quantum_rerank_batch(Q, X=X, idx=idx, top_k=10, n_qubits=10, layers=L)
+    assert torch.all(pos[:, 0] <= 17) and torch.all(ids[:, 0] == qrow)      # (a random id may name the same row earlier)
+    assert torch.all(scores[:, :-1] >= scores[:, 1:])
+    # spot checks against the oracle
+    for i, j in ((0, 0), (2048, 999), (4095, 500)):
+        want = oq.feature_map_fidelity(Q[i].cpu().numpy(), X[idx[i, j]].cpu().numpy(), 10, L)
+        assert float(F[i, j]) == pytest.approx(want, rel=1e-10, abs=1e-16)
+
+
 def test_overlap_policies_give_identical_results_back_to_back(cuda):
     """Programmatic dependent launch: consecutive launches on one stream overlap, results must not change."""
     import torch
