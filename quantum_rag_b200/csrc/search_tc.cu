@@ -501,6 +501,24 @@ __device__ __forceinline__ float sortable2f(uint32_t u) {
 
 struct RadixSel { int hist[256]; uint32_t prefix; int remaining; int count; };     // lives in shared memory
 
+// f(load(j)) for j = start, start + stride, ... < n, with U independent loads in flight per thread
+// (one load at a time makes the select kernels latency-bound: ncu showed 28 % of the samples on the
+// first use of each loaded value).
+template <int U, class Load, class F>
+__device__ __forceinline__ void for_strided(int start, int n, int stride, Load load, F f) {
+    for (int i = start; i < n; i += U * stride) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = i + u * stride;
+            v[u] = j < n ? load(j) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < n) f(v[u]);
+    }
+}
+
 // k-th largest (1-based) of the values `for_each` enumerates (each thread its own part; the
 // enumeration must be repeatable and hold at least k values).  Radix select, 4 x 8 bits.
 template <class ForEach>
@@ -517,14 +535,38 @@ __device__ float block_kth_largest(RadixSel& rs, int k, ForEach for_each) {
             if ((u & mask) == prefix) atomicAdd(&rs.hist[(u >> (8 * pass)) & 255u], 1);
         });
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int remaining = rs.remaining, d = 255;
-            for (; d > 0; --d) {
-                if (rs.hist[d] >= remaining) break;
-                remaining -= rs.hist[d];
+        if (threadIdx.x < 32) {
+            // warp 0: the bin d (from the top) where the running count reaches `remaining`.  Lane l owns bins
+            // 255-8l .. 248-8l; an exclusive scan over lanes gives the count above each lane's bins.
+            const int lane = threadIdx.x;
+            int h[8], mine = 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { h[u] = rs.hist[255 - 8 * lane - u]; mine += h[u]; }
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL_MASK, incl, o);
+                if (lane >= o) incl += t;
             }
-            rs.remaining = remaining;
-            rs.prefix = prefix | ((uint32_t)d << (8 * pass));
+            const int remaining = rs.remaining;
+            const int above = incl - mine;
+            const bool here = above < remaining && incl >= remaining;        // exactly one lane (total >= remaining)
+            const unsigned who = __ballot_sync(FULL_MASK, here);
+            const int total = __shfl_sync(FULL_MASK, incl, 31);
+            if (who == 0) {                                                  // fewer than `remaining` values: bin 0
+                if (lane == 0) { rs.remaining = remaining - (total - rs.hist[0]); rs.prefix = prefix; }
+            } else if (here) {
+                int rem = remaining - above, d = 255 - 8 * lane;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (h[u] >= rem) break;
+                    rem -= h[u];
+                    --d;
+                }
+                if (d < 255 - 8 * lane - 7) d = 255 - 8 * lane - 7;
+                rs.remaining = rem;
+                rs.prefix = prefix | ((uint32_t)d << (8 * pass));
+            }
         }
         __syncthreads();
     }
@@ -541,7 +583,12 @@ __device__ void block_topk_values(RadixSel& rs, int k, int total, ForEach for_ea
     const bool all = total < k;
     for_each([&](float v) {
         if (all || v > t) {
-            const int pos = atomicAdd(&rs.count, 1);
+            const unsigned am = __activemask();                 // one atomic per converged group
+            const int lane = threadIdx.x & 31, leader = __ffs(am) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&rs.count, __popc(am));
+            base = __shfl_sync(am, base, leader);
+            const int pos = base + __popc(am & ((1u << lane) - 1u));
             if (pos < k) out[pos] = v;
         }
     });
@@ -555,7 +602,7 @@ __global__ void __launch_bounds__(256) bucket_topk_kernel(const float* __restric
     __shared__ RadixSel rs;
     const int q = blockIdx.x;
     const float* row = bmax + (size_t)q * nbuckets;
-    auto fe = [&](auto f) { for (int i = threadIdx.x; i < nbuckets; i += blockDim.x) f(row[i]); };
+    auto fe = [&](auto f) { for_strided<8>(threadIdx.x, nbuckets, blockDim.x, [&](int j) { return row[j]; }, f); };
     block_topk_values(rs, k, nbuckets, fe, bm_top + (size_t)q * k);
 }
 
@@ -570,12 +617,15 @@ __global__ void __launch_bounds__(256) tau_union_kernel(const float* __restrict_
     float mk = neg_inf_f();
     if (bm_top_all != nullptr) {
         auto fe = [&](auto f) {
-            for (int i = threadIdx.x; i < G * k; i += blockDim.x) f(bm_top_all[((size_t)(i / k) * nq + q) * k + (i % k)]);
+            for (int g = 0; g < G; ++g) {
+                const float* row = bm_top_all + ((size_t)g * nq + q) * k;
+                for_strided<4>(threadIdx.x, k, blockDim.x, [&](int j) { return row[j]; }, f);
+            }
         };
         mk = block_kth_largest(rs, k, fe);
     } else if (nbuckets >= k) {
         const float* row = bmax + (size_t)q * nbuckets;
-        auto fe = [&](auto f) { for (int i = threadIdx.x; i < nbuckets; i += blockDim.x) f(row[i]); };
+        auto fe = [&](auto f) { for_strided<8>(threadIdx.x, nbuckets, blockDim.x, [&](int j) { return row[j]; }, f); };
         mk = block_kth_largest(rs, k, fe);
     }
     if (threadIdx.x == 0) {
@@ -609,7 +659,7 @@ __global__ void __launch_bounds__(256) surv_topk_kernel(const unsigned int* __re
     auto fe = [&](auto f) {
         for (int sgi = warp; sgi < nseg; sgi += nwarps) {
             const float2* sp = sv + (size_t)sgi * seg_cap;
-            for (int i = lane; i < seg_n[sgi]; i += 32) f(sp[i].x);
+            for_strided<4>(lane, seg_n[sgi], 32, [&](int j) { return sp[j].x; }, f);
         }
     };
     block_topk_values(rs, k, s_n, fe, ap_top + (size_t)q * k);
@@ -671,7 +721,10 @@ __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParam
     float ak = neg_inf_f();
     if (p.ap_top_all != nullptr) {
         auto fe = [&](auto f) {
-            for (int i = tid; i < p.G * k; i += XS_THREADS) f(p.ap_top_all[((size_t)(i / k) * p.nq + q) * k + (i % k)]);
+            for (int g = 0; g < p.G; ++g) {
+                const float* row = p.ap_top_all + ((size_t)g * p.nq + q) * k;
+                for_strided<4>(tid, k, XS_THREADS, [&](int j) { return row[j]; }, f);
+            }
         };
         ak = block_kth_largest(rs, k, fe);                                  // starts and ends with __syncthreads()
     } else {
@@ -687,7 +740,7 @@ __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParam
             auto fe = [&](auto f) {
                 for (int sgi = warp; sgi < p.nseg; sgi += XS_WARPS) {
                     const float2* sp = sv + (size_t)sgi * p.seg_cap;
-                    for (int i = lane; i < seg_n[sgi]; i += 32) f(sp[i].x);
+                    for_strided<4>(lane, seg_n[sgi], 32, [&](int j) { return sp[j].x; }, f);
                 }
             };
             ak = block_kth_largest(rs, k, fe);
@@ -702,7 +755,12 @@ __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParam
         for (int i = lane; i < seg_n[sgi]; i += 32) {
             const float2 e = sp[i];
             if (e.x >= thr) {
-                const int pos = atomicAdd(&s_m, 1);
+                const unsigned am = __activemask();             // one atomic per converged group
+                const int leader = __ffs(am) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(&s_m, __popc(am));
+                base = __shfl_sync(am, base, leader);
+                const int pos = base + __popc(am & ((1u << lane) - 1u));
                 if (pos < p.cand_cap) cand[pos] = __float_as_int(e.y);
             }
         }
