@@ -752,9 +752,15 @@ __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParam
     // candidates (any order: the final sort is a total order on (score, id))
     for (int sgi = warp; sgi < p.nseg; sgi += XS_WARPS) {
         const float2* sp = sv + (size_t)sgi * p.seg_cap;
-        for (int i = lane; i < seg_n[sgi]; i += 32) {
-            const float2 e = sp[i];
-            if (e.x >= thr) {
+        const int sn = seg_n[sgi];
+        for (int i0 = lane; i0 < sn; i0 += 128) {
+          float2 ev[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) ev[u] = (i0 + 32 * u < sn) ? sp[i0 + 32 * u] : make_float2(neg_inf_f(), 0.f);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 e = ev[u];
+            if (i0 + 32 * u < sn && e.x >= thr) {
                 const unsigned am = __activemask();             // one atomic per converged group
                 const int leader = __ffs(am) - 1;
                 int base = 0;
@@ -763,6 +769,7 @@ __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParam
                 const int pos = base + __popc(am & ((1u << lane) - 1u));
                 if (pos < p.cand_cap) cand[pos] = __float_as_int(e.y);
             }
+          }
         }
     }
     const double nq2 = xs_stage_query(p.Q + (size_t)q * D, D, qs, red);     // ends with __syncthreads()
