@@ -332,31 +332,32 @@ __global__ void __launch_bounds__(MAXT, 1) fmap_warp_kernel(const FmapWarpParams
         const int64_t c0 = (u % p.chunks_per_q) * p.chunk;
         int64_t cnt = p.C - c0;
         if (cnt > p.chunk) cnt = p.chunk;
-        bool first = true;
-        for (int64_t t = warp; t <= cnt; t += W) {
+        // every warp runs every round (uniform trip count).  Starting each round with a barrier, so that the warps
+        // stream the same straight-line code together and share instruction fetches, was measured: no gain.
+        for (int64_t t = warp; t - warp <= cnt; t += W) {
+            const bool active = t <= cnt;
             const int64_t j = qi * p.C + c0 + (t - 1);
-            const float* row;
-            bool missing = false;
-            if (t == 0) {
-                row = p.Q + qi * p.D;
-            } else if (p.cand) {
-                row = p.cand + (size_t)j * p.D;
-            } else {
-                const int64_t id = p.idx[j];
-                missing = id < 0;
-                row = p.X + (size_t)(missing ? 0 : id) * p.D;
-            }
-            const bool zero = fw_evolve(row, p.D, p.layers, a, st, gates, tn, tab);
-            if (t == 0) {
+            const float* row = nullptr;
+            bool missing = false, zero = false;
+            if (active) {
+                if (t == 0) {
+                    row = p.Q + qi * p.D;
+                } else if (p.cand) {
+                    row = p.cand + (size_t)j * p.D;
+                } else {
+                    const int64_t id = p.idx[j];
+                    missing = id < 0;
+                    row = p.X + (size_t)(missing ? 0 : id) * p.D;
+                }
+                zero = fw_evolve(row, p.D, p.layers, a, st, gates, tn, tab);
+                if (t == 0) {
 #pragma unroll
-                for (int k = 0; k < 32; ++k) qstate[k * 33 + lane] = a[k];
-                if (lane == 0) q_zero = zero;
+                    for (int k = 0; k < 32; ++k) qstate[k * 33 + lane] = a[k];
+                    if (lane == 0) q_zero = zero;
+                }
             }
-            if (first) {
-                __syncthreads();                             // query state of this unit is in place
-                first = false;
-            }
-            if (t > 0) {
+            if (t == warp) __syncthreads();                  // round 0: the query state of this unit is in place
+            if (active && t > 0) {
                 double re = 0.0, im = 0.0;                   // <psi_d | psi_q> = sum conj(d) q
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
@@ -375,7 +376,6 @@ __global__ void __launch_bounds__(MAXT, 1) fmap_warp_kernel(const FmapWarpParams
                 }
             }
         }
-        if (first) __syncthreads();                          // warps without an item still join the barrier
         __syncthreads();                                     // everyone is done with qstate before the next unit
     }
 }
