@@ -7,6 +7,7 @@ Layout
     reranker/    drop-in for the reference's src/reranker classes
     index.py     faiss IndexFlat (IxF2 / IxFI) reader, writer and searchable wrapper
     sharded.py   row-sharded search + rerank over torch.distributed
+    service.py   search -> select -> rerank service and the HTTP routes (/rerank, /search_rerank)
 """
 from . import _lib  # noqa: F401
 

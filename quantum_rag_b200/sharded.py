@@ -260,3 +260,28 @@ class ShardedSearchRerank:
         ss, si = self.search(Q, k1)
         top, ids = self.rerank(Q, si, min(k2, k1))
         return ShardedResult(top, ids, ss, si)
+
+
+_PATHS: dict = {}
+
+
+def sharded_search_rerank(q, X_shard, k1: int = 1000, k2: int = 10, group: Optional[dist.ProcessGroup] = None,
+                          metric: str = "cosine", n_total: Optional[int] = None) -> ShardedResult:
+    """Functional form named in SURVEY.md section 8b: ``sharded_search_rerank(q, X_shard, k1, k2, group)``.
+
+    The prepared shard (bf16 shadow, corpus bound) is cached per (shard tensor, metric, group), so repeated calls pay
+    only for the search.  ``n_total`` defaults to the sum of the shard sizes over the group (one small all-reduce on the
+    first call); shards must follow ``shard_bounds`` (contiguous, balanced).
+    """
+    key = (X_shard.data_ptr(), tuple(X_shard.shape), metric, id(group))
+    path = _PATHS.get(key)
+    if path is None:
+        if n_total is None:
+            n = torch.tensor([X_shard.shape[0]], dtype=torch.int64, device=X_shard.device)
+            if dist.is_initialized() and dist.get_world_size(group) > 1:
+                dist.all_reduce(n, group=group)
+            n_total = int(n[0])
+        path = ShardedSearchRerank(X_shard, n_total, metric, group)
+        _PATHS.clear()                      # one resident shard per process: do not pin stale corpora
+        _PATHS[key] = path
+    return path(q, k1, k2)

@@ -74,3 +74,19 @@ def test_sharded_path_matches_oracle_and_single_shard(cuda, metric):
         top, ids, ss, si = _emulated(Xd, Qd, G, k1, k2, metric, phased)
         assert torch.equal(si, res.search_ids) and torch.equal(ss, res.search_scores), f"G={G} phased={phased}"
         assert torch.equal(ids, res.ids) and torch.equal(top, res.scores), f"G={G} phased={phased}"
+
+
+def test_functional_form_and_cache(cuda):
+    """``sharded_search_rerank(q, X_shard, k1, k2, group)`` = the class, shard prepared once."""
+    import torch
+    from quantum_rag_b200 import sharded
+    rng = np.random.RandomState(9)
+    X = torch.from_numpy(rng.standard_normal((5000, 384)).astype(np.float32)).cuda()
+    Q = torch.from_numpy(rng.standard_normal((5, 384)).astype(np.float32)).cuda()
+    a = sharded.sharded_search_rerank(Q, X, k1=50, k2=7)
+    path = next(iter(sharded._PATHS.values()))
+    b = sharded.sharded_search_rerank(Q, X, k1=50, k2=7)
+    assert next(iter(sharded._PATHS.values())) is path and len(sharded._PATHS) == 1
+    ref = sharded.ShardedSearchRerank(X, 5000, "cosine")(Q, 50, 7)
+    for r in (a, b):
+        assert torch.equal(r.ids, ref.ids) and torch.equal(r.scores, ref.scores)
