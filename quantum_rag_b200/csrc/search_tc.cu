@@ -530,10 +530,24 @@ __device__ float block_kth_largest(RadixSel& rs, int k, ForEach for_each) {
         __syncthreads();
         const uint32_t prefix = rs.prefix;
         const uint32_t mask = pass == 3 ? 0u : (0xffffffffu << (8 * (pass + 1)));
+        // scores cluster (same sign and exponent): in the upper passes nearly every value falls into one bin and
+        // per-value atomics on one shared address serialise.  Each thread run-length-merges its consecutive values.
+        uint32_t last_bin = 0xffffffffu;
+        int run = 0;
         for_each([&](float v) {
             const uint32_t u = f2sortable(v);
-            if ((u & mask) == prefix) atomicAdd(&rs.hist[(u >> (8 * pass)) & 255u], 1);
+            if ((u & mask) == prefix) {
+                const uint32_t bin = (u >> (8 * pass)) & 255u;
+                if (bin == last_bin) {
+                    ++run;
+                } else {
+                    if (run) atomicAdd(&rs.hist[last_bin], run);
+                    last_bin = bin;
+                    run = 1;
+                }
+            }
         });
+        if (run) atomicAdd(&rs.hist[last_bin], run);
         __syncthreads();
         if (threadIdx.x < 32) {
             // warp 0: the bin d (from the top) where the running count reaches `remaining`.  Lane l owns bins
