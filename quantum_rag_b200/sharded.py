@@ -274,7 +274,10 @@ def sharded_search_rerank(q, X_shard, k1: int = 1000, k2: int = 10, group: Optio
     first call); shards must follow ``shard_bounds`` (contiguous, balanced).
     """
     key = (X_shard.data_ptr(), tuple(X_shard.shape), metric, id(group))
-    path = _PATHS.get(key)
+    hit = _PATHS.get(key)
+    # the cache entry keeps the shard tensor alive, so a matching pointer means the same storage; rows modified in
+    # place after the first call need a fresh ShardedSearchRerank (the bf16 shadow is built once)
+    path = hit[1] if hit is not None and hit[0] is X_shard else None
     if path is None:
         if n_total is None:
             n = torch.tensor([X_shard.shape[0]], dtype=torch.int64, device=X_shard.device)
@@ -283,5 +286,5 @@ def sharded_search_rerank(q, X_shard, k1: int = 1000, k2: int = 10, group: Optio
             n_total = int(n[0])
         path = ShardedSearchRerank(X_shard, n_total, metric, group)
         _PATHS.clear()                      # one resident shard per process: do not pin stale corpora
-        _PATHS[key] = path
+        _PATHS[key] = (X_shard, path)
     return path(q, k1, k2)

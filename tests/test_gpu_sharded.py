@@ -84,9 +84,9 @@ def test_functional_form_and_cache(cuda):
     X = torch.from_numpy(rng.standard_normal((5000, 384)).astype(np.float32)).cuda()
     Q = torch.from_numpy(rng.standard_normal((5, 384)).astype(np.float32)).cuda()
     a = sharded.sharded_search_rerank(Q, X, k1=50, k2=7)
-    path = next(iter(sharded._PATHS.values()))
+    path = next(iter(sharded._PATHS.values()))[1]
     b = sharded.sharded_search_rerank(Q, X, k1=50, k2=7)
-    assert next(iter(sharded._PATHS.values())) is path and len(sharded._PATHS) == 1
+    assert next(iter(sharded._PATHS.values()))[1] is path and len(sharded._PATHS) == 1
     ref = sharded.ShardedSearchRerank(X, 5000, "cosine")(Q, 50, 7)
     for r in (a, b):
         assert torch.equal(r.ids, ref.ids) and torch.equal(r.scores, ref.scores)
