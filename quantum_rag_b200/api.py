@@ -163,6 +163,12 @@ def sort_scores(scores: ArrayLike, top_k: Optional[int] = None, descending: bool
         s = s[None, :]
     nq, C = s.shape
     k = C if top_k is None else max(0, min(int(top_k), C))
+    if C > MAX_SORT_LEN:
+        # Longer than the in-kernel sort accepts (no BASELINE config is: the longest list is k1 = 1000).  The
+        # reference sorts any length (quantum.py:70-72), so the drop-in must not fail: order on the device with the
+        # library's stable sort -- same (score, position) order, still no host round trip.
+        srt, perm = torch.sort(s, dim=1, descending=descending, stable=True)
+        return perm[:, :k].to(torch.int32).contiguous(), srt[:, :k].contiguous()
     perm = torch.empty((nq, k), dtype=torch.int32, device=s.device)
     srt = torch.empty((nq, k), dtype=torch.float64, device=s.device)
     lib = _lib.load()

@@ -52,6 +52,20 @@ def test_known_answers_through_the_class(cuda, kat):
     assert ab == ["ab", "ba"]                          # exact tie keeps input order
 
 
+def test_lists_longer_than_the_kernel_sort(cuda):
+    """5 000 documents (> QRAG_MAX_SORT_LEN): the reference sorts any length, so must the drop-in; ties stay stable."""
+    rnd = random.Random(5)
+    texts = _texts(rnd, 4997) + ["ab", "ba", "ab"]
+    rnd.shuffle(texts)
+    docs = [Document(str(i), t) for i, t in enumerate(texts)]
+    rr = QuantumReranker()
+    for top_k in (None, 7):
+        got = rr.rerank("which ad is this", docs, top_k)
+        want = oq.quantum_rerank_strings("which ad is this", texts, top_k, 4)
+        assert [int(d.id) for d, _ in got] == [i for i, _ in want]
+        assert np.allclose([s for _, s in got], [s for _, s in want], rtol=1e-12, atol=0)
+
+
 def test_other_method_gives_half_in_input_order(cuda):
     rr = QuantumReranker({"method": "swap_test"})
     docs = [Document(str(i), t) for i, t in enumerate(["x", "y", "z"])]
