@@ -170,11 +170,24 @@ class ClassicalReranker:
     def _score_embeddings(self, query: str, documents: List[Document]) -> List[Tuple[Document, float]]:
         """Whole list scored and ordered on the GPU: (score desc, input position asc)."""
         from .. import api
+        import torch
         q, x = self._embeddings(query, documents)
-        scores, ids = api.search_topk(q, x, k=len(documents), metric=self.method)
-        scores = scores[0].cpu().tolist()
-        ids = ids[0].cpu().tolist()
         sign = -1.0 if self.method == "l2" else 1.0        # higher is better for every method
+        n, kmax = len(documents), 2048                     # the exact search returns at most 2048 per call
+        if n <= kmax:
+            scores, ids = api.search_topk(q, x, k=n, metric=self.method)
+            scores, ids = scores[0], ids[0]
+        else:
+            # longer lists: every chunk scored completely, scores scattered back to input order, one stable sort
+            full = torch.empty(n, dtype=torch.float64, device=api._device())
+            for lo in range(0, n, kmax):
+                hi = min(n, lo + kmax)
+                s, i = api.search_topk(q, x[lo:hi], k=hi - lo, metric=self.method)
+                full[lo + i[0]] = sign * s[0]
+            perm, srt = api.sort_scores(full[None, :], None, descending=True)
+            scores, ids = sign * srt[0], perm[0]
+        scores = scores.cpu().tolist()
+        ids = ids.cpu().tolist()
         return [(documents[i], sign * s) for s, i in zip(scores, ids)]
 
     # ----------------------------------------------------------------- rerank

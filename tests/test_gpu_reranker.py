@@ -126,3 +126,24 @@ def test_classical_embedding_methods(cuda, method, mid):
     docs_m = [Document(str(i), f"doc {i}", metadata={"embedding": emb[i]}) for i in range(30)]
     rr2 = ClassicalReranker({"method": method, "query_embedding": qv})
     assert [docs_m.index(d) for d, _ in rr2.rerank("the query", docs_m, 12)] == i[0].tolist()
+
+
+@pytest.mark.parametrize("method,mid", [("cosine", osr.METRIC_COSINE), ("l2", osr.METRIC_L2)])
+def test_classical_embedding_methods_long_list(cuda, method, mid):
+    """More documents than one exact-search call returns (2048): chunked scoring, one stable sort."""
+    rng = np.random.RandomState(8)
+    n = 5000
+    emb = rng.standard_normal((n, 32)).astype(np.float32)
+    emb[4100] = emb[17]                                                          # tie across chunks
+    qv = rng.standard_normal(32).astype(np.float32)
+    docs = [Document(str(i), f"d{i}", metadata={"embedding": emb[i]}) for i in range(n)]
+    rr = ClassicalReranker({"method": method, "query_embedding": qv})
+    got = rr.rerank("q", docs, top_k=None)
+    assert len(got) == n
+    order = [int(d.id) for d, _ in got]
+    sc = np.array([v for _, v in got])
+    assert np.all(sc[:-1] >= sc[1:]) and sorted(order) == list(range(n))
+    assert order.index(17) + 1 == order.index(4100)                              # equal scores keep input order
+    s, i = osr.exact_search(qv[None], emb, 100, mid)
+    sign = -1.0 if method == "l2" else 1.0
+    assert order[:100] == i[0].tolist() and np.allclose(sc[:100], sign * s[0], rtol=1e-12, atol=1e-13)
