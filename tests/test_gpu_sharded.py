@@ -90,3 +90,32 @@ def test_functional_form_and_cache(cuda):
     ref = sharded.ShardedSearchRerank(X, 5000, "cosine")(Q, 50, 7)
     for r in (a, b):
         assert torch.equal(r.ids, ref.ids) and torch.equal(r.scores, ref.scores)
+
+
+def test_config4_full_size_properties(cuda):
+    """BASELINE config 4 at full corpus size (10M x 384, top-1000 -> rerank -> top-10), 128 queries: planted answers,
+    the exact CUDA-core search on a subset, and shard invariance (8 emulated shards == 1 shard, bit for bit)."""
+    import torch
+    from quantum_rag_b200 import api
+    from quantum_rag_b200.sharded import ShardedSearchRerank
+    N, D, nq, k1, k2 = 10_000_000, 384, 128, 1000, 10
+    X = torch.empty((N, D), dtype=torch.float32, device="cuda")
+    for b in range(0, N, 1 << 20):                               # generated in blocks: no 15 GB temporaries
+        g = torch.Generator(device="cuda").manual_seed(4000 + b)
+        n = min(1 << 20, N - b)
+        X[b:b + n] = torch.nn.functional.normalize(torch.randn(n, D, generator=g, device="cuda"), dim=1)
+    g = torch.Generator(device="cuda").manual_seed(1234 + 4)
+    Q = torch.nn.functional.normalize(torch.randn(nq, D, generator=g, device="cuda"), dim=1)
+    planted = torch.arange(nq, device="cuda") * 78_001 + 11      # spread over all eight shards
+    X[planted] = Q
+    res = ShardedSearchRerank(X, N, "cosine")(Q, k1, k2)
+    assert torch.equal(res.search_ids[:, 0], planted) and torch.equal(res.ids[:, 0], planted)
+    assert torch.allclose(res.scores[:, 0], torch.ones(nq, dtype=torch.float64, device="cuda"), atol=1e-12)
+    assert torch.all(res.search_scores[:, :-1] >= res.search_scores[:, 1:]) and torch.all(res.scores[:, :-1] >= res.scores[:, 1:])
+    assert all(len(set(row)) == k1 for row in res.search_ids[:4].cpu().tolist())          # no duplicates in a list
+    sub = torch.tensor([0, 63, 127], device="cuda")
+    es, ei = api.search_topk(Q[sub], X, k1, "cosine")
+    assert torch.equal(res.search_ids[sub], ei) and torch.equal(res.search_scores[sub], es)
+    top, ids, ss, si = _emulated(X, Q, 8, k1, k2, "cosine", True)
+    assert torch.equal(si, res.search_ids) and torch.equal(ss, res.search_scores)
+    assert torch.equal(ids, res.ids) and torch.equal(top, res.scores)
