@@ -165,7 +165,8 @@ int qrag_search_topk(const float* Q, int nq, const float* X, int64_t N, int D, i
 
 /* bf16 shadow of the corpus for one metric, built once per index (shard):
  *   Xb [N, Kp] bf16 with Kp from qrag_index_prepared_dims (IP: x; cosine: x/|x|;
- *   L2: [x, hi(|x|^2), lo(|x|^2)]), aux [4] floats (aux[0] = max |x|). */
+ *   L2: [x, hi(|x|^2), lo(|x|^2)]), aux [4] floats (aux[0] = max |x|, aux[1] = max over rows of
+ *   the measured bf16 rounding-error norm |b - bf16(b)|: the filter's error bound uses both). */
 int qrag_index_prepared_dims(int D, int metric, int* Kp);
 int qrag_index_prepare(const float* X, int64_t N, int D, int metric,
                        uint16_t* Xb, float* aux, void* stream);
@@ -183,7 +184,7 @@ int qrag_search_topk_tc(const float* Q, int nq, const float* X, const uint16_t* 
  *    qrag_search_topk_tc is the G = 1 composition)
  *   begin   bm_top [nq, k]: this shard's k largest sampled bucket maxima
  *   filter  bm_top_all [G, nq, k] (all-gathered) -> tau; ap_top [nq, k]: this shard's k best
- *           approximate scores.  aux[0] must hold the maximum |x| over ALL shards.
+ *           approximate scores.  aux[0] and aux[1] must hold their maxima over ALL shards.
  *   finish  ap_top_all [G, nq, k] (all-gathered) -> exact, sorted list of this shard's members of
  *           the global top-k (ids -1 padded); merge the G lists with qrag_topk_merge. */
 int qrag_search_tc_begin(const float* Q, int nq, const uint16_t* Xb, int64_t N, int D, int k, int metric,

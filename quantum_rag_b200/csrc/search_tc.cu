@@ -431,7 +431,8 @@ __global__ void __launch_bounds__(256) index_prepare_kernel(const float* __restr
     const double n2 = warp_sum(part);
     const double nrm = sqrt(n2);
     __nv_bfloat16* o = Xb + (size_t)row * Kp;
-    for (int j = lane; j < Kp; j += 32) {
+    double err2 = 0.0;                                           // |b - bf16(b)|^2 over the D data columns (exact: the
+    for (int j = lane; j < Kp; j += 32) {                        // difference of an fp32 and its bf16 rounding is an fp32)
         float v = 0.f;
         if (j < D) {
             v = x[j];
@@ -441,18 +442,23 @@ __global__ void __launch_bounds__(256) index_prepare_kernel(const float* __restr
             const float hi = __bfloat162float(__float2bfloat16_rn(n2f));
             v = (j == D) ? hi : (n2f - hi);
         }
-        o[j] = __float2bfloat16_rn(v);
+        const __nv_bfloat16 r = __float2bfloat16_rn(v);
+        o[j] = r;
+        if (j < D) { const double d = (double)(v - __bfloat162float(r)); err2 = fma(d, d, err2); }
     }
+    err2 = warp_sum(err2);
     if (lane == 0) {
         const float up = __double2float_ru(nrm);                 // max |x| (rounded up); floats >= 0 order like ints
         atomicMax(reinterpret_cast<int*>(aux), __float_as_int(up));
+        const float eup = __double2float_ru(sqrt(err2) * 1.000001);   // max over rows of the rounding-error norm
+        atomicMax(reinterpret_cast<int*>(aux) + 1, __float_as_int(eup));
     }
 }
 
 // one warp per query row: bf16 query operand for the metric, |q| rounded up
 __global__ void __launch_bounds__(256) query_prepare_kernel(const float* __restrict__ Q, int nq, int nq_pad, int D, int Kp,
                                                             int metric, __nv_bfloat16* __restrict__ Qb,
-                                                            float* __restrict__ qnorm) {
+                                                            float* __restrict__ qnorm, float* __restrict__ qerr) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= nq_pad) return;
@@ -462,12 +468,14 @@ __global__ void __launch_bounds__(256) query_prepare_kernel(const float* __restr
         return;
     }
     const float* x = Q + (size_t)row * D;
-    double part = 0.0;
+    double part = 0.0, err2 = 0.0;
     for (int j = lane; j < Kp; j += 32) {
         float v = 0.f;
         if (j < D) {
             v = x[j];
             part = fma((double)v, (double)v, part);
+            const double d = (double)(v - __bfloat162float(__float2bfloat16_rn(v)));    // q - bf16(q), exact
+            err2 = fma(d, d, err2);
             if (metric == QRAG_METRIC_L2) v *= 2.f;              // exact in bf16: bf16(2q) == 2 bf16(q)
         } else if (metric == QRAG_METRIC_L2 && j < D + 2) {
             v = -1.f;
@@ -475,18 +483,35 @@ __global__ void __launch_bounds__(256) query_prepare_kernel(const float* __restr
         o[j] = __float2bfloat16_rn(v);
     }
     part = warp_sum(part);
-    if (lane == 0) qnorm[row] = __double2float_ru(sqrt(part));
+    err2 = warp_sum(err2);
+    if (lane == 0) {
+        qnorm[row] = __double2float_ru(sqrt(part));
+        qerr[row] = __double2float_ru(sqrt(err2) * 1.000001);
+    }
 }
 
-// Bound on |approximate - exact| in the units of the approximate score, per unit of |q| (a) and
-// absolute (b): eps = a |q| + b.  bf16 rounding of both operands (2^-9 each, plus the cross term),
-// fp32 accumulation of Kp exact products inside the tensor core (Kp * 2^-22, generous), Cauchy-Schwarz.
-__device__ __forceinline__ float tc_eps(int metric, int Kp, float qn, float xmax) {
-    const float c = 0.00390625f + 0.0000153f + (float)Kp * 2.4e-7f;
+// Bound on |approximate - exact| in the units of the approximate score.  With a = the query operand, b = the
+// document operand, a~ = bf16(a), b~ = bf16(b):  a~.b~ - a.b = (a~ - a).b~ + a.(b~ - b), so by Cauchy-Schwarz
+//     |a~.b~ - a.b| <= |a~ - a| |b~| + |a| |b~ - b|.
+// The rounding-error norms are MEASURED, not assumed: qe = |q - bf16(q)| per query (query_prepare_kernel), xe = the
+// maximum over the corpus rows of |b - bf16(b)| (index_prepare_kernel, aux[1]; reduced over shards like aux[0]).
+// A worst-case constant would be 2^-8 per operand (bf16 keeps 8 significant bits), twice what random data shows
+// (~1.65e-3 |x|), and 2^-9 -- what this bound assumed before -- is not a bound at all.  On top: fp32 accumulation of
+// Kp exact bf16 products inside the tensor core, Kp * 2^-22 of |a~||b~| (generous).
+__device__ __forceinline__ float tc_eps(int metric, int Kp, float qn, float qe, float xmax, float xe) {
+    const float g = (float)Kp * 2.4e-7f;
     float e;
-    if (metric == QRAG_METRIC_IP) e = c * qn * xmax;
-    else if (metric == QRAG_METRIC_COSINE) e = c * qn * 1.0000002f;
-    else e = 2.f * c * qn * xmax + 3.1e-5f * xmax * xmax;        // + hi/lo split of |x|^2 (2^-15, generous)
+    if (metric == QRAG_METRIC_IP) {
+        const float xt = xmax + xe;                              // |x~| <= |x| + |x~ - x|
+        e = qe * xt + qn * xe + g * (qn + qe) * xt;
+    } else if (metric == QRAG_METRIC_COSINE) {
+        const float xt = 1.0000002f + xe;                        // rows are normalised in fp32 before the rounding
+        e = qe * xt + qn * (xe + 2.4e-7f) + g * (qn + qe) * xt;
+    } else {
+        // s' = 2 q.x - |x|^2 with |x|^2 split into hi + lo (relative error 2^-15, generous) in two extra columns
+        const float xt = xmax + xe;
+        e = 2.f * (qe * xt + qn * xe) + 3.1e-5f * xmax * xmax + g * (2.f * (qn + qe) * xt + 1.01f * xmax * xmax);
+    }
     return e * 1.0001f + 1e-30f;
 }
 
@@ -623,7 +648,8 @@ __global__ void __launch_bounds__(256) bucket_topk_kernel(const float* __restric
 // per query: m_k = k-th largest bucket maximum over all G shards' lists; tau = m_k - 2 eps, rounded down
 // (single shard: bm_top_all == nullptr and the k-th largest is taken straight from this shard's bucket maxima)
 __global__ void __launch_bounds__(256) tau_union_kernel(const float* __restrict__ bm_top_all, int G, int nq, int k, int metric,
-                                                        int Kp, const float* __restrict__ qnorm, const float* __restrict__ aux,
+                                                        int Kp, const float* __restrict__ qnorm, const float* __restrict__ qerr,
+                                                        const float* __restrict__ aux,
                                                         const float* __restrict__ bmax, int nbuckets,
                                                         float* __restrict__ tau, float* __restrict__ eps) {
     __shared__ RadixSel rs;
@@ -643,7 +669,7 @@ __global__ void __launch_bounds__(256) tau_union_kernel(const float* __restrict_
         mk = block_kth_largest(rs, k, fe);
     }
     if (threadIdx.x == 0) {
-        const float e = tc_eps(metric, Kp, qnorm[q], aux[0]);
+        const float e = tc_eps(metric, Kp, qnorm[q], qerr[q], aux[0], aux[1]);
         eps[q] = e;
         float t = mk - 2.f * e;                                   // -inf stays -inf (fewer than k buckets)
         t = t - fabsf(t) * 2.4e-7f - 1e-37f;                      // the subtraction above rounds to nearest: step down
@@ -686,6 +712,7 @@ struct TcFinalParams {
     int G; const float* ap_top_all;          // [G, nq, k] the k best approximate scores of every shard
     const unsigned int* cnt; const float2* surv; const float* eps;
     double* out_scores; int64_t* out_ids; int32_t* status;
+    int* cand_rows; double* cand_key; int* cand_m;     // [nq, cand_cap], [nq, cand_cap], [nq, 2] (count, overflow)
 };
 
 template <typename K, typename T>
@@ -706,26 +733,22 @@ __device__ void bitonic_sort_kt(K* key, T* tag, int P) {
     }
 }
 
-// One CTA per query: a_k = k-th best approximate score over all shards (from their top-k lists),
-// candidates = this shard's survivors >= a_k - 2 eps, exact rescoring, sort by (score, id).
-template <bool VEC>
-__global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int D = p.D, Dpad = (D + 3) & ~3;
-    double* qs = reinterpret_cast<double*>(smem_raw);
-    double* red = qs + Dpad;
-    double* ckey = red + XS_WARPS;                                          // [cand_cap]
-    int* cand = reinterpret_cast<int*>(ckey + p.cand_cap);                  // [cand_cap] corpus rows = the sort tags
-    int* seg_n = cand + p.cand_cap;                                         // [nseg]   (12 B per candidate)
+// The final stage is three kernels, so that each runs at the occupancy its work allows (as one kernel, 55 KB of
+// shared memory and 78 registers held it to 3 CTAs per SM and its phases could not overlap: ncu, k = 1000).
+//
+// (1) one CTA per query: a_k = k-th best approximate score over all shards (from their top-k lists; single shard:
+// from this query's survivor segments), candidates = this shard's survivors >= a_k - 2 eps -> cand_rows, cand_m.
+__global__ void __launch_bounds__(XS_THREADS) tc_collect_kernel(const TcFinalParams p) {
     __shared__ RadixSel rs;
-    __shared__ int s_m, s_bad;
+    __shared__ int seg_n[TC_MAX_SEGS];
+    __shared__ int s_m, s_bad, s_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = p.q0 + blockIdx.x;
     const int k = p.k;
-    const bool l2 = p.metric == QRAG_METRIC_L2;
     const float2* sv = p.surv + (size_t)q * p.cap;
+    int* cand = p.cand_rows + (size_t)q * p.cand_cap;
 
-    if (tid == 0) { s_m = 0; s_bad = 0; }
+    if (tid == 0) { s_m = 0; s_bad = 0; s_total = 0; }
     __syncthreads();
     for (int sgi = tid; sgi < p.nseg; sgi += XS_THREADS) {
         const unsigned int c = p.cnt[(size_t)q * TC_MAX_SEGS + sgi];
@@ -742,9 +765,6 @@ __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParam
         };
         ak = block_kth_largest(rs, k, fe);                                  // starts and ends with __syncthreads()
     } else {
-        // single shard: the k-th best approximate score straight from this query's survivor segments
-        __shared__ int s_total;
-        if (tid == 0) s_total = 0;
         __syncthreads();
         int mine = 0;
         for (int sgi = tid; sgi < p.nseg; sgi += XS_THREADS) mine += seg_n[sgi];
@@ -768,66 +788,99 @@ __global__ void __launch_bounds__(XS_THREADS) tc_final_kernel(const TcFinalParam
         const float2* sp = sv + (size_t)sgi * p.seg_cap;
         const int sn = seg_n[sgi];
         for (int i0 = lane; i0 < sn; i0 += 128) {
-          float2 ev[4];
+            float2 ev[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) ev[u] = (i0 + 32 * u < sn) ? sp[i0 + 32 * u] : make_float2(neg_inf_f(), 0.f);
+            for (int u = 0; u < 4; ++u) ev[u] = (i0 + 32 * u < sn) ? sp[i0 + 32 * u] : make_float2(neg_inf_f(), 0.f);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float2 e = ev[u];
-            if (i0 + 32 * u < sn && e.x >= thr) {
-                const unsigned am = __activemask();             // one atomic per converged group
-                const int leader = __ffs(am) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(&s_m, __popc(am));
-                base = __shfl_sync(am, base, leader);
-                const int pos = base + __popc(am & ((1u << lane) - 1u));
-                if (pos < p.cand_cap) cand[pos] = __float_as_int(e.y);
-            }
-          }
-        }
-    }
-    const double nq2 = xs_stage_query(p.Q + (size_t)q * D, D, qs, red);     // ends with __syncthreads()
-    int m = s_m;
-    int bad = s_bad;
-    if (m > p.cand_cap) { m = p.cand_cap; bad = 1; }
-    int P2 = 1;
-    while (P2 < m) P2 <<= 1;
-    for (int r0 = warp * XS_ROWS; r0 < P2; r0 += XS_WARPS * XS_ROWS) {
-        if (r0 >= m) {
-            if (lane < XS_ROWS && r0 + lane < P2) { ckey[r0 + lane] = pos_inf(); cand[r0 + lane] = 0x7fffffff; }
-            continue;
-        }
-        const float* rp[XS_ROWS];
-#pragma unroll
-        for (int i = 0; i < XS_ROWS; ++i) {
-            const int r = (r0 + i < m) ? r0 + i : r0;
-            rp[i] = p.X + (size_t)cand[r] * D;
-        }
-        double nd2;
-        const double tot = xs_score4<VEC>(rp, qs, D, l2, lane, nd2);
-        __syncwarp();                                                       // every lane has read its cand[] entries
-        if ((lane & 7) == 0) {
-            const int i = lane >> 3, r = r0 + i;
-            if (r < m) {
-                ckey[r] = xs_key(p.metric, tot, nd2, nq2);                  // the tag stays the row: id = id_base + row
-            } else if (r < P2) {
-                ckey[r] = pos_inf();
-                cand[r] = 0x7fffffff;
+            for (int u = 0; u < 4; ++u) {
+                const float2 e = ev[u];
+                if (i0 + 32 * u < sn && e.x >= thr) {
+                    const unsigned am = __activemask();             // one atomic per converged group
+                    const int leader = __ffs(am) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(&s_m, __popc(am));
+                    base = __shfl_sync(am, base, leader);
+                    const int pos = base + __popc(am & ((1u << lane) - 1u));
+                    if (pos < p.cand_cap) cand[pos] = __float_as_int(e.y);
+                }
             }
         }
     }
     __syncthreads();
-    bitonic_sort_kt<double, int>(ckey, cand, P2);
+    if (tid == 0) {
+        int m = s_m, bad = s_bad;
+        if (m > p.cand_cap) { m = p.cand_cap; bad = 1; }
+        p.cand_m[2 * q] = m;
+        p.cand_m[2 * q + 1] = bad;
+    }
+}
+
+// (2) exact rescoring, grid (queries, chunks of XS_RESCORE_ROWS candidates): small CTAs, many resident, so the row
+// gathers run at memory-level parallelism instead of behind one CTA's select and sort.  Same device code as the
+// CUDA-core search (exact_score.cuh): a row's key does not depend on which kernel or batch scored it.
+constexpr int XS_RESCORE_ROWS = 256;
+template <bool VEC>
+__global__ void __launch_bounds__(XS_THREADS) tc_rescore_kernel(const TcFinalParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int q = p.q0 + blockIdx.x;
+    const int m = p.cand_m[2 * q];
+    const int c0 = blockIdx.y * XS_RESCORE_ROWS;
+    if (c0 >= m) return;
+    const int D = p.D, Dpad = (D + 3) & ~3;
+    double* qs = reinterpret_cast<double*>(smem_raw);
+    double* red = qs + Dpad;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool l2 = p.metric == QRAG_METRIC_L2;
+    const int* cand = p.cand_rows + (size_t)q * p.cand_cap;
+    double* ckey = p.cand_key + (size_t)q * p.cand_cap;
+    const double nq2 = xs_stage_query(p.Q + (size_t)q * D, D, qs, red);     // ends with __syncthreads()
+    const int c1 = (c0 + XS_RESCORE_ROWS < m) ? c0 + XS_RESCORE_ROWS : m;
+    for (int r0 = c0 + warp * XS_ROWS; r0 < c1; r0 += XS_WARPS * XS_ROWS) {
+        const float* rp[XS_ROWS];
+#pragma unroll
+        for (int i = 0; i < XS_ROWS; ++i) {
+            const int r = (r0 + i < c1) ? r0 + i : r0;
+            rp[i] = p.X + (size_t)cand[r] * D;
+        }
+        double nd2;
+        const double tot = xs_score4<VEC>(rp, qs, D, l2, lane, nd2);
+        if ((lane & 7) == 0) {
+            const int r = r0 + (lane >> 3);
+            if (r < c1) ckey[r] = xs_key(p.metric, tot, nd2, nq2);
+        }
+    }
+}
+
+// (3) one CTA per query: sort the (key, row) pairs by (score, id), write the shard's list and its status.
+__global__ void __launch_bounds__(XS_THREADS) tc_sort_kernel(const TcFinalParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int q = p.q0 + blockIdx.x;
+    const int k = p.k;
+    const bool l2 = p.metric == QRAG_METRIC_L2;
+    const int m = p.cand_m[2 * q];
+    int P2 = 1;
+    while (P2 < m) P2 <<= 1;
+    double* ckey = reinterpret_cast<double*>(smem_raw);                     // [P2]
+    int* ctag = reinterpret_cast<int*>(ckey + P2);                          // [P2] corpus rows = the sort tags
+    const int* cand = p.cand_rows + (size_t)q * p.cand_cap;
+    const double* gkey = p.cand_key + (size_t)q * p.cand_cap;
+    for (int i = tid; i < P2; i += XS_THREADS) {
+        ckey[i] = i < m ? gkey[i] : pos_inf();
+        ctag[i] = i < m ? cand[i] : 0x7fffffff;
+    }
+    __syncthreads();
+    bitonic_sort_kt<double, int>(ckey, ctag, P2);
     for (int i = tid; i < k; i += XS_THREADS) {
         double kv = pos_inf();
         long long tv = 0x7fffffffffffffffLL;
-        if (i < m && cand[i] != 0x7fffffff) { kv = ckey[i]; tv = p.id_base + cand[i]; }
+        if (i < m && ctag[i] != 0x7fffffff) { kv = ckey[i]; tv = p.id_base + ctag[i]; }
         if (tv == 0x7fffffffffffffffLL) { tv = -1; kv = l2 ? pos_inf() : -pos_inf(); }
         else if (!l2) kv = -kv;
         p.out_scores[(size_t)q * k + i] = kv;
         p.out_ids[(size_t)q * k + i] = tv;
     }
-    if (tid == 0) p.status[q] = bad;
+    if (tid == 0) p.status[q] = p.cand_m[2 * q + 1];
 }
 
 // --------------------------------------------------------------------------------- host side
@@ -871,7 +924,8 @@ struct TcPlan {
     int Kp, kchunks, ksteps_last, stages, a_resident, stage_bytes, cg, nq_pad, groups, ntiles, sample, nsample_tiles, nbuckets;
     int cand_cap, cap;
     size_t smem_gemm, smem_final;
-    size_t off_qb, off_qnorm, off_bmax, off_tau, off_eps, off_cnt, off_surv, off_bmtop, off_aptop, total;
+    size_t off_qb, off_qnorm, off_bmax, off_tau, off_eps, off_cnt, off_surv, off_bmtop, off_aptop, off_crow, off_ckey,
+        off_cm, total;
 };
 
 static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPlan* pl) {
@@ -931,11 +985,11 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPl
     if (cand_cap > TC_MAX_CAND) cand_cap = TC_MAX_CAND;
     pl->cand_cap = cand_cap;
     const int Dpad = (D + 3) & ~3;
-    pl->smem_final = (size_t)(Dpad + XS_WARPS) * 8 + (size_t)cand_cap * 12 + TC_MAX_SEGS * 4;
+    pl->smem_final = (size_t)(Dpad + XS_WARPS) * 8;           // tc_rescore: the staged query (tc_sort: 12 B per candidate)
     QRAG_REQUIRE(pl->smem_final <= budget, QRAG_ERR_UNSUPPORTED, "D=%d too large for the rescoring stage", D);
     size_t off = 0;
     pl->off_qb = off; off = align_up(off + (size_t)pl->nq_pad * pl->Kp * 2, 256);
-    pl->off_qnorm = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
+    pl->off_qnorm = off; off = align_up(off + (size_t)pl->nq_pad * 8, 256);      // |q| and |q - bf16(q)| per query
     pl->off_bmax = off; off = align_up(off + (size_t)pl->nq_pad * pl->nbuckets * 4, 256);
     pl->off_tau = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
     pl->off_eps = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
@@ -943,6 +997,9 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPl
     pl->off_surv = off; off = align_up(off + (size_t)pl->nq_pad * cap * 8, 256);
     pl->off_bmtop = off; off = align_up(off + (size_t)pl->nq_pad * k * 4, 256);
     pl->off_aptop = off; off = align_up(off + (size_t)pl->nq_pad * k * 4, 256);
+    pl->off_crow = off; off = align_up(off + (size_t)pl->nq_pad * cand_cap * 4, 256);
+    pl->off_ckey = off; off = align_up(off + (size_t)pl->nq_pad * cand_cap * 8, 256);
+    pl->off_cm = off; off = align_up(off + (size_t)pl->nq_pad * 2 * 4, 256);
     pl->total = off + 256;
     return QRAG_OK;
 }
@@ -952,6 +1009,7 @@ struct TcWs {
     TcPlan pl;
     __nv_bfloat16* Qb; float* qnorm; float* bmax; float* tau; float* eps; unsigned int* cnt; float2* surv;
     float* bmtop; float* aptop;
+    int* crow; double* ckey; int* cm;
 };
 
 static int tc_ws(int nq, int64_t N, int D, int k, int metric, int shards, void* workspace, size_t workspace_bytes, TcWs* w) {
@@ -971,6 +1029,9 @@ static int tc_ws(int nq, int64_t N, int D, int k, int metric, int shards, void* 
     w->surv = reinterpret_cast<float2*>(ws + pl.off_surv);
     w->bmtop = reinterpret_cast<float*>(ws + pl.off_bmtop);
     w->aptop = reinterpret_cast<float*>(ws + pl.off_aptop);
+    w->crow = reinterpret_cast<int*>(ws + pl.off_crow);
+    w->ckey = reinterpret_cast<double*>(ws + pl.off_ckey);
+    w->cm = reinterpret_cast<int*>(ws + pl.off_cm);
     return QRAG_OK;
 }
 
@@ -1096,7 +1157,8 @@ extern "C" int qrag_search_tc_begin(const float* Q, int nq, const uint16_t* Xb, 
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const TcPlan& pl = w.pl;
-    query_prepare_kernel<<<(unsigned)ceil_div(pl.nq_pad, 8), 256, 0, st>>>(Q, nq, pl.nq_pad, D, pl.Kp, metric, w.Qb, w.qnorm);
+    query_prepare_kernel<<<(unsigned)ceil_div(pl.nq_pad, 8), 256, 0, st>>>(Q, nq, pl.nq_pad, D, pl.Kp, metric, w.Qb, w.qnorm,
+                                                                           w.qnorm + pl.nq_pad);
     QRAG_LAUNCH_CHECK("query_prepare_kernel");
     rc = tc_gemm_pass<TC_MODE_BUCKET>(w, nq, N, Xb, st, [](int, int, int, int) { return QRAG_OK; });
     if (rc) return rc;
@@ -1117,7 +1179,7 @@ extern "C" int qrag_search_tc_filter(int nq, const uint16_t* Xb, const float* au
     int rc = tc_ws(nq, N, D, k, metric, G, workspace, workspace_bytes, &w);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    tau_union_kernel<<<nq, 256, 0, st>>>(bm_top_all, G, nq, k, metric, w.pl.Kp, w.qnorm, aux, w.bmax, w.pl.nbuckets, w.tau,
+    tau_union_kernel<<<nq, 256, 0, st>>>(bm_top_all, G, nq, k, metric, w.pl.Kp, w.qnorm, w.qnorm + w.pl.nq_pad, aux, w.bmax, w.pl.nbuckets, w.tau,
                                          w.eps);
     QRAG_LAUNCH_CHECK("tau_union_kernel");
     return tc_gemm_pass<TC_MODE_FILTER>(w, nq, N, Xb, st, [&](int q0, int q1, int nseg, int seg_cap) {
@@ -1148,17 +1210,23 @@ extern "C" int qrag_search_tc_finish(const float* Q, int nq, const float* X, int
         g0 += L.groups;
         if (q1 <= q0) continue;
         TcFinalParams fp{Q, X, q0, nq, N, D, k, metric, id_base, TC_EPI_SPLIT * L.cpg, pl.cap / (TC_EPI_SPLIT * L.cpg),
-                         pl.cap, pl.cand_cap, G, ap_top_all, w.cnt, w.surv, w.eps, out_scores, out_ids, status};
-        if (vec) {
-            QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)pl.smem_final));
-            tc_final_kernel<true><<<q1 - q0, XS_THREADS, pl.smem_final, st>>>(fp);
-        } else {
-            QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)pl.smem_final));
-            tc_final_kernel<false><<<q1 - q0, XS_THREADS, pl.smem_final, st>>>(fp);
+                         pl.cap, pl.cand_cap, G, ap_top_all, w.cnt, w.surv, w.eps, out_scores, out_ids, status,
+                         w.crow, w.ckey, w.cm};
+        tc_collect_kernel<<<q1 - q0, XS_THREADS, 0, st>>>(fp);
+        QRAG_LAUNCH_CHECK("tc_collect_kernel");
+        const dim3 rgrid((unsigned)(q1 - q0), (unsigned)ceil_div(pl.cand_cap, XS_RESCORE_ROWS));
+        if (pl.smem_final > 48 * 1024) {
+            QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_rescore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_final));
+            QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_rescore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_final));
         }
-        QRAG_LAUNCH_CHECK("tc_final_kernel");
+        if (vec) tc_rescore_kernel<true><<<rgrid, XS_THREADS, pl.smem_final, st>>>(fp);
+        else     tc_rescore_kernel<false><<<rgrid, XS_THREADS, pl.smem_final, st>>>(fp);
+        QRAG_LAUNCH_CHECK("tc_rescore_kernel");
+        const size_t smem_sort = (size_t)pl.cand_cap * 12;
+        if (smem_sort > 48 * 1024)
+            QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
+        tc_sort_kernel<<<q1 - q0, XS_THREADS, smem_sort, st>>>(fp);
+        QRAG_LAUNCH_CHECK("tc_sort_kernel");
     }
     return QRAG_OK;
 }

@@ -55,8 +55,9 @@ class CudaEngine:
         return self.index.search(Q, k)
 
     def sync_corpus_bound(self, all_reduce_max):
-        """The filter's error bound uses max |x| over the WHOLE corpus: reduce it once per index."""
-        all_reduce_max(self.index.aux[:1])
+        """The filter's error bound uses max |x| and the largest bf16 rounding-error norm over the WHOLE corpus
+        (aux[0], aux[1]): reduce them once per index."""
+        all_reduce_max(self.index.aux[:2])
 
     def search_sharded(self, Q, k, all_gather, shards):
         """This shard's members of the global top-k (thresholds exchanged through ``all_gather``)."""

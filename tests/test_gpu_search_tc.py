@@ -82,6 +82,40 @@ def test_tc_search_k_larger_than_shard(cuda):
     _compare_with_exact(api, Q, X, 64, "ip")
 
 
+def test_adversarial_bf16_rounding_is_covered_by_the_bound(cuda):
+    """Operands built so that bf16 rounding moves the approximate scores as far as it can: the query's first 32
+    components and the A documents sit just below a rounding midpoint (round DOWN by 2^-8 relative), the other 32
+    components and the B documents just above it (round UP).  Exactly, the 40 A documents beat the 200 B documents
+    (32.274 vs 32.258); in bf16 every B document beats every A document by 0.47.  A filter margin from an assumed
+    2^-9 per operand (0.36 here) drops the true top-40; the measured bound (0.69) must keep them."""
+    import torch
+    from quantum_rag_b200 import api
+    D, N, k = 72, 4096, 40
+    d = 2.0 ** -13
+    q = np.zeros(D, np.float32)
+    q[:32], q[32:64], q[64] = 1 + 2.0 ** -8 - d, 1 + 2.0 ** -8 + d, 0.25
+    xa = np.zeros(D, np.float32)
+    xa[:32], xa[64] = 1 + 2.0 ** -8 - d, 0.125
+    xb = np.zeros(D, np.float32)
+    xb[32:64] = 1 + 2.0 ** -8 + d
+    X = (np.random.RandomState(0).standard_normal((N, D)) * 0.01).astype(np.float32)
+    ia, ib = np.arange(100, 140), np.arange(1000, 1200)
+    X[ia], X[ib] = xa, xb
+    Q = np.stack([q, q * 2.0, q])
+    # the construction really is adversarial: in bf16 arithmetic the B documents win
+    bf = lambda a: torch.from_numpy(a).bfloat16().float().numpy().astype(np.float64)     # noqa: E731
+    approx = bf(X) @ bf(q)
+    assert approx[ib].min() - approx[ia].max() > 0.45
+    for metric in ("ip", "l2"):
+        index = api.FlatIndexTC(X, metric)
+        s, i = index.search(Q, k)
+        es, ei = api.search_topk(Q, X, k, metric)
+        assert index.last_fallback == 0
+        assert torch.equal(i, ei) and torch.equal(s, es), metric
+    s, i = api.FlatIndexTC(X, "ip").search(Q, k)
+    assert i[0].cpu().tolist() == ia.tolist() and i[1].cpu().tolist() == ia.tolist()   # ties in id order
+
+
 def test_config3_full_size_properties(cuda):
     """BASELINE config 3 (1M x 384 unit rows, top-100) through size-independent properties."""
     import torch

@@ -24,9 +24,9 @@ def _emulated(X, Q, G, k1, k2, metric, phased):
         engines.append((lo, hi, CudaEngine(X[lo:hi], metric, lo)))
     if phased:
         # the three phases of every shard with the exchanges emulated by stack (what NCCL does under torchrun)
-        xmax = torch.stack([e.index.aux[:1] for _, _, e in engines]).max()
+        bound = torch.stack([e.index.aux[:2] for _, _, e in engines]).max(dim=0).values
         for _, _, e in engines:
-            e.index.aux[:1] = xmax
+            e.index.aux[:2] = bound
         bm_all = torch.stack([e.index.tc_begin(Q, k1, G) for _, _, e in engines])
         ap_all = torch.stack([e.index.tc_filter(bm_all) for _, _, e in engines])
         lists = []
