@@ -176,7 +176,7 @@ def bench_search(api, peaks, steps=20):
                                 "threshold, filter pass, exact rescoring); peak = measured cuBLAS bf16 burst"},
            "kernels": ["qrag::sim_gemm_kernel<0> (sampled bucket-max pass)", "qrag::bucket_topk_kernel",
                        "qrag::tau_union_kernel", "qrag::sim_gemm_kernel<1> (filter pass)", "qrag::surv_topk_kernel",
-                       "qrag::tc_final_kernel (exact fp64 rescoring + sort)"]}
+                       "qrag::tc_collect_kernel / tc_rescore_kernel / tc_sort_kernel (candidates, exact fp64 rescoring, sort)"]}
     del index, X
     torch.cuda.empty_cache()
     return out
