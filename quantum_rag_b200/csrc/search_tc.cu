@@ -852,7 +852,7 @@ __global__ void __launch_bounds__(XS_THREADS) tc_rescore_kernel(const TcFinalPar
 }
 
 // (3) one CTA per query: sort the (key, row) pairs by (score, id), write the shard's list and its status.
-__global__ void __launch_bounds__(XS_THREADS) tc_sort_kernel(const TcFinalParams p) {
+__global__ void __launch_bounds__(1024) tc_sort_kernel(const TcFinalParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int q = p.q0 + blockIdx.x;
@@ -865,13 +865,13 @@ __global__ void __launch_bounds__(XS_THREADS) tc_sort_kernel(const TcFinalParams
     int* ctag = reinterpret_cast<int*>(ckey + P2);                          // [P2] corpus rows = the sort tags
     const int* cand = p.cand_rows + (size_t)q * p.cand_cap;
     const double* gkey = p.cand_key + (size_t)q * p.cand_cap;
-    for (int i = tid; i < P2; i += XS_THREADS) {
+    for (int i = tid; i < P2; i += blockDim.x) {
         ckey[i] = i < m ? gkey[i] : pos_inf();
         ctag[i] = i < m ? cand[i] : 0x7fffffff;
     }
     __syncthreads();
     bitonic_sort_kt<double, int>(ckey, ctag, P2);
-    for (int i = tid; i < k; i += XS_THREADS) {
+    for (int i = tid; i < k; i += blockDim.x) {
         double kv = pos_inf();
         long long tv = 0x7fffffffffffffffLL;
         if (i < m && ctag[i] != 0x7fffffff) { kv = ckey[i]; tv = p.id_base + ctag[i]; }
@@ -1225,7 +1225,9 @@ extern "C" int qrag_search_tc_finish(const float* Q, int nq, const float* X, int
         const size_t smem_sort = (size_t)pl.cand_cap * 12;
         if (smem_sort > 48 * 1024)
             QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
-        tc_sort_kernel<<<q1 - q0, XS_THREADS, smem_sort, st>>>(fp);
+        // one compare-exchange per thread and stage: half the candidate capacity, within [256, 1024] threads
+        const int sort_threads = pl.cand_cap / 2 < 256 ? 256 : (pl.cand_cap / 2 > 1024 ? 1024 : pl.cand_cap / 2);
+        tc_sort_kernel<<<q1 - q0, sort_threads, smem_sort, st>>>(fp);
         QRAG_LAUNCH_CHECK("tc_sort_kernel");
     }
     return QRAG_OK;
