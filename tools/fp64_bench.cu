@@ -80,8 +80,8 @@ void run(int warps_per_sched, double* sink, long long* cyc) {
 int main() {
     double* sink; long long* cyc;
     cudaMalloc(&sink, 8); cudaMalloc(&cyc, 8);
-    for (int w = 1; w <= 4; ++w) { run<2>(w, sink, cyc); run<4>(w, sink, cyc); run<8>(w, sink, cyc); run<16>(w, sink, cyc); run<32>(w, sink, cyc); }
+    for (int w = 1; w <= 4; ++w) { run<2>(w, sink, cyc); run<4>(w, sink, cyc); run<8>(w, sink, cyc); run<16>(w, sink, cyc); run<32>(w, sink, cyc); if (w <= 2) { run<64>(w, sink, cyc); run<100>(w, sink, cyc); } }
     for (int sk = 0; sk <= 1; ++sk)
-        for (int w = 1; w <= 2; ++w) { run_straight<8>(w, sink, cyc, sk); run_straight<64>(w, sink, cyc, sk); run_straight<256>(w, sink, cyc, sk); run_straight<512>(w, sink, cyc, sk); run_straight<1024>(w, sink, cyc, sk); }
+        for (int w = 1; w <= 2; ++w) { run_straight<8>(w, sink, cyc, sk); run_straight<64>(w, sink, cyc, sk); run_straight<96>(w, sink, cyc, sk); run_straight<128>(w, sink, cyc, sk); run_straight<192>(w, sink, cyc, sk); run_straight<256>(w, sink, cyc, sk); run_straight<512>(w, sink, cyc, sk); run_straight<1024>(w, sink, cyc, sk); }
     return 0;
 }
