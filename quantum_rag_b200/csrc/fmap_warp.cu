@@ -43,6 +43,7 @@ namespace {
 constexpr int FW_N = 10;
 constexpr int FW_DIM = 1 << FW_N;
 constexpr int FW_ST = FW_DIM + 32;                          // state stride: rows of 32 amplitudes + 1 of padding
+constexpr int FW_STAGE = FW_DIM + (FW_DIM >> 5) * 4;        // fp32 row staging: 4 floats of padding per 32
 
 struct FmapWarpParams {
     const float* Q; const float* cand; const float* X; const int64_t* idx;
@@ -245,14 +246,37 @@ __device__ __forceinline__ void fw_layers(double (&r)[32], double2 (&a)[32], int
 
 // Evolves one fp32 row into the state after `layers` blocks WITHOUT the last CX chain, in the
 // final register layout of fw_layers.  Returns |row| == 0.  smem regions are private to the warp.
-__device__ __forceinline__ bool fw_evolve(const float* __restrict__ row, int D, int layers, double2 (&a)[32],
-                                       double2* __restrict__ st, FwGate* __restrict__ gates,
-                                       double* __restrict__ tn, double2* __restrict__ tab) {
+__device__ __forceinline__ bool fw_row_vec(const float* row, int D) {
+    return ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+}
+
+// Asynchronous copy of a (16-byte aligned, D % 4 == 0) row into the warp's padded staging buffer, zero-filled past
+// D: issued while the previous state is still being evolved, so a state does not start with an HBM round trip.
+__device__ __forceinline__ void fw_prefetch_row(const float* __restrict__ row, int D, float* __restrict__ stage) {
     const int lane = threadIdx.x & 31;
-    float* stage = reinterpret_cast<float*>(st);             // aliases the state buffer until the first transpose
+#pragma unroll
+    for (int r = 0; r < FW_DIM / 128; ++r) {
+        const int m = lane + 32 * r;                         // float4 index
+        const bool in = 4 * m < D;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stage + 4 * m + (m >> 3) * 4);
+        const float* src = in ? row + 4 * m : row;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(in ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// `stage` holds the row if `staged` (prefetched by the previous call), else it is loaded here.  `next_row` (or
+// nullptr) is prefetched into `stage` as soon as this row has been consumed; returns through `*next_staged`.
+__device__ __forceinline__ bool fw_evolve(const float* __restrict__ row, int D, int layers, double2 (&a)[32],
+                                       double2* __restrict__ st, float* __restrict__ stage, bool staged,
+                                       const float* __restrict__ next_row, bool* next_staged,
+                                       FwGate* __restrict__ gates, double* __restrict__ tn, double2* __restrict__ tab) {
+    const int lane = threadIdx.x & 31;
     // ---- row -> padded staging (coalesced; 4 floats of padding per 32)
-    const bool vec = ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
-    if (vec) {
+    const bool vec = fw_row_vec(row, D);
+    if (staged) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (vec) {
 #pragma unroll
         for (int r = 0; r < FW_DIM / 128; ++r) {
             const int m = lane + 32 * r;                     // float4 index
@@ -298,6 +322,8 @@ __device__ __forceinline__ bool fw_evolve(const float* __restrict__ row, int D, 
     }
     const bool fast = __all_sync(FULL_MASK, small);
     __syncwarp();                                            // gates visible; staging fully consumed
+    *next_staged = next_row != nullptr && fw_row_vec(next_row, D);
+    if (*next_staged) fw_prefetch_row(next_row, D, stage);
     if (fast) fw_layers<true>(r, a, layers, st, gates, tn, tab);
     else      fw_layers<false>(r, a, layers, st, gates, tn, tab);
     return zero;
@@ -316,6 +342,9 @@ __global__ void __launch_bounds__(MAXT, 1) fmap_warp_kernel(const FmapWarpParams
     FwGate* gates = reinterpret_cast<FwGate*>(qstate + FW_ST + (size_t)W * (FW_ST + 32)) + warp * p.layers * FW_N;
     double* tn = reinterpret_cast<double*>(reinterpret_cast<FwGate*>(qstate + FW_ST + (size_t)W * (FW_ST + 32)) +
                                            (size_t)W * p.layers * FW_N) + warp * p.layers * FW_N;
+    float* stage = reinterpret_cast<float*>(reinterpret_cast<double*>(reinterpret_cast<FwGate*>(
+                       qstate + FW_ST + (size_t)W * (FW_ST + 32)) + (size_t)W * p.layers * FW_N) +
+                   (size_t)W * p.layers * FW_N) + (size_t)warp * FW_STAGE;
     __shared__ int q_zero;
 
     double2 a[32];
@@ -326,22 +355,27 @@ __global__ void __launch_bounds__(MAXT, 1) fmap_warp_kernel(const FmapWarpParams
         if (cnt > p.chunk) cnt = p.chunk;
         // every warp runs every round (uniform trip count).  Starting each round with a barrier, so that the warps
         // stream the same straight-line code together and share instruction fetches, was measured: no gain.
+        bool staged = false;                                 // the first row of a unit is loaded directly
+        auto row_of = [&](int64_t t, bool* missing) -> const float* {
+            *missing = false;
+            if (t == 0) return p.Q + qi * p.D;
+            const int64_t j = qi * p.C + c0 + (t - 1);
+            if (p.cand) return p.cand + (size_t)j * p.D;
+            const int64_t id = p.idx[j];
+            *missing = id < 0;
+            return p.X + (size_t)(*missing ? 0 : id) * p.D;
+        };
         for (int64_t t = warp; t - warp <= cnt; t += W) {
             const bool active = t <= cnt;
             const int64_t j = qi * p.C + c0 + (t - 1);
-            const float* row = nullptr;
             bool missing = false, zero = false;
             if (active) {
-                if (t == 0) {
-                    row = p.Q + qi * p.D;
-                } else if (p.cand) {
-                    row = p.cand + (size_t)j * p.D;
-                } else {
-                    const int64_t id = p.idx[j];
-                    missing = id < 0;
-                    row = p.X + (size_t)(missing ? 0 : id) * p.D;
-                }
-                zero = fw_evolve(row, p.D, p.layers, a, st, gates, tn, tab);
+                const float* row = row_of(t, &missing);
+                bool nmiss = false;
+                const float* next_row = (t + W <= cnt) ? row_of(t + W, &nmiss) : nullptr;
+                bool next_staged = false;
+                zero = fw_evolve(row, p.D, p.layers, a, st, stage, staged, next_row, &next_staged, gates, tn, tab);
+                staged = next_staged;
                 if (t == 0) {
 #pragma unroll
                     for (int k = 0; k < 32; ++k) qstate[k * 33 + lane] = a[k];
@@ -376,7 +410,7 @@ __global__ void __launch_bounds__(MAXT, 1) fmap_warp_kernel(const FmapWarpParams
 
 size_t fmap_warp_smem(int W, int layers) {
     return (size_t)(1 + W) * FW_ST * sizeof(double2) + (size_t)W * 32 * sizeof(double2) +
-           (size_t)W * layers * FW_N * (sizeof(FwGate) + sizeof(double));
+           (size_t)W * layers * FW_N * (sizeof(FwGate) + sizeof(double)) + (size_t)W * FW_STAGE * sizeof(float);
 }
 
 // Returns QRAG_OK and sets *handled when the shape is served by this kernel (n = 10).
