@@ -314,9 +314,10 @@ __device__ __forceinline__ bool fw_evolve(const float* __restrict__ row, int D, 
         const int comp = t % D;
         const double an = (double)stage[comp + (comp >> 5) * 4] * inv;
         FwGate g;
-        sincospi(0.5 * an, &g.s, &g.c);
-        sincospi(0.25 * an, &g.sp, &g.cp);
-        gates[t] = g;
+        sincospi(0.25 * an, &g.sp, &g.cp);                   // RZ half angle a pi / 4; the RY half angle is twice that:
+        g.s = 2.0 * g.sp * g.cp;                             // sin 2x = 2 sin x cos x
+        g.c = fma(-2.0 * g.sp, g.sp, 1.0);                   // cos 2x = 1 - 2 sin^2 x (|x| <= pi/4: no cancellation
+        gates[t] = g;                                        //  beyond 1e-16 absolute)
         tn[t] = g.s / g.c;
         small = small && (fabs(an) <= 0.5);
     }
