@@ -63,6 +63,10 @@ class CudaEngine:
         """This shard's members of the global top-k (thresholds exchanged through ``all_gather``)."""
         return self.index.search_sharded(Q, k, all_gather, shards)
 
+    def search_exact(self, Q, k):
+        """Exact CUDA-core search of this shard (the rerun path for queries the filter could not certify)."""
+        return self.api.search_topk(Q, self.index.X, k, self.metric, self.index.id_base)
+
     def merge(self, scores, ids, k_out):
         return self.api.topk_merge(scores, ids, k_out, self.metric)
 
@@ -143,9 +147,8 @@ class ShardedSearchRerank:
             flagged = torch.nonzero(bad).flatten()
             self._mark("status_sync")
             if flagged.numel():                                   # identical on every rank after the reduce
-                from . import api
                 Qd = Q if isinstance(Q, torch.Tensor) else torch.as_tensor(Q)
-                s2, i2 = api.search_topk(Qd.to(s.device)[flagged], self.engine.index.X, k1, self.metric, self.lo)
+                s2, i2 = self.engine.search_exact(Qd.to(s.device)[flagged], k1)
                 s[flagged] = s2
                 i[flagged] = i2
         else:

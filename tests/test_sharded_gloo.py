@@ -127,3 +127,68 @@ def test_sharded_equals_single_rank(world, metric, n, k1, k2):
     X, Q = _data(n, d, nq)
     rs, ri = osr.topk_from_scores(OracleEngine(X, metric, 0)._scores(Q), k1, metric)
     assert np.array_equal(want[5], ri)
+
+
+class PhasedOracleEngine(OracleEngine):
+    """OracleEngine with the phase-split search of the CUDA engine: a shard returns only ITS members of the global
+    top-k (padded with id -1) plus a per-query status, so the list cut, the status reduce and both fall-back routes of
+    ShardedSearchRerank run on CPU.  ``flag_query`` makes one rank report that query as uncertified."""
+
+    def __init__(self, X_shard, metric, id_base, flag_query=None):
+        super().__init__(X_shard, metric, id_base)
+        self.flag_query = flag_query
+
+    def search_exact(self, Q, k):
+        return self.search(Q, k)
+
+    def search_sharded(self, Q, k, all_gather, shards):
+        s, i = self.search(Q, k)                                              # this shard's best k
+        key = s if self.metric == osr.METRIC_L2 else -s
+        key = torch.where(i >= 0, key, torch.full_like(key, float("inf")))
+        allk = all_gather(key)                                                # [G, nq, k]
+        kth = torch.sort(allk.permute(1, 0, 2).reshape(key.shape[0], -1), dim=1).values[:, k - 1:k]
+        keep = (key <= kth) & (i >= 0)                                        # ties at the k-th key are kept: a superset
+        pad_s = float("inf") if self.metric == osr.METRIC_L2 else float("-inf")
+        s = torch.where(keep, s, torch.full_like(s, pad_s))
+        i = torch.where(keep, i, torch.full_like(i, -1))
+        status = torch.zeros(key.shape[0], dtype=torch.int32)
+        if self.flag_query is not None:
+            status[self.flag_query] = 1
+            s[self.flag_query] = pad_s                                        # an uncertified list may hold anything
+            i[self.flag_query] = -1
+        return s, i, status
+
+
+def _phased_worker(rank, world, port, n, d, nq, k1, k2, metric, skew, flag, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        X, Q = _data(n, d, nq)
+        if skew:                                     # every neighbour of query 2 lives in shard 0: its list overflows the cut
+            X[:k1 + 5] = Q[2] + 1e-3 * np.random.RandomState(5).standard_normal((k1 + 5, d)).astype(np.float32)
+        lo, hi = shard_bounds(n, world, rank)
+        eng = PhasedOracleEngine(X[lo:hi], metric, lo, flag_query=(1 if flag and rank == world - 1 else None))
+        path = ShardedSearchRerank(torch.from_numpy(X[lo:hi]), n, metric, engine=eng)
+        res = path(torch.from_numpy(Q), k1, k2)
+        out[rank] = (res.scores.numpy(), res.ids.numpy(), res.search_ids is not None)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("skew,flag", [(False, False), (True, False), (False, True)])
+def test_phased_search_cut_and_fallback_routes(skew, flag):
+    """(no skew, no flag) takes the query-partitioned form with cut lists; a skewed corpus overflows the cut and a
+    flagged query fails the certificate: both must fall back to the all-gather form and still give the exact answer."""
+    world, metric, n, d, nq, k1, k2 = 4, osr.METRIC_COSINE, 2000, 16, 6, 300, 9
+    X, Q = _data(n, d, nq)
+    if skew:
+        X[:k1 + 5] = Q[2] + 1e-3 * np.random.RandomState(5).standard_normal((k1 + 5, d)).astype(np.float32)
+    eng = OracleEngine(X, metric, 0)
+    want = ShardedSearchRerank(torch.from_numpy(X), n, metric, engine=eng)(torch.from_numpy(Q), k1, k2)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_phased_worker, args=(world, _free_port(), n, d, nq, k1, k2, metric, skew, flag, out), nprocs=world, join=True)
+    for rank in range(world):
+        scores, ids, fell_back = out[rank]
+        assert np.array_equal(ids, want.ids.numpy()) and np.array_equal(scores, want.scores.numpy()), rank
+        assert fell_back == (skew or flag)            # the all-gather form materialises the merged search lists
