@@ -194,7 +194,7 @@ using namespace qrag;
 extern "C" int qrag_search_workspace(int nq, int64_t N, int D, int k, size_t* bytes) {
     QRAG_REQUIRE(bytes != nullptr, QRAG_ERR_INVALID, "bytes is null");
     QRAG_REQUIRE(nq >= 0 && N >= 0 && D > 0, QRAG_ERR_INVALID, "bad sizes");
-    int chunk, kk, nchunks, group;
+    int chunk = 0, kk = 0, nchunks = 0, group = 0;
     int rc = search_plan(nq, N, k, &chunk, &kk, &nchunks, &group);
     if (rc) return rc;
     const size_t lvl0 = (size_t)nq * nchunks * kk;
@@ -210,7 +210,7 @@ extern "C" int qrag_search_topk(const float* Q, int nq, const float* X, int64_t 
     QRAG_REQUIRE(X != nullptr || N == 0, QRAG_ERR_INVALID, "X is null");
     QRAG_REQUIRE(nq >= 0 && N >= 0 && D > 0, QRAG_ERR_INVALID, "bad sizes nq=%d N=%lld D=%d", nq, (long long)N, D);
     QRAG_REQUIRE(metric >= 0 && metric <= 2, QRAG_ERR_INVALID, "unknown metric %d", metric);
-    int chunk, kk, nchunks, group;
+    int chunk = 0, kk = 0, nchunks = 0, group = 0;
     int rc = search_plan(nq, N, k, &chunk, &kk, &nchunks, &group);
     if (rc) return rc;
     if (nq == 0) return QRAG_OK;
