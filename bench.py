@@ -252,10 +252,20 @@ def bench_sharded(world, rank, steps=5):
     h = hashlib.sha256()
     for x in (res.ids, res.scores):
         h.update(x.cpu().numpy().tobytes())
-    out = {"workload": "config 4: 10,000,000 docs x 384-d row-sharded, 1024 queries, per-shard top-1000 -> NCCL "
-                       "all-gather -> merge -> quantum rerank (9 qubits) -> top-10", "n_gpus": world, "scaling": "strong",
+    # the packed NCCL route of this very run against the plain one on 8 queries: exact CUDA-core search of every
+    # shard, all-gather, merge, stand-alone fidelity kernel, all-reduce(MAX), stable sort
+    sub = torch.arange(0, nq, nq // 8, device=dev)[:8]
+    ref = path.exact_reference(Q[sub], k1, k2)
+    same = bool(torch.equal(ref.ids, res.ids[sub]) and torch.equal(ref.scores, res.scores[sub]))
+    path.profile = {}
+    path(Q, k1, k2)
+    stages = {k: round(v, 4) for k, v in path.profile.items()}
+    out = {"workload": "config 4: 10,000,000 docs x 384-d row-sharded, 1024 queries, per-shard top-1000 (rerank fidelity "
+                       "fused into the exact rescoring) -> NCCL all-to-all to the query's owner -> merge -> quantum "
+                       "rerank (9 qubits) -> top-10", "n_gpus": world, "scaling": "strong",
            "ms_per_batch": ms, "search_scores_per_s": nq * N / (ms * 1e-3), "reranked_queries_per_s": nq / (ms * 1e-3),
-           "fallback_queries": path.engine.index.last_fallback,
+           "rerun_all_gather_form": path.last_rerun, "equals_exact_route_on_8_queries": same,
+           "collectives_per_batch": 0 if world == 1 else 4, "stage_ms_rank0": stages,
            "result_sha256": h.hexdigest(), "note": "result_sha256 must not depend on n_gpus (bit-identical rankings)"}
     del path, X
     torch.cuda.empty_cache()

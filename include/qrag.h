@@ -176,17 +176,28 @@ int qrag_search_topk_tc(const float* Q, int nq, const float* X, const uint16_t* 
                         double* out_scores, int64_t* out_ids, int32_t* status,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* Diagnostic: out [nq, N] = every approximate score of the filter GEMM (bf16 operands, fp32 accumulation in
+ * tensor memory), in the units the filter thresholds use (IP / cosine: the similarity; L2: 2 q.x - |x|^2).  This is
+ * the quantity the filter's error bound is a bound on; tests measure the bound's terms with it.  Workspace as for
+ * qrag_search_tc_workspace(nq, N, D, 1, metric, 1). */
+int qrag_search_tc_scores(const float* Q, int nq, const uint16_t* Xb, int64_t N, int D, int metric, float* out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* The same search split at its two exchange points, for a corpus sharded over G GPUs (the
  * all-gathers in between are the caller's: quantum_rag_b200/sharded.py issues them with NCCL).
  * Thresholds come from ALL shards, so every shard filters and rescores only ~ (k + margin) / G
  * candidates and the work scales with 1/G.  The workspace carries state between the phases.
  *   (`shards` = G sizes the sample and the workspace: the same value in the workspace query and every phase;
  *    qrag_search_topk_tc is the G = 1 composition)
- *   begin   bm_top [nq, k]: this shard's k largest sampled bucket maxima
- *   filter  bm_top_all [G, nq, k] (all-gathered) -> tau; ap_top [nq, k]: this shard's k best
+ * The threshold lists travel cut to kt = qrag_search_tc_exchange_len(k, G) entries (k for G = 1, else
+ * min(k, 2k/G + 64 rounded up to 32)): the k-th largest of the union of the G cut lists is still a valid
+ * threshold, and the exact one unless a single shard holds more than kt of the global top k.
+ *   begin   bm_top [nq, kt]: this shard's kt largest sampled bucket maxima
+ *   filter  bm_top_all [G, nq, kt] (all-gathered) -> tau; ap_top [nq, kt]: this shard's kt best
  *           approximate scores.  aux[0] and aux[1] must hold their maxima over ALL shards.
- *   finish  ap_top_all [G, nq, k] (all-gathered) -> exact, sorted list of this shard's members of
+ *   finish  ap_top_all [G, nq, kt] (all-gathered) -> exact, sorted list of this shard's members of
  *           the global top-k (ids -1 padded); merge the G lists with qrag_topk_merge. */
+int qrag_search_tc_exchange_len(int k, int G, int* len);
 int qrag_search_tc_begin(const float* Q, int nq, const uint16_t* Xb, int64_t N, int D, int k, int metric,
                          int shards /* = G of the later phases */,
                          float* bm_top, void* workspace, size_t workspace_bytes, void* stream);
@@ -197,6 +208,25 @@ int qrag_search_tc_finish(const float* Q, int nq, const float* X, int64_t N, int
                           int64_t id_base, const float* ap_top_all, int G,
                           double* out_scores, int64_t* out_ids, int32_t* status,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* Search + quantum rerank (BASELINE config 4) without a second pass over the rows: `finish_packed` is `finish`
+ * with the shard's list written as one record per query, cut to its kk best entries, carrying the amplitude-
+ * encoded fidelity (q.d)^2 / (|q|^2 |d|^2) of every entry -- computed by the exact rescoring from the same
+ * read of the row, bit-identical to qrag_amp_fidelity.  Record of query q at pack + q * (3 kk + 1), int64 words:
+ *   [0]            entries in the record | bad << 32   (bad: the shard could not certify the query, or had more
+ *                                                       than kk entries; the caller must rerun such a query)
+ *   [1, kk]        search scores (fp64 bits), best first       [kk+1, 2kk]  ids (-1 padding)
+ *   [2kk+1, 3kk]   fidelities (fp64 bits)
+ * The records of query q travel to the rank that owns q (one all-to-all; sharded.py), where
+ * `qrag_owner_finalize` merges the G lists by rank, keeps the global top-k1 and orders it by
+ * (fidelity desc, position in the merged list asc) -- QuantumReranker.rerank's stable sort, quantum.py:70-76.
+ *   recv [G, per, 3 kk + 1]  record of owned query j from every shard;  q_base + j = the query's global number
+ *   out  [per, 2 k2 + 1]     k2 fidelities (fp64 bits), k2 ids, status (!= 0: some shard flagged the query) */
+int qrag_search_tc_finish_packed(const float* Q, int nq, const float* X, int64_t N, int D, int k, int metric,
+                                 int64_t id_base, const float* ap_top_all, int G, int kk, int64_t* pack,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+int qrag_owner_finalize(const int64_t* recv, int G, int per, int kk, int k1, int k2, int metric,
+                        int q_base, int nq, int64_t* out, void* stream);
 
 /* ---------------------------------------------------------------------------
  * (3) Merge of per-shard top-k lists after the all-gather: scores/ids

@@ -62,6 +62,22 @@ def exact_search(Q: np.ndarray, X: np.ndarray, k: int, metric: int = METRIC_L2, 
     return topk_from_scores(exact_scores(Q, X, metric), k, metric, id_base)
 
 
+def exact_search_chunked(Q: np.ndarray, X: np.ndarray, k: int, metric: int = METRIC_L2, id_base: int = 0,
+                         chunk: int = 1 << 16):
+    """``exact_search`` for a corpus too large to score at once: chunks of rows, running canonical top-k
+    (each chunk's list merged into the running one with ``merge_topk``; same result as one pass)."""
+    run_s = run_i = None
+    for lo in range(0, X.shape[0], chunk):
+        s, i = exact_search(Q, X[lo:lo + chunk], k, metric, id_base + lo)
+        if run_s is None:
+            run_s, run_i = s, i
+        else:
+            run_s, run_i = merge_topk(np.stack([run_s, s]), np.stack([run_i, i]), k, metric)
+    if run_s is None:
+        return exact_search(Q, X, k, metric, id_base)
+    return run_s, run_i
+
+
 def merge_topk(scores: np.ndarray, ids: np.ndarray, k_out: int, metric: int) -> Tuple[np.ndarray, np.ndarray]:
     """Merge per-shard lists ``[G, nq, k]`` into the global ``[nq, k_out]`` list.
 
@@ -81,6 +97,72 @@ def merge_topk(scores: np.ndarray, ids: np.ndarray, k_out: int, metric: int) -> 
         out_s = np.concatenate([out_s, np.full((nq, pad), np.inf if metric == METRIC_L2 else -np.inf)], axis=1)
         out_i = np.concatenate([out_i, np.full((nq, pad), -1, dtype=np.int64)], axis=1)
     return out_s, out_i
+
+
+# --------------------------------------------------------------------------
+# The packed search + rerank exchange (include/qrag.h: qrag_search_tc_finish_packed /
+# qrag_owner_finalize; builder-defined, the reference is single-process).  A record is
+# 3 kk + 1 int64 words: header (entries | bad << 32), kk score bits, kk ids, kk fidelity bits.
+# --------------------------------------------------------------------------
+def pack_records(scores: np.ndarray, ids: np.ndarray, fid: np.ndarray, kk: int, metric: int,
+                 bad: np.ndarray = None) -> np.ndarray:
+    """Per-shard sorted lists [nq, k] (ids -1 padded) -> records [nq, 3 kk + 1], cut to kk entries."""
+    nq, k = ids.shape
+    valid = (ids >= 0).sum(axis=1)
+    rec = np.zeros((nq, 3 * kk + 1), dtype=np.int64)
+    pad_s = np.inf if metric == METRIC_L2 else -np.inf
+    s = np.full((nq, kk), pad_s, dtype=np.float64)
+    i = np.full((nq, kk), -1, dtype=np.int64)
+    f = np.full((nq, kk), -np.inf, dtype=np.float64)
+    w = min(k, kk)
+    keep = np.arange(w)[None, :] < np.minimum(valid, kk)[:, None]
+    s[:, :w] = np.where(keep, scores[:, :w], pad_s)
+    i[:, :w] = np.where(keep, ids[:, :w], -1)
+    f[:, :w] = np.where(keep, fid[:, :w], -np.inf)
+    flag = (valid > kk).astype(np.int64)
+    if bad is not None:
+        flag |= (np.asarray(bad) != 0).astype(np.int64)
+    rec[:, 0] = np.minimum(valid, kk) | (flag << 32)
+    rec[:, 1:1 + kk] = s.view(np.int64)
+    rec[:, 1 + kk:1 + 2 * kk] = i
+    rec[:, 1 + 2 * kk:] = f.view(np.int64)
+    return rec
+
+
+def owner_finalize(recv: np.ndarray, kk: int, k1: int, k2: int, metric: int, q_base: int = 0,
+                   nq: int = None) -> np.ndarray:
+    """recv [G, per, 3 kk + 1] -> out [per, 2 k2 + 1]: merge the G lists in (score, id) order, keep the global
+    top-k1, order by (fidelity desc, merged position asc) -- Python's stable sorted(reverse=True),
+    quantum.py:70-76 -- and keep k2; last word = status (some shard flagged the query)."""
+    G, per, _ = recv.shape
+    out = np.empty((per, 2 * k2 + 1), dtype=np.int64)
+    for j in range(per):
+        if nq is not None and q_base + j >= nq:
+            out[j, :k2] = np.full(k2, -np.inf).view(np.int64)
+            out[j, k2:2 * k2] = -1
+            out[j, 2 * k2] = 0
+            continue
+        entries, bad = [], 0
+        for g in range(G):
+            r = recv[g, j]
+            n = min(max(int(r[0] & 0xFFFFFFFF), 0), kk)
+            bad |= int(r[0] >> 32 != 0)
+            s = r[1:1 + kk].view(np.float64)
+            f = r[1 + 2 * kk:].view(np.float64)
+            for e in range(n):
+                key = s[e] if metric == METRIC_L2 else -s[e]
+                entries.append((key, int(r[1 + kk + e]), f[e]))
+        entries.sort(key=lambda t: (t[0], t[1]))
+        members = entries[:k1]
+        order = sorted(range(len(members)), key=lambda p: members[p][2], reverse=True)[:k2]     # stable
+        fo = np.full(k2, -np.inf)
+        io = np.full(k2, -1, dtype=np.int64)
+        for t, p_ in enumerate(order):
+            fo[t], io[t] = members[p_][2], members[p_][1]
+        out[j, :k2] = fo.view(np.int64)
+        out[j, k2:2 * k2] = io
+        out[j, 2 * k2] = bad
+    return out
 
 
 # --------------------------------------------------------------------------

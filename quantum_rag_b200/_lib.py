@@ -52,6 +52,13 @@ PROTOTYPES: Dict[str, tuple] = {
                                       c_void_p, c_void_p, c_size_t, c_void_p]),
     "qrag_search_tc_finish": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_void_p,
                                       c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "qrag_search_tc_scores": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                      c_void_p]),
+    "qrag_search_tc_exchange_len": (c_int, [c_int, c_int, POINTER(c_int)]),
+    "qrag_search_tc_finish_packed": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_void_p,
+                                             c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "qrag_owner_finalize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                    c_void_p]),
     "qrag_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p]),
 }

@@ -293,47 +293,88 @@ class FlatIndexTC:
                                            ws.numel(), _stream()))
         return Qd, scores, ids, status
 
-    # ---- the search split at its two exchange points (corpus sharded over G GPUs) ----
-    def tc_begin(self, Q: ArrayLike, k: int, shards: int) -> torch.Tensor:
-        """Phase 1 of a search over ``shards`` shards: bm_top [nq, k] fp32, this shard's k largest sampled bucket maxima."""
+    def approx_scores(self, Q: ArrayLike) -> torch.Tensor:
+        """Diagnostic (include/qrag.h: qrag_search_tc_scores): fp32 [nq, N], every approximate score of the filter GEMM."""
         Qd = _dev(Q, torch.float32)
         if Qd.dim() == 1:
             Qd = Qd[None, :]
         nq = Qd.shape[0]
+        ws = self._workspace(nq, 1)
+        out = torch.empty((nq, self.N), dtype=torch.float32, device=Qd.device)
+        _lib.check(_lib.load().qrag_search_tc_scores(_ptr(Qd), nq, _ptr(self.Xb), self.N, self.D, self.metric, _ptr(out),
+                                                     _ptr(ws), ws.numel(), _stream()))
+        return out
+
+    # ---- the search split at its two exchange points (corpus sharded over G GPUs) ----
+    def tc_begin(self, Q: ArrayLike, k: int, shards: int) -> Optional[torch.Tensor]:
+        """Phase 1 of a search over ``shards`` shards: bm_top [nq, kt] fp32, this shard's kt largest sampled bucket
+        maxima (kt = exchange_len(k, shards)); a single shard keeps them in the workspace and returns None."""
+        Qd = _dev(Q, torch.float32)
+        if Qd.dim() == 1:
+            Qd = Qd[None, :]
+        if Qd.shape[1] != self.D:
+            raise ValueError("Q [nq, D] must match the index dimension")
+        nq = Qd.shape[0]
         ws = self._workspace(nq, k, shards)
-        bm_top = torch.empty((nq, k), dtype=torch.float32, device=Qd.device)
+        kt = exchange_len(k, shards)
+        bm_top = torch.empty((nq, kt), dtype=torch.float32, device=Qd.device) if shards > 1 else None
         _lib.check(_lib.load().qrag_search_tc_begin(_ptr(Qd), nq, _ptr(self.Xb), self.N, self.D, k, self.metric, shards,
                                                     _ptr(bm_top), _ptr(ws), ws.numel(), _stream()))
-        self._phase = (Qd, k, ws, shards)
+        self._phase = (Qd, k, ws, shards, kt)
         return bm_top
 
-    def tc_filter(self, bm_top_all: torch.Tensor) -> torch.Tensor:
-        """Phase 2: bm_top_all [G, nq, k] from every shard -> ap_top [nq, k], this shard's k best approximate scores."""
-        Qd, k, ws, shards = self._phase
+    def tc_filter(self, bm_top_all: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """Phase 2: bm_top_all [G, nq, kt] from every shard -> ap_top [nq, kt], this shard's kt best approximate scores."""
+        Qd, k, ws, shards, kt = self._phase
         nq = Qd.shape[0]
-        bm = bm_top_all.contiguous()
-        if bm.shape[0] != shards:
-            raise ValueError("bm_top_all must hold one list per shard")
-        ap_top = torch.empty((nq, k), dtype=torch.float32, device=Qd.device)
+        bm = ap_top = None
+        if shards > 1:
+            bm = bm_top_all.contiguous()
+            if tuple(bm.shape) != (shards, nq, kt):
+                raise ValueError(f"bm_top_all must be [{shards}, {nq}, {kt}]")
+            ap_top = torch.empty((nq, kt), dtype=torch.float32, device=Qd.device)
         _lib.check(_lib.load().qrag_search_tc_filter(nq, _ptr(self.Xb), _ptr(self.aux), self.N, self.D, k, self.metric,
-                                                     _ptr(bm), bm.shape[0], _ptr(ap_top), _ptr(ws), ws.numel(),
-                                                     _stream()))
+                                                     _ptr(bm), shards, _ptr(ap_top), _ptr(ws), ws.numel(), _stream()))
         return ap_top
 
-    def tc_finish(self, ap_top_all: torch.Tensor):
-        """Phase 3: ap_top_all [G, nq, k] -> (scores, ids, status): this shard's exact, sorted members of the
-        global top-k (ids -1 padded); status != 0 flags a query this shard could not certify."""
-        Qd, k, ws, shards = self._phase
-        nq = Qd.shape[0]
+    def _ap(self, ap_top_all):
+        Qd, k, ws, shards, kt = self._phase
+        if shards == 1:
+            return None
         ap = ap_top_all.contiguous()
+        if tuple(ap.shape) != (shards, Qd.shape[0], kt):
+            raise ValueError(f"ap_top_all must be [{shards}, {Qd.shape[0]}, {kt}]")
+        return ap
+
+    def tc_finish(self, ap_top_all: Optional[torch.Tensor]):
+        """Phase 3: ap_top_all [G, nq, kt] -> (scores, ids, status): this shard's exact, sorted members of the
+        global top-k (ids -1 padded); status != 0 flags a query this shard could not certify."""
+        Qd, k, ws, shards, kt = self._phase
+        nq = Qd.shape[0]
+        ap = self._ap(ap_top_all)
         scores = torch.empty((nq, k), dtype=torch.float64, device=Qd.device)
         ids = torch.empty((nq, k), dtype=torch.int64, device=Qd.device)
         status = torch.zeros(nq, dtype=torch.int32, device=Qd.device)
         _lib.check(_lib.load().qrag_search_tc_finish(_ptr(Qd), nq, _ptr(self.X), self.N, self.D, k, self.metric,
-                                                     self.id_base, _ptr(ap), ap.shape[0], _ptr(scores), _ptr(ids),
+                                                     self.id_base, _ptr(ap), shards, _ptr(scores), _ptr(ids),
                                                      _ptr(status), _ptr(ws), ws.numel(), _stream()))
         self._phase = None
         return scores, ids, status
+
+    def tc_finish_packed(self, ap_top_all: Optional[torch.Tensor], kk: int, pack: torch.Tensor) -> torch.Tensor:
+        """Phase 3, packed (include/qrag.h): the shard's list of every query as a record [3 kk + 1] of int64 words --
+        header, kk search scores, kk ids, kk amplitude fidelities -- written into ``pack[:nq]``."""
+        Qd, k, ws, shards, kt = self._phase
+        nq = Qd.shape[0]
+        ap = self._ap(ap_top_all)
+        if pack.dtype != torch.int64 or pack.dim() != 2 or pack.shape[0] < nq or pack.shape[1] != 3 * kk + 1 \
+                or not pack.is_contiguous():
+            raise ValueError(f"pack must be a contiguous int64 [>= {nq}, {3 * kk + 1}] tensor")
+        _lib.check(_lib.load().qrag_search_tc_finish_packed(_ptr(Qd), nq, _ptr(self.X), self.N, self.D, k, self.metric,
+                                                            self.id_base, _ptr(ap), shards, kk, _ptr(pack), _ptr(ws),
+                                                            ws.numel(), _stream()))
+        self._phase = None
+        return pack
 
     def search_sharded(self, Q: ArrayLike, k: int, all_gather, shards: int):
         """This shard's part of a search over G shards: ``all_gather(t)`` must return ``[G, *t.shape]``.
@@ -341,9 +382,10 @@ class FlatIndexTC:
         Thresholds are global, so the shard filters and rescores only ~ (k + margin) / G rows.
         ``self.aux[0]`` must already hold the maximum |x| over all shards (see sharded.py).
         """
-        bm_all = all_gather(self.tc_begin(Q, k, shards))
-        ap_all = all_gather(self.tc_filter(bm_all))
-        return self.tc_finish(ap_all)
+        bm = self.tc_begin(Q, k, shards)
+        bm_all = all_gather(bm) if shards > 1 else None
+        ap = self.tc_filter(bm_all)
+        return self.tc_finish(all_gather(ap) if shards > 1 else None)
 
     def search(self, Q: ArrayLike, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         if self.N == 0:
@@ -356,6 +398,27 @@ class FlatIndexTC:
             scores[flagged] = s2
             ids[flagged] = i2
         return scores, ids
+
+
+def exchange_len(k: int, shards: int) -> int:
+    """Entries of the lists the shards of a G-way search exchange (and of the packed records): include/qrag.h."""
+    n = ctypes.c_int(0)
+    _lib.check(_lib.load().qrag_search_tc_exchange_len(int(k), int(shards), ctypes.byref(n)))
+    return n.value
+
+
+def owner_finalize(recv: torch.Tensor, kk: int, k1: int, k2: int, metric, q_base: int, nq: int,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Owner side of the search + rerank exchange (include/qrag.h): recv [G, per, 3 kk + 1] int64 records ->
+    out [per, 2 k2 + 1] int64 (k2 fidelity bits, k2 ids, status)."""
+    if recv.dtype != torch.int64 or recv.dim() != 3 or recv.shape[2] != 3 * kk + 1 or not recv.is_contiguous():
+        raise ValueError("recv must be a contiguous int64 [G, per, 3 kk + 1] tensor")
+    G, per = recv.shape[0], recv.shape[1]
+    if out is None:
+        out = torch.empty((per, 2 * k2 + 1), dtype=torch.int64, device=recv.device)
+    _lib.check(_lib.load().qrag_owner_finalize(_ptr(recv), G, per, kk, k1, k2, metric_id(metric), int(q_base), int(nq),
+                                               _ptr(out), _stream()))
+    return out
 
 
 def topk_merge(scores: ArrayLike, ids: ArrayLike, k_out: int, metric="l2") -> Tuple[torch.Tensor, torch.Tensor]:

@@ -113,6 +113,63 @@ __device__ __forceinline__ double xs_score4(const float* const (&rp)[XS_ROWS], c
     return tot;
 }
 
+// L2 scoring that also returns q.d and |d|^2 of the same rows (the packed search + rerank form needs the
+// amplitude fidelity of an L2 candidate from the one read of its row).  The L2 sum goes through the same
+// instruction sequence as in xs_score4, q.d and |d|^2 through the sequence of the non-L2 form, so all three
+// agree bit for bit with what the separate kernels compute.
+template <bool VEC>
+__device__ __forceinline__ double xs_score4_l2dot(const float* const (&rp)[XS_ROWS], const double* qs, int D, int lane,
+                                                  double& nd2, double& dot) {
+    double acc[8], acd[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i] = 0.0; acd[i] = 0.0; }
+    if (VEC) {
+        const int D4 = D >> 2;
+#pragma unroll 2
+        for (int j = lane; j < D4; j += 32) {
+            float4 v[XS_ROWS];
+#pragma unroll
+            for (int i = 0; i < XS_ROWS; ++i) v[i] = ldg_stream(reinterpret_cast<const float4*>(rp[i]) + j);
+            const double2 qa = *reinterpret_cast<const double2*>(qs + 4 * j);
+            const double2 qb = *reinterpret_cast<const double2*>(qs + 4 * j + 2);
+            const double qv[4] = {qa.x, qa.y, qb.x, qb.y};
+#pragma unroll
+            for (int i = 0; i < XS_ROWS; ++i) {
+                const double d[4] = {(double)v[i].x, (double)v[i].y, (double)v[i].z, (double)v[i].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const double t = qv[e] - d[e];
+                    acc[2 * i] = fma(t, t, acc[2 * i]);
+                    acc[2 * i + 1] = fma(d[e], d[e], acc[2 * i + 1]);
+                    acd[2 * i] = fma(qv[e], d[e], acd[2 * i]);
+                }
+            }
+        }
+    } else {
+        for (int j = lane; j < D; j += 32) {
+            const double qv = qs[j];
+#pragma unroll
+            for (int i = 0; i < XS_ROWS; ++i) {
+                const double d = (double)__ldg(rp[i] + j);
+                const double t = qv - d;
+                acc[2 * i] = fma(t, t, acc[2 * i]);
+                acc[2 * i + 1] = fma(d, d, acc[2 * i + 1]);
+                acd[2 * i] = fma(qv, d, acd[2 * i]);
+            }
+        }
+    }
+    const double tot = xs_reduce4pairs(acc, lane);
+    nd2 = __shfl_down_sync(FULL_MASK, tot, 4);
+    dot = xs_reduce4pairs(acd, lane);
+    return tot;
+}
+
+// Amplitude-encoded fidelity (q.d)^2 / (|q|^2 |d|^2) from the reduced sums: the expression of amp_fidelity.cu.
+__device__ __forceinline__ double xs_fidelity(double dot, double nd2, double nq2) {
+    const double den = nq2 * nd2;
+    return den > 0.0 ? (dot * dot) / den : 0.0;
+}
+
 // Sort key (ascending = better) of a row from its reduced sums.
 __device__ __forceinline__ double xs_key(int metric, double tot, double nd2, double nq2) {
     if (metric == QRAG_METRIC_L2) return tot;

@@ -56,7 +56,7 @@ constexpr int TC_CAP_MAX = 131072;    // within these bounds (TcPlan::cap)
 constexpr int TC_MAX_CAND = 8192;     // largest exact-rescore capacity per query
 constexpr int TC_MAX_SEGS = 640;      // survivor-list segments per query (TC_EPI_SPLIT per CTA of the query's group)
 constexpr int TC_MAX_STAGES = 10;
-constexpr int TC_MODE_BUCKET = 0, TC_MODE_FILTER = 1;
+constexpr int TC_MODE_BUCKET = 0, TC_MODE_FILTER = 1, TC_MODE_DUMP = 2;
 
 struct TcGemmParams {
     int kchunks;            // ceil(Kp / 64)
@@ -78,6 +78,7 @@ struct TcGemmParams {
     int seg_cap;            // survivor slots per (query, CTA, column quarter) segment
     unsigned int* cnt;      // [nq, TC_MAX_SEGS] survivors found per segment, may exceed seg_cap (filter)
     float2* surv;           // [nq, cap] (score, row as int bits), segment s at s * seg_cap (filter)
+    float* dump;            // [nq, N] every approximate score (TC_MODE_DUMP: the diagnostic qrag_search_tc_scores)
 };
 
 // ------------------------------------------------------------------ PTX wrappers (tcgen05 / TMA)
@@ -237,7 +238,7 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int g = (unit_id % ugroups) * CG + (int)rank;
     const int u0 = unit_id / ugroups;
     const int cpg = (gridDim.x / CG) / ugroups;
-    const int step = MODE == TC_MODE_BUCKET ? p.sample : 1;
+    const int step = MODE == TC_MODE_BUCKET ? p.sample : 1;       // the filter and dump passes visit every tile
     const int nunits = (p.ntiles + step - 1) / step;          // tiles this pass visits
 
     if (warp == 0) {
@@ -363,6 +364,14 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             // one 32-column chunk of this thread's row: bucket maximum, or threshold test and survivor append
             auto process = [&](uint32_t (&r)[32], const int c0) {
                 if (p.debug_skip == 3) { if ((r[0] ^ r[31]) == 0x12345u) found += 1; return; }
+                if (MODE == TC_MODE_DUMP) {
+                    if (qvalid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (doc0 + c0 + j < p.N) p.dump[(size_t)q * p.N + doc0 + c0 + j] = __uint_as_float(r[j]);
+                    }
+                    return;
+                }
                 if (ragged) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
@@ -647,7 +656,8 @@ __global__ void __launch_bounds__(256) bucket_topk_kernel(const float* __restric
 
 // per query: m_k = k-th largest bucket maximum over all G shards' lists; tau = m_k - 2 eps, rounded down
 // (single shard: bm_top_all == nullptr and the k-th largest is taken straight from this shard's bucket maxima)
-__global__ void __launch_bounds__(256) tau_union_kernel(const float* __restrict__ bm_top_all, int G, int nq, int k, int metric,
+__global__ void __launch_bounds__(256) tau_union_kernel(const float* __restrict__ bm_top_all, int G, int nq, int k, int kt,
+                                                        int metric,
                                                         int Kp, const float* __restrict__ qnorm, const float* __restrict__ qerr,
                                                         const float* __restrict__ aux,
                                                         const float* __restrict__ bmax, int nbuckets,
@@ -658,11 +668,11 @@ __global__ void __launch_bounds__(256) tau_union_kernel(const float* __restrict_
     if (bm_top_all != nullptr) {
         auto fe = [&](auto f) {
             for (int g = 0; g < G; ++g) {
-                const float* row = bm_top_all + ((size_t)g * nq + q) * k;
-                for_strided<4>(threadIdx.x, k, blockDim.x, [&](int j) { return row[j]; }, f);
+                const float* row = bm_top_all + ((size_t)g * nq + q) * kt;
+                for_strided<4>(threadIdx.x, kt, blockDim.x, [&](int j) { return row[j]; }, f);
             }
         };
-        mk = block_kth_largest(rs, k, fe);
+        if ((int64_t)G * kt >= k) mk = block_kth_largest(rs, k, fe);
     } else if (nbuckets >= k) {
         const float* row = bmax + (size_t)q * nbuckets;
         auto fe = [&](auto f) { for_strided<8>(threadIdx.x, nbuckets, blockDim.x, [&](int j) { return row[j]; }, f); };
@@ -677,42 +687,84 @@ __global__ void __launch_bounds__(256) tau_union_kernel(const float* __restrict_
     }
 }
 
-// per query: the k largest approximate scores among this shard's survivors -> ap_top [nq, k]
+// per query: the kt largest approximate scores among this shard's survivors -> ap_top [nq, kt]
+// The survivors' scores are copied into shared memory once (up to SV_CACHE of them; a longer list keeps its tail in
+// global memory), so the four radix passes and the collection read HBM/L2 once instead of five times.
+constexpr int SV_CACHE = 18432;        // floats: 72 KB, three CTAs per SM
 __global__ void __launch_bounds__(256) surv_topk_kernel(const unsigned int* __restrict__ cnt, const float2* __restrict__ surv,
-                                                        int q0, int nseg, int seg_cap, int cap, int k,
+                                                        int q0, int nseg, int seg_cap, int cap, int kt,
                                                         float* __restrict__ ap_top) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* vals = reinterpret_cast<float*>(smem_raw);                  // [SV_CACHE]
     __shared__ RadixSel rs;
     __shared__ int seg_n[TC_MAX_SEGS];
-    __shared__ int s_n;
+    __shared__ int seg_off[TC_MAX_SEGS + 1];
     const int q = q0 + blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    for (int sgi = threadIdx.x; sgi < nseg; sgi += blockDim.x) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int sgi = tid; sgi < nseg; sgi += blockDim.x) {
         const unsigned int c = cnt[(size_t)q * TC_MAX_SEGS + sgi];
-        const int c2 = c < (unsigned)seg_cap ? (int)c : seg_cap;
-        seg_n[sgi] = c2;
-        atomicAdd(&s_n, c2);
+        seg_n[sgi] = c < (unsigned)seg_cap ? (int)c : seg_cap;
     }
     __syncthreads();
+    if (warp == 0) {                                                   // exclusive scan of the segment lengths
+        int carry = 0;
+        for (int b = 0; b < nseg; b += 32) {
+            const int v = b + lane < nseg ? seg_n[b + lane] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL_MASK, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (b + lane < nseg) seg_off[b + lane] = carry + incl - v;
+            carry += __shfl_sync(FULL_MASK, incl, 31);
+        }
+        if (lane == 0) seg_off[nseg] = carry;
+    }
+    __syncthreads();
+    const int total = seg_off[nseg];
+    const int ncached = total < SV_CACHE ? total : SV_CACHE;
     const float2* sv = surv + (size_t)q * cap;
+    for (int sgi = warp; sgi < nseg; sgi += nwarps) {
+        const float2* sp = sv + (size_t)sgi * seg_cap;
+        const int off = seg_off[sgi];
+        int n = seg_n[sgi];
+        if (off + n > SV_CACHE) n = off < SV_CACHE ? SV_CACHE - off : 0;
+        for (int i0 = lane; i0 < n; i0 += 128) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = i0 + 32 * u < n ? sp[i0 + 32 * u].x : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + 32 * u < n) vals[off + i0 + 32 * u] = v[u];
+        }
+    }
+    __syncthreads();
     auto fe = [&](auto f) {
-        for (int sgi = warp; sgi < nseg; sgi += nwarps) {
-            const float2* sp = sv + (size_t)sgi * seg_cap;
-            for_strided<4>(lane, seg_n[sgi], 32, [&](int j) { return sp[j].x; }, f);
+        for_strided<4>(tid, ncached, (int)blockDim.x, [&](int j) { return vals[j]; }, f);
+        if (total > SV_CACHE) {                                        // block-uniform: the uncached tail
+            for (int sgi = warp; sgi < nseg; sgi += nwarps) {
+                const int off = seg_off[sgi], n = seg_n[sgi];
+                if (off + n <= SV_CACHE) continue;
+                const int first = off < SV_CACHE ? SV_CACHE - off : 0;
+                const float2* sp = sv + (size_t)sgi * seg_cap + first;
+                for_strided<4>(lane, n - first, 32, [&](int j) { return sp[j].x; }, f);
+            }
         }
     };
-    block_topk_values(rs, k, s_n, fe, ap_top + (size_t)q * k);
+    block_topk_values(rs, kt, total, fe, ap_top + (size_t)q * kt);
 }
 
 // ---------------------------------------------------------------------------------- final stage
 struct TcFinalParams {
     const float* Q; const float* X; int q0; int nq; int64_t N; int D; int k; int metric; int64_t id_base;
     int nseg, seg_cap, cap, cand_cap;
-    int G; const float* ap_top_all;          // [G, nq, k] the k best approximate scores of every shard
+    int G; int kt; const float* ap_top_all;  // [G, nq, kt] the kt best approximate scores of every shard
     const unsigned int* cnt; const float2* surv; const float* eps;
     double* out_scores; int64_t* out_ids; int32_t* status;
     int* cand_rows; double* cand_key; int* cand_m;     // [nq, cand_cap], [nq, cand_cap], [nq, 2] (count, overflow)
+    double* cand_fid;                                  // [nq, cand_cap] amplitude fidelity of the row (packed form) or null
+    long long* pack; int kk;                           // packed form: [nq, 3 kk + 1] records cut to kk entries, or null
 };
 
 template <typename K, typename T>
@@ -759,11 +811,12 @@ __global__ void __launch_bounds__(XS_THREADS) tc_collect_kernel(const TcFinalPar
     if (p.ap_top_all != nullptr) {
         auto fe = [&](auto f) {
             for (int g = 0; g < p.G; ++g) {
-                const float* row = p.ap_top_all + ((size_t)g * p.nq + q) * k;
-                for_strided<4>(tid, k, XS_THREADS, [&](int j) { return row[j]; }, f);
+                const float* row = p.ap_top_all + ((size_t)g * p.nq + q) * p.kt;
+                for_strided<4>(tid, p.kt, XS_THREADS, [&](int j) { return row[j]; }, f);
             }
         };
-        ak = block_kth_largest(rs, k, fe);                                  // starts and ends with __syncthreads()
+        if ((int64_t)p.G * p.kt >= k) ak = block_kth_largest(rs, k, fe);     // starts and ends with __syncthreads()
+        else __syncthreads();
     } else {
         __syncthreads();
         int mine = 0;
@@ -842,11 +895,21 @@ __global__ void __launch_bounds__(XS_THREADS) tc_rescore_kernel(const TcFinalPar
             const int r = (r0 + i < c1) ? r0 + i : r0;
             rp[i] = p.X + (size_t)cand[r] * D;
         }
-        double nd2;
-        const double tot = xs_score4<VEC>(rp, qs, D, l2, lane, nd2);
+        double nd2, dot;
+        double tot;
+        if (l2 && p.cand_fid != nullptr) {
+            tot = xs_score4_l2dot<VEC>(rp, qs, D, lane, nd2, dot);
+        } else {
+            tot = xs_score4<VEC>(rp, qs, D, l2, lane, nd2);
+            dot = tot;
+        }
         if ((lane & 7) == 0) {
             const int r = r0 + (lane >> 3);
-            if (r < c1) ckey[r] = xs_key(p.metric, tot, nd2, nq2);
+            if (r < c1) {
+                ckey[r] = xs_key(p.metric, tot, nd2, nq2);
+                // the rerank's fidelity from the same read of the row (bit-identical to amp_fidelity.cu)
+                if (p.cand_fid != nullptr) p.cand_fid[(size_t)q * p.cand_cap + r] = xs_fidelity(dot, nd2, nq2);
+            }
         }
     }
 }
@@ -881,6 +944,150 @@ __global__ void __launch_bounds__(1024) tc_sort_kernel(const TcFinalParams p) {
         p.out_ids[(size_t)q * k + i] = tv;
     }
     if (tid == 0) p.status[q] = p.cand_m[2 * q + 1];
+}
+
+// (3') packed form of (3) for the search + rerank path: the sorted list goes straight into the record the exchange
+// sends to the query's owner -- [0] header (valid entries | bad << 32), then kk score bits, kk ids, kk fidelity bits
+// -- cut to the kk best entries.  The sort tag is row << 13 | candidate slot (rows are unique within a list, so the
+// order is still (score, id)); the slot finds the row's fidelity after the sort.
+constexpr int TC_SLOT_BITS = 13;
+static_assert((1 << TC_SLOT_BITS) >= TC_MAX_CAND, "a candidate slot must fit the tag");
+__global__ void __launch_bounds__(1024) tc_sort_pack_kernel(const TcFinalParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int q = p.q0 + blockIdx.x;
+    const int k = p.k, kk = p.kk;
+    const bool l2 = p.metric == QRAG_METRIC_L2;
+    const int m = p.cand_m[2 * q];
+    int P2 = 1;
+    while (P2 < m) P2 <<= 1;
+    double* ckey = reinterpret_cast<double*>(smem_raw);                     // [P2]
+    long long* ctag = reinterpret_cast<long long*>(ckey + P2);              // [P2]
+    const int* cand = p.cand_rows + (size_t)q * p.cand_cap;
+    const double* gkey = p.cand_key + (size_t)q * p.cand_cap;
+    const double* gfid = p.cand_fid + (size_t)q * p.cand_cap;
+    for (int i = tid; i < P2; i += blockDim.x) {
+        ckey[i] = i < m ? gkey[i] : pos_inf();
+        ctag[i] = i < m ? (((long long)cand[i] << TC_SLOT_BITS) | i) : 0x7fffffffffffffffLL;
+    }
+    __syncthreads();
+    bitonic_sort_kt<double, long long>(ckey, ctag, P2);
+    const int valid = m < k ? m : k;                                        // this shard's list has min(m, k) entries
+    long long* rec = p.pack + (size_t)q * (3 * (size_t)kk + 1);
+    for (int i = tid; i < kk; i += blockDim.x) {
+        double sv = l2 ? pos_inf() : -pos_inf(), fv = -pos_inf();
+        long long id = -1;
+        if (i < valid) {
+            const long long t = ctag[i];
+            sv = l2 ? ckey[i] : -ckey[i];
+            id = p.id_base + (t >> TC_SLOT_BITS);
+            fv = gfid[(int)(t & ((1 << TC_SLOT_BITS) - 1))];
+        }
+        rec[1 + i] = __double_as_longlong(sv);
+        rec[1 + kk + i] = id;
+        rec[1 + 2 * kk + i] = __double_as_longlong(fv);
+    }
+    if (tid == 0) {
+        const long long bad = (p.cand_m[2 * q + 1] != 0 || valid > kk) ? 1 : 0;
+        rec[0] = (long long)(valid < kk ? valid : kk) | (bad << 32);
+    }
+}
+
+// Owner side of the search + rerank exchange: one CTA per owned query.  recv [G, per, 3 kk + 1] holds, from every
+// shard, the record tc_sort_pack_kernel wrote for this query.  The G sorted lists are merged by RANK -- an entry's
+// position in the global (score, id) order is its own position plus, for every other list, the number of entries
+// that sort before it (binary search) -- so nothing is moved; entries with rank < k1 are the global top-k1, and
+// they are ordered by (fidelity desc, rank asc), the reference's stable sort (quantum.py:70-76).
+// out [per, 2 k2 + 1]: k2 fidelity bits, k2 ids, status (some shard could not certify the query / cut its list).
+struct OwnerParams {
+    const long long* recv; int G, per, kk, k1, k2, l2, q_base, nq;
+    long long* out;
+};
+constexpr int OWNER_MAX_G = 256;
+__global__ void __launch_bounds__(1024) owner_finalize_kernel(const OwnerParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_valid[OWNER_MAX_G];
+    __shared__ int s_bad, s_total;
+    const int tid = threadIdx.x;
+    const int j = blockIdx.x, q = p.q_base + j;
+    const int G = p.G, kk = p.kk, k1 = p.k1, k2 = p.k2;
+    const size_t rec = 3 * (size_t)kk + 1;
+    long long* out = p.out + (size_t)j * (2 * (size_t)k2 + 1);
+    if (q >= p.nq) {                                            // padding query of the last owner
+        for (int i = tid; i < k2; i += blockDim.x) { out[i] = __double_as_longlong(-pos_inf()); out[k2 + i] = -1; }
+        if (tid == 0) out[2 * k2] = 0;
+        return;
+    }
+    if (tid == 0) { s_bad = 0; s_total = 0; }
+    __syncthreads();
+    for (int g = tid; g < G; g += blockDim.x) {
+        const long long h = p.recv[((size_t)g * p.per + j) * rec];
+        int v = (int)(h & 0xffffffffLL);
+        if (v < 0) v = 0;
+        if (v > kk) v = kk;
+        s_valid[g] = v;
+        atomicAdd(&s_total, v);
+        if (h >> 32) s_bad = 1;
+    }
+    __syncthreads();
+    int members = s_total < k1 ? s_total : k1;
+    int P = 1;
+    while (P < members) P <<= 1;
+    double* key = reinterpret_cast<double*>(smem_raw);                      // [G kk] ascending = better
+    long long* ids = reinterpret_cast<long long*>(key + (size_t)G * kk);    // [G kk]
+    double* mkey = reinterpret_cast<double*>(ids + (size_t)G * kk);         // [P] -fidelity of the member at a rank
+    int* mtag = reinterpret_cast<int*>(mkey + P);                           // [P] the rank (sort tag)
+    int* mslot = mtag + P;                                                  // [P] rank -> entry
+    const int total_slots = G * kk;
+    for (int e = tid; e < total_slots; e += blockDim.x) {
+        const int g = e / kk, i = e - g * kk;
+        if (i < s_valid[g]) {
+            const long long* r = p.recv + ((size_t)g * p.per + j) * rec;
+            const double sv = __longlong_as_double(r[1 + i]);
+            key[e] = p.l2 ? sv : -sv;
+            ids[e] = r[1 + kk + i];
+        }
+    }
+    // every rank slot starts empty: with well-formed input (ids unique over the lists) ranks 0 .. members-1 are each
+    // written exactly once below; malformed input leaves holes that come out as padding instead of wild reads
+    for (int i = tid; i < P; i += blockDim.x) { mkey[i] = pos_inf(); mtag[i] = 0x7fffffff; mslot[i] = -1; }
+    __syncthreads();
+    for (int e = tid; e < total_slots; e += blockDim.x) {
+        const int g = e / kk, i = e - g * kk;
+        if (i >= s_valid[g]) continue;
+        const double ke = key[e];
+        const long long ie = ids[e];
+        int rank = i;
+        for (int h = 0; h < G; ++h) {
+            if (h == g) continue;
+            int lo = 0, hi = s_valid[h];                         // first entry of list h that does NOT sort before e
+            const double* kh = key + (size_t)h * kk;
+            const long long* ih = ids + (size_t)h * kk;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const double km = kh[mid];
+                if (km < ke || (km == ke && ih[mid] < ie)) lo = mid + 1;
+                else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < members) {
+            const double f = __longlong_as_double(p.recv[((size_t)g * p.per + j) * rec + 1 + 2 * kk + i]);
+            mkey[rank] = -f;
+            mtag[rank] = rank;
+            mslot[rank] = e;
+        }
+    }
+    __syncthreads();
+    bitonic_sort_kt<double, int>(mkey, mtag, P);
+    for (int i = tid; i < k2; i += blockDim.x) {
+        double f = -pos_inf();
+        long long id = -1;
+        if (i < members && mtag[i] != 0x7fffffff) { f = -mkey[i]; id = ids[mslot[mtag[i]]]; }
+        out[i] = __double_as_longlong(f);
+        out[k2 + i] = id;
+    }
+    if (tid == 0) out[2 * k2] = s_bad;
 }
 
 // --------------------------------------------------------------------------------- host side
@@ -923,10 +1130,21 @@ static int tc_kp(int D, int metric) { return (int)align_up((size_t)D + (metric =
 struct TcPlan {
     int Kp, kchunks, ksteps_last, stages, a_resident, stage_bytes, cg, nq_pad, groups, ntiles, sample, nsample_tiles, nbuckets;
     int cand_cap, cap;
+    int kt;                 // entries of the threshold lists the shards exchange (tc_exchange_len)
     size_t smem_gemm, smem_final;
-    size_t off_qb, off_qnorm, off_bmax, off_tau, off_eps, off_cnt, off_surv, off_bmtop, off_aptop, off_crow, off_ckey,
+    size_t off_qb, off_qnorm, off_bmax, off_tau, off_eps, off_cnt, off_surv, off_crow, off_ckey, off_cfid,
         off_cm, total;
 };
+
+// Lists exchanged between the shards of a G-way search travel cut to this many entries.  A shard holds ~ k / G of
+// the global top-k; the k-th largest of the union of the G lists' first kt entries is still a valid threshold (every
+// entry is a distinct document, so at least k documents reach it) and equals the exact one unless a single shard
+// holds more than kt of the top k -- then it is merely lower (more survivors, never a wrong result).
+static int tc_exchange_len(int k, int shards) {
+    if (shards <= 1) return k;
+    const int64_t kt = (2 * (int64_t)k / shards + 64 + 31) / 32 * 32;
+    return kt < k ? (int)kt : k;
+}
 
 static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPlan* pl) {
     QRAG_REQUIRE(nq >= 0 && N >= 0 && D > 0, QRAG_ERR_INVALID, "bad sizes nq=%d N=%lld D=%d", nq, (long long)N, D);
@@ -984,6 +1202,7 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPl
     }
     if (cand_cap > TC_MAX_CAND) cand_cap = TC_MAX_CAND;
     pl->cand_cap = cand_cap;
+    pl->kt = tc_exchange_len(k, shards);
     const int Dpad = (D + 3) & ~3;
     pl->smem_final = (size_t)(Dpad + XS_WARPS) * 8;           // tc_rescore: the staged query (tc_sort: 12 B per candidate)
     QRAG_REQUIRE(pl->smem_final <= budget, QRAG_ERR_UNSUPPORTED, "D=%d too large for the rescoring stage", D);
@@ -995,10 +1214,9 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPl
     pl->off_eps = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
     pl->off_cnt = off; off = align_up(off + (size_t)pl->nq_pad * TC_MAX_SEGS * 4, 256);
     pl->off_surv = off; off = align_up(off + (size_t)pl->nq_pad * cap * 8, 256);
-    pl->off_bmtop = off; off = align_up(off + (size_t)pl->nq_pad * k * 4, 256);
-    pl->off_aptop = off; off = align_up(off + (size_t)pl->nq_pad * k * 4, 256);
     pl->off_crow = off; off = align_up(off + (size_t)pl->nq_pad * cand_cap * 4, 256);
     pl->off_ckey = off; off = align_up(off + (size_t)pl->nq_pad * cand_cap * 8, 256);
+    pl->off_cfid = off; off = align_up(off + (size_t)pl->nq_pad * cand_cap * 8, 256);
     pl->off_cm = off; off = align_up(off + (size_t)pl->nq_pad * 2 * 4, 256);
     pl->total = off + 256;
     return QRAG_OK;
@@ -1008,8 +1226,8 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPl
 struct TcWs {
     TcPlan pl;
     __nv_bfloat16* Qb; float* qnorm; float* bmax; float* tau; float* eps; unsigned int* cnt; float2* surv;
-    float* bmtop; float* aptop;
-    int* crow; double* ckey; int* cm;
+    int* crow; double* ckey; double* cfid; int* cm;
+    float* dump = nullptr;  // qrag_search_tc_scores only
 };
 
 static int tc_ws(int nq, int64_t N, int D, int k, int metric, int shards, void* workspace, size_t workspace_bytes, TcWs* w) {
@@ -1027,10 +1245,9 @@ static int tc_ws(int nq, int64_t N, int D, int k, int metric, int shards, void* 
     w->eps = reinterpret_cast<float*>(ws + pl.off_eps);
     w->cnt = reinterpret_cast<unsigned int*>(ws + pl.off_cnt);
     w->surv = reinterpret_cast<float2*>(ws + pl.off_surv);
-    w->bmtop = reinterpret_cast<float*>(ws + pl.off_bmtop);
-    w->aptop = reinterpret_cast<float*>(ws + pl.off_aptop);
     w->crow = reinterpret_cast<int*>(ws + pl.off_crow);
     w->ckey = reinterpret_cast<double*>(ws + pl.off_ckey);
+    w->cfid = reinterpret_cast<double*>(ws + pl.off_cfid);
     w->cm = reinterpret_cast<int*>(ws + pl.off_cm);
     return QRAG_OK;
 }
@@ -1089,7 +1306,7 @@ static int tc_gemm_pass(const TcWs& w, int nq, int64_t N, const uint16_t* Xb, cu
     gp.kchunks = pl.kchunks; gp.ksteps_last = pl.ksteps_last; gp.stages = pl.stages;
     gp.a_resident = pl.a_resident; gp.stage_bytes = pl.stage_bytes;
     gp.nq = nq; gp.N = N; gp.ntiles = pl.ntiles; gp.sample = pl.sample; gp.nbuckets = pl.nbuckets;
-    gp.tau = w.tau; gp.bmax = w.bmax; gp.cnt = w.cnt; gp.surv = w.surv;
+    gp.tau = w.tau; gp.bmax = w.bmax; gp.cnt = w.cnt; gp.surv = w.surv; gp.dump = w.dump;
     if (const char* e = getenv("QRAG_TC_DEBUG_SKIP")) gp.debug_skip = atoi(e);
     const int units = MODE == TC_MODE_BUCKET ? pl.nsample_tiles : pl.ntiles;
     for (int g0 = 0; g0 < pl.groups;) {
@@ -1163,10 +1380,28 @@ extern "C" int qrag_search_tc_begin(const float* Q, int nq, const uint16_t* Xb, 
     rc = tc_gemm_pass<TC_MODE_BUCKET>(w, nq, N, Xb, st, [](int, int, int, int) { return QRAG_OK; });
     if (rc) return rc;
     if (bm_top != nullptr) {                                   // single shard: the threshold kernel reads bmax itself
-        bucket_topk_kernel<<<nq, 256, 0, st>>>(w.bmax, pl.nbuckets, k, bm_top);
+        bucket_topk_kernel<<<nq, 256, 0, st>>>(w.bmax, pl.nbuckets, pl.kt, bm_top);
         QRAG_LAUNCH_CHECK("bucket_topk_kernel");
     }
     return QRAG_OK;
+}
+
+// diagnostic: the approximate score matrix of the filter GEMM, i.e. what tc_eps is a bound on
+extern "C" int qrag_search_tc_scores(const float* Q, int nq, const uint16_t* Xb, int64_t N, int D, int metric, float* out,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+    QRAG_REQUIRE(Q && Xb && out, QRAG_ERR_INVALID, "null pointer argument");
+    QRAG_REQUIRE((uintptr_t)Xb % 16 == 0, QRAG_ERR_INVALID, "Xb must be 16-byte aligned");
+    if (nq == 0) return QRAG_OK;
+    TcWs w;
+    int rc = tc_ws(nq, N, D, 1, metric, 1, workspace, workspace_bytes, &w);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const TcPlan& pl = w.pl;
+    query_prepare_kernel<<<(unsigned)ceil_div(pl.nq_pad, 8), 256, 0, st>>>(Q, nq, pl.nq_pad, D, pl.Kp, metric, w.Qb, w.qnorm,
+                                                                           w.qnorm + pl.nq_pad);
+    QRAG_LAUNCH_CHECK("query_prepare_kernel");
+    w.dump = out;
+    return tc_gemm_pass<TC_MODE_DUMP>(w, nq, N, Xb, st, [](int, int, int, int) { return QRAG_OK; });
 }
 
 // phase 2: threshold from all shards' bucket maxima, filter GEMM, the shard's k best approximate scores
@@ -1179,23 +1414,26 @@ extern "C" int qrag_search_tc_filter(int nq, const uint16_t* Xb, const float* au
     int rc = tc_ws(nq, N, D, k, metric, G, workspace, workspace_bytes, &w);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    tau_union_kernel<<<nq, 256, 0, st>>>(bm_top_all, G, nq, k, metric, w.pl.Kp, w.qnorm, w.qnorm + w.pl.nq_pad, aux, w.bmax, w.pl.nbuckets, w.tau,
+    tau_union_kernel<<<nq, 256, 0, st>>>(bm_top_all, G, nq, k, w.pl.kt, metric, w.pl.Kp, w.qnorm, w.qnorm + w.pl.nq_pad, aux, w.bmax, w.pl.nbuckets, w.tau,
                                          w.eps);
     QRAG_LAUNCH_CHECK("tau_union_kernel");
     return tc_gemm_pass<TC_MODE_FILTER>(w, nq, N, Xb, st, [&](int q0, int q1, int nseg, int seg_cap) {
         if (ap_top == nullptr) return (int)QRAG_OK;            // single shard: the final stage selects by itself
-        surv_topk_kernel<<<q1 - q0, 256, 0, st>>>(w.cnt, w.surv, q0, nseg, seg_cap, w.pl.cap, k, ap_top);
+        QRAG_CUDA_CHECK(cudaFuncSetAttribute(surv_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(SV_CACHE * sizeof(float))));
+        surv_topk_kernel<<<q1 - q0, 256, SV_CACHE * sizeof(float), st>>>(w.cnt, w.surv, q0, nseg, seg_cap, w.pl.cap, w.pl.kt,
+                                                                         ap_top);
         QRAG_LAUNCH_CHECK("surv_topk_kernel");
         return QRAG_OK;
     });
 }
 
-// phase 3: candidates against the global k-th best approximate score, exact rescoring, sorted shard list
-extern "C" int qrag_search_tc_finish(const float* Q, int nq, const float* X, int64_t N, int D, int k, int metric,
-                                     int64_t id_base, const float* ap_top_all, int G, double* out_scores, int64_t* out_ids,
-                                     int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
-    QRAG_REQUIRE(Q && X && out_scores && out_ids && status && G >= 1 && (ap_top_all || G == 1), QRAG_ERR_INVALID,
-                 "bad argument");
+// phase 3: candidates against the global k-th best approximate score, exact rescoring, sorted shard list --
+// either as (scores, ids, status) arrays or, packed != nullptr, as the per-query records of the search + rerank
+// exchange (tc_sort_pack_kernel), which also carry the amplitude fidelity of every entry.
+static int tc_finish_impl(const float* Q, int nq, const float* X, int64_t N, int D, int k, int metric, int64_t id_base,
+                          const float* ap_top_all, int G, double* out_scores, int64_t* out_ids, int32_t* status,
+                          long long* pack, int kk, void* workspace, size_t workspace_bytes, void* stream) {
     if (nq == 0) return QRAG_OK;
     TcWs w;
     int rc = tc_ws(nq, N, D, k, metric, G, workspace, workspace_bytes, &w);
@@ -1210,8 +1448,8 @@ extern "C" int qrag_search_tc_finish(const float* Q, int nq, const float* X, int
         g0 += L.groups;
         if (q1 <= q0) continue;
         TcFinalParams fp{Q, X, q0, nq, N, D, k, metric, id_base, TC_EPI_SPLIT * L.cpg, pl.cap / (TC_EPI_SPLIT * L.cpg),
-                         pl.cap, pl.cand_cap, G, ap_top_all, w.cnt, w.surv, w.eps, out_scores, out_ids, status,
-                         w.crow, w.ckey, w.cm};
+                         pl.cap, pl.cand_cap, G, pl.kt, ap_top_all, w.cnt, w.surv, w.eps, out_scores, out_ids, status,
+                         w.crow, w.ckey, w.cm, pack ? w.cfid : nullptr, pack, kk};
         tc_collect_kernel<<<q1 - q0, XS_THREADS, 0, st>>>(fp);
         QRAG_LAUNCH_CHECK("tc_collect_kernel");
         const dim3 rgrid((unsigned)(q1 - q0), (unsigned)ceil_div(pl.cand_cap, XS_RESCORE_ROWS));
@@ -1222,14 +1460,70 @@ extern "C" int qrag_search_tc_finish(const float* Q, int nq, const float* X, int
         if (vec) tc_rescore_kernel<true><<<rgrid, XS_THREADS, pl.smem_final, st>>>(fp);
         else     tc_rescore_kernel<false><<<rgrid, XS_THREADS, pl.smem_final, st>>>(fp);
         QRAG_LAUNCH_CHECK("tc_rescore_kernel");
-        const size_t smem_sort = (size_t)pl.cand_cap * 12;
-        if (smem_sort > 48 * 1024)
-            QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
         // one compare-exchange per thread and stage: half the candidate capacity, within [256, 1024] threads
         const int sort_threads = pl.cand_cap / 2 < 256 ? 256 : (pl.cand_cap / 2 > 1024 ? 1024 : pl.cand_cap / 2);
-        tc_sort_kernel<<<q1 - q0, sort_threads, smem_sort, st>>>(fp);
-        QRAG_LAUNCH_CHECK("tc_sort_kernel");
+        if (pack != nullptr) {
+            const size_t smem_sort = (size_t)pl.cand_cap * 16;
+            if (smem_sort > 48 * 1024)
+                QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_sort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
+            tc_sort_pack_kernel<<<q1 - q0, sort_threads, smem_sort, st>>>(fp);
+            QRAG_LAUNCH_CHECK("tc_sort_pack_kernel");
+        } else {
+            const size_t smem_sort = (size_t)pl.cand_cap * 12;
+            if (smem_sort > 48 * 1024)
+                QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
+            tc_sort_kernel<<<q1 - q0, sort_threads, smem_sort, st>>>(fp);
+            QRAG_LAUNCH_CHECK("tc_sort_kernel");
+        }
     }
+    return QRAG_OK;
+}
+
+extern "C" int qrag_search_tc_finish(const float* Q, int nq, const float* X, int64_t N, int D, int k, int metric,
+                                     int64_t id_base, const float* ap_top_all, int G, double* out_scores, int64_t* out_ids,
+                                     int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+    QRAG_REQUIRE(Q && X && out_scores && out_ids && status && G >= 1 && (ap_top_all || G == 1), QRAG_ERR_INVALID,
+                 "bad argument");
+    return tc_finish_impl(Q, nq, X, N, D, k, metric, id_base, ap_top_all, G, out_scores, out_ids, status, nullptr, 0,
+                          workspace, workspace_bytes, stream);
+}
+
+extern "C" int qrag_search_tc_exchange_len(int k, int G, int* len) {
+    QRAG_REQUIRE(len != nullptr && k >= 1 && G >= 1, QRAG_ERR_INVALID, "bad argument");
+    *len = tc_exchange_len(k, G);
+    return QRAG_OK;
+}
+
+extern "C" int qrag_search_tc_finish_packed(const float* Q, int nq, const float* X, int64_t N, int D, int k, int metric,
+                                            int64_t id_base, const float* ap_top_all, int G, int kk, int64_t* pack,
+                                            void* workspace, size_t workspace_bytes, void* stream) {
+    QRAG_REQUIRE(Q && X && pack && G >= 1 && (ap_top_all || G == 1), QRAG_ERR_INVALID, "bad argument");
+    QRAG_REQUIRE(kk >= 1 && kk <= k, QRAG_ERR_INVALID, "kk=%d outside [1, k=%d]", kk, k);
+    return tc_finish_impl(Q, nq, X, N, D, k, metric, id_base, ap_top_all, G, nullptr, nullptr, nullptr,
+                          reinterpret_cast<long long*>(pack), kk, workspace, workspace_bytes, stream);
+}
+
+extern "C" int qrag_owner_finalize(const int64_t* recv, int G, int per, int kk, int k1, int k2, int metric, int q_base,
+                                   int nq, int64_t* out, void* stream) {
+    QRAG_REQUIRE(recv && out, QRAG_ERR_INVALID, "null pointer argument");
+    QRAG_REQUIRE(G >= 1 && G <= OWNER_MAX_G, QRAG_ERR_UNSUPPORTED, "owner merge supports 1 <= G <= %d (got %d)", OWNER_MAX_G, G);
+    QRAG_REQUIRE(per >= 0 && kk >= 1 && k1 >= 1 && k2 >= 1 && k2 <= k1 && q_base >= 0 && nq >= 0, QRAG_ERR_INVALID,
+                 "bad sizes per=%d kk=%d k1=%d k2=%d", per, kk, k1, k2);
+    QRAG_REQUIRE(metric >= 0 && metric <= 2, QRAG_ERR_INVALID, "unknown metric %d", metric);
+    if (per == 0) return QRAG_OK;
+    const DeviceProps& dp = device_props();
+    QRAG_REQUIRE(dp.ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
+    const int64_t slots = (int64_t)G * kk;
+    const int members_max = (int)(slots < k1 ? slots : k1);
+    const size_t smem = (size_t)slots * 16 + (size_t)next_pow2(members_max) * 16;
+    QRAG_REQUIRE(smem + 2048 <= (size_t)dp.max_smem_optin, QRAG_ERR_UNSUPPORTED,
+                 "owner merge of %d lists x %d entries needs %zu B of shared memory", G, kk, smem);
+    if (smem > 40 * 1024)                                  // the kernel also holds ~1 KB of static shared memory
+        QRAG_CUDA_CHECK(cudaFuncSetAttribute(owner_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OwnerParams op{reinterpret_cast<const long long*>(recv), G, per, kk, k1, k2, metric == QRAG_METRIC_L2 ? 1 : 0, q_base,
+                   nq, reinterpret_cast<long long*>(out)};
+    owner_finalize_kernel<<<per, 1024, smem, (cudaStream_t)stream>>>(op);
+    QRAG_LAUNCH_CHECK("owner_finalize_kernel");
     return QRAG_OK;
 }
 

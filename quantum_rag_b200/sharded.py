@@ -6,18 +6,24 @@ this is the multi-GPU form BASELINE.json's config 4 asks for:
     corpus rows   contiguous row partition, rank g owns rows [lo_g, hi_g); global id = lo_g + row
     queries       replicated on every rank
     search        per shard: tcgen05 filter GEMM + exact rescoring (FlatIndexTC); the filter
-                  thresholds are global (two [nq, k1] fp32 all-gathers between the phases), so a
-                  shard rescores only its ~1/G share of the global top-k1
-    exchange 1    ONE all-gather of the per-shard lists, [nq, k1] x (fp64 score, int64 id)
-    merge         every rank merges the G lists to the global top-k1 (same kernel as the
-                  single-GPU merge, so the order is the canonical (score, id) order)
-    rerank        owner-computes: a rank scores only the members of the global list that live
-                  in its shard (amplitude-encoded fidelity, rows gathered by TMA); no embedding
-                  ever crosses NVLink
-    exchange 2    ONE all-reduce(MAX) of [nq, k1] fp64 (non-owners hold -inf)
-    final         stable sort by (fidelity desc, position in the merged list asc), top-k2
+                  thresholds are global (two small fp32 all-gathers of [nq, kt] between the phases,
+                  kt ~ 2 k1 / G), so a shard rescores only its ~1/G share of the global top-k1
+    rerank        fused into the rescoring: the kernel that reads a candidate row for its exact
+                  search score also emits its amplitude-encoded fidelity (same bits as
+                  qrag_amp_fidelity), so no row is read twice and no embedding crosses NVLink
+    exchange      ONE all-to-all: the shard's sorted list of query q -- one record of
+                  (score, id, fidelity) x kk, written by the sort kernel in the send layout --
+                  goes to the rank that owns q (queries are partitioned over the ranks)
+    owner         one kernel per rank: merge the G lists by rank (binary searches, nothing moves),
+                  keep the global top-k1, order by (fidelity desc, position asc), keep k2
+    result        one small all-gather of [nq / G, k2] (fidelity, id, status) -> every rank
 
-Every per-row number (search score, fidelity) is computed by the same kernel from the same fp32
+Four collectives per batch, three of them latency-sized; no torch arithmetic between the kernels.
+``return_search_lists=True`` runs the all-gather form instead (every rank materialises the merged
+[nq, k1] search lists): per-shard lists all-gathered, merged on every rank, owner-computes rerank,
+all-reduce(MAX).  It is also the rerun route when some shard could not certify a query.
+
+Every per-row number (search score, fidelity) is computed by the same device code from the same fp32
 row whatever the sharding, and the merges are total orders, so the result for G ranks is
 bit-identical to the result for 1 rank (tests/test_sharded_gloo.py, tests/test_gpu_sharded.py).
 
@@ -32,6 +38,14 @@ from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+def exchange_len(k: int, world: int) -> int:
+    """Entries of the threshold lists and of the packed records that travel between the shards: k for one
+    shard, else min(k, 2k/G + 64 rounded up to 32) (= qrag_search_tc_exchange_len; tests/test_host_logic.py)."""
+    if world <= 1:
+        return int(k)
+    return int(min(k, -(-(2 * k // world + 64) // 32) * 32))
 
 
 def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
@@ -62,6 +76,19 @@ class CudaEngine:
     def search_sharded(self, Q, k, all_gather, shards):
         """This shard's members of the global top-k (thresholds exchanged through ``all_gather``)."""
         return self.index.search_sharded(Q, k, all_gather, shards)
+
+    # ---- packed search + rerank (include/qrag.h: qrag_search_tc_finish_packed / qrag_owner_finalize) ----
+    def packed_begin(self, Q, k, shards):
+        return self.index.tc_begin(Q, k, shards)
+
+    def packed_filter(self, bm_all):
+        return self.index.tc_filter(bm_all)
+
+    def packed_finish(self, ap_all, kk, pack):
+        return self.index.tc_finish_packed(ap_all, kk, pack)
+
+    def owner_finalize(self, recv, kk, k1, k2, q_base, nq, out):
+        return self.api.owner_finalize(recv, kk, k1, k2, self.metric, q_base, nq, out)
 
     def search_exact(self, Q, k):
         """Exact CUDA-core search of this shard (the rerun path for queries the filter could not certify)."""
@@ -95,12 +122,17 @@ class ShardedSearchRerank:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n_total = int(n_total)
+        if self.n_total < self.world:
+            # every rank computes the same bounds, so every rank raises: no rank is left waiting in a collective
+            raise ValueError(f"{self.n_total} rows cannot be sharded over {self.world} ranks (an empty shard)")
         self.lo, self.hi = shard_bounds(self.n_total, self.world, self.rank)
         if X_shard.shape[0] != self.hi - self.lo:
             raise ValueError(f"rank {self.rank} owns rows [{self.lo}, {self.hi}) but got {X_shard.shape[0]} rows")
         self.metric = metric
         self.profile = None          # set to {} to collect per-stage CUDA-event timings (ms) of the next call
         self._marks = []
+        self._bufs = {}
+        self.last_rerun = 0          # 1 if the last call had to rerun through the all-gather form
         self.engine = engine if engine is not None else CudaEngine(X_shard, metric, self.lo)
         if hasattr(self.engine, "sync_corpus_bound"):
             self.engine.sync_corpus_bound(self._all_reduce_max)
@@ -136,7 +168,7 @@ class ShardedSearchRerank:
     def search(self, Q, k1: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """Global top-k1 (identical on every rank): per-shard search, all-gather of the lists, merge.
 
-        With the CUDA engine and G > 1 the shards also exchange their filter thresholds (two [nq, k1]
+        With the CUDA engine and G > 1 the shards also exchange their filter thresholds (two [nq, kt]
         fp32 all-gathers inside the search), so that each shard rescores only its ~1/G share of the
         global list; any query a shard could not certify makes every rank rerun it exactly.
         """
@@ -179,86 +211,90 @@ class ShardedSearchRerank:
         self._flush_marks()
         return top, ids
 
-    def _all_to_all(self, t: torch.Tensor) -> torch.Tensor:
-        """t [G, ...]: slice g goes to rank g; returns [G, ...] with slice g received from rank g."""
-        out = torch.empty_like(t)
-        dist.all_to_all_single(out, t.contiguous(), group=self.group)
-        return out
+    def exact_reference(self, Q, k1: int, k2: int) -> ShardedResult:
+        """The same answer by the plain route, for checking the packed path inside a run (every rank must call it):
+        exact CUDA-core search of each shard (no tensor cores, no thresholds), all-gather of the lists, merge on
+        every rank, owner-computes fidelity with the stand-alone kernel, all-reduce(MAX), stable sort."""
+        s, i = self.engine.search_exact(Q, k1)
+        gathered = self._all_gather(torch.stack([s.view(torch.int64), i], dim=0))
+        ss, si = self.engine.merge(gathered[:, 0].contiguous().view(torch.float64), gathered[:, 1].contiguous(), k1)
+        top, ids = self.rerank(Q, si, min(k2, k1))
+        return ShardedResult(top, ids, ss, si)
+
+    def _buffers(self, nq: int, kk: int, k2: int, device):
+        """Exchange buffers of the packed path, allocated once per shape (send rows beyond nq stay zero: empty records)."""
+        key = (nq, kk, k2, str(device))
+        b = self._bufs.get(key)
+        if b is None:
+            per = -(-nq // self.world)
+            rec, orec = 3 * kk + 1, 2 * k2 + 1
+            b = {"per": per,
+                 "send": torch.zeros((per * self.world, rec), dtype=torch.int64, device=device),
+                 "recv": torch.empty((self.world, per, rec), dtype=torch.int64, device=device),
+                 "out": torch.empty((per, orec), dtype=torch.int64, device=device),
+                 "res": torch.empty((self.world, per, orec), dtype=torch.int64, device=device)}
+            self._bufs = {key: b}
+        return b
 
     def _owner_pipeline(self, Q, k1: int, k2: int) -> Optional[ShardedResult]:
-        """G > 1: everything after the shard search is partitioned BY QUERY, so it scales with 1/G too.
-
-        Each rank scores the fidelity of its own list entries (its rows, no communication), then one
-        all-to-all sends (search score, id, fidelity) of query q to the rank owning q; the owner merges the
-        G lists into the global top-k1 order, ranks by (fidelity desc, position asc) and keeps k2; one small
-        all-gather returns the [nq, k2] result to every rank.  Lists are cut to the longest valid prefix found
-        on any rank before they travel.  Returns None if some query could not be certified (caller falls back).
-        """
-        dev_lists = self.engine.search_sharded(Q, k1, self._all_gather, self.world) \
-            if hasattr(self.engine, "search_sharded") else self.engine.search(Q, k1) + (None,)
-        s, i, status = dev_lists
-        self._mark("search_phases")
-        nq = s.shape[0]
-        # Lists travel cut to kk entries.  A shard holds ~ k1 / G members of the global top-k1; kk leaves 2x that
-        # plus 64, and the cut is VERIFIED at the end of the call (one host sync, after everything is queued): if
-        # any shard had more valid entries than kk, or flagged a query, the caller reruns the all-gather form.
-        kk = k1 if status is None else max(1, min(k1, -(-(2 * k1 // self.world + 64) // 32) * 32))
-        valid = (i >= 0).sum(dim=1).max().to(torch.int64).reshape(1)
-        flag = status.max().to(torch.int64).reshape(1) if status is not None else torch.zeros_like(valid)
-        meta = self._all_reduce_max(torch.cat([flag, valid]))
-        self._mark("status_reduce")
-        s, i = s[:, :kk].contiguous(), i[:, :kk].contiguous()
-        own = i >= 0
-        f = self.engine.fidelity_rows(Q, torch.where(own, i - self.lo, torch.full_like(i, -1)))
-        self._mark("rerank_fidelity")
-        # pack [nq_pad, 3, kk] int64 (score bits, id, fidelity bits), queries padded to a multiple of G
-        per = -(-nq // self.world)
-        pack = torch.full((per * self.world, 3, kk), -1, dtype=torch.int64, device=s.device)
-        pack[:nq, 0], pack[:nq, 1], pack[:nq, 2] = s.view(torch.int64), i, f.view(torch.int64)
-        recv = self._all_to_all(pack.view(self.world, per, 3, kk))           # [G (source shard), per, 3, kk]
+        """The packed path (module docstring): search phases, ONE all-to-all of per-query records to the query's
+        owner, one owner kernel, one small all-gather of the result.  Returns None if some shard could not
+        certify a query or had to cut a list (the caller reruns through the all-gather form); that verdict
+        travels with the result, so the single host sync of the path is the last thing it does."""
+        G, eng = self.world, self.engine
+        if not isinstance(Q, torch.Tensor):
+            Q = torch.as_tensor(Q)
+        nq = Q.shape[0]
+        kk = exchange_len(k1, G)
+        k2 = min(k2, k1)
+        bm = eng.packed_begin(Q, k1, G)
+        bm_all = self._all_gather(bm) if G > 1 else None
+        self._mark("begin+gather")
+        ap = eng.packed_filter(bm_all)
+        ap_all = self._all_gather(ap) if G > 1 else None
+        self._mark("filter+gather")
+        dev = getattr(eng, "device", Q.device)
+        buf = self._buffers(nq, kk, k2, dev)
+        per = buf["per"]
+        eng.packed_finish(ap_all, kk, buf["send"])
+        self._mark("finish_packed")
+        if G > 1:
+            dist.all_to_all_single(buf["recv"].view(G * per, -1), buf["send"], group=self.group)
+            recv = buf["recv"]
+        else:
+            recv = buf["send"].view(1, per, -1)
         self._mark("all_to_all")
-        gs = recv[:, :, 0].contiguous().view(torch.float64)
-        gi = recv[:, :, 1].contiguous()
-        gf = recv[:, :, 2].contiguous().view(torch.float64)
-        # carry the source slot through the merge in the low 20 bits of the tag: ids are unique, so the order
-        # (score, id << 20 | slot) is the canonical (score, id) order
-        slot = (torch.arange(self.world, device=s.device)[:, None, None] * kk +
-                torch.arange(kk, device=s.device)[None, None, :]).expand(self.world, per, kk)
-        tagged = torch.where(gi >= 0, (gi << 20) | slot, gi)
-        k_m = min(k1, self.world * kk)
-        ms, mt = self.engine.merge(gs, tagged, k_m)
-        mi = torch.where(mt >= 0, mt >> 20, mt)
-        src = torch.where(mt >= 0, mt & 0xFFFFF, torch.zeros_like(mt))
-        f_all = gf.permute(1, 0, 2).reshape(per, self.world * kk)
-        mf = torch.gather(f_all, 1, src)
-        mf = torch.where(mt >= 0, mf, torch.full_like(mf, float("-inf")))
-        self._mark("merge")
-        k2 = min(k2, k_m)
-        pos, top = self.engine.sort_scores(mf, k2)
-        ids = torch.gather(mi, 1, pos.long())
-        out = self._all_gather(torch.stack([top.view(torch.int64), ids], dim=0))          # [G, 2, per, k2]
-        top_all = out[:, 0].reshape(self.world * per, k2)[:nq].contiguous().view(torch.float64)
-        ids_all = out[:, 1].reshape(self.world * per, k2)[:nq].contiguous()
-        self._mark("final_sort")
-        flagged, max_valid = (int(v) for v in meta.cpu().tolist())          # the one host sync of the path
+        out = eng.owner_finalize(recv, kk, k1, k2, self.rank * per, nq, buf["out"])
+        self._mark("owner_finalize")
+        if G > 1:
+            dist.all_gather_into_tensor(buf["res"].view(G * per, -1), out, group=self.group)
+            res = buf["res"].view(G * per, -1)[:nq]
+        else:
+            res = out[:nq]
+        top = res[:, :k2].contiguous().view(torch.float64)
+        ids = res[:, k2:2 * k2].contiguous()
+        self._mark("result_gather")
+        bad = int(res[:, 2 * k2].max()) if nq else 0                 # the one host sync of the path
         self._flush_marks()
-        if flagged or max_valid > kk:
+        if bad:
             return None
-        return ShardedResult(top_all, ids_all, None, None)
+        return ShardedResult(top, ids, None, None)
 
     def __call__(self, Q, k1: int = 1000, k2: int = 10, return_search_lists: bool = False) -> ShardedResult:
         """Top-k2 by amplitude fidelity among the global top-k1 of the search (identical on every rank).
 
         ``return_search_lists`` also materialises the merged [nq, k1] search lists on every rank (the
-        all-gather form of the path); without it, G > 1 takes the query-partitioned form.
+        all-gather form of the path); without it the packed, query-partitioned form runs (any G).
         """
         if self.n_total >= (1 << 40):
             raise ValueError("corpus too large: ids must stay below 2**40")
         self._mark("start")
-        if self.world > 1 and not return_search_lists:
+        self.last_rerun = 0
+        if not return_search_lists and hasattr(self.engine, "packed_finish"):
             res = self._owner_pipeline(Q, k1, k2)
             if res is not None:
                 return res
+            self.last_rerun = 1
             self._marks = []
             self._mark("start")
         ss, si = self.search(Q, k1)

@@ -121,22 +121,30 @@ def test_config3_full_size_properties(cuda):
     import torch
     from quantum_rag_b200 import api
     g = torch.Generator(device="cuda").manual_seed(1234 + 3)
-    N, D, nq, k = 1_000_000, 384, 256, 100
+    N, D, nq, k = 1_000_000, 384, 1024, 100
     X = torch.nn.functional.normalize(torch.randn(N, D, generator=g, device="cuda"), dim=1)
     Q = torch.nn.functional.normalize(torch.randn(nq, D, generator=g, device="cuda"), dim=1)
     planted = torch.arange(nq, device="cuda") * 3001 + 7
+    osub = [0, 341, 682, 1023]                           # checked against the NumPy oracle below
+    twice = torch.ones(nq, dtype=torch.bool, device="cuda")
+    twice[osub] = False                                  # (no exact ties there: a BLAS product need not tie bit for bit)
     X[planted] = Q                                       # every query has itself in the corpus
-    X[planted + 1] = Q                                   # ... twice: exact tie, smaller id first
+    X[planted[twice] + 1] = Q[twice]                     # ... twice: exact tie, smaller id first
     index = api.FlatIndexTC(X, "cosine")
     s, i = index.search(Q, k)
     assert index.last_fallback == 0
-    assert torch.equal(i[:, 0], planted) and torch.equal(i[:, 1], planted + 1)
-    assert torch.all(s[:, 0] == s[:, 1]) and torch.allclose(s[:, 0], torch.ones_like(s[:, 0]), atol=1e-6)
+    assert torch.equal(i[:, 0], planted) and torch.equal(i[twice, 1], planted[twice] + 1)
+    assert torch.all(s[twice, 0] == s[twice, 1]) and torch.allclose(s[:, 0], torch.ones_like(s[:, 0]), atol=1e-6)
     assert torch.all(s[:, :-1] >= s[:, 1:])              # sorted
     # a subset of queries against the exact CUDA-core search: identical ids and bits
     sub = torch.arange(0, nq, 37, device="cuda")
     es, ei = api.search_topk(Q[sub], X, k, "cosine")
     assert torch.equal(i[sub], ei) and torch.equal(s[sub], es)
+    # ... and four queries against the NumPy oracle over the whole 1M-row corpus (chunked): identical ids,
+    # scores within fp64 rounding of the oracle's (different summation order)
+    rs, ri = osr.exact_search_chunked(Q[osub].cpu().numpy(), X.cpu().numpy(), k, osr.METRIC_COSINE)
+    assert np.array_equal(i[osub].cpu().numpy(), ri)
+    assert np.allclose(s[osub].cpu().numpy(), rs, rtol=1e-12, atol=1e-15)
     # sharding: merging two half-corpus searches reproduces the full search
     h = N // 2
     a = api.FlatIndexTC(X[:h], "cosine", id_base=0).search(Q, k)
@@ -163,3 +171,59 @@ def test_flat_index_file_roundtrip_and_search(cuda, piers, tmp_path):
     assert names[0] == [labels[i] for i in piers["top20_ids"][0, :3]]
     idx.write(str(tmp_path / "again.faiss"))
     assert (tmp_path / "again.faiss").read_bytes() == path.read_bytes()
+
+
+@pytest.mark.parametrize("D", [384, 1536])
+def test_tensor_core_accumulation_error_is_inside_the_bound(cuda, D):
+    """The third term of the filter's error bound (search_tc.cu tc_eps: g = Kp * 2.4e-7 of |a||b| for the fp32
+    accumulation inside the tensor core) MEASURED: operands exactly representable in bf16, so that operand rounding
+    contributes nothing and |TMEM score - fp64 dot of the same operands| is the accumulation error alone.
+    Data: random signs (cancellation), all-positive (the accumulator grows, every add rounds at its largest ulp),
+    and magnitudes spread over 2^-6 .. 2^6."""
+    import torch
+    from quantum_rag_b200 import api
+    g = torch.Generator(device="cuda").manual_seed(77 + D)
+    N, nq = 8192, 256
+    bf = lambda t: t.bfloat16().float()                                            # noqa: E731
+    X = torch.randn(N, D, generator=g, device="cuda")
+    X[N // 4:N // 2] = X[N // 4:N // 2].abs() + 1.0                                # all positive, similar size
+    X[N // 2:3 * N // 4] *= torch.exp2(torch.randint(-6, 7, (N // 4, D), generator=g, device="cuda").float())
+    Q = torch.randn(nq, D, generator=g, device="cuda")
+    Q[nq // 2:] = Q[nq // 2:].abs() + 1.0
+    X, Q = bf(X), bf(Q)
+    Kp = (D + 15) // 16 * 16
+    worst = 0.0
+    for metric in ("ip",):
+        index = api.FlatIndexTC(X, metric)
+        assert torch.equal(index.Xb[:, :D].float(), X)                             # the shadow IS the data: no rounding
+        S = index.approx_scores(Q).double()
+        exact = Q.double() @ X.double().T
+        scale = Q.double().norm(dim=1)[:, None] * X.double().norm(dim=1)[None, :]
+        ratio = ((S - exact).abs() / scale).max().item()
+        worst = max(worst, ratio)
+    # measured on B200: ~1e-7 * small factor; the bound's constant is Kp * 2.4e-7
+    assert worst <= Kp * 2.4e-7, f"accumulation error {worst:.3e} |a||b| exceeds the bound's {Kp * 2.4e-7:.3e}"
+    assert worst > 0.0                                                             # the probe really measures something
+    print(f"D={D}: measured max accumulation error = {worst:.3e} |a||b|; bound term = {Kp * 2.4e-7:.3e}")
+
+
+def test_approx_scores_within_eps_of_exact(cuda):
+    """The whole bound, measured: |approximate - exact| <= eps for every (query, document) pair on ordinary data,
+    with eps recomputed here from the bound's published formula and the measured rounding-error norms."""
+    import torch
+    from quantum_rag_b200 import api
+    g = torch.Generator(device="cuda").manual_seed(5)
+    N, nq, D = 20000, 64, 384
+    X = torch.randn(N, D, generator=g, device="cuda") * torch.rand(N, 1, generator=g, device="cuda") * 3
+    Q = torch.randn(nq, D, generator=g, device="cuda")
+    index = api.FlatIndexTC(X, "ip")
+    S = index.approx_scores(Q).double()
+    exact = Q.double() @ X.double().T
+    qb = Q.bfloat16().float()
+    qn, qe = Q.double().norm(dim=1), (Q - qb).double().norm(dim=1)
+    xmax, xe = float(index.aux[0]), float(index.aux[1])
+    gk = 384 * 2.4e-7
+    eps = qe * (xmax + xe) + qn * xe + gk * (qn + qe) * (xmax + xe)
+    err = (S - exact).abs().max(dim=1).values
+    assert torch.all(err <= eps), (err / eps).max().item()
+    assert (err / eps).max().item() > 0.01                                         # and it is not vacuous by orders of magnitude

@@ -49,6 +49,43 @@ def _emulated(X, Q, G, k1, k2, metric, phased):
     return top, torch.gather(si, 1, pos.long()), ss, si
 
 
+def _emulated_packed(X, Q, G, k1, k2, metric, check_owner_vs_oracle=True):
+    """The packed form for G shards on one device: phases of every shard in lockstep, the two threshold
+    all-gathers emulated by stack, the all-to-all by slicing every shard's send buffer per owner."""
+    import torch
+    from quantum_rag_b200 import api
+    from quantum_rag_b200.sharded import CudaEngine, exchange_len, shard_bounds
+    n, nq = X.shape[0], Q.shape[0]
+    engines = [CudaEngine(X[lo:hi], metric, lo) for lo, hi in (shard_bounds(n, G, r) for r in range(G))]
+    bound = torch.stack([e.index.aux[:2] for e in engines]).max(dim=0).values
+    for e in engines:
+        e.index.aux[:2] = bound
+    kk, per = exchange_len(k1, G), -(-nq // G)
+    assert kk == api.exchange_len(k1, G)
+    bm = [e.packed_begin(Q, k1, G) for e in engines]
+    bm_all = torch.stack(bm) if G > 1 else None
+    ap = [e.packed_filter(bm_all) for e in engines]
+    ap_all = torch.stack(ap) if G > 1 else None
+    sends = []
+    for e in engines:
+        send = torch.zeros((per * G, 3 * kk + 1), dtype=torch.int64, device=X.device)
+        e.packed_finish(ap_all, kk, send)
+        sends.append(send.view(G, per, -1))
+    outs = []
+    mid = {"cosine": osr.METRIC_COSINE, "l2": osr.METRIC_L2, "ip": osr.METRIC_IP}[metric]
+    for r in range(G):
+        recv = torch.stack([snd[r] for snd in sends]).contiguous()                # [G, per, rec]: what rank r receives
+        out = engines[r].owner_finalize(recv, kk, k1, min(k2, k1), r * per, nq, None)
+        if check_owner_vs_oracle:
+            want = osr.owner_finalize(recv.cpu().numpy(), kk, k1, min(k2, k1), mid, r * per, nq)
+            assert np.array_equal(out.cpu().numpy(), want), f"owner kernel != oracle (rank {r} of {G})"
+        outs.append(out)
+    res = torch.cat(outs)[:nq]
+    k2 = min(k2, k1)
+    assert int(res[:, 2 * k2].max()) == 0, "a shard flagged a query"
+    return res[:, :k2].contiguous().view(torch.float64), res[:, k2:2 * k2].contiguous()
+
+
 @pytest.mark.parametrize("metric", ["cosine", "l2", "ip"])
 def test_sharded_path_matches_oracle_and_single_shard(cuda, metric):
     import torch
@@ -61,7 +98,11 @@ def test_sharded_path_matches_oracle_and_single_shard(cuda, metric):
     X[n // 2 + 5] = X[1]
     Q[0] = X[1]
     Xd, Qd = torch.from_numpy(X).cuda(), torch.from_numpy(Q).cuda()
-    res = ShardedSearchRerank(Xd, n, metric)(Qd, k1, k2)                 # world size 1, CUDA engine
+    path = ShardedSearchRerank(Xd, n, metric)                            # world size 1, CUDA engine
+    res = path(Qd, k1, k2, return_search_lists=True)                     # the all-gather form (materialises the lists)
+    own = path(Qd, k1, k2)                                               # the packed form
+    assert own.search_ids is None and path.last_rerun == 0
+    assert torch.equal(own.ids, res.ids) and torch.equal(own.scores, res.scores)
     # oracle: exact search, then amplitude fidelity of the found rows, stable order
     mid = {"cosine": osr.METRIC_COSINE, "l2": osr.METRIC_L2, "ip": osr.METRIC_IP}[metric]
     rs, ri = osr.exact_search(Q, X, k1, mid)
@@ -74,6 +115,36 @@ def test_sharded_path_matches_oracle_and_single_shard(cuda, metric):
         top, ids, ss, si = _emulated(Xd, Qd, G, k1, k2, metric, phased)
         assert torch.equal(si, res.search_ids) and torch.equal(ss, res.search_scores), f"G={G} phased={phased}"
         assert torch.equal(ids, res.ids) and torch.equal(top, res.scores), f"G={G} phased={phased}"
+    for G in (1, 2, 3, 5, 8):
+        top, ids = _emulated_packed(Xd, Qd, G, k1, k2, metric)
+        assert torch.equal(ids, res.ids) and torch.equal(top, res.scores), f"packed G={G}"
+
+
+def test_owner_finalize_vs_oracle_random_records(cuda):
+    """qrag_owner_finalize against the NumPy restatement on synthetic records: ties in score (id decides) and in
+    fidelity (merged position decides), short and empty lists, flagged shards, padding queries, k2 == k1."""
+    import torch
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(11)
+    for G, per, kk, k1, k2, metric in ((1, 3, 40, 40, 40, "cosine"), (2, 4, 17, 20, 5, "l2"), (8, 5, 320, 1000, 10, "cosine"),
+                                       (3, 2, 64, 100, 100, "ip"), (5, 3, 8, 64, 3, "l2")):
+        mid = {"cosine": osr.METRIC_COSINE, "l2": osr.METRIC_L2, "ip": osr.METRIC_IP}[metric]
+        recv = np.zeros((G, per, 3 * kk + 1), dtype=np.int64)
+        for j in range(per):
+            ids = rng.permutation(G * kk * 4)[:G * kk].reshape(G, kk)
+            for g in range(G):
+                n = int(rng.choice([0, 1, kk // 2, kk]))
+                sc = np.round(rng.standard_normal(n), 1)                          # coarse: many exact score ties
+                fid = np.round(rng.random_sample(n), 1)                           # and fidelity ties
+                key = sc if mid == osr.METRIC_L2 else -sc
+                order = np.lexsort((ids[g, :n], key))
+                s = np.full((1, kk), 0.0); i = np.full((1, kk), -1, dtype=np.int64); f = np.full((1, kk), 0.0)
+                s[0, :n], i[0, :n], f[0, :n] = sc[order], ids[g, :n][order], fid[order]
+                recv[g, j] = osr.pack_records(s, i, f, kk, mid, bad=np.array([int(rng.random_sample() < 0.1)]))[0]
+        nq = 100 + per - 1                                                        # the last owned query is padding
+        want = osr.owner_finalize(recv, kk, k1, k2, mid, 100, nq)
+        got = api.owner_finalize(torch.from_numpy(recv).cuda(), kk, k1, k2, metric, 100, nq)
+        assert np.array_equal(got.cpu().numpy(), want), (G, per, kk, k1, k2, metric)
 
 
 def test_functional_form_and_cache(cuda):
@@ -108,7 +179,10 @@ def test_config4_full_size_properties(cuda):
     Q = torch.nn.functional.normalize(torch.randn(nq, D, generator=g, device="cuda"), dim=1)
     planted = torch.arange(nq, device="cuda") * 78_001 + 11      # spread over all eight shards
     X[planted] = Q
-    res = ShardedSearchRerank(X, N, "cosine")(Q, k1, k2)
+    path = ShardedSearchRerank(X, N, "cosine")
+    res = path(Q, k1, k2, return_search_lists=True)
+    own = path(Q, k1, k2)
+    assert path.last_rerun == 0 and torch.equal(own.ids, res.ids) and torch.equal(own.scores, res.scores)
     assert torch.equal(res.search_ids[:, 0], planted) and torch.equal(res.ids[:, 0], planted)
     assert torch.allclose(res.scores[:, 0], torch.ones(nq, dtype=torch.float64, device="cuda"), atol=1e-12)
     assert torch.all(res.search_scores[:, :-1] >= res.search_scores[:, 1:]) and torch.all(res.scores[:, :-1] >= res.scores[:, 1:])
@@ -119,3 +193,6 @@ def test_config4_full_size_properties(cuda):
     top, ids, ss, si = _emulated(X, Q, 8, k1, k2, "cosine", True)
     assert torch.equal(si, res.search_ids) and torch.equal(ss, res.search_scores)
     assert torch.equal(ids, res.ids) and torch.equal(top, res.scores)
+    for G in (2, 8):
+        top, ids = _emulated_packed(X, Q, G, k1, k2, "cosine", check_owner_vs_oracle=(G == 8))
+        assert torch.equal(ids, res.ids) and torch.equal(top, res.scores), f"packed G={G}"

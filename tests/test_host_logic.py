@@ -164,3 +164,16 @@ def test_metadata_sidecar_only_plain_lists(tmp_path):
     p.write_bytes(pickle.dumps(np.arange(3)))              # needs a global -> refused, never executed
     with pytest.raises(pickle.UnpicklingError):
         qidx.load_metadata(str(p))
+
+
+def test_exchange_len_matches_the_library(libqrag):
+    """sharded.exchange_len (host logic) == qrag_search_tc_exchange_len (what the kernels size their lists with)."""
+    import ctypes
+    from quantum_rag_b200.sharded import exchange_len
+    for k in (1, 7, 10, 100, 999, 1000, 2048):
+        for world in (1, 2, 3, 4, 8, 16, 64):
+            n = ctypes.c_int(0)
+            assert libqrag.qrag_search_tc_exchange_len(k, world, ctypes.byref(n)) == 0
+            assert n.value == exchange_len(k, world), (k, world)
+            assert 1 <= n.value <= k and (world == 1) <= (n.value == k)
+            assert world * n.value >= k                      # the union of the cut lists still holds k entries

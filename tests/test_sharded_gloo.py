@@ -1,9 +1,10 @@
 """Multi-rank logic of the sharded search + rerank on CPU: world_size 2 and 3 over gloo.
 
-The exchange steps (row partition, id_base, packed all-gather, merge, owner-computes rerank,
-all-reduce(MAX), final stable sort) run for real over ``torch.distributed``; the per-rank compute is
-the NumPy oracle plugged in as the engine (the CUDA engine is exercised by tests/test_gpu_sharded.py).
-The G-rank result must equal the 1-rank result bit for bit, ties included.
+The exchange steps run for real over ``torch.distributed``: row partition and id_base, the packed form (two
+threshold all-gathers, ONE all-to-all of per-query records to the query's owner, owner merge, result all-gather)
+and the all-gather form (lists all-gathered, merge, owner-computes rerank, all-reduce(MAX), stable sort).  The
+per-rank compute is the NumPy oracle plugged in as the engine (the CUDA engine is exercised by
+tests/test_gpu_sharded.py).  The G-rank result must equal the 1-rank result bit for bit, ties included.
 """
 import os
 import socket
@@ -16,15 +17,17 @@ import torch.multiprocessing as mp
 
 from oracle import quantum as oq
 from oracle import search as osr
-from quantum_rag_b200.sharded import ShardedSearchRerank, shard_bounds
+from quantum_rag_b200.sharded import ShardedSearchRerank, exchange_len, shard_bounds
 
 
 class OracleEngine:
     """CPU stand-in for CudaEngine: every per-row number depends on that row only (no BLAS blocking)."""
 
-    def __init__(self, X_shard, metric, id_base):
+    def __init__(self, X_shard, metric, id_base, flag_query=None):
         self.X = np.asarray(X_shard, dtype=np.float32)
         self.metric, self.id_base = metric, id_base
+        self.flag_query = flag_query          # this shard reports that query as uncertified
+        self.device = torch.device("cpu")
 
     def _scores(self, Q):
         Q64, X64 = np.asarray(Q, np.float32).astype(np.float64), self.X.astype(np.float64)
@@ -57,6 +60,42 @@ class OracleEngine:
     def sort_scores(self, scores, k):
         order = oq.rank_rows(scores.numpy(), k)
         return torch.from_numpy(order.astype(np.int32)), torch.from_numpy(np.take_along_axis(scores.numpy(), order, 1))
+
+    # ---- the packed form: same protocol as CudaEngine (thresholds from the union of the cut lists) ----
+    def _keys(self, s, i):
+        key = s if self.metric == osr.METRIC_L2 else -s
+        return torch.where(i >= 0, key, torch.full_like(key, float("inf")))
+
+    def packed_begin(self, Q, k, shards):
+        s, i = self.search(Q, k)
+        self._pk = (Q, k, shards, s, i, self._keys(s, i))
+        return self._pk[5][:, :exchange_len(k, shards)].contiguous() if shards > 1 else None
+
+    def packed_filter(self, bm_all):
+        Q, k, shards, s, i, key = self._pk
+        assert bm_all is None or tuple(bm_all.shape) == (shards, key.shape[0], exchange_len(k, shards))
+        return key[:, :exchange_len(k, shards)].contiguous() if shards > 1 else None
+
+    def packed_finish(self, ap_all, kk, pack):
+        Q, k, shards, s, i, key = self._pk
+        nq = key.shape[0]
+        keep = i >= 0
+        if shards > 1:      # k-th best key of the union of the cut lists: valid, exact unless one shard holds > kt
+            kth = torch.sort(ap_all.permute(1, 0, 2).reshape(nq, -1), dim=1).values[:, k - 1:k]
+            keep = keep & (key <= kth)
+        pad_s = float("inf") if self.metric == osr.METRIC_L2 else float("-inf")
+        s = torch.where(keep, s, torch.full_like(s, pad_s))
+        i = torch.where(keep, i, torch.full_like(i, -1))
+        f = self.fidelity_rows(Q, torch.where(keep, i - self.id_base, torch.full_like(i, -1)))
+        bad = np.zeros(nq, dtype=np.int64)
+        if self.flag_query is not None:
+            bad[self.flag_query] = 1
+        pack[:nq] = torch.from_numpy(osr.pack_records(s.numpy(), i.numpy(), f.numpy(), kk, self.metric, bad))
+        return pack
+
+    def owner_finalize(self, recv, kk, k1, k2, q_base, nq, out):
+        out.copy_(torch.from_numpy(osr.owner_finalize(recv.numpy(), kk, k1, k2, self.metric, q_base, nq)))
+        return out
 
 
 def _data(n, d, nq, seed=0):
@@ -95,8 +134,11 @@ def _worker(rank, world, port, n, d, nq, k1, k2, metric, out):
 def _single(n, d, nq, k1, k2, metric):
     X, Q = _data(n, d, nq)
     eng = OracleEngine(X, metric, 0)
-    res = ShardedSearchRerank(torch.from_numpy(X), n, metric, engine=eng)(torch.from_numpy(Q), k1, k2)
-    return (res.scores.numpy(), res.ids.numpy(), res.scores.numpy(), res.ids.numpy(),
+    path = ShardedSearchRerank(torch.from_numpy(X), n, metric, engine=eng)
+    own = path(torch.from_numpy(Q), k1, k2)                                       # packed form, one shard
+    assert own.search_ids is None
+    res = path(torch.from_numpy(Q), k1, k2, return_search_lists=True)
+    return (own.scores.numpy(), own.ids.numpy(), res.scores.numpy(), res.ids.numpy(),
             res.search_scores.numpy(), res.search_ids.numpy())
 
 
@@ -130,13 +172,9 @@ def test_sharded_equals_single_rank(world, metric, n, k1, k2):
 
 
 class PhasedOracleEngine(OracleEngine):
-    """OracleEngine with the phase-split search of the CUDA engine: a shard returns only ITS members of the global
-    top-k (padded with id -1) plus a per-query status, so the list cut, the status reduce and both fall-back routes of
-    ShardedSearchRerank run on CPU.  ``flag_query`` makes one rank report that query as uncertified."""
-
-    def __init__(self, X_shard, metric, id_base, flag_query=None):
-        super().__init__(X_shard, metric, id_base)
-        self.flag_query = flag_query
+    """OracleEngine with the phase-split search of the CUDA engine in the all-gather form too: a shard returns only
+    ITS members of the global top-k (padded with id -1) plus a per-query status, so the status reduce and the exact
+    rerun of ShardedSearchRerank.search run on CPU.  ``flag_query`` makes one rank report that query as uncertified."""
 
     def search_exact(self, Q, k):
         return self.search(Q, k)

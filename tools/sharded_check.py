@@ -82,11 +82,16 @@ def main():
     h = hashlib.sha256()
     for x in (res.ids, res.scores):
         h.update(x.cpu().numpy().tobytes())
+    # the packed NCCL route against the plain one (exact CUDA-core search, all-gather, merge, stand-alone fidelity)
+    sub = torch.arange(0, a.nq, max(1, a.nq // 8), device=dev)[:8]
+    ref = path.exact_reference(Q[sub], a.k1, a.k2)
+    same = bool(torch.equal(ref.ids, res.ids[sub]) and torch.equal(ref.scores, res.scores[sub]))
     if rank == 0:
         ms = float(t[0])
         print(json.dumps({"gpus": world, "N": a.N, "nq": a.nq, "k1": a.k1, "k2": a.k2, "ms_per_batch": ms,
                           "search_scores_per_s": a.nq * a.N / ms * 1e3, "reranked_queries_per_s": a.nq / ms * 1e3,
-                          "fallback_queries": path.engine.index.last_fallback, "stage_ms_rank0": prof, "result_sha256": h.hexdigest()}), flush=True)
+                          "rerun_all_gather_form": path.last_rerun, "equals_exact_route_on_8_queries": same,
+                          "stage_ms_rank0": prof, "result_sha256": h.hexdigest()}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
