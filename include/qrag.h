@@ -46,11 +46,17 @@ extern "C" {
 
 #define QRAG_MAX_QUBITS      12   /* 2^12 complex128 amplitudes staged in shared memory */
 #define QRAG_MAX_SORT_LEN  4096   /* longest per-query list the in-kernel sorts accept   */
+#define QRAG_TC_HIST_BINS   256   /* per-query survivor-score histogram of the tensor-core search */
 
 const char* qrag_last_error(void);
 int         qrag_version(void);
 /* sm count / compute capability of the current device */
 int         qrag_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Measured FP64 FMA rate of the current device (thread-level fused multiply-adds per second; x2 = flop/s): the
+ * roofline the statevector kernels are reported against (MEASURED_PEAKS.json carries HBM and bf16 only).
+ * Runs a short register-only kernel on `stream` and SYNCHRONISES.  scratch: 8 bytes of device memory. */
+int qrag_probe_fp64_fma_rate(double* fma_per_s, double* scratch, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Stream-overlap policy of the streaming kernels (process-wide, default SAFE).
@@ -189,23 +195,30 @@ int qrag_search_tc_scores(const float* Q, int nq, const uint16_t* Xb, int64_t N,
  * candidates and the work scales with 1/G.  The workspace carries state between the phases.
  *   (`shards` = G sizes the sample and the workspace: the same value in the workspace query and every phase;
  *    qrag_search_topk_tc is the G = 1 composition)
- * The threshold lists travel cut to kt = qrag_search_tc_exchange_len(k, G) entries (k for G = 1, else
- * min(k, 2k/G + 64 rounded up to 32)): the k-th largest of the union of the G cut lists is still a valid
- * threshold, and the exact one unless a single shard holds more than kt of the global top k.
- *   begin   bm_top [nq, kt]: this shard's kt largest sampled bucket maxima
- *   filter  bm_top_all [G, nq, kt] (all-gathered) -> tau; ap_top [nq, kt]: this shard's kt best
- *           approximate scores.  aux[0] and aux[1] must hold their maxima over ALL shards.
- *   finish  ap_top_all [G, nq, kt] (all-gathered) -> exact, sorted list of this shard's members of
- *           the global top-k (ids -1 padded); merge the G lists with qrag_topk_merge. */
+ * Two small exchanges, both the caller's:
+ *   (1) all-gather of bm_top [nq, kt], this shard's kt largest sampled bucket maxima, kt =
+ *       qrag_search_tc_exchange_len(k, G) (k for G = 1, else min(k, 2k/G + 64 rounded up to 32)): the k-th
+ *       largest of the union of the G cut lists is a valid filter threshold, and the exact one unless a
+ *       single shard holds more than kt of the global top k;
+ *   (2) all-reduce(SUM) of hist [nq, QRAG_TC_HIST_BINS] int32: the filter pass counts every survivor into a
+ *       per-query histogram of its approximate score (uniform bins from the threshold up, laid out identically
+ *       on every shard because the threshold is global); the highest bin edge with k survivors at or above it
+ *       bounds the k-th best approximate score from below, which is all the candidate cut needs.
+ *   begin   bm_top [nq, kt]
+ *   filter  bm_top_all [G, nq, kt] (all-gathered) -> tau, filter GEMM -> hist [nq, QRAG_TC_HIST_BINS] of THIS
+ *           shard.  aux[0] and aux[1] must hold their maxima over ALL shards.
+ *   finish  hist_all = hist summed over the shards -> exact, sorted list of this shard's members of the
+ *           global top-k (ids -1 padded); merge the G lists with qrag_topk_merge.
+ *   (G = 1: bm_top, bm_top_all, hist and hist_all may be NULL; the workspace carries them.) */
 int qrag_search_tc_exchange_len(int k, int G, int* len);
 int qrag_search_tc_begin(const float* Q, int nq, const uint16_t* Xb, int64_t N, int D, int k, int metric,
                          int shards /* = G of the later phases */,
                          float* bm_top, void* workspace, size_t workspace_bytes, void* stream);
 int qrag_search_tc_filter(int nq, const uint16_t* Xb, const float* aux, int64_t N, int D, int k, int metric,
-                          const float* bm_top_all, int G, float* ap_top,
+                          const float* bm_top_all, int G, int32_t* hist,
                           void* workspace, size_t workspace_bytes, void* stream);
 int qrag_search_tc_finish(const float* Q, int nq, const float* X, int64_t N, int D, int k, int metric,
-                          int64_t id_base, const float* ap_top_all, int G,
+                          int64_t id_base, const int32_t* hist_all, int G,
                           double* out_scores, int64_t* out_ids, int32_t* status,
                           void* workspace, size_t workspace_bytes, void* stream);
 
@@ -223,7 +236,7 @@ int qrag_search_tc_finish(const float* Q, int nq, const float* X, int64_t N, int
  *   recv [G, per, 3 kk + 1]  record of owned query j from every shard;  q_base + j = the query's global number
  *   out  [per, 2 k2 + 1]     k2 fidelities (fp64 bits), k2 ids, status (!= 0: some shard flagged the query) */
 int qrag_search_tc_finish_packed(const float* Q, int nq, const float* X, int64_t N, int D, int k, int metric,
-                                 int64_t id_base, const float* ap_top_all, int G, int kk, int64_t* pack,
+                                 int64_t id_base, const int32_t* hist_all, int G, int kk, int64_t* pack,
                                  void* workspace, size_t workspace_bytes, void* stream);
 int qrag_owner_finalize(const int64_t* recv, int G, int per, int kk, int k1, int k2, int metric,
                         int q_base, int nq, int64_t* out, void* stream);
@@ -231,9 +244,14 @@ int qrag_owner_finalize(const int64_t* recv, int G, int per, int kk, int k1, int
 /* ---------------------------------------------------------------------------
  * (3) Merge of per-shard top-k lists after the all-gather: scores/ids
  * [G, nq, k] -> [nq, k_out] in the canonical order; id < 0 is padding.
+ * Up to G * k = 8192 entries per query are merged by one kernel and need no workspace (NULL, 0);
+ * beyond that the lists are merged in groups over several levels through a workspace of
+ * qrag_topk_merge_workspace bytes (any G; k <= 4096).
  * ------------------------------------------------------------------------- */
+int qrag_topk_merge_workspace(int G, int nq, int k, int k_out, size_t* bytes);
 int qrag_topk_merge(const double* scores, const int64_t* ids, int G, int nq, int k, int k_out,
-                    int metric, double* out_scores, int64_t* out_ids, void* stream);
+                    int metric, double* out_scores, int64_t* out_ids,
+                    void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

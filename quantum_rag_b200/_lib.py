@@ -16,7 +16,9 @@ from typing import Dict, List, Optional
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libqrag.so")
-SOURCES = ["lib.cu", "amp_fidelity.cu", "amp_stream.cu", "sv_kernels.cu", "fmap_warp.cu", "search_exact.cu", "search_tc.cu"]
+SOURCES = ["lib.cu", "probe.cu", "amp_fidelity.cu", "amp_stream.cu", "sv_kernels.cu", "fmap_warp.cu", "search_exact.cu", "search_tc.cu"]
+# Kernel-tuning hooks (environment switches that skip or re-shape work inside product kernels) compile only with
+# -DQRAG_TUNING, which is NOT in these flags: the shipped library reads no environment variable.
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -27,6 +29,7 @@ PROTOTYPES: Dict[str, tuple] = {
     "qrag_last_error": (c_char_p, []),
     "qrag_version": (c_int, []),
     "qrag_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "qrag_probe_fp64_fma_rate": (c_int, [POINTER(c_double), c_void_p, c_void_p]),
     "qrag_set_overlap": (c_int, [c_int]),
     "qrag_get_overlap": (c_int, []),
     "qrag_set_fmap_kernel": (c_int, [c_int]),
@@ -59,8 +62,9 @@ PROTOTYPES: Dict[str, tuple] = {
                                              c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "qrag_owner_finalize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                     c_void_p]),
+    "qrag_topk_merge_workspace": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "qrag_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
-                                c_void_p]),
+                                c_void_p, c_size_t, c_void_p]),
 }
 
 ERROR_NAMES = {-1: "QRAG_ERR_INVALID", -2: "QRAG_ERR_CUDA", -3: "QRAG_ERR_UNSUPPORTED", -4: "QRAG_ERR_WORKSPACE",

@@ -23,6 +23,7 @@ _METRICS = {"ip": METRIC_IP, "inner_product": METRIC_IP, "l2": METRIC_L2, "cosin
 
 MAX_QUBITS = 12
 MAX_SORT_LEN = 4096
+HIST_BINS = 256          # QRAG_TC_HIST_BINS
 
 ArrayLike = Union[torch.Tensor, np.ndarray]
 
@@ -75,6 +76,14 @@ FMAP_AUTO, FMAP_GENERIC = 0, 1
 def set_fmap_kernel(mode: int) -> None:
     """Feature-map kernel choice (include/qrag.h): FMAP_AUTO or FMAP_GENERIC (shared-memory kernel everywhere)."""
     _lib.check(_lib.load().qrag_set_fmap_kernel(int(mode)))
+
+
+def probe_fp64_fma_rate() -> float:
+    """Measured FP64 fused multiply-adds per second of the current device (include/qrag.h); synchronises."""
+    scratch = torch.zeros(1, dtype=torch.float64, device=_device())
+    rate = ctypes.c_double(0.0)
+    _lib.check(_lib.load().qrag_probe_fp64_fma_rate(ctypes.byref(rate), _ptr(scratch), _stream()))
+    return rate.value
 
 
 def qubits_for(dim: int) -> int:
@@ -324,49 +333,50 @@ class FlatIndexTC:
         return bm_top
 
     def tc_filter(self, bm_top_all: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
-        """Phase 2: bm_top_all [G, nq, kt] from every shard -> ap_top [nq, kt], this shard's kt best approximate scores."""
+        """Phase 2: bm_top_all [G, nq, kt] from every shard -> hist [nq, HIST_BINS] int32, this shard's survivor
+        histogram (to be summed over the shards); a single shard keeps it in the workspace and returns None."""
         Qd, k, ws, shards, kt = self._phase
         nq = Qd.shape[0]
-        bm = ap_top = None
+        bm = hist = None
         if shards > 1:
             bm = bm_top_all.contiguous()
             if tuple(bm.shape) != (shards, nq, kt):
                 raise ValueError(f"bm_top_all must be [{shards}, {nq}, {kt}]")
-            ap_top = torch.empty((nq, kt), dtype=torch.float32, device=Qd.device)
+            hist = torch.empty((nq, HIST_BINS), dtype=torch.int32, device=Qd.device)
         _lib.check(_lib.load().qrag_search_tc_filter(nq, _ptr(self.Xb), _ptr(self.aux), self.N, self.D, k, self.metric,
-                                                     _ptr(bm), shards, _ptr(ap_top), _ptr(ws), ws.numel(), _stream()))
-        return ap_top
+                                                     _ptr(bm), shards, _ptr(hist), _ptr(ws), ws.numel(), _stream()))
+        return hist
 
-    def _ap(self, ap_top_all):
+    def _hist(self, hist_all):
         Qd, k, ws, shards, kt = self._phase
         if shards == 1:
             return None
-        ap = ap_top_all.contiguous()
-        if tuple(ap.shape) != (shards, Qd.shape[0], kt):
-            raise ValueError(f"ap_top_all must be [{shards}, {Qd.shape[0]}, {kt}]")
-        return ap
+        h = hist_all.contiguous()
+        if tuple(h.shape) != (Qd.shape[0], HIST_BINS) or h.dtype != torch.int32:
+            raise ValueError(f"hist_all must be int32 [{Qd.shape[0]}, {HIST_BINS}]")
+        return h
 
-    def tc_finish(self, ap_top_all: Optional[torch.Tensor]):
-        """Phase 3: ap_top_all [G, nq, kt] -> (scores, ids, status): this shard's exact, sorted members of the
-        global top-k (ids -1 padded); status != 0 flags a query this shard could not certify."""
+    def tc_finish(self, hist_all: Optional[torch.Tensor]):
+        """Phase 3: hist_all = the survivor histograms summed over the shards -> (scores, ids, status): this shard's
+        exact, sorted members of the global top-k (ids -1 padded); status != 0 flags a query this shard could not certify."""
         Qd, k, ws, shards, kt = self._phase
         nq = Qd.shape[0]
-        ap = self._ap(ap_top_all)
+        h = self._hist(hist_all)
         scores = torch.empty((nq, k), dtype=torch.float64, device=Qd.device)
         ids = torch.empty((nq, k), dtype=torch.int64, device=Qd.device)
         status = torch.zeros(nq, dtype=torch.int32, device=Qd.device)
         _lib.check(_lib.load().qrag_search_tc_finish(_ptr(Qd), nq, _ptr(self.X), self.N, self.D, k, self.metric,
-                                                     self.id_base, _ptr(ap), shards, _ptr(scores), _ptr(ids),
+                                                     self.id_base, _ptr(h), shards, _ptr(scores), _ptr(ids),
                                                      _ptr(status), _ptr(ws), ws.numel(), _stream()))
         self._phase = None
         return scores, ids, status
 
-    def tc_finish_packed(self, ap_top_all: Optional[torch.Tensor], kk: int, pack: torch.Tensor) -> torch.Tensor:
+    def tc_finish_packed(self, hist_all: Optional[torch.Tensor], kk: int, pack: torch.Tensor) -> torch.Tensor:
         """Phase 3, packed (include/qrag.h): the shard's list of every query as a record [3 kk + 1] of int64 words --
         header, kk search scores, kk ids, kk amplitude fidelities -- written into ``pack[:nq]``."""
         Qd, k, ws, shards, kt = self._phase
         nq = Qd.shape[0]
-        ap = self._ap(ap_top_all)
+        ap = self._hist(hist_all)
         if pack.dtype != torch.int64 or pack.dim() != 2 or pack.shape[0] < nq or pack.shape[1] != 3 * kk + 1 \
                 or not pack.is_contiguous():
             raise ValueError(f"pack must be a contiguous int64 [>= {nq}, {3 * kk + 1}] tensor")
@@ -376,16 +386,17 @@ class FlatIndexTC:
         self._phase = None
         return pack
 
-    def search_sharded(self, Q: ArrayLike, k: int, all_gather, shards: int):
-        """This shard's part of a search over G shards: ``all_gather(t)`` must return ``[G, *t.shape]``.
+    def search_sharded(self, Q: ArrayLike, k: int, all_gather, all_reduce_sum, shards: int):
+        """This shard's part of a search over G shards: ``all_gather(t)`` must return ``[G, *t.shape]`` and
+        ``all_reduce_sum(t)`` the sum of ``t`` over the shards.
 
         Thresholds are global, so the shard filters and rescores only ~ (k + margin) / G rows.
         ``self.aux[0]`` must already hold the maximum |x| over all shards (see sharded.py).
         """
         bm = self.tc_begin(Q, k, shards)
         bm_all = all_gather(bm) if shards > 1 else None
-        ap = self.tc_filter(bm_all)
-        return self.tc_finish(all_gather(ap) if shards > 1 else None)
+        hist = self.tc_filter(bm_all)
+        return self.tc_finish(all_reduce_sum(hist) if shards > 1 else None)
 
     def search(self, Q: ArrayLike, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         if self.N == 0:
@@ -431,8 +442,11 @@ def topk_merge(scores: ArrayLike, ids: ArrayLike, k_out: int, metric="l2") -> Tu
     out_s = torch.empty((nq, k_out), dtype=torch.float64, device=s.device)
     out_i = torch.empty((nq, k_out), dtype=torch.int64, device=s.device)
     lib = _lib.load()
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(lib.qrag_topk_merge_workspace(G, nq, k, k_out, ctypes.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=s.device) if nbytes.value else None
     _lib.check(lib.qrag_topk_merge(_ptr(s), _ptr(i), G, nq, k, k_out, metric_id(metric), _ptr(out_s), _ptr(out_i),
-                                   _stream()))
+                                   _ptr(ws), nbytes.value, _stream()))
     return out_s, out_i
 
 

@@ -513,11 +513,17 @@ int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, co
     const DeviceProps& dp = device_props();
     QRAG_REQUIRE(dp.ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
     if (D % 4 != 0 || D > 8192) return QRAG_OK;
-    if (getenv("QRAG_AMP_STREAM_OFF")) return QRAG_OK;          // tuning: force the plain-load kernel
+#ifdef QRAG_TUNING
+    if (getenv("QRAG_AMP_STREAM_OFF")) return QRAG_OK;          // force the plain-load kernel
+#endif
     // Gathered candidates (X + idx) are one 4*D-byte bulk copy per row; the copy engine's per-operation cost
     // caps that form at ~2.5 TB/s for 1.5 KB rows, while the plain-load kernel (12 x 16 B loads in flight per
     // lane) reaches 3.2 - 4.1 TB/s on the same input.  The streaming kernel keeps the dense form.
+#ifdef QRAG_TUNING
     if (cand == nullptr && !getenv("QRAG_AMP_STREAM_GATHER")) return QRAG_OK;
+#else
+    if (cand == nullptr) return QRAG_OK;
+#endif
     if (((uintptr_t)Q | (uintptr_t)(cand ? cand : X)) % 16 != 0) return QRAG_OK;
     if (nq < 1 || C < 1) return QRAG_OK;
 
@@ -535,8 +541,10 @@ int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, co
     while (rb > 1 && (size_t)rb * D * 4 > 8 * 1024) rb >>= 1;
     int g = AS_CWARPS;
     while (g > 1 && (size_t)g * rb * D * 4 > 24 * 1024) g >>= 1;
+#ifdef QRAG_TUNING
     if (const char* e = getenv("QRAG_AMP_STREAM_RB")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) rb = v; }
     if (const char* e = getenv("QRAG_AMP_STREAM_G")) { const int v = atoi(e); if (v >= 1 && v <= 16 && !(v & (v - 1))) g = v; }
+#endif
     size_t smem_bytes = 0;
     while (plan_stream(p, rb, g, fused, budget, &smem_bytes) < 2) {
         if (g > 1) g >>= 1;

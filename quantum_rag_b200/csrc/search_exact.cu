@@ -277,20 +277,91 @@ extern "C" int qrag_search_topk(const float* Q, int nq, const float* X, int64_t 
     }
 }
 
+// levels of a merge of G lists of k entries when G * k exceeds what one CTA sorts at once: groups of `group` lists
+// are merged to min(k_out, ...) entries each until one list remains
+static int merge_group(int k) {
+    int g = MERGE_MAX / (k > 0 ? k : 1);
+    return g < 2 ? 2 : g;
+}
+
+extern "C" int qrag_topk_merge_workspace(int G, int nq, int k, int k_out, size_t* bytes) {
+    QRAG_REQUIRE(bytes != nullptr, QRAG_ERR_INVALID, "bytes is null");
+    QRAG_REQUIRE(G >= 1 && nq >= 0 && k >= 1 && k_out >= 1, QRAG_ERR_INVALID, "bad sizes G=%d nq=%d k=%d k_out=%d", G, nq, k,
+                 k_out);
+    *bytes = 0;
+    if ((int64_t)G * k <= MERGE_MAX) return QRAG_OK;
+    const int kl = k_out < k ? k_out : k;                    // entries a group keeps: no list can contribute more
+    QRAG_REQUIRE(2 * (int64_t)(k > kl ? k : kl) <= MERGE_MAX, QRAG_ERR_UNSUPPORTED, "lists of %d entries are too long to merge", k);
+    const int g1 = merge_group(k);
+    const size_t l1 = (size_t)nq * ceil_div(G, g1) * kl;
+    const size_t l2 = (size_t)nq * ceil_div(ceil_div(G, g1), merge_group(kl)) * kl;
+    *bytes = align_up(l1 * 16, 256) + align_up(l2 * 16, 256) + 256;
+    return QRAG_OK;
+}
+
 extern "C" int qrag_topk_merge(const double* scores, const int64_t* ids, int G, int nq, int k, int k_out, int metric,
-                               double* out_scores, int64_t* out_ids, void* stream) {
+                               double* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream) {
     QRAG_REQUIRE(scores && ids && out_scores && out_ids, QRAG_ERR_INVALID, "null pointer argument");
     QRAG_REQUIRE(G >= 1 && nq >= 0 && k >= 1 && k_out >= 1, QRAG_ERR_INVALID, "bad sizes G=%d nq=%d k=%d k_out=%d", G,
                  nq, k, k_out);
     QRAG_REQUIRE(metric >= 0 && metric <= 2, QRAG_ERR_INVALID, "unknown metric %d", metric);
-    QRAG_REQUIRE((int64_t)G * k <= MERGE_MAX, QRAG_ERR_UNSUPPORTED, "G*k=%lld exceeds %d", (long long)G * k, MERGE_MAX);
     if (nq == 0) return QRAG_OK;
     QRAG_REQUIRE(device_props().ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
+    cudaStream_t st = (cudaStream_t)stream;
     MergeParams mp{};
     mp.in_key = scores; mp.in_tag = reinterpret_cast<const long long*>(ids);
     mp.stride_l = (int64_t)nq * k; mp.stride_q = k;
-    mp.nlists = G; mp.kin = k; mp.group = G; mp.nq = nq; mp.raw_scores = 1; mp.metric = metric;
-    mp.out_key = out_scores; mp.out_tag = reinterpret_cast<long long*>(out_ids);
-    mp.kout = k_out; mp.final_out = 1;
-    return launch_merge(mp, (cudaStream_t)stream);
+    mp.nlists = G; mp.kin = k; mp.nq = nq; mp.raw_scores = 1; mp.metric = metric;
+    if ((int64_t)G * k <= MERGE_MAX) {                       // one level
+        mp.group = G;
+        mp.out_key = out_scores; mp.out_tag = reinterpret_cast<long long*>(out_ids);
+        mp.kout = k_out; mp.final_out = 1;
+        return launch_merge(mp, st);
+    }
+    // several levels, ping-ponging between two workspace buffers of (key, tag) lists
+    size_t need = 0;
+    int rc = qrag_topk_merge_workspace(G, nq, k, k_out, &need);
+    if (rc) return rc;
+    QRAG_REQUIRE(workspace != nullptr && workspace_bytes >= need, QRAG_ERR_WORKSPACE,
+                 "merge of %d lists x %d entries needs a workspace of %zu bytes (qrag_topk_merge_workspace), got %zu", G, k,
+                 need, workspace_bytes);
+    const int kl = k_out < k ? k_out : k;
+    const int g1 = merge_group(k);
+    const size_t l1 = (size_t)nq * ceil_div(G, g1) * kl;
+    unsigned char* base = reinterpret_cast<unsigned char*>(align_up((size_t)workspace, 256));
+    double* key_a = reinterpret_cast<double*>(base);
+    long long* tag_a = reinterpret_cast<long long*>(key_a + l1);
+    unsigned char* base_b = base + align_up(l1 * 16, 256);
+    const size_t l2 = (size_t)nq * ceil_div(ceil_div(G, g1), merge_group(kl)) * kl;
+    double* key_b = reinterpret_cast<double*>(base_b);
+    long long* tag_b = reinterpret_cast<long long*>(key_b + l2);
+    // level 1: raw (score, id) lists -> keys/tags
+    mp.group = g1; mp.kout = kl; mp.final_out = 0;
+    mp.out_key = key_a; mp.out_tag = tag_a;
+    rc = launch_merge(mp, st);
+    if (rc) return rc;
+    int nlists = (int)ceil_div(G, g1);
+    const double* in_key = key_a; const long long* in_tag = tag_a;
+    double* ok = key_b; long long* ot = tag_b;
+    const int g2 = merge_group(kl);
+    while (true) {
+        const int ngroups = (nlists + g2 - 1) / g2;
+        MergeParams m2{};
+        m2.in_key = in_key; m2.in_tag = in_tag;
+        m2.stride_q = (int64_t)nlists * kl; m2.stride_l = kl;
+        m2.nlists = nlists; m2.kin = kl; m2.group = g2; m2.nq = nq; m2.metric = metric;
+        if (ngroups == 1) {
+            m2.kout = k_out; m2.final_out = 1;
+            m2.out_key = out_scores; m2.out_tag = reinterpret_cast<long long*>(out_ids);
+            return launch_merge(m2, st);
+        }
+        m2.kout = kl;
+        m2.out_key = ok; m2.out_tag = ot;
+        rc = launch_merge(m2, st);
+        if (rc) return rc;
+        const double* nk = ok; const long long* nt = ot;
+        ok = const_cast<double*>(in_key); ot = const_cast<long long*>(in_tag);
+        in_key = nk; in_tag = nt;
+        nlists = ngroups;
+    }
 }

@@ -57,6 +57,7 @@ constexpr int TC_MAX_CAND = 8192;     // largest exact-rescore capacity per quer
 constexpr int TC_MAX_SEGS = 640;      // survivor-list segments per query (TC_EPI_SPLIT per CTA of the query's group)
 constexpr int TC_MAX_STAGES = 10;
 constexpr int TC_MODE_BUCKET = 0, TC_MODE_FILTER = 1, TC_MODE_DUMP = 2;
+constexpr int TC_HIST_BINS = QRAG_TC_HIST_BINS;   // survivor-score histogram per query (filter pass -> a_k)
 
 struct TcGemmParams {
     int kchunks;            // ceil(Kp / 64)
@@ -73,7 +74,9 @@ struct TcGemmParams {
     int nbuckets;           // buckets per query in pass 1 = nsample_tiles * 8
     const float* tau;       // [nq] (filter)
     float* bmax;            // [nq, nbuckets] (bucket)
-    int debug_skip;         // TUNING ONLY
+#ifdef QRAG_TUNING
+    int debug_skip;         // kernel-tuning builds only (-DQRAG_TUNING): 1 / 3 / 4 skip parts of the epilogue
+#endif
     int cap;                // survivor slots per query
     int seg_cap;            // survivor slots per (query, CTA, column quarter) segment
     unsigned int* cnt;      // [nq, TC_MAX_SEGS] survivors found per segment, may exceed seg_cap (filter)
@@ -363,7 +366,9 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const uint32_t t0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * TC_BN + (uint32_t)half * TC_EPI_COLS;
             // one 32-column chunk of this thread's row: bucket maximum, or threshold test and survivor append
             auto process = [&](uint32_t (&r)[32], const int c0) {
+#ifdef QRAG_TUNING
                 if (p.debug_skip == 3) { if ((r[0] ^ r[31]) == 0x12345u) found += 1; return; }
+#endif
                 if (MODE == TC_MODE_DUMP) {
                     if (qvalid) {
 #pragma unroll
@@ -385,7 +390,9 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < w; ++j) t[j] = fmaxf(t[j], t[j + w]);
                 const float m = t[0];
+#ifdef QRAG_TUNING
                 if (p.debug_skip == 4) { if (m == 1234.5f) found += 1; return; }
+#endif
                 if (MODE == TC_MODE_BUCKET) {
                     if (qvalid) p.bmax[(size_t)q * p.nbuckets + (size_t)u * (TC_BN / TC_BUCKET) + (c0 >> 5)] = m;
                 } else if (m >= tau) {
@@ -400,7 +407,10 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 }
             };
             static_assert(TC_EPI_COLS == 64, "the epilogue below issues both of a warp's chunk loads up front");
-            if (p.debug_skip != 1) {
+#ifdef QRAG_TUNING
+            if (p.debug_skip != 1)
+#endif
+            {
                 uint32_t ra[32], rb[32];
                 tmem_ld32(t0, ra);
                 tmem_ld32(t0 + 32, rb);
@@ -655,111 +665,87 @@ __global__ void __launch_bounds__(256) bucket_topk_kernel(const float* __restric
 }
 
 // per query: m_k = k-th largest bucket maximum over all G shards' lists; tau = m_k - 2 eps, rounded down
-// (single shard: bm_top_all == nullptr and the k-th largest is taken straight from this shard's bucket maxima)
+// (single shard: bm_top_all == nullptr and the k-th largest is taken straight from this shard's bucket maxima).
+// Also lays out the query's survivor histogram (surv_hist_kernel): TC_HIST_BINS uniform bins from tau up to the
+// largest sampled bucket maximum (scores above it land in the last bin).
 __global__ void __launch_bounds__(256) tau_union_kernel(const float* __restrict__ bm_top_all, int G, int nq, int k, int kt,
                                                         int metric,
                                                         int Kp, const float* __restrict__ qnorm, const float* __restrict__ qerr,
                                                         const float* __restrict__ aux,
                                                         const float* __restrict__ bmax, int nbuckets,
-                                                        float* __restrict__ tau, float* __restrict__ eps) {
+                                                        float* __restrict__ tau, float* __restrict__ eps,
+                                                        float* __restrict__ hinv) {
     __shared__ RadixSel rs;
+    __shared__ float s_max[8];
     const int q = blockIdx.x;
-    float mk = neg_inf_f();
+    float mk = neg_inf_f(), top = neg_inf_f();
+    auto track = [&](auto f) { return [&top, f](float v) { top = fmaxf(top, v); f(v); }; };
     if (bm_top_all != nullptr) {
         auto fe = [&](auto f) {
             for (int g = 0; g < G; ++g) {
                 const float* row = bm_top_all + ((size_t)g * nq + q) * kt;
-                for_strided<4>(threadIdx.x, kt, blockDim.x, [&](int j) { return row[j]; }, f);
+                for_strided<4>(threadIdx.x, kt, blockDim.x, [&](int j) { return row[j]; }, track(f));
             }
         };
         if ((int64_t)G * kt >= k) mk = block_kth_largest(rs, k, fe);
     } else if (nbuckets >= k) {
         const float* row = bmax + (size_t)q * nbuckets;
-        auto fe = [&](auto f) { for_strided<8>(threadIdx.x, nbuckets, blockDim.x, [&](int j) { return row[j]; }, f); };
+        auto fe = [&](auto f) { for_strided<8>(threadIdx.x, nbuckets, blockDim.x, [&](int j) { return row[j]; }, track(f)); };
         mk = block_kth_largest(rs, k, fe);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) top = fmaxf(top, __shfl_xor_sync(FULL_MASK, top, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = top;
+    __syncthreads();
     if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) top = fmaxf(top, s_max[w]);
         const float e = tc_eps(metric, Kp, qnorm[q], qerr[q], aux[0], aux[1]);
         eps[q] = e;
         float t = mk - 2.f * e;                                   // -inf stays -inf (fewer than k buckets)
         t = t - fabsf(t) * 2.4e-7f - 1e-37f;                      // the subtraction above rounds to nearest: step down
         tau[q] = t;
+        // The bins reach 1.6x beyond the largest SAMPLED maximum: the corpus holds ~ `sample` times more documents
+        // above it than the sample does, and all of them share the last bin -- if that bin alone held k survivors the
+        // cut could not be placed any higher (measured: 1 % of the queries at 1/39 sampling without the extension).
+        const float width = 1.6f * (top - t);                     // > 0 whenever both are finite (top >= m_k > tau)
+        hinv[q] = (width > 0.f && width < 3.0e38f) ? (float)(TC_HIST_BINS - 1) / width : 0.f;
     }
 }
 
-// per query: the kt largest approximate scores among this shard's survivors -> ap_top [nq, kt]
-// The survivors' scores are copied into shared memory once (up to SV_CACHE of them; a longer list keeps its tail in
-// global memory), so the four radix passes and the collection read HBM/L2 once instead of five times.
-constexpr int SV_CACHE = 18432;        // floats: 72 KB, three CTAs per SM
-__global__ void __launch_bounds__(256) surv_topk_kernel(const unsigned int* __restrict__ cnt, const float2* __restrict__ surv,
-                                                        int q0, int nseg, int seg_cap, int cap, int kt,
-                                                        float* __restrict__ ap_top) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* vals = reinterpret_cast<float*>(smem_raw);                  // [SV_CACHE]
-    __shared__ RadixSel rs;
-    __shared__ int seg_n[TC_MAX_SEGS];
-    __shared__ int seg_off[TC_MAX_SEGS + 1];
+// per query: histogram of this shard's survivors over their approximate score, bin = min(BINS - 1, (v - tau) * hinv).
+// One pass over the survivor lists.  It replaces a select over them and, sharded, the exchange of k scores per query
+// and shard by an all-reduce(SUM) of TC_HIST_BINS counters: the bins are laid out identically on every shard (tau and
+// hinv come from the all-gathered bucket maxima), and the highest bin edge with k survivors at or above it bounds
+// the k-th best approximate score from below, which is all the candidate cut needs.  (int)NaN == 0, +inf saturates.
+// (Counting in the filter GEMM's epilogue instead was measured: +14 % on the GEMM, whose epilogue is its critical path.)
+__global__ void __launch_bounds__(256) surv_hist_kernel(const unsigned int* __restrict__ cnt, const float2* __restrict__ surv,
+                                                        int q0, int nseg, int seg_cap, int cap,
+                                                        const float* __restrict__ tau, const float* __restrict__ hinv,
+                                                        int* __restrict__ hist) {
+    __shared__ int h[TC_HIST_BINS];
     const int q = q0 + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    for (int sgi = tid; sgi < nseg; sgi += blockDim.x) {
-        const unsigned int c = cnt[(size_t)q * TC_MAX_SEGS + sgi];
-        seg_n[sgi] = c < (unsigned)seg_cap ? (int)c : seg_cap;
-    }
+    for (int i = tid; i < TC_HIST_BINS; i += blockDim.x) h[i] = 0;
     __syncthreads();
-    if (warp == 0) {                                                   // exclusive scan of the segment lengths
-        int carry = 0;
-        for (int b = 0; b < nseg; b += 32) {
-            const int v = b + lane < nseg ? seg_n[b + lane] : 0;
-            int incl = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(FULL_MASK, incl, o);
-                if (lane >= o) incl += t;
-            }
-            if (b + lane < nseg) seg_off[b + lane] = carry + incl - v;
-            carry += __shfl_sync(FULL_MASK, incl, 31);
-        }
-        if (lane == 0) seg_off[nseg] = carry;
-    }
-    __syncthreads();
-    const int total = seg_off[nseg];
-    const int ncached = total < SV_CACHE ? total : SV_CACHE;
+    const float t = tau[q], hv = hinv[q];
     const float2* sv = surv + (size_t)q * cap;
     for (int sgi = warp; sgi < nseg; sgi += nwarps) {
+        const unsigned int c = cnt[(size_t)q * TC_MAX_SEGS + sgi];
+        const int n = c < (unsigned)seg_cap ? (int)c : seg_cap;
         const float2* sp = sv + (size_t)sgi * seg_cap;
-        const int off = seg_off[sgi];
-        int n = seg_n[sgi];
-        if (off + n > SV_CACHE) n = off < SV_CACHE ? SV_CACHE - off : 0;
-        for (int i0 = lane; i0 < n; i0 += 128) {
-            float v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = i0 + 32 * u < n ? sp[i0 + 32 * u].x : 0.f;
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (i0 + 32 * u < n) vals[off + i0 + 32 * u] = v[u];
-        }
+        for_strided<4>(lane, n, 32, [&](int j) { return sp[j].x; },
+                       [&](float v) { atomicAdd(&h[max(0, min(TC_HIST_BINS - 1, (int)((v - t) * hv)))], 1); });
     }
     __syncthreads();
-    auto fe = [&](auto f) {
-        for_strided<4>(tid, ncached, (int)blockDim.x, [&](int j) { return vals[j]; }, f);
-        if (total > SV_CACHE) {                                        // block-uniform: the uncached tail
-            for (int sgi = warp; sgi < nseg; sgi += nwarps) {
-                const int off = seg_off[sgi], n = seg_n[sgi];
-                if (off + n <= SV_CACHE) continue;
-                const int first = off < SV_CACHE ? SV_CACHE - off : 0;
-                const float2* sp = sv + (size_t)sgi * seg_cap + first;
-                for_strided<4>(lane, n - first, 32, [&](int j) { return sp[j].x; }, f);
-            }
-        }
-    };
-    block_topk_values(rs, kt, total, fe, ap_top + (size_t)q * kt);
+    for (int i = tid; i < TC_HIST_BINS; i += blockDim.x) hist[(size_t)q * TC_HIST_BINS + i] = h[i];
 }
 
 // ---------------------------------------------------------------------------------- final stage
 struct TcFinalParams {
     const float* Q; const float* X; int q0; int nq; int64_t N; int D; int k; int metric; int64_t id_base;
     int nseg, seg_cap, cap, cand_cap;
-    int G; int kt; const float* ap_top_all;  // [G, nq, kt] the kt best approximate scores of every shard
+    const int* hist;                         // [nq, TC_HIST_BINS] survivors per score bin, summed over ALL shards
+    const float* tau; const float* hinv;     // [nq] the histogram's origin and bins per unit of score
     const unsigned int* cnt; const float2* surv; const float* eps;
     double* out_scores; int64_t* out_ids; int32_t* status;
     int* cand_rows; double* cand_key; int* cand_m;     // [nq, cand_cap], [nq, cand_cap], [nq, 2] (count, overflow)
@@ -788,52 +774,65 @@ __device__ void bitonic_sort_kt(K* key, T* tag, int P) {
 // The final stage is three kernels, so that each runs at the occupancy its work allows (as one kernel, 55 KB of
 // shared memory and 78 registers held it to 3 CTAs per SM and its phases could not overlap: ncu, k = 1000).
 //
-// (1) one CTA per query: a_k = k-th best approximate score over all shards (from their top-k lists; single shard:
-// from this query's survivor segments), candidates = this shard's survivors >= a_k - 2 eps -> cand_rows, cand_m.
+// (1) one CTA per query: a_k = a lower bound of the k-th best approximate score over all shards, read off the
+// survivor histogram the filter pass built (summed over the shards by the caller): the highest bin edge that still
+// has k survivors at or above it.  Candidates = this shard's survivors >= a_k - 2 eps -> cand_rows, cand_m.
 __global__ void __launch_bounds__(XS_THREADS) tc_collect_kernel(const TcFinalParams p) {
-    __shared__ RadixSel rs;
     __shared__ int seg_n[TC_MAX_SEGS];
-    __shared__ int s_m, s_bad, s_total;
+    __shared__ int s_m, s_bad;
+    __shared__ float s_ak;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = p.q0 + blockIdx.x;
     const int k = p.k;
     const float2* sv = p.surv + (size_t)q * p.cap;
     int* cand = p.cand_rows + (size_t)q * p.cand_cap;
 
-    if (tid == 0) { s_m = 0; s_bad = 0; s_total = 0; }
+    if (tid == 0) { s_m = 0; s_bad = 0; }
     __syncthreads();
     for (int sgi = tid; sgi < p.nseg; sgi += XS_THREADS) {
         const unsigned int c = p.cnt[(size_t)q * TC_MAX_SEGS + sgi];
         seg_n[sgi] = c < (unsigned)p.seg_cap ? (int)c : p.seg_cap;
         if (c > (unsigned)p.seg_cap) s_bad = 1;
     }
-    float ak = neg_inf_f();
-    if (p.ap_top_all != nullptr) {
-        auto fe = [&](auto f) {
-            for (int g = 0; g < p.G; ++g) {
-                const float* row = p.ap_top_all + ((size_t)g * p.nq + q) * p.kt;
-                for_strided<4>(tid, p.kt, XS_THREADS, [&](int j) { return row[j]; }, f);
-            }
-        };
-        if ((int64_t)p.G * p.kt >= k) ak = block_kth_largest(rs, k, fe);     // starts and ends with __syncthreads()
-        else __syncthreads();
-    } else {
-        __syncthreads();
-        int mine = 0;
-        for (int sgi = tid; sgi < p.nseg; sgi += XS_THREADS) mine += seg_n[sgi];
-        if (mine) atomicAdd(&s_total, mine);
-        __syncthreads();
-        if (s_total >= k) {
-            auto fe = [&](auto f) {
-                for (int sgi = warp; sgi < p.nseg; sgi += XS_WARPS) {
-                    const float2* sp = sv + (size_t)sgi * p.seg_cap;
-                    for_strided<4>(lane, seg_n[sgi], 32, [&](int j) { return sp[j].x; }, f);
-                }
-            };
-            ak = block_kth_largest(rs, k, fe);
+    if (warp == 0) {
+        // lane l owns bins 8l .. 8l+7; suffix counts from the top bin down; j* = the largest bin index with at least k
+        // survivors in bins >= j*.  Every survivor v in a bin >= j has (v - tau) * hinv >= j up to two fp32 roundings,
+        // so tau + (j / hinv)(1 - 4e-6), stepped down once more for the final add, is <= all of them.
+        static_assert(TC_HIST_BINS == 256, "8 bins per lane");
+        const int* h = p.hist + (size_t)q * TC_HIST_BINS + 8 * lane;
+        int c[8], mine = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { c[u] = h[u]; mine += c[u]; }
+        int incl = mine;                                    // sum over lanes >= this one (suffix scan)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_down_sync(FULL_MASK, incl, o);
+            if (lane + o < 32) incl += t;
         }
-        __syncthreads();
+        int above = incl - mine, jbest = -1;                // survivors in the bins above this lane's
+#pragma unroll
+        for (int u = 7; u >= 0; --u) {
+            above += c[u];
+            if (jbest < 0 && above >= k) jbest = 8 * lane + u;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) jbest = max(jbest, __shfl_xor_sync(FULL_MASK, jbest, o));
+        if (lane == 0) {
+            float ak = neg_inf_f();                         // fewer than k survivors in total: keep them all
+            if (jbest >= 0) {
+                const float t = p.tau[q], hv = p.hinv[q];
+                ak = t;
+                if (jbest > 0 && hv > 0.f) {
+                    ak = t + ((float)jbest / hv) * (1.f - 4e-6f);
+                    ak = ak - fabsf(ak) * 2.4e-7f - 1e-37f;
+                    ak = fmaxf(ak, t);
+                }
+            }
+            s_ak = ak;
+        }
     }
+    __syncthreads();
+    const float ak = s_ak;
     float thr = ak - 2.f * p.eps[q];                                        // -inf stays -inf
     thr = thr - fabsf(thr) * 2.4e-7f - 1e-37f;
     // candidates (any order: the final sort is a total order on (score, id))
@@ -1132,8 +1131,8 @@ struct TcPlan {
     int cand_cap, cap;
     int kt;                 // entries of the threshold lists the shards exchange (tc_exchange_len)
     size_t smem_gemm, smem_final;
-    size_t off_qb, off_qnorm, off_bmax, off_tau, off_eps, off_cnt, off_surv, off_crow, off_ckey, off_cfid,
-        off_cm, total;
+    size_t off_qb, off_qnorm, off_bmax, off_tau, off_eps, off_hinv, off_hist, off_cnt, off_surv, off_crow, off_ckey,
+        off_cfid, off_cm, total;
 };
 
 // Lists exchanged between the shards of a G-way search travel cut to this many entries.  A shard holds ~ k / G of
@@ -1164,7 +1163,10 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPl
     const size_t budget = (size_t)dp.max_smem_optin;
     pl->a_resident = (1024 + 256 + a_bytes + 3 * (size_t)TC_B_STAGE <= budget) ? 1 : 0;
     // CTA pairs (cta_group::2) whenever there are at least two query groups and the query tile is resident
-    pl->cg = (pl->a_resident && nq > TC_BM && !getenv("QRAG_TC_NO_PAIR")) ? 2 : 1;
+    pl->cg = (pl->a_resident && nq > TC_BM) ? 2 : 1;
+#ifdef QRAG_TUNING
+    if (getenv("QRAG_TC_NO_PAIR")) pl->cg = 1;
+#endif
     pl->stage_bytes = pl->a_resident ? TC_B_STAGE / pl->cg : TC_B_STAGE + TC_A_CHUNK;
     const size_t fixed = 1024 + 256 + (pl->a_resident ? a_bytes : 0);
     int stages = (int)((budget - fixed) / pl->stage_bytes);
@@ -1212,6 +1214,8 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPl
     pl->off_bmax = off; off = align_up(off + (size_t)pl->nq_pad * pl->nbuckets * 4, 256);
     pl->off_tau = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
     pl->off_eps = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
+    pl->off_hinv = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
+    pl->off_hist = off; off = align_up(off + (size_t)pl->nq_pad * TC_HIST_BINS * 4, 256);
     pl->off_cnt = off; off = align_up(off + (size_t)pl->nq_pad * TC_MAX_SEGS * 4, 256);
     pl->off_surv = off; off = align_up(off + (size_t)pl->nq_pad * cap * 8, 256);
     pl->off_crow = off; off = align_up(off + (size_t)pl->nq_pad * cand_cap * 4, 256);
@@ -1225,7 +1229,8 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPl
 // workspace carved the same way by every phase of one search (the phases share state through it)
 struct TcWs {
     TcPlan pl;
-    __nv_bfloat16* Qb; float* qnorm; float* bmax; float* tau; float* eps; unsigned int* cnt; float2* surv;
+    __nv_bfloat16* Qb; float* qnorm; float* bmax; float* tau; float* eps; float* hinv; int* hist; unsigned int* cnt;
+    float2* surv;
     int* crow; double* ckey; double* cfid; int* cm;
     float* dump = nullptr;  // qrag_search_tc_scores only
 };
@@ -1243,6 +1248,8 @@ static int tc_ws(int nq, int64_t N, int D, int k, int metric, int shards, void* 
     w->bmax = reinterpret_cast<float*>(ws + pl.off_bmax);
     w->tau = reinterpret_cast<float*>(ws + pl.off_tau);
     w->eps = reinterpret_cast<float*>(ws + pl.off_eps);
+    w->hinv = reinterpret_cast<float*>(ws + pl.off_hinv);
+    w->hist = reinterpret_cast<int*>(ws + pl.off_hist);
     w->cnt = reinterpret_cast<unsigned int*>(ws + pl.off_cnt);
     w->surv = reinterpret_cast<float2*>(ws + pl.off_surv);
     w->crow = reinterpret_cast<int*>(ws + pl.off_crow);
@@ -1307,7 +1314,9 @@ static int tc_gemm_pass(const TcWs& w, int nq, int64_t N, const uint16_t* Xb, cu
     gp.a_resident = pl.a_resident; gp.stage_bytes = pl.stage_bytes;
     gp.nq = nq; gp.N = N; gp.ntiles = pl.ntiles; gp.sample = pl.sample; gp.nbuckets = pl.nbuckets;
     gp.tau = w.tau; gp.bmax = w.bmax; gp.cnt = w.cnt; gp.surv = w.surv; gp.dump = w.dump;
+#ifdef QRAG_TUNING
     if (const char* e = getenv("QRAG_TC_DEBUG_SKIP")) gp.debug_skip = atoi(e);
+#endif
     const int units = MODE == TC_MODE_BUCKET ? pl.nsample_tiles : pl.ntiles;
     for (int g0 = 0; g0 < pl.groups;) {
         const TcLaunch L = tc_launch_at(pl, g0, units);
@@ -1404,26 +1413,24 @@ extern "C" int qrag_search_tc_scores(const float* Q, int nq, const uint16_t* Xb,
     return tc_gemm_pass<TC_MODE_DUMP>(w, nq, N, Xb, st, [](int, int, int, int) { return QRAG_OK; });
 }
 
-// phase 2: threshold from all shards' bucket maxima, filter GEMM, the shard's k best approximate scores
+// phase 2: threshold from all shards' bucket maxima, filter GEMM, then this shard's survivors counted into the
+// per-query score histogram (hist [nq, QRAG_TC_HIST_BINS], or the workspace's own when hist == nullptr)
 extern "C" int qrag_search_tc_filter(int nq, const uint16_t* Xb, const float* aux, int64_t N, int D, int k, int metric,
-                                     const float* bm_top_all, int G, float* ap_top, void* workspace, size_t workspace_bytes,
+                                     const float* bm_top_all, int G, int32_t* hist, void* workspace, size_t workspace_bytes,
                                      void* stream) {
-    QRAG_REQUIRE(Xb && aux && G >= 1 && (bm_top_all || G == 1) && (ap_top || G == 1), QRAG_ERR_INVALID, "bad argument");
+    QRAG_REQUIRE(Xb && aux && G >= 1 && (bm_top_all || G == 1), QRAG_ERR_INVALID, "bad argument");
     if (nq == 0) return QRAG_OK;
     TcWs w;
     int rc = tc_ws(nq, N, D, k, metric, G, workspace, workspace_bytes, &w);
     if (rc) return rc;
+    if (hist != nullptr) w.hist = hist;
     cudaStream_t st = (cudaStream_t)stream;
-    tau_union_kernel<<<nq, 256, 0, st>>>(bm_top_all, G, nq, k, w.pl.kt, metric, w.pl.Kp, w.qnorm, w.qnorm + w.pl.nq_pad, aux, w.bmax, w.pl.nbuckets, w.tau,
-                                         w.eps);
+    tau_union_kernel<<<nq, 256, 0, st>>>(bm_top_all, G, nq, k, w.pl.kt, metric, w.pl.Kp, w.qnorm, w.qnorm + w.pl.nq_pad, aux,
+                                         w.bmax, w.pl.nbuckets, w.tau, w.eps, w.hinv);
     QRAG_LAUNCH_CHECK("tau_union_kernel");
     return tc_gemm_pass<TC_MODE_FILTER>(w, nq, N, Xb, st, [&](int q0, int q1, int nseg, int seg_cap) {
-        if (ap_top == nullptr) return (int)QRAG_OK;            // single shard: the final stage selects by itself
-        QRAG_CUDA_CHECK(cudaFuncSetAttribute(surv_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(SV_CACHE * sizeof(float))));
-        surv_topk_kernel<<<q1 - q0, 256, SV_CACHE * sizeof(float), st>>>(w.cnt, w.surv, q0, nseg, seg_cap, w.pl.cap, w.pl.kt,
-                                                                         ap_top);
-        QRAG_LAUNCH_CHECK("surv_topk_kernel");
+        surv_hist_kernel<<<q1 - q0, 256, 0, st>>>(w.cnt, w.surv, q0, nseg, seg_cap, w.pl.cap, w.tau, w.hinv, w.hist);
+        QRAG_LAUNCH_CHECK("surv_hist_kernel");
         return QRAG_OK;
     });
 }
@@ -1432,7 +1439,7 @@ extern "C" int qrag_search_tc_filter(int nq, const uint16_t* Xb, const float* au
 // either as (scores, ids, status) arrays or, packed != nullptr, as the per-query records of the search + rerank
 // exchange (tc_sort_pack_kernel), which also carry the amplitude fidelity of every entry.
 static int tc_finish_impl(const float* Q, int nq, const float* X, int64_t N, int D, int k, int metric, int64_t id_base,
-                          const float* ap_top_all, int G, double* out_scores, int64_t* out_ids, int32_t* status,
+                          const int32_t* hist_all, int G, double* out_scores, int64_t* out_ids, int32_t* status,
                           long long* pack, int kk, void* workspace, size_t workspace_bytes, void* stream) {
     if (nq == 0) return QRAG_OK;
     TcWs w;
@@ -1448,7 +1455,8 @@ static int tc_finish_impl(const float* Q, int nq, const float* X, int64_t N, int
         g0 += L.groups;
         if (q1 <= q0) continue;
         TcFinalParams fp{Q, X, q0, nq, N, D, k, metric, id_base, TC_EPI_SPLIT * L.cpg, pl.cap / (TC_EPI_SPLIT * L.cpg),
-                         pl.cap, pl.cand_cap, G, pl.kt, ap_top_all, w.cnt, w.surv, w.eps, out_scores, out_ids, status,
+                         pl.cap, pl.cand_cap, hist_all ? hist_all : w.hist, w.tau, w.hinv, w.cnt, w.surv, w.eps, out_scores,
+                         out_ids, status,
                          w.crow, w.ckey, w.cm, pack ? w.cfid : nullptr, pack, kk};
         tc_collect_kernel<<<q1 - q0, XS_THREADS, 0, st>>>(fp);
         QRAG_LAUNCH_CHECK("tc_collect_kernel");
@@ -1480,11 +1488,11 @@ static int tc_finish_impl(const float* Q, int nq, const float* X, int64_t N, int
 }
 
 extern "C" int qrag_search_tc_finish(const float* Q, int nq, const float* X, int64_t N, int D, int k, int metric,
-                                     int64_t id_base, const float* ap_top_all, int G, double* out_scores, int64_t* out_ids,
+                                     int64_t id_base, const int32_t* hist_all, int G, double* out_scores, int64_t* out_ids,
                                      int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
-    QRAG_REQUIRE(Q && X && out_scores && out_ids && status && G >= 1 && (ap_top_all || G == 1), QRAG_ERR_INVALID,
+    QRAG_REQUIRE(Q && X && out_scores && out_ids && status && G >= 1 && (hist_all || G == 1), QRAG_ERR_INVALID,
                  "bad argument");
-    return tc_finish_impl(Q, nq, X, N, D, k, metric, id_base, ap_top_all, G, out_scores, out_ids, status, nullptr, 0,
+    return tc_finish_impl(Q, nq, X, N, D, k, metric, id_base, hist_all, G, out_scores, out_ids, status, nullptr, 0,
                           workspace, workspace_bytes, stream);
 }
 
@@ -1495,11 +1503,11 @@ extern "C" int qrag_search_tc_exchange_len(int k, int G, int* len) {
 }
 
 extern "C" int qrag_search_tc_finish_packed(const float* Q, int nq, const float* X, int64_t N, int D, int k, int metric,
-                                            int64_t id_base, const float* ap_top_all, int G, int kk, int64_t* pack,
+                                            int64_t id_base, const int32_t* hist_all, int G, int kk, int64_t* pack,
                                             void* workspace, size_t workspace_bytes, void* stream) {
-    QRAG_REQUIRE(Q && X && pack && G >= 1 && (ap_top_all || G == 1), QRAG_ERR_INVALID, "bad argument");
+    QRAG_REQUIRE(Q && X && pack && G >= 1 && (hist_all || G == 1), QRAG_ERR_INVALID, "bad argument");
     QRAG_REQUIRE(kk >= 1 && kk <= k, QRAG_ERR_INVALID, "kk=%d outside [1, k=%d]", kk, k);
-    return tc_finish_impl(Q, nq, X, N, D, k, metric, id_base, ap_top_all, G, nullptr, nullptr, nullptr,
+    return tc_finish_impl(Q, nq, X, N, D, k, metric, id_base, hist_all, G, nullptr, nullptr, nullptr,
                           reinterpret_cast<long long*>(pack), kk, workspace, workspace_bytes, stream);
 }
 

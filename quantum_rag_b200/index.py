@@ -13,6 +13,8 @@ retrieval step without faiss: it parses the file format observed in the referenc
 from __future__ import annotations
 
 import io
+import json
+import os
 import pickle
 import struct
 from typing import List, Optional, Sequence, Tuple
@@ -61,6 +63,53 @@ def load_metadata(path: str) -> List:
     return data
 
 
+# ------------------------------------------------------------------------------------------------
+# JSON side-car: the safe replacement for the pickle the ingest tool appends to (store_in_faiss.py:111-122).
+#   {"format": "qrag-labels", "version": 1, "count": N, "labels": [label of row 0, label of row 1, ...]}
+# A label is a string (the reference stores "show/episode_sha"), a number, null, or a flat JSON object of those.
+# ------------------------------------------------------------------------------------------------
+LABELS_FORMAT, LABELS_VERSION = "qrag-labels", 1
+
+
+def dump_labels(labels: Sequence, path: str) -> None:
+    """Write the id -> label side-car (row i of the index carries ``labels[i]``)."""
+    doc = {"format": LABELS_FORMAT, "version": LABELS_VERSION, "count": len(labels), "labels": list(labels)}
+    tmp = path + ".tmp"
+    with open(tmp, "w", encoding="utf-8") as fh:
+        json.dump(doc, fh, ensure_ascii=False, allow_nan=False)
+    os.replace(tmp, path)                       # the reference rewrites its pickle in place; this never leaves half a file
+
+
+def load_labels(path: str) -> List:
+    with open(path, "r", encoding="utf-8") as fh:
+        doc = json.load(fh)
+    if not isinstance(doc, dict) or doc.get("format") != LABELS_FORMAT:
+        raise ValueError(f"{path}: not a {LABELS_FORMAT} side-car")
+    if doc.get("version") != LABELS_VERSION:
+        raise ValueError(f"{path}: side-car version {doc.get('version')!r}, this reader understands {LABELS_VERSION}")
+    labels = doc.get("labels")
+    if not isinstance(labels, list) or doc.get("count") != len(labels):
+        raise ValueError(f"{path}: label count does not match the header")
+    return labels
+
+
+def convert_metadata_pickle(pickle_path: str, json_path: Optional[str] = None) -> str:
+    """One-shot converter: the reference's ``*_metadata.pkl`` (a plain list, read with the restricted unpickler)
+    -> the JSON side-car next to it.  Returns the path written."""
+    labels = load_metadata(pickle_path)
+    if json_path is None:
+        root = pickle_path[:-len("_metadata.pkl")] if pickle_path.endswith("_metadata.pkl") else os.path.splitext(pickle_path)[0]
+        json_path = root + "_labels.json"
+    dump_labels(labels, json_path)
+    return json_path
+
+
+def sidecar_paths(index_path: str):
+    """(json, pickle) side-car paths the ingest convention implies for ``<name>.faiss``."""
+    root = index_path[:-len(".faiss")] if index_path.endswith(".faiss") else index_path
+    return root + "_labels.json", root + "_metadata.pkl"
+
+
 class FlatIndex:
     """``faiss.IndexFlat``-like wrapper over the B200 search: ``search(x, k) -> (D, I)``."""
 
@@ -76,14 +125,24 @@ class FlatIndex:
 
     @classmethod
     def read(cls, path: str, metadata_path: Optional[str] = None) -> "FlatIndex":
+        """``metadata_path``: a ``.json`` side-car, or the reference's pickle (restricted unpickler).  Without it the
+        JSON side-car next to the index (``<name>_labels.json``) is used when present -- never the pickle implicitly."""
         with open(path, "rb") as fh:
             x, metric_type = parse_ixf(fh.read())
-        labels = load_metadata(metadata_path) if metadata_path else None
+        labels = None
+        if metadata_path is None:
+            cand = sidecar_paths(path)[0]
+            metadata_path = cand if os.path.exists(cand) else None
+        if metadata_path is not None:
+            labels = load_labels(metadata_path) if metadata_path.endswith(".json") else load_metadata(metadata_path)
         return cls(np.array(x), metric_type, labels)
 
-    def write(self, path: str) -> None:
+    def write(self, path: str, with_labels: bool = True) -> None:
+        """The ``IxF2`` / ``IxFI`` file faiss would write, plus the JSON side-car when the index has labels."""
         with open(path, "wb") as fh:
             fh.write(dump_ixf(self._tc.X.cpu().numpy(), self.metric_type))
+        if with_labels and self.labels is not None:
+            dump_labels(self.labels, sidecar_paths(path)[0])
 
     def search(self, x, k: int):
         """faiss contract: distances (squared L2 ascending / inner product descending) and int64 labels, -1 padded.

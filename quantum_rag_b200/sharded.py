@@ -6,8 +6,9 @@ this is the multi-GPU form BASELINE.json's config 4 asks for:
     corpus rows   contiguous row partition, rank g owns rows [lo_g, hi_g); global id = lo_g + row
     queries       replicated on every rank
     search        per shard: tcgen05 filter GEMM + exact rescoring (FlatIndexTC); the filter
-                  thresholds are global (two small fp32 all-gathers of [nq, kt] between the phases,
-                  kt ~ 2 k1 / G), so a shard rescores only its ~1/G share of the global top-k1
+                  thresholds are global (an all-gather of [nq, kt] fp32 bucket maxima, kt ~ 2 k1 / G,
+                  and an all-reduce of a [nq, 256] int32 survivor histogram between the phases), so a
+                  shard rescores only its ~1/G share of the global top-k1
     rerank        fused into the rescoring: the kernel that reads a candidate row for its exact
                   search score also emits its amplitude-encoded fidelity (same bits as
                   qrag_amp_fidelity), so no row is read twice and no embedding crosses NVLink
@@ -73,9 +74,9 @@ class CudaEngine:
         (aux[0], aux[1]): reduce them once per index."""
         all_reduce_max(self.index.aux[:2])
 
-    def search_sharded(self, Q, k, all_gather, shards):
+    def search_sharded(self, Q, k, all_gather, all_reduce_sum, shards):
         """This shard's members of the global top-k (thresholds exchanged through ``all_gather``)."""
-        return self.index.search_sharded(Q, k, all_gather, shards)
+        return self.index.search_sharded(Q, k, all_gather, all_reduce_sum, shards)
 
     # ---- packed search + rerank (include/qrag.h: qrag_search_tc_finish_packed / qrag_owner_finalize) ----
     def packed_begin(self, Q, k, shards):
@@ -84,8 +85,8 @@ class CudaEngine:
     def packed_filter(self, bm_all):
         return self.index.tc_filter(bm_all)
 
-    def packed_finish(self, ap_all, kk, pack):
-        return self.index.tc_finish_packed(ap_all, kk, pack)
+    def packed_finish(self, hist_all, kk, pack):
+        return self.index.tc_finish_packed(hist_all, kk, pack)
 
     def owner_finalize(self, recv, kk, k1, k2, q_base, nq, out):
         return self.api.owner_finalize(recv, kk, k1, k2, self.metric, q_base, nq, out)
@@ -159,6 +160,11 @@ class ShardedSearchRerank:
         dist.all_gather_into_tensor(out, t, group=self.group)           # concatenation along dim 0
         return out.view((self.world,) + tuple(t.shape))
 
+    def _all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
     def _all_reduce_max(self, t: torch.Tensor) -> torch.Tensor:
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
@@ -168,12 +174,12 @@ class ShardedSearchRerank:
     def search(self, Q, k1: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """Global top-k1 (identical on every rank): per-shard search, all-gather of the lists, merge.
 
-        With the CUDA engine and G > 1 the shards also exchange their filter thresholds (two [nq, kt]
-        fp32 all-gathers inside the search), so that each shard rescores only its ~1/G share of the
+        With the CUDA engine and G > 1 the shards also exchange their filter thresholds (an all-gather and
+        an all-reduce inside the search), so that each shard rescores only its ~1/G share of the
         global list; any query a shard could not certify makes every rank rerun it exactly.
         """
         if self.world > 1 and hasattr(self.engine, "search_sharded"):
-            s, i, status = self.engine.search_sharded(Q, k1, self._all_gather, self.world)
+            s, i, status = self.engine.search_sharded(Q, k1, self._all_gather, self._all_reduce_sum, self.world)
             self._mark("search_phases")
             bad = self._all_reduce_max(status.clone())
             flagged = torch.nonzero(bad).flatten()
@@ -237,7 +243,7 @@ class ShardedSearchRerank:
         return b
 
     def _owner_pipeline(self, Q, k1: int, k2: int) -> Optional[ShardedResult]:
-        """The packed path (module docstring): search phases, ONE all-to-all of per-query records to the query's
+        """The packed path (module docstring): search phases (two threshold exchanges), ONE all-to-all of per-query records to the query's
         owner, one owner kernel, one small all-gather of the result.  Returns None if some shard could not
         certify a query or had to cut a list (the caller reruns through the all-gather form); that verdict
         travels with the result, so the single host sync of the path is the last thing it does."""
@@ -250,13 +256,14 @@ class ShardedSearchRerank:
         bm = eng.packed_begin(Q, k1, G)
         bm_all = self._all_gather(bm) if G > 1 else None
         self._mark("begin+gather")
-        ap = eng.packed_filter(bm_all)
-        ap_all = self._all_gather(ap) if G > 1 else None
-        self._mark("filter+gather")
+        hist = eng.packed_filter(bm_all)
+        if G > 1:
+            self._all_reduce_sum(hist)
+        self._mark("filter+reduce")
         dev = getattr(eng, "device", Q.device)
         buf = self._buffers(nq, kk, k2, dev)
         per = buf["per"]
-        eng.packed_finish(ap_all, kk, buf["send"])
+        eng.packed_finish(hist, kk, buf["send"])
         self._mark("finish_packed")
         if G > 1:
             dist.all_to_all_single(buf["recv"].view(G * per, -1), buf["send"], group=self.group)

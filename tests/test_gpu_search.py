@@ -81,3 +81,29 @@ def test_merge_equals_single_shard_search(cuda, name, mid):
                              np.stack([p[1].cpu().numpy() for p in parts[:1]]), 60, mid)
     gs, gi = api.topk_merge(parts[0][0][None], parts[0][1][None], 60, name)
     assert np.array_equal(gi.cpu().numpy(), oi)
+
+
+@pytest.mark.parametrize("G,k,k_out,name,mid", [(20, 1000, 1000, "cosine", osr.METRIC_COSINE), (300, 100, 100, "l2", osr.METRIC_L2),
+                                              (9, 1000, 10, "ip", osr.METRIC_IP), (40, 2048, 2048, "l2", osr.METRIC_L2),
+                                              (8, 1000, 1000, "ip", osr.METRIC_IP)])
+def test_merge_of_more_entries_than_one_kernel_sorts(cuda, G, k, k_out, name, mid):
+    """G * k above 8192 entries per query (16 shards x top-1000, or many small shards): merged over several
+    levels through a workspace, same canonical order as the oracle's one-shot merge; padding and ties included."""
+    import torch
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(G + k)
+    nq = 3
+    scores = np.round(rng.standard_normal((G, nq, k)), 2)                     # coarse: many score ties across shards
+    ids = np.stack([rng.permutation(G * k * 2)[:G * k].reshape(G, k) for _ in range(nq)], axis=1).astype(np.int64)
+    key = scores if mid == osr.METRIC_L2 else -scores
+    order = np.lexsort((ids, key), axis=2)                                    # every shard list sorted canonically
+    scores, ids = np.take_along_axis(scores, order, 2), np.take_along_axis(ids, order, 2)
+    short = rng.randint(0, G, size=3)                                         # some shards hold fewer than k entries
+    for g in short:
+        n = rng.randint(0, k)
+        ids[g, :, n:] = -1
+        scores[g, :, n:] = np.inf if mid == osr.METRIC_L2 else -np.inf
+    ws, wi = osr.merge_topk(scores, ids, k_out, mid)
+    gs, gi = api.topk_merge(torch.from_numpy(scores).cuda(), torch.from_numpy(ids).cuda(), k_out, name)
+    assert np.array_equal(gi.cpu().numpy(), wi)
+    assert np.array_equal(gs.cpu().numpy(), ws)

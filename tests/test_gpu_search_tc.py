@@ -124,7 +124,7 @@ def test_config3_full_size_properties(cuda):
     N, D, nq, k = 1_000_000, 384, 1024, 100
     X = torch.nn.functional.normalize(torch.randn(N, D, generator=g, device="cuda"), dim=1)
     Q = torch.nn.functional.normalize(torch.randn(nq, D, generator=g, device="cuda"), dim=1)
-    planted = torch.arange(nq, device="cuda") * 3001 + 7
+    planted = torch.arange(nq, device="cuda") * 971 + 7
     osub = [0, 341, 682, 1023]                           # checked against the NumPy oracle below
     twice = torch.ones(nq, dtype=torch.bool, device="cuda")
     twice[osub] = False                                  # (no exact ties there: a BLAS product need not tie bit for bit)
@@ -171,6 +171,10 @@ def test_flat_index_file_roundtrip_and_search(cuda, piers, tmp_path):
     assert names[0] == [labels[i] for i in piers["top20_ids"][0, :3]]
     idx.write(str(tmp_path / "again.faiss"))
     assert (tmp_path / "again.faiss").read_bytes() == path.read_bytes()
+    # write() left the JSON side-car next to the index; read() picks it up without being told (never the pickle)
+    again = qidx.FlatIndex.read(str(tmp_path / "again.faiss"))
+    assert again.labels == labels and (tmp_path / "again_labels.json").exists()
+    assert qidx.FlatIndex.read(str(path)).labels is None               # piers.faiss has only a pickle beside it
 
 
 @pytest.mark.parametrize("D", [384, 1536])

@@ -28,10 +28,10 @@ def _emulated(X, Q, G, k1, k2, metric, phased):
         for _, _, e in engines:
             e.index.aux[:2] = bound
         bm_all = torch.stack([e.index.tc_begin(Q, k1, G) for _, _, e in engines])
-        ap_all = torch.stack([e.index.tc_filter(bm_all) for _, _, e in engines])
+        hist_all = torch.stack([e.index.tc_filter(bm_all) for _, _, e in engines]).sum(dim=0, dtype=torch.int32)
         lists = []
         for _, _, e in engines:
-            s, i, status = e.index.tc_finish(ap_all)
+            s, i, status = e.index.tc_finish(hist_all)
             assert int(status.count_nonzero()) == 0
             lists.append((s, i))
     else:
@@ -51,7 +51,7 @@ def _emulated(X, Q, G, k1, k2, metric, phased):
 
 def _emulated_packed(X, Q, G, k1, k2, metric, check_owner_vs_oracle=True):
     """The packed form for G shards on one device: phases of every shard in lockstep, the two threshold
-    all-gathers emulated by stack, the all-to-all by slicing every shard's send buffer per owner."""
+    exchanges emulated by stack / sum, the all-to-all by slicing every shard's send buffer per owner."""
     import torch
     from quantum_rag_b200 import api
     from quantum_rag_b200.sharded import CudaEngine, exchange_len, shard_bounds
@@ -64,8 +64,8 @@ def _emulated_packed(X, Q, G, k1, k2, metric, check_owner_vs_oracle=True):
     assert kk == api.exchange_len(k1, G)
     bm = [e.packed_begin(Q, k1, G) for e in engines]
     bm_all = torch.stack(bm) if G > 1 else None
-    ap = [e.packed_filter(bm_all) for e in engines]
-    ap_all = torch.stack(ap) if G > 1 else None
+    hists = [e.packed_filter(bm_all) for e in engines]
+    ap_all = torch.stack(hists).sum(dim=0, dtype=torch.int32) if G > 1 else None       # the all-reduce(SUM)
     sends = []
     for e in engines:
         send = torch.zeros((per * G, 3 * kk + 1), dtype=torch.int64, device=X.device)

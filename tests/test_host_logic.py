@@ -177,3 +177,34 @@ def test_exchange_len_matches_the_library(libqrag):
             assert n.value == exchange_len(k, world), (k, world)
             assert 1 <= n.value <= k and (world == 1) <= (n.value == k)
             assert world * n.value >= k                      # the union of the cut lists still holds k entries
+
+
+def test_json_sidecar_roundtrip_and_pickle_conversion(tmp_path):
+    """(f)4: the JSON id -> label side-car replaces the pickle of store_in_faiss.py:111-122."""
+    import json
+    import pickle
+    from quantum_rag_b200 import index as qidx
+    labels = ["Piers_Morgan_Uncensored/02c7ef14", "show/ünïcode ✓", 'quote " and \\ backslash', "", "show/a"]
+    jp = tmp_path / "idx_labels.json"
+    qidx.dump_labels(labels, str(jp))
+    assert qidx.load_labels(str(jp)) == labels
+    doc = json.loads(jp.read_text(encoding="utf-8"))
+    assert doc["format"] == "qrag-labels" and doc["version"] == 1 and doc["count"] == len(labels)
+    # the reference's pickle (a plain list of str) converts in one call, through the restricted unpickler
+    pk = tmp_path / "piers_morgan_faiss_index_metadata.pkl"
+    pk.write_bytes(pickle.dumps(labels))
+    out = qidx.convert_metadata_pickle(str(pk))
+    assert out == str(tmp_path / "piers_morgan_faiss_index_labels.json") and qidx.load_labels(out) == labels
+    assert qidx.sidecar_paths(str(tmp_path / "piers_morgan_faiss_index.faiss")) == (out, str(pk))
+    # malformed side-cars are refused: wrong format tag, unknown version, count mismatch
+    for bad in ({"format": "other", "version": 1, "count": 0, "labels": []},
+                {"format": "qrag-labels", "version": 2, "count": 0, "labels": []},
+                {"format": "qrag-labels", "version": 1, "count": 3, "labels": ["a"]},
+                ["a", "b"]):
+        jp.write_text(json.dumps(bad))
+        with pytest.raises(ValueError):
+            qidx.load_labels(str(jp))
+    # a pickle that needs a global is still refused by the converter (never executed)
+    pk.write_bytes(pickle.dumps(np.arange(3)))
+    with pytest.raises(pickle.UnpicklingError):
+        qidx.convert_metadata_pickle(str(pk))

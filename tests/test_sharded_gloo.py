@@ -72,17 +72,24 @@ class OracleEngine:
         return self._pk[5][:, :exchange_len(k, shards)].contiguous() if shards > 1 else None
 
     def packed_filter(self, bm_all):
+        """The threshold (k-th best key of the union of the cut lists: valid, exact unless one shard holds > kt) is
+        known after the all-gather; what gets summed over the shards is how many entries each holds at or above it."""
         Q, k, shards, s, i, key = self._pk
-        assert bm_all is None or tuple(bm_all.shape) == (shards, key.shape[0], exchange_len(k, shards))
-        return key[:, :exchange_len(k, shards)].contiguous() if shards > 1 else None
+        nq = key.shape[0]
+        if shards == 1:
+            return None
+        assert tuple(bm_all.shape) == (shards, nq, exchange_len(k, shards))
+        self._kth = torch.sort(bm_all.permute(1, 0, 2).reshape(nq, -1), dim=1).values[:, k - 1:k]
+        return ((key <= self._kth) & (i >= 0)).sum(dim=1, keepdim=True).to(torch.int32)
 
-    def packed_finish(self, ap_all, kk, pack):
+    def packed_finish(self, hist_all, kk, pack):
         Q, k, shards, s, i, key = self._pk
         nq = key.shape[0]
         keep = i >= 0
-        if shards > 1:      # k-th best key of the union of the cut lists: valid, exact unless one shard holds > kt
-            kth = torch.sort(ap_all.permute(1, 0, 2).reshape(nq, -1), dim=1).values[:, k - 1:k]
-            keep = keep & (key <= kth)
+        if shards > 1:
+            keep = keep & (key <= self._kth)
+            # the all-reduce really summed over the shards: a finite threshold has at least k entries at or above it
+            assert hist_all.shape == (nq, 1) and bool((hist_all[:, 0] >= k * torch.isfinite(self._kth[:, 0])).all())
         pad_s = float("inf") if self.metric == osr.METRIC_L2 else float("-inf")
         s = torch.where(keep, s, torch.full_like(s, pad_s))
         i = torch.where(keep, i, torch.full_like(i, -1))
@@ -179,7 +186,7 @@ class PhasedOracleEngine(OracleEngine):
     def search_exact(self, Q, k):
         return self.search(Q, k)
 
-    def search_sharded(self, Q, k, all_gather, shards):
+    def search_sharded(self, Q, k, all_gather, all_reduce_sum, shards):
         s, i = self.search(Q, k)                                              # this shard's best k
         key = s if self.metric == osr.METRIC_L2 else -s
         key = torch.where(i >= 0, key, torch.full_like(key, float("inf")))

@@ -2,7 +2,7 @@
 """One-GPU probe of what ONE rank of the G-GPU sharded search + rerank (config 4) spends per stage.
 
 A shard of N / G rows runs the packed path (quantum_rag_b200/sharded.py); the collectives are emulated on the
-device (the threshold all-gathers by replicating the shard's own lists G times, the all-to-all by handing the
+device (the threshold exchanges by replicating the shard's own list / histogram G times, the all-to-all by handing the
 owner kernel its own records G times: same sizes and statistics as G equal shards, no NVLink time).  Reports
 CUDA-event time per stage, the eager total and the total replayed from a CUDA graph (no CPU launch gaps).
 
@@ -54,11 +54,12 @@ def main():
         m("begin (query_prepare, bucket GEMM, bucket_topk)")
         bm_all = fake(bm)
         m("[emulated all-gather 1]")
-        apt = index.tc_filter(bm_all)
-        m("filter (tau_union, filter GEMM, surv_topk)")
-        ap_all = fake(apt)
-        m("[emulated all-gather 2]")
-        index.tc_finish_packed(ap_all, kk, send)
+        hist = index.tc_filter(bm_all)
+        m("filter (tau_union, filter GEMM + survivor histogram)")
+        if G > 1:
+            hist *= G
+        m("[emulated all-reduce]")
+        index.tc_finish_packed(hist, kk, send)
         m("finish_packed (collect, rescore + fidelity, sort + pack)")
         recv = send.view(G, per, -1)[:1].expand(G, per, 3 * kk + 1).contiguous()
         ids = recv[:, :, 1 + kk:1 + 2 * kk]                           # copies of one shard's lists: make the ids distinct
