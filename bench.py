@@ -144,45 +144,105 @@ def corpus_rows(lo, hi, dim, device):
     return out
 
 
-def bench_search(api, peaks, steps=20):
-    """BASELINE config 3 on one GPU: cosine top-100 of 1024 queries over 1M x 384 docs (tcgen05 filter GEMM +
-    exact rescoring).  Reported beside the headline; the tensor roofline uses the ALGORITHMIC flops 2*D per score."""
+def bench_search(api, peaks, steps=20, oracle_check=False):
+    """BASELINE config 3 on one GPU: cosine top-100 over 1M x 384 docs (tcgen05 filter GEMM + exact rescoring) for
+    1024 queries (the config), and for 1 and 4096 queries.  Reported beside the headline; the tensor
+    roofline uses the ALGORITHMIC flops 2*D per score, the HBM roofline (nq = 1) the bf16 shadow read once."""
     import torch
-    N, nq, k = 1_000_000, 1024, 100
+    N, k = 1_000_000, 100
     X = corpus_rows(0, N, D, torch.device("cuda"))
     g = torch.Generator(device="cuda").manual_seed(1234 + 3)
-    Q = torch.nn.functional.normalize(torch.randn(nq, D, generator=g, device="cuda"), dim=1)
+    Qall = torch.nn.functional.normalize(torch.randn(4096, D, generator=g, device="cuda"), dim=1)
     index = api.FlatIndexTC(X, "cosine")
-    for _ in range(3):
-        _, s, i, st = index.search_async(Q, k)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        index.search_async(Q, k)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+
+    def timed(nq, reps):
+        Q = Qall[:nq].contiguous()
+        for _ in range(3):
+            _, s, i, st = index.search_async(Q, k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            index.search_async(Q, k)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, Q, s, i, st
+
+    ms, Q, s, i, st = timed(1024, steps)
+    nq = 1024
     sub = torch.arange(0, nq, 128, device="cuda")
     es, ei = api.search_topk(Q[sub], X, k, "cosine")
     tf = 2.0 * D * nq * N / (ms * 1e-3) / 1e12
-    peak = float(peaks.get("bf16_tflops", 1590.0))
     out = {"workload": "config 3: cosine top-100, 1024 queries x 1,000,000 docs x 384-d, one B200", "ms_per_batch": ms,
            "scores_per_s": nq * N / (ms * 1e-3), "queries_per_s": nq / (ms * 1e-3),
            "flagged_queries": int(st.count_nonzero()),
            "identical_to_exact_search": bool(torch.equal(i[sub], ei) and torch.equal(s[sub], es)),
-           "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
                         "note": "algorithmic flops (2*D per score) / wall time of the whole search (bucket pass, "
                                 "threshold, filter pass, exact rescoring); peak = measured cuBLAS bf16 burst"},
-           "kernels": ["qrag::sim_gemm_kernel<0> (sampled bucket-max pass)", "qrag::bucket_topk_kernel",
-                       "qrag::tau_union_kernel", "qrag::sim_gemm_kernel<1> (filter pass)", "qrag::surv_topk_kernel",
+           "kernels": ["qrag::sim_gemm_kernel<0> (sampled bucket-max pass)", "qrag::tau_union_kernel",
+                       "qrag::sim_gemm_kernel<1> (filter pass)", "qrag::surv_hist_kernel",
                        "qrag::tc_collect_kernel / tc_rescore_kernel / tc_sort_kernel (candidates, exact fp64 rescoring, sort)"]}
+    if oracle_check:
+        # four queries against the NumPy oracle over the whole 1M-row corpus (chunked): ids identical, scores to rounding
+        from oracle import search as osr
+        osub = [0, 341, 682, 1023]
+        rs, ri = osr.exact_search_chunked(Q[osub].cpu().numpy(), X.cpu().numpy(), k, osr.METRIC_COSINE)
+        out["ids_equal_numpy_oracle_4_queries"] = bool(np.array_equal(i[osub].cpu().numpy(), ri))
+        out["max_score_diff_vs_oracle"] = float(np.abs(s[osub].cpu().numpy() - rs).max())
+    ms1, _, _, _, st1 = timed(1, 50)
+    gbs = N * index.Kp * 2 / (ms1 * 1e-3) / 1e9
+    out["nq_1"] = {"ms_per_batch": ms1, "scores_per_s": N / (ms1 * 1e-3), "flagged_queries": int(st1.count_nonzero()),
+                   "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
+                                "note": "one query: the bf16 shadow of the corpus (768 MB) is read once per pass, and there "
+                                        "are two passes' worth of work (sampled bucket pass + filter pass); bytes = N*Kp*2"}}
+    ms4, _, _, _, st4 = timed(4096, max(3, steps // 4))
+    tf4 = 2.0 * D * 4096 * N / (ms4 * 1e-3) / 1e12
+    out["nq_4096"] = {"ms_per_batch": ms4, "scores_per_s": 4096 * N / (ms4 * 1e-3), "flagged_queries": int(st4.count_nonzero()),
+                      "roofline": {"bound": "tensor", "achieved": tf4, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf4 / peak_tf}}
     del index, X
     torch.cuda.empty_cache()
     return out
 
 
-def bench_feature_map(api, steps=3):
+def bench_circuit(api, fma_rate, steps=20):
+    """K1, the reference circuit itself (quantum.py:138-167: RY/RZ per qubit + CX chain, exact complex128 statevector,
+    |<psi_d|psi_q>|^2): (a) the string-API shape, n = 4 qubits, 1000 queries x 100 documents of 8-component mock
+    embeddings; (b) the angle-circuit variant of config 2: n = 9 qubits on the first 9 components of the
+    384-d embeddings.  Bound: FP64 pipe; flops per score = 12 n 2^n + 8 2^n, peak = 2 x the measured FMA rate."""
+    import torch
+    res = {}
+    for name, n, vec_len in (("n4_string_api_shape", 4, 8), ("n9_config2_angle_variant", 9, 9)):
+        g = torch.Generator(device="cuda").manual_seed(1234 + 20 + n)
+        q = torch.rand(NQ, vec_len, generator=g, device="cuda", dtype=torch.float64)
+        d = torch.rand(NQ * C, vec_len, generator=g, device="cuda", dtype=torch.float64)
+        for _ in range(3):
+            out = api.sv_fidelity_angle(q, d, docs_per_query=C, n_qubits=n, layers=1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = api.sv_fidelity_angle(q, d, docs_per_query=C, n_qubits=n, layers=1)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        flops = (12 * n + 8) * (1 << n)
+        rate = NQ * C / (ms * 1e-3)
+        q2 = q[:1].repeat(2, 1)
+        self_f = float(api.sv_fidelity_angle(q2[:1], q2[1:], docs_per_query=1, n_qubits=n, layers=1)[0])
+        res[name] = {"n_qubits": n, "pairs": NQ * C, "ms_per_batch": ms, "scores_per_s": rate,
+                     "self_fidelity_err": abs(self_f - 1.0), "in_unit_interval": bool(((out >= -1e-12) & (out <= 1 + 1e-12)).all()),
+                     "roofline": {"bound": "fp64 pipe", "achieved": rate * flops / 1e12, "peak": 2 * fma_rate / 1e12,
+                                  "unit": "TFLOP/s (fp64)", "frac": rate * flops / (2 * fma_rate),
+                                  "flops_per_score": flops, "peak_source": "qrag_probe_fp64_fma_rate, measured in this run"}}
+    res["kernels"] = ["qrag::sv_angle_warp_kernel (n <= 5: one warp per state, shuffles)",
+                      "qrag::sv_cta_kernel (n >= 6: 2^n complex128 amplitudes staged in shared memory)"]
+    return res
+
+
+def bench_feature_map(api, fma_rate, steps=3):
     """BASELINE config 5 on one GPU: 4096 queries x 1000 candidates x 1024-d, 10 qubits, amplitude state followed
     by L = 4 feature-map layers (builder-defined), complex128.  Bound: the FP64 pipe, not HBM."""
     import torch
@@ -205,13 +265,14 @@ def bench_feature_map(api, steps=3):
     self_f = float(api.amp_fidelity(Q[:1], cand=cand[:1, :1], n_qubits=n, layers=L)[0, 0])
     rate = nq * C / (ms * 1e-3)
     fp64_instr = 3.7e3 * 32                                               # measured FP64 thread-instructions per state (ncu)
-    fp64_peak = 148 * 64 * 1.965e9                                        # 64 FP64 FMA lanes per clock per SM
+    fp64_peak = fma_rate                                                  # measured in this run (qrag_probe_fp64_fma_rate)
     res = {"workload": "config 5: 4096 queries x 1000 candidates x 1024-d, 10 qubits, amplitude state + 4 feature-map "
                        "layers, complex128 statevector", "ms_per_batch": ms, "scores_per_s": rate,
            "self_fidelity_err": abs(self_f - 1.0), "finite": bool(torch.isfinite(out).all()),
            "roofline": {"bound": "fp64 pipe", "achieved_fp64_inst_per_s": rate * fp64_instr, "peak": fp64_peak,
                         "frac": rate * fp64_instr / fp64_peak,
                         "hbm_gbs": rate * 4 * dim / 1e9,
+                        "peak_source": "qrag_probe_fp64_fma_rate, measured in this run (thread-level FMA/s)",
                         "note": "3.7e3 FP64 warp instructions per state (profiles/r01_fmap_warp_*); HBM traffic is the "
                                 "4 KB candidate row, far from the HBM roofline"},
            "kernels": ["qrag::fmap_warp_kernel<256> (warp per state, 32 amplitudes per lane in registers)"]}
@@ -220,7 +281,7 @@ def bench_feature_map(api, steps=3):
     return res
 
 
-def bench_sharded(world, rank, steps=5):
+def bench_sharded(world, rank, steps=10):
     """BASELINE config 4: 10M x 384 docs row-sharded over the ranks, top-1000 per shard -> NCCL all-gather ->
     merge -> amplitude-encoded quantum rerank -> top-10.  Strong scaling: the corpus is fixed, time is max over ranks."""
     import hashlib
@@ -236,19 +297,31 @@ def bench_sharded(world, rank, steps=5):
     path = ShardedSearchRerank(X, N, "cosine")
     for _ in range(2):
         res = path(Q, k1, k2)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        res = path(Q, k1, k2)
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t[0])
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), out
+
+    # serving loop: `steps` batches queued back to back (path.submit), every batch's certificate read and its result
+    # taken inside the timed region (PendingResult.result) -- nothing is skipped, the host just does not idle the GPU
+    # between batches.  And the latency form: one batch at a time, the host waits for it before queueing the next.
+    reps = []
+    for _ in range(3):
+        ms_r, res = timed(lambda: [p.result() for p in [path.submit(Q, k1, k2) for _ in range(steps)]][-1])
+        reps.append(ms_r)
+    ms = sorted(reps)[1]
+    ms_sync, res_sync = timed(lambda: [path(Q, k1, k2) for _ in range(steps)][-1])
+    assert torch.equal(res_sync.ids, res.ids) and torch.equal(res_sync.scores, res.scores)
     h = hashlib.sha256()
     for x in (res.ids, res.scores):
         h.update(x.cpu().numpy().tobytes())
@@ -264,6 +337,9 @@ def bench_sharded(world, rank, steps=5):
                        "fused into the exact rescoring) -> NCCL all-to-all to the query's owner -> merge -> quantum "
                        "rerank (9 qubits) -> top-10", "n_gpus": world, "scaling": "strong",
            "ms_per_batch": ms, "search_scores_per_s": nq * N / (ms * 1e-3), "reranked_queries_per_s": nq / (ms * 1e-3),
+           "timing": f"median of 3 runs of {steps} batches queued back to back (submit), each batch verified and read "
+                     "inside the timed region; CUDA events, max over ranks",
+           "ms_per_batch_runs": [round(x, 4) for x in reps], "ms_per_batch_one_at_a_time": ms_sync,
            "rerun_all_gather_form": path.last_rerun, "equals_exact_route_on_8_queries": same,
            "collectives_per_batch": 0 if world == 1 else 4, "stage_ms_rank0": stages,
            "result_sha256": h.hexdigest(), "note": "result_sha256 must not depend on n_gpus (bit-identical rankings)"}
@@ -407,9 +483,30 @@ def run_b200(args):
                                                                                region_ms[len(region_ms) // 2])
 
     # ---- e2e: host (pinned) buffers in, host results out, through the public API ----
+    # Staging buffers live on the GPU's own NUMA node (hostmem.py): with 8 ranks on one socket's memory the copies,
+    # not PCIe, were the limit in round 1.  The affinity is restored before the CPU baseline uses all cores.
+    from quantum_rag_b200 import hostmem
+    full_affinity = os.sched_getaffinity(0)
+    numa = hostmem.bind_to_gpu_numa_node(local) if not args.no_numa else {"node": None, "reason": "--no-numa"}
     hQ, hC = make_batch(SEED + 1000 * rank + 999)
     hQ, hC = hQ.pin_memory(), hC.pin_memory()
-    pipe = api.HostRerankPipeline(NQ, C, D, TOPK, NQUBITS, chunks=8)
+    # the ceiling of this leg: a plain copy of the same pinned buffer (cudaMemcpyAsync, all ranks at the same time)
+    probe_dst = torch.empty_like(hC, device="cuda")
+    for _ in range(2):
+        probe_dst.copy_(hC, non_blocking=True)
+    barrier()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(5):
+        probe_dst.copy_(hC, non_blocking=True)
+    pe1.record()
+    barrier()
+    h2d_probe = torch.tensor([5 * hC.numel() * 4 / (pe0.elapsed_time(pe1) * 1e-3) / 1e9], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(h2d_probe, op=dist.ReduceOp.MIN)              # the slowest rank's copy rate
+    h2d_probe_gbs = float(h2d_probe[0])
+    del probe_dst
+    pipe = api.HostRerankPipeline(NQ, C, D, TOPK, NQUBITS, chunks=args.e2e_chunks)
     e2e_steps = 1 if args.no_e2e else max(3, min(args.steps, 50))
     for _ in range(0 if args.no_e2e else 3):
         pipe(hQ, hC)
@@ -440,7 +537,11 @@ def run_b200(args):
               "api": "quantum_rag_b200.api.HostIdRerankPipeline (pinned host queries + candidate ids in, corpus of "
                      f"{corpus.shape[0]} rows resident in HBM, rows gathered by TMA, (score, id) top-k out to pinned host)",
               "note": "wall clock per rank (not reduced over ranks)"}
+    id_host = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:           # the same id-shaped input for the CPU figure
+        id_host = (hQ2.numpy().copy(), hI.numpy().copy(), corpus.cpu().numpy(), hO2.numpy().copy())
     del idpipe, corpus
+    os.sched_setaffinity(0, full_affinity)
 
     t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -475,8 +576,14 @@ def run_b200(args):
             "reranked_queries_per_s": value / C,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                    "api": "quantum_rag_b200.api.HostRerankPipeline (pinned host tensors in/out, 8 slices on 2 streams)",
+                    "api": f"quantum_rag_b200.api.HostRerankPipeline (pinned host tensors in/out, {args.e2e_chunks} slices on 2 streams)",
                     "h2d_gbs": h2d_bytes * e2e_steps / (e2e_ms * 1e-3) / 1e9,
+                    "roofline": {"bound": "pcie h2d", "peak": h2d_probe_gbs, "unit": "GB/s",
+                                 "achieved": h2d_bytes * e2e_steps / (e2e_ms * 1e-3) / 1e9,
+                                 "frac": h2d_bytes * e2e_steps / (e2e_ms * 1e-3) / 1e9 / h2d_probe_gbs,
+                                 "peak_source": "plain non_blocking copy of the same pinned candidate buffer (155 MB x 5), all "
+                                                "ranks at once, slowest rank, measured in this run"},
+                    "numa": numa,
                     "note": "bound by the host-to-device copy of the fp32 candidates (PCIe), not by the kernel",
                     "reranked_queries_per_s": e2e_value / C},
             "e2e_resident_corpus": e2e_id,
@@ -497,8 +604,11 @@ def run_b200(args):
         if sharded is not None:
             line["sharded_search_rerank"] = sharded
         if world == 1 and not args.no_extra:
-            line["search"] = bench_search(api, peaks)
-            line["feature_map"] = bench_feature_map(api)
+            fma_rate = api.probe_fp64_fma_rate()
+            line["search"] = bench_search(api, peaks, oracle_check=not args.no_cpu_baseline)
+            line["circuit"] = bench_circuit(api, fma_rate)
+            line["feature_map"] = bench_feature_map(api, fma_rate)
+            line["measured_fp64_fma_per_s"] = fma_rate
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             Qn, cn = host_sets0
@@ -516,6 +626,28 @@ def run_b200(args):
             torch.cuda.synchronize()
             want = np.concatenate([r for r in ranks if r is not None], axis=0)
             line["parity_vs_oracle"] = bool(np.array_equal(pos.cpu().numpy(), want))
+            # the retrieval-shaped input on the CPU: gather the rows named by the ids, score, rank (oracle), same threads
+            Qi, Ii, Xh, gpu_ids = id_host
+            from concurrent.futures import ThreadPoolExecutor
+            from oracle import quantum as oq
+            bnd = np.linspace(0, NQ, cores + 1).astype(int)
+
+            def id_work(t):
+                a, b = bnd[t], bnd[t + 1]
+                if a == b:
+                    return np.zeros((0, TOPK), dtype=np.int64)
+                order = oq.rank_rows(oq.amplitude_fidelity_batch(Qi[a:b], Xh[Ii[a:b]]), TOPK)
+                return np.take_along_axis(Ii[a:b], order, 1)
+            t0 = time.perf_counter()
+            id_passes = 0
+            while time.perf_counter() - t0 < 4.0:
+                with ThreadPoolExecutor(max_workers=cores) as ex:
+                    id_want = np.concatenate(list(ex.map(id_work, range(cores))), axis=0)
+                id_passes += 1
+            id_dt = time.perf_counter() - t0
+            line["e2e_resident_corpus"]["cpu_value"] = id_passes * scores_per_step / id_dt
+            line["e2e_resident_corpus"]["vs_cpu"] = line["e2e_resident_corpus"]["value"] / (id_passes * scores_per_step / id_dt)
+            line["e2e_resident_corpus"]["ids_equal_oracle"] = bool(np.array_equal(gpu_ids, id_want))
             line["cpu_baseline"] = {
                 "value": passes * scores_per_step / cpu_dt, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"{passes} full passes of the {NQ}x{C} batch, NumPy fp64 vectorised oracle on {cores} threads",
@@ -540,6 +672,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: a single untimed-quality e2e pass")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (configs 3, 4 and 5)")
     ap.add_argument("--no-spinup", action="store_true", help="profiling runs: skip the 0.2 s clock spin-up")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the e2e staging buffers to the GPU's NUMA node")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="slices of the end-to-end pipeline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -138,9 +138,14 @@ int qrag_amp_rerank(const float* Q, int nq,
  * of quantum.py:70-76 / classical.py:302-308 for nq lists of C scores.
  *   descending != 0: (score desc, position asc); else (score asc, position asc).
  *   out_perm [nq, top_k] int32 positions; out_sorted [nq, top_k] optional.
+ * Lists of up to QRAG_MAX_SORT_LEN scores are sorted in shared memory and need no workspace (NULL, 0);
+ * longer lists (any C < 2^31; the reference sorts any length) are sorted in blocks and merged level by
+ * level through a workspace of qrag_sort_scores_workspace bytes.
  * ------------------------------------------------------------------------- */
+int qrag_sort_scores_workspace(int nq, int64_t C, size_t* bytes);
 int qrag_sort_scores_stable(const double* scores, int nq, int64_t C, int top_k, int descending,
-                            int32_t* out_perm, double* out_sorted, void* stream);
+                            int32_t* out_perm, double* out_sorted,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------
  * (1e) The reference's text-hash embedding (quantum.py:169-185) for a batch of

@@ -172,17 +172,19 @@ def sort_scores(scores: ArrayLike, top_k: Optional[int] = None, descending: bool
         s = s[None, :]
     nq, C = s.shape
     k = C if top_k is None else max(0, min(int(top_k), C))
-    if C > MAX_SORT_LEN:
-        # Longer than the in-kernel sort accepts (no BASELINE config is: the longest list is k1 = 1000).  The
-        # reference sorts any length (quantum.py:70-72), so the drop-in must not fail: order on the device with the
-        # library's stable sort -- same (score, position) order, still no host round trip.
-        srt, perm = torch.sort(s, dim=1, descending=descending, stable=True)
-        return perm[:, :k].to(torch.int32).contiguous(), srt[:, :k].contiguous()
     perm = torch.empty((nq, k), dtype=torch.int32, device=s.device)
     srt = torch.empty((nq, k), dtype=torch.float64, device=s.device)
     lib = _lib.load()
-    _lib.check(lib.qrag_sort_scores_stable(_ptr(s), nq, C, k, 1 if descending else 0, _ptr(perm), _ptr(srt),
-                                           _stream()))
+    # lists longer than the shared-memory sort (the reference sorts any length, quantum.py:70-72) go through the
+    # library's block-sort + global-memory merge, which needs a workspace; lists of 65535+ queries go in slices
+    nbytes = ctypes.c_size_t(0)
+    step = nq if C <= MAX_SORT_LEN else min(nq, 65535)
+    _lib.check(lib.qrag_sort_scores_workspace(step, C, ctypes.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=s.device) if nbytes.value else None
+    for a in range(0, nq, max(step, 1)):
+        b = min(nq, a + step)
+        _lib.check(lib.qrag_sort_scores_stable(_ptr(s[a:b]), b - a, C, k, 1 if descending else 0, _ptr(perm[a:b]),
+                                               _ptr(srt[a:b]), _ptr(ws), nbytes.value, _stream()))
     return perm, srt
 
 

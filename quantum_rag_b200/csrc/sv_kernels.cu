@@ -388,35 +388,6 @@ __global__ void mock_embedding_kernel(const uint32_t* __restrict__ seeds, int64_
     for (int i = 0; i < 2 * n_qubits; ++i) o[i] = o[i] / nrm;
 }
 
-// ===========================================================================
-// Segmented stable sort (quantum.py:70-76, classical.py:302-308)
-// ===========================================================================
-__global__ void __launch_bounds__(256) sort_scores_kernel(const double* __restrict__ scores, int nq, int64_t C,
-                                                          int top_k, int descending, int32_t* __restrict__ out_perm,
-                                                          double* __restrict__ out_sorted) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    int P = 1;
-    while (P < C) P <<= 1;
-    double* key = reinterpret_cast<double*>(smem_raw);
-    int* tag = reinterpret_cast<int*>(key + P);
-    for (int q = blockIdx.x; q < nq; q += gridDim.x) {
-        const double* s = scores + (size_t)q * C;
-        for (int i = threadIdx.x; i < P; i += blockDim.x) {
-            const bool real = i < C;
-            const double v = real ? s[i] : 0.0;
-            key[i] = real ? (descending ? -v : v) : pos_inf();
-            tag[i] = real ? i : TagPad<int>::value();
-        }
-        __syncthreads();
-        block_bitonic_sort<int>(key, tag, P);
-        for (int i = threadIdx.x; i < top_k; i += blockDim.x) {
-            out_perm[(size_t)q * top_k + i] = tag[i];
-            if (out_sorted) out_sorted[(size_t)q * top_k + i] = descending ? -key[i] : key[i];
-        }
-        __syncthreads();
-    }
-}
-
 }  // namespace qrag
 
 using namespace qrag;
@@ -465,24 +436,5 @@ extern "C" int qrag_mock_embedding(const uint32_t* seeds, int64_t n, int n_qubit
     const int64_t grid = ceil_div(n, 128);
     mock_embedding_kernel<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(seeds, n, n_qubits, out);
     QRAG_LAUNCH_CHECK("mock_embedding_kernel");
-    return QRAG_OK;
-}
-
-extern "C" int qrag_sort_scores_stable(const double* scores, int nq, int64_t C, int top_k, int descending,
-                                       int32_t* out_perm, double* out_sorted, void* stream) {
-    QRAG_REQUIRE(scores && out_perm, QRAG_ERR_INVALID, "null pointer argument");
-    QRAG_REQUIRE(nq >= 0 && C >= 0, QRAG_ERR_INVALID, "bad sizes nq=%d C=%lld", nq, (long long)C);
-    QRAG_REQUIRE(C <= QRAG_MAX_SORT_LEN, QRAG_ERR_UNSUPPORTED, "C=%lld > %d", (long long)C, QRAG_MAX_SORT_LEN);
-    QRAG_REQUIRE(top_k >= 0 && top_k <= C, QRAG_ERR_INVALID, "top_k=%d outside [0, C=%lld]", top_k, (long long)C);
-    if (nq == 0 || C == 0 || top_k == 0) return QRAG_OK;
-    const DeviceProps& dp = device_props();
-    QRAG_REQUIRE(dp.ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
-    const size_t smem = (size_t)next_pow2(C) * (sizeof(double) + sizeof(int));
-    if (smem > 48 * 1024)
-        QRAG_CUDA_CHECK(cudaFuncSetAttribute(sort_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = nq < dp.sm_count * 32 ? nq : dp.sm_count * 32;
-    sort_scores_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(scores, nq, C, top_k, descending, out_perm,
-                                                                  out_sorted);
-    QRAG_LAUNCH_CHECK("sort_scores_kernel");
     return QRAG_OK;
 }

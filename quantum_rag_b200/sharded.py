@@ -114,6 +114,31 @@ class ShardedResult:
     search_ids: torch.Tensor      # [nq, k1] int64 merged search ids
 
 
+class PendingResult:
+    """A batch queued by ``ShardedSearchRerank.submit``.  ``result()`` waits for it, reads the certificate flag (the one
+    host synchronisation of the path) and, if some shard could not certify a query or had to cut a list, reruns the
+    batch through the all-gather form -- identically on every rank, because the flag was all-gathered with the result."""
+
+    def __init__(self, path, Q, k1, k2, top, ids, flag):
+        self.path, self.Q, self.k1, self.k2 = path, Q, k1, k2
+        self.top, self.ids, self.flag = top, ids, flag
+        self._done = None
+
+    def result(self) -> ShardedResult:
+        if self._done is None:
+            bad = int(self.flag.item())
+            self.path._flush_marks()
+            if bad:
+                self.path.last_rerun = 1
+                self.path._marks = []
+                ss, si = self.path.search(self.Q, self.k1)
+                top, ids = self.path.rerank(self.Q, si, self.k2)
+                self._done = ShardedResult(top, ids, ss, si)
+            else:
+                self._done = ShardedResult(self.top, self.ids, None, None)
+        return self._done
+
+
 class ShardedSearchRerank:
     """Search the row-sharded corpus, merge over the process group, quantum-rerank the merged list."""
 
@@ -133,10 +158,16 @@ class ShardedSearchRerank:
         self.profile = None          # set to {} to collect per-stage CUDA-event timings (ms) of the next call
         self._marks = []
         self._bufs = {}
+        self._graphs = {}
         self.last_rerun = 0          # 1 if the last call had to rerun through the all-gather form
         self.engine = engine if engine is not None else CudaEngine(X_shard, metric, self.lo)
         if hasattr(self.engine, "sync_corpus_bound"):
             self.engine.sync_corpus_bound(self._all_reduce_max)
+
+    def close(self) -> None:
+        """Drop the captured CUDA graphs (``submit(graph=True)``).  Call it before ``destroy_process_group``: a graph
+        that holds NCCL kernels must not outlive the communicator (observed: the teardown hangs otherwise)."""
+        self._graphs = {}
 
     def _mark(self, name: str) -> None:
         if self.profile is not None:
@@ -242,17 +273,14 @@ class ShardedSearchRerank:
             self._bufs = {key: b}
         return b
 
-    def _owner_pipeline(self, Q, k1: int, k2: int) -> Optional[ShardedResult]:
-        """The packed path (module docstring): search phases (two threshold exchanges), ONE all-to-all of per-query records to the query's
-        owner, one owner kernel, one small all-gather of the result.  Returns None if some shard could not
-        certify a query or had to cut a list (the caller reruns through the all-gather form); that verdict
-        travels with the result, so the single host sync of the path is the last thing it does."""
+    def _enqueue_packed(self, Q, k1: int, k2: int):
+        """Queue one batch of the packed path on the current stream (no host synchronisation):
+        search phases with their two threshold exchanges, ONE all-to-all of per-query records to the query's owner,
+        one owner kernel, one small all-gather.  Returns (fidelity [nq, k2], ids [nq, k2], flag [1]) device tensors;
+        flag != 0 means some shard could not certify a query or had to cut a list."""
         G, eng = self.world, self.engine
-        if not isinstance(Q, torch.Tensor):
-            Q = torch.as_tensor(Q)
         nq = Q.shape[0]
         kk = exchange_len(k1, G)
-        k2 = min(k2, k1)
         bm = eng.packed_begin(Q, k1, G)
         bm_all = self._all_gather(bm) if G > 1 else None
         self._mark("begin+gather")
@@ -278,14 +306,47 @@ class ShardedSearchRerank:
             res = buf["res"].view(G * per, -1)[:nq]
         else:
             res = out[:nq]
-        top = res[:, :k2].contiguous().view(torch.float64)
+        top = res[:, :k2].contiguous().view(torch.float64)         # copies: the exchange buffers are reused by the next batch
         ids = res[:, k2:2 * k2].contiguous()
+        flag = res[:, 2 * k2].max().reshape(1) if nq else torch.zeros(1, dtype=torch.int64, device=dev)
         self._mark("result_gather")
-        bad = int(res[:, 2 * k2].max()) if nq else 0                 # the one host sync of the path
-        self._flush_marks()
-        if bad:
-            return None
-        return ShardedResult(top, ids, None, None)
+        return top, ids, flag
+
+    def submit(self, Q, k1: int = 1000, k2: int = 10, graph: bool = False) -> "PendingResult":
+        """Queue one batch of the packed path and return at once; ``PendingResult.result()`` is where the host waits.
+        Batches submitted back to back keep the GPU busy while the host queues the next one (a serving loop).
+        ``graph=True`` replays the batch from a CUDA graph captured on the first call with this shape (collectives
+        included), so the host cost per batch is one graph launch.  Every rank must make the same calls."""
+        if self.n_total >= (1 << 40):
+            raise ValueError("corpus too large: ids must stay below 2**40")
+        if not isinstance(Q, torch.Tensor):
+            Q = torch.as_tensor(Q)
+        k2 = min(k2, k1)
+        if not graph:
+            self._mark("start")
+            top, ids, flag = self._enqueue_packed(Q, k1, k2)
+            return PendingResult(self, Q, k1, k2, top, ids, flag)
+        key = (tuple(Q.shape), k1, k2)
+        g = self._graphs.get(key)
+        if g is None:
+            static_q = torch.empty_like(Q, device=getattr(self.engine, "device", Q.device))
+            static_q.copy_(Q)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                           # warm-up outside the capture (lazy inits, allocations)
+                self._enqueue_packed(static_q, k1, k2)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg, capture_error_mode="thread_local"):   # the NCCL watchdog thread keeps polling
+                outs = self._enqueue_packed(static_q, k1, k2)
+            g = (cg, static_q, outs)
+            self._graphs = {key: g}                                 # one captured shape at a time
+        cg, static_q, (top, ids, flag) = g
+        static_q.copy_(Q, non_blocking=True)
+        cg.replay()
+        # the graph's outputs are overwritten by the next replay: hand out copies (stream-ordered, no host sync)
+        return PendingResult(self, Q, k1, k2, top.clone(), ids.clone(), flag.clone())
 
     def __call__(self, Q, k1: int = 1000, k2: int = 10, return_search_lists: bool = False) -> ShardedResult:
         """Top-k2 by amplitude fidelity among the global top-k1 of the search (identical on every rank).
@@ -295,15 +356,10 @@ class ShardedSearchRerank:
         """
         if self.n_total >= (1 << 40):
             raise ValueError("corpus too large: ids must stay below 2**40")
-        self._mark("start")
         self.last_rerun = 0
         if not return_search_lists and hasattr(self.engine, "packed_finish"):
-            res = self._owner_pipeline(Q, k1, k2)
-            if res is not None:
-                return res
-            self.last_rerun = 1
-            self._marks = []
-            self._mark("start")
+            return self.submit(Q, k1, k2).result()
+        self._mark("start")
         ss, si = self.search(Q, k1)
         top, ids = self.rerank(Q, si, min(k2, k1))
         return ShardedResult(top, ids, ss, si)

@@ -293,3 +293,22 @@ def test_overlap_policies_give_identical_results_back_to_back(cuda):
     assert np.array_equal(base[0][1].cpu().numpy(), want)
     with pytest.raises(Exception):
         api.set_overlap(7)
+
+
+@pytest.mark.parametrize("nq,C,top_k,descending", [(3, 5000, None, True), (2, 100000, 25, True), (1, 100000, None, False),
+                                                   (5, 4097, 4097, True), (4, 12289, 7, False), (1, 4096, None, True)])
+def test_long_stable_sort_vs_oracle(cuda, nq, C, top_k, descending):
+    """Lists longer than the shared-memory sort (block sort + global-memory merge levels, no library sort on the
+    path): the reference's `sorted(..., reverse=True)` order -- ties keep their input order -- at C = 5 000 and 100 000."""
+    import torch
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(C % 1000 + nq)
+    scores = np.round(rng.standard_normal((nq, C)), 2)                  # two decimals: thousands of exact ties
+    scores[:, C // 2] = scores[:, 1]
+    perm, srt = api.sort_scores(torch.from_numpy(scores).cuda(), top_k, descending=descending)
+    k = C if top_k is None else top_k
+    for q in range(nq):
+        want = oq.stable_rank(scores[q].tolist(), k) if descending else \
+            sorted(range(C), key=lambda i: scores[q, i])[:k]             # Python's sort is stable either way
+        assert perm[q].cpu().tolist() == want
+        assert np.array_equal(srt[q].cpu().numpy(), scores[q][want])

@@ -147,6 +147,27 @@ def test_owner_finalize_vs_oracle_random_records(cuda):
         assert np.array_equal(got.cpu().numpy(), want), (G, per, kk, k1, k2, metric)
 
 
+def test_submit_pipelined_and_graph_replay(cuda):
+    """``submit`` queues batches without a host sync (results read later, still verified); ``graph=True`` replays the
+    batch from a CUDA graph.  Both give the bits of the synchronous call, for changing queries of one shape."""
+    import torch
+    from quantum_rag_b200.sharded import ShardedSearchRerank
+    rng = np.random.RandomState(21)
+    X = torch.from_numpy(rng.standard_normal((20000, 384)).astype(np.float32)).cuda()
+    Qs = [torch.from_numpy(rng.standard_normal((9, 384)).astype(np.float32)).cuda() for _ in range(4)]
+    path = ShardedSearchRerank(X, 20000, "cosine")
+    want = [path(Q, 100, 10) for Q in Qs]
+    pend = [path.submit(Q, 100, 10) for Q in Qs]                       # four batches in flight
+    for p, w in zip(pend, want):
+        r = p.result()
+        assert torch.equal(r.ids, w.ids) and torch.equal(r.scores, w.scores)
+    pend = [path.submit(Q, 100, 10, graph=True) for Q in Qs]           # captured on the first call, replayed after
+    for p, w in zip(pend, want):
+        r = p.result()
+        assert torch.equal(r.ids, w.ids) and torch.equal(r.scores, w.scores)
+    path.close()
+
+
 def test_functional_form_and_cache(cuda):
     """``sharded_search_rerank(q, X_shard, k1, k2, group)`` = the class, shard prepared once."""
     import torch

@@ -208,3 +208,24 @@ def test_json_sidecar_roundtrip_and_pickle_conversion(tmp_path):
     pk.write_bytes(pickle.dumps(np.arange(3)))
     with pytest.raises(pickle.UnpicklingError):
         qidx.convert_metadata_pickle(str(pk))
+
+
+def test_numa_binding_helpers(tmp_path):
+    """hostmem: cpulist parsing and the sysfs lookups behind bind_to_gpu_numa_node (a fake sysfs tree)."""
+    from quantum_rag_b200 import hostmem
+    assert hostmem.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert hostmem.parse_cpulist("") == [] and hostmem.parse_cpulist("5") == [5]
+    dev = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    node = tmp_path / "devices/system/node/node1"
+    node.mkdir(parents=True)
+    (node / "cpulist").write_text("56-111,168-223\n")
+    assert hostmem.gpu_numa_node("00000000:1B:00.0", sysfs=str(tmp_path)) == 1      # CUDA's 8-digit domain, upper case
+    assert hostmem.gpu_numa_node("0000:1b:00.0", sysfs=str(tmp_path)) == 1
+    assert hostmem.gpu_numa_node("0000:ff:00.0", sysfs=str(tmp_path)) is None
+    (dev / "numa_node").write_text("-1\n")
+    assert hostmem.gpu_numa_node("0000:1b:00.0", sysfs=str(tmp_path)) is None       # platform does not say
+    cpus = hostmem.node_cpus(1, sysfs=str(tmp_path))
+    assert len(cpus) == 112 and cpus[0] == 56 and cpus[-1] == 223
+    assert hostmem.node_cpus(7, sysfs=str(tmp_path)) == []
