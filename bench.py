@@ -444,7 +444,7 @@ def run_b200(args):
 
     def step(i):
         Qd, cd = sets[i % nsets]
-        _lib.check(lib.qrag_amp_rerank(api._ptr(Qd), NQ, api._ptr(cd), None, None, C, D, NQUBITS, TOPK,
+        _lib.check(lib.qrag_amp_rerank(api._ptr(Qd), NQ, api._ptr(cd), None, 0, None, C, D, NQUBITS, TOPK,
                                        api._ptr(scores), api._ptr(pos), None, api._stream()))
 
     # spin-up (clocks, caches, lazy module load), then the W warm-up steps asked for

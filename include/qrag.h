@@ -101,14 +101,15 @@ int qrag_sv_fidelity_angle(const double* qvec, int nq,
  * The encoding quantum.py:156 names as the real scheme; builder-defined.
  *
  *   Q [nq, D] fp32.  Candidates are either dense  cand [nq, C, D]  (X, idx NULL)
- *   or gathered rows  X[idx[q, c]]  of a corpus X [N, D] (cand NULL).
+ *   or gathered rows  X[idx[q, c]]  of a corpus X [N, D] (cand NULL; N is ignored for the dense form).
+ *   An idx outside [0, N) is padding: it scores -inf and sorts last -- never an out-of-bounds read.
  *   State = zero-pad(x) / |x| on n_qubits (needs D <= 2^n_qubits), followed by
  *   `layers` blocks of the reference circuit with angles x^[(l*n+i) % D].
  *   layers == 0: F = (q.d)^2 / (|q|^2 |d|^2), evaluated with fp64 accumulation.
  *   out64 [nq, C] (required), out32 [nq, C] (optional, rounded from out64).
  * ------------------------------------------------------------------------- */
 int qrag_amp_fidelity(const float* Q, int nq,
-                      const float* cand, const float* X, const int64_t* idx,
+                      const float* cand, const float* X, int64_t N, const int64_t* idx,
                       int64_t C, int D, int n_qubits, int layers,
                       double* out64, float* out32, void* stream);
 
@@ -128,7 +129,7 @@ int qrag_set_fmap_kernel(int mode);
  *   list, out_ids [nq, top_k] = idx[q, pos] (optional; needs idx).
  * ------------------------------------------------------------------------- */
 int qrag_amp_rerank(const float* Q, int nq,
-                    const float* cand, const float* X, const int64_t* idx,
+                    const float* cand, const float* X, int64_t N, const int64_t* idx,
                     int64_t C, int D, int n_qubits, int top_k,
                     double* out_scores, int32_t* out_pos, int64_t* out_ids,
                     void* stream);

@@ -35,9 +35,9 @@ PROTOTYPES: Dict[str, tuple] = {
     "qrag_set_fmap_kernel": (c_int, [c_int]),
     "qrag_sv_fidelity_angle": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                                        c_void_p, c_void_p]),
-    "qrag_amp_fidelity": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+    "qrag_amp_fidelity": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                                   c_void_p, c_void_p, c_void_p]),
-    "qrag_amp_rerank": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+    "qrag_amp_rerank": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "qrag_sort_scores_workspace": (c_int, [c_int, c_int64, POINTER(c_size_t)]),
     "qrag_sort_scores_stable": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
@@ -97,11 +97,15 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into the in-tree ``libqrag.so``."""
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, tuning: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into the in-tree ``libqrag.so``.
+
+    ``tuning=True`` adds -DQRAG_TUNING (kernel-tuning switches read from the environment; tools/sweep_amp.py) -- never
+    what ships: rebuild without it (``build(force=True)``) afterwards."""
+    if not force and not tuning and not _stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC_DIR, s) for s in SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-DQRAG_TUNING"] if tuning else []) + ["-o", LIB_PATH] + [
+        os.path.join(CSRC_DIR, s) for s in SOURCES]
     if verbose:
         print(" ".join(cmd))
     proc = subprocess.run(cmd, capture_output=True, text=True)

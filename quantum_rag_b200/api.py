@@ -55,6 +55,10 @@ def _ptr(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def _nrows(t: Optional[torch.Tensor]) -> int:
+    return int(t.shape[0]) if t is not None else 0
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -121,7 +125,7 @@ def sv_fidelity_angle(qvec: ArrayLike, dvec: ArrayLike, doc_query: Optional[Arra
     return out
 
 
-def _cand_args(Q, cand, X, idx, check_bounds=False):
+def _cand_args(Q, cand, X, idx):
     Qd = _dev(Q, torch.float32)
     if Qd.dim() != 2:
         raise ValueError("Q must be [nq, D]")
@@ -139,8 +143,6 @@ def _cand_args(Q, cand, X, idx, check_bounds=False):
     i = _dev(idx, torch.int64)
     if Xd.dim() != 2 or Xd.shape[1] != D or i.dim() != 2 or i.shape[0] != nq:
         raise ValueError("X must be [N, D] and idx [nq, C]")
-    if check_bounds and i.numel() and (int(i.max()) >= Xd.shape[0]):     # device sync; opt-in
-        raise IndexError("idx out of range for X")
     return Qd, None, Xd, i, i.shape[1]
 
 
@@ -157,7 +159,7 @@ def amp_fidelity(Q: ArrayLike, cand: Optional[ArrayLike] = None, X: Optional[Arr
     out = torch.empty((nq, C), dtype=torch.float64, device=Qd.device)
     out32 = torch.empty((nq, C), dtype=torch.float32, device=Qd.device) if want_fp32 else None
     lib = _lib.load()
-    _lib.check(lib.qrag_amp_fidelity(_ptr(Qd), nq, _ptr(c), _ptr(Xd), _ptr(i), C, D, n, layers, _ptr(out),
+    _lib.check(lib.qrag_amp_fidelity(_ptr(Qd), nq, _ptr(c), _ptr(Xd), _nrows(Xd), _ptr(i), C, D, n, layers, _ptr(out),
                                      _ptr(out32), _stream()))
     return (out, out32) if want_fp32 else out
 
@@ -205,11 +207,11 @@ def quantum_rerank_batch(Q: ArrayLike, cand: Optional[ArrayLike] = None, X: Opti
         scores = torch.empty((nq, k), dtype=torch.float64, device=Qd.device)
         pos = torch.empty((nq, k), dtype=torch.int32, device=Qd.device)
         ids = torch.empty((nq, k), dtype=torch.int64, device=Qd.device) if i is not None else None
-        _lib.check(lib.qrag_amp_rerank(_ptr(Qd), nq, _ptr(c), _ptr(Xd), _ptr(i), C, D, n, k, _ptr(scores),
+        _lib.check(lib.qrag_amp_rerank(_ptr(Qd), nq, _ptr(c), _ptr(Xd), _nrows(Xd), _ptr(i), C, D, n, k, _ptr(scores),
                                        _ptr(pos), _ptr(ids), _stream()))
         return scores, pos, ids
     full = torch.empty((nq, C), dtype=torch.float64, device=Qd.device)
-    _lib.check(lib.qrag_amp_fidelity(_ptr(Qd), nq, _ptr(c), _ptr(Xd), _ptr(i), C, D, n, layers, _ptr(full), None,
+    _lib.check(lib.qrag_amp_fidelity(_ptr(Qd), nq, _ptr(c), _ptr(Xd), _nrows(Xd), _ptr(i), C, D, n, layers, _ptr(full), None,
                                      _stream()))
     pos, scores = sort_scores(full, k)
     ids = torch.gather(i, 1, pos.long()) if i is not None else None
@@ -492,7 +494,7 @@ class HostRerankPipeline:
             with torch.cuda.stream(s):
                 dq.copy_(Q_host[a:b], non_blocking=True)
                 dc.copy_(cand_host[a:b], non_blocking=True)
-                _lib.check(lib.qrag_amp_rerank(_ptr(dq), b - a, _ptr(dc), None, None, self.C, self.D, self.n, self.k,
+                _lib.check(lib.qrag_amp_rerank(_ptr(dq), b - a, _ptr(dc), None, 0, None, self.C, self.D, self.n, self.k,
                                                _ptr(self.dS[a:b]), _ptr(self.dP[a:b]), None,
                                                ctypes.c_void_p(s.cuda_stream)))
                 self.hS[a:b].copy_(self.dS[a:b], non_blocking=True)
@@ -530,7 +532,7 @@ class HostIdRerankPipeline:
         lib = _lib.load()
         self.dQ.copy_(Q_host, non_blocking=True)
         self.dI.copy_(idx_host, non_blocking=True)
-        _lib.check(lib.qrag_amp_rerank(_ptr(self.dQ), self.nq, None, _ptr(self.X), _ptr(self.dI), self.C, self.D, self.n,
+        _lib.check(lib.qrag_amp_rerank(_ptr(self.dQ), self.nq, None, _ptr(self.X), self.X.shape[0], _ptr(self.dI), self.C, self.D, self.n,
                                        self.k, _ptr(self.dS), _ptr(self.dP), _ptr(self.dO), _stream()))
         self.hS.copy_(self.dS, non_blocking=True)
         self.hO.copy_(self.dO, non_blocking=True)

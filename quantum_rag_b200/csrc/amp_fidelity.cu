@@ -26,6 +26,7 @@ struct AmpParams {
     const float* Q;        // [nq, D]
     const float* cand;     // [nq, C, D] or null
     const float* X;        // [N, D] or null
+    int64_t N;             // rows of X: an idx outside [0, N) is padding (scores -inf), never an out-of-bounds read
     const int64_t* idx;    // [nq, C] or null
     int nq;
     int64_t C;
@@ -138,8 +139,9 @@ __global__ void __launch_bounds__(AMP_THREADS) amp_fidelity_kernel(const AmpPara
                     rp[i] = p.cand + ((size_t)q * C + r) * D;
                 } else {
                     int64_t id = p.idx[(size_t)q * C + r];
-                    missing |= (id < 0 ? 1u : 0u) << i;
-                    rp[i] = p.X + (size_t)(id < 0 ? 0 : id) * D;
+                    const bool pad = id < 0 || id >= p.N;
+                    missing |= (pad ? 1u : 0u) << i;
+                    rp[i] = p.X + (size_t)(pad ? 0 : id) * D;
                 }
             }
             double acc[8];
@@ -283,12 +285,13 @@ int amp_fidelity_fused(const AmpParams& p, cudaStream_t st) { return dispatch_am
 
 using namespace qrag;
 
-static int check_amp_common(const float* Q, int nq, const float* cand, const float* X, const int64_t* idx,
+static int check_amp_common(const float* Q, int nq, const float* cand, const float* X, int64_t N, const int64_t* idx,
                             int64_t C, int D, int n_qubits) {
     QRAG_REQUIRE(Q != nullptr, QRAG_ERR_INVALID, "Q is null");
     QRAG_REQUIRE(nq >= 0 && C >= 0 && D > 0, QRAG_ERR_INVALID, "bad sizes nq=%d C=%lld D=%d", nq, (long long)C, D);
     QRAG_REQUIRE((cand != nullptr) != (X != nullptr && idx != nullptr), QRAG_ERR_INVALID,
                  "pass either cand, or X together with idx");
+    QRAG_REQUIRE(cand != nullptr || N >= 1, QRAG_ERR_INVALID, "X needs its row count N >= 1 (got %lld)", (long long)N);
     QRAG_REQUIRE(n_qubits >= 1 && n_qubits <= 30, QRAG_ERR_INVALID, "n_qubits=%d out of range", n_qubits);
     QRAG_REQUIRE((int64_t)D <= ((int64_t)1 << n_qubits), QRAG_ERR_INVALID,
                  "D=%d does not fit %d qubits (2^n=%lld amplitudes)", D, n_qubits, (long long)1 << n_qubits);
@@ -296,37 +299,37 @@ static int check_amp_common(const float* Q, int nq, const float* cand, const flo
 }
 
 namespace qrag {
-int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, const int64_t* idx, int64_t C, int D,
+int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, int64_t N, const int64_t* idx, int64_t C, int D,
                    bool fused, double* out64, float* out32, int top_k, double* out_scores, int32_t* out_pos,
                    int64_t* out_ids, cudaStream_t st, bool* handled);                          // amp_stream.cu
-int fmap_fidelity(const float* Q, int nq, const float* cand, const float* X, const int64_t* idx, int64_t C, int D,
+int fmap_fidelity(const float* Q, int nq, const float* cand, const float* X, int64_t N, const int64_t* idx, int64_t C, int D,
                   int n_qubits, int layers, double* out64, float* out32, cudaStream_t st);   // sv_kernels.cu
 }
 
-extern "C" int qrag_amp_fidelity(const float* Q, int nq, const float* cand, const float* X, const int64_t* idx,
+extern "C" int qrag_amp_fidelity(const float* Q, int nq, const float* cand, const float* X, int64_t N, const int64_t* idx,
                                  int64_t C, int D, int n_qubits, int layers, double* out64, float* out32,
                                  void* stream) {
-    int rc = check_amp_common(Q, nq, cand, X, idx, C, D, n_qubits);
+    int rc = check_amp_common(Q, nq, cand, X, N, idx, C, D, n_qubits);
     if (rc) return rc;
     QRAG_REQUIRE(out64 != nullptr, QRAG_ERR_INVALID, "out64 is null");
     QRAG_REQUIRE(layers >= 0, QRAG_ERR_INVALID, "layers=%d", layers);
     if (nq == 0 || C == 0) return QRAG_OK;
     if (layers > 0)
-        return fmap_fidelity(Q, nq, cand, X, idx, C, D, n_qubits, layers, out64, out32, (cudaStream_t)stream);
+        return fmap_fidelity(Q, nq, cand, X, N, idx, C, D, n_qubits, layers, out64, out32, (cudaStream_t)stream);
     bool handled = false;
-    rc = amp_stream_try(Q, nq, cand, X, idx, C, D, false, out64, out32, 0, nullptr, nullptr, nullptr,
+    rc = amp_stream_try(Q, nq, cand, X, N, idx, C, D, false, out64, out32, 0, nullptr, nullptr, nullptr,
                         (cudaStream_t)stream, &handled);
     if (rc || handled) return rc;
     AmpParams p{};           // rows that are not 16-byte aligned: plain load kernel
-    p.Q = Q; p.cand = cand; p.X = X; p.idx = idx; p.nq = nq; p.C = C; p.D = D;
+    p.Q = Q; p.cand = cand; p.X = X; p.N = N; p.idx = idx; p.nq = nq; p.C = C; p.D = D;
     p.out64 = out64; p.out32 = out32;
     return amp_fidelity_plain(p, (cudaStream_t)stream);
 }
 
-extern "C" int qrag_amp_rerank(const float* Q, int nq, const float* cand, const float* X, const int64_t* idx,
+extern "C" int qrag_amp_rerank(const float* Q, int nq, const float* cand, const float* X, int64_t N, const int64_t* idx,
                                int64_t C, int D, int n_qubits, int top_k, double* out_scores, int32_t* out_pos,
                                int64_t* out_ids, void* stream) {
-    int rc = check_amp_common(Q, nq, cand, X, idx, C, D, n_qubits);
+    int rc = check_amp_common(Q, nq, cand, X, N, idx, C, D, n_qubits);
     if (rc) return rc;
     QRAG_REQUIRE(out_scores && out_pos, QRAG_ERR_INVALID, "out_scores/out_pos is null");
     QRAG_REQUIRE(C >= 1 && C <= QRAG_MAX_SORT_LEN, QRAG_ERR_UNSUPPORTED,
@@ -335,11 +338,11 @@ extern "C" int qrag_amp_rerank(const float* Q, int nq, const float* cand, const 
     QRAG_REQUIRE(out_ids == nullptr || idx != nullptr, QRAG_ERR_INVALID, "out_ids needs idx");
     if (nq == 0) return QRAG_OK;
     bool handled = false;
-    rc = amp_stream_try(Q, nq, cand, X, idx, C, D, true, nullptr, nullptr, top_k, out_scores, out_pos, out_ids,
+    rc = amp_stream_try(Q, nq, cand, X, N, idx, C, D, true, nullptr, nullptr, top_k, out_scores, out_pos, out_ids,
                         (cudaStream_t)stream, &handled);
     if (rc || handled) return rc;
     AmpParams p{};
-    p.Q = Q; p.cand = cand; p.X = X; p.idx = idx; p.nq = nq; p.C = C; p.D = D;
+    p.Q = Q; p.cand = cand; p.X = X; p.N = N; p.idx = idx; p.nq = nq; p.C = C; p.D = D;
     p.top_k = top_k; p.out_scores = out_scores; p.out_pos = out_pos; p.out_ids = out_ids;
     return amp_fidelity_fused(p, (cudaStream_t)stream);
 }

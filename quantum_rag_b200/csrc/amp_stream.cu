@@ -47,6 +47,7 @@ constexpr int AS_HDR_BYTES = 1280;
 
 struct AmpStreamParams {
     const float* Q; const float* cand; const float* X; const int64_t* idx;
+    int64_t N;          // rows of X: an idx outside [0, N) is padding
     int nq; int64_t C; int D;
     int G;              // consumer warps per team; a team drains one tile of R = G * RB rows together
     int R;              // rows per tile (one bulk copy, one pair of barriers)
@@ -224,6 +225,8 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
                 int64_t ida = -1, idb = -1;
                 if (lane < nr) ida = p.idx[(size_t)q * C + r0 + lane];
                 if (lane + 32 < nr) idb = p.idx[(size_t)q * C + r0 + lane + 32];
+                if (ida >= p.N) ida = -1;
+                if (idb >= p.N) idb = -1;
                 const int nvalid = __popc(__ballot_sync(FULL_MASK, ida >= 0)) + __popc(__ballot_sync(FULL_MASK, idb >= 0));
                 if (lane == 0) mbar_arrive_expect_tx(&full[st], (uint32_t)nvalid * row_bytes);
                 __syncwarp();
@@ -423,7 +426,10 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
         const bool owner = (lane & (2 * LPV - 1)) == 0 && i < nr;
         const int64_t c = r0 + i;
         double den = nq2 * nd2;
-        if (owner && p.idx && p.idx[(size_t)q * C + c] < 0) den = -1.0;
+        if (owner && p.idx) {
+            const int64_t id = p.idx[(size_t)q * C + c];
+            if (id < 0 || id >= p.N) den = -1.0;
+        }
         if (p.fused) {
             const int buf = qs % NB;           // free: the producer waited for the rankers before issuing this query
             if (owner) sc[(size_t)buf * P + c] = make_double2(tot, den);
@@ -506,7 +512,7 @@ static int plan_stream(AmpStreamParams& p, int rb, int g, bool fused, size_t bud
 }
 
 // Returns QRAG_OK and sets *handled = true if the streaming kernel took the job.
-int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, const int64_t* idx, int64_t C, int D,
+int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, int64_t N, const int64_t* idx, int64_t C, int D,
                    bool fused, double* out64, float* out32, int top_k, double* out_scores, int32_t* out_pos,
                    int64_t* out_ids, cudaStream_t st, bool* handled) {
     *handled = false;
@@ -528,7 +534,7 @@ int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, co
     if (nq < 1 || C < 1) return QRAG_OK;
 
     AmpStreamParams p{};
-    p.Q = Q; p.cand = cand; p.X = X; p.idx = idx; p.nq = nq; p.C = C; p.D = D;
+    p.Q = Q; p.cand = cand; p.X = X; p.N = N; p.idx = idx; p.nq = nq; p.C = C; p.D = D;
     p.out64 = out64; p.out32 = out32; p.top_k = top_k; p.out_scores = out_scores; p.out_pos = out_pos;
     p.out_ids = out_ids; p.fused = fused ? 1 : 0;
     p.overlap = overlap_mode();

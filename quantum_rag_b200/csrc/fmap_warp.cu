@@ -47,6 +47,7 @@ constexpr int FW_STAGE = FW_DIM + (FW_DIM >> 5) * 4;        // fp32 row staging:
 
 struct FmapWarpParams {
     const float* Q; const float* cand; const float* X; const int64_t* idx;
+    int64_t N;
     int64_t C; int D; int nq; int layers;
     int64_t chunk; int chunks_per_q; int64_t units;
     double* out; float* out32;
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(MAXT, 1) fmap_warp_kernel(const FmapWarpParams
             const int64_t j = qi * p.C + c0 + (t - 1);
             if (p.cand) return p.cand + (size_t)j * p.D;
             const int64_t id = p.idx[j];
-            *missing = id < 0;
+            *missing = id < 0 || id >= p.N;
             return p.X + (size_t)(*missing ? 0 : id) * p.D;
         };
         for (int64_t t = warp; t - warp <= cnt; t += W) {
@@ -415,7 +416,7 @@ size_t fmap_warp_smem(int W, int layers) {
 }
 
 // Returns QRAG_OK and sets *handled when the shape is served by this kernel (n = 10).
-int fmap_warp_try(const float* Q, int nq, const float* cand, const float* X, const int64_t* idx, int64_t C, int D,
+int fmap_warp_try(const float* Q, int nq, const float* cand, const float* X, int64_t N, const int64_t* idx, int64_t C, int D,
                   int n_qubits, int layers, double* out64, float* out32, cudaStream_t st, bool* handled) {
     *handled = false;
     if (n_qubits != FW_N || layers < 1 || D < 1 || D > FW_DIM) return QRAG_OK;
@@ -427,7 +428,7 @@ int fmap_warp_try(const float* Q, int nq, const float* cand, const float* X, con
     while (W > 1 && fmap_warp_smem(W, layers) + 64 > (size_t)dp.max_smem_optin) --W;
     if (fmap_warp_smem(W, layers) + 64 > (size_t)dp.max_smem_optin) return QRAG_OK;    // layers too deep: generic kernel
     FmapWarpParams p{};
-    p.Q = Q; p.cand = cand; p.X = X; p.idx = idx; p.C = C; p.D = D; p.nq = nq; p.layers = layers;
+    p.Q = Q; p.cand = cand; p.X = X; p.idx = idx; p.N = N; p.C = C; p.D = D; p.nq = nq; p.layers = layers;
     p.out = out64; p.out32 = out32;
     // a unit should fill at least one round of the CTA (query + W-1 candidates); prefer >= 2 units per SM
     int64_t cpq = ceil_div(2 * (int64_t)dp.sm_count, nq);

@@ -129,7 +129,7 @@ struct SvCtaParams {
     const double* qvec; const double* dvec; const int32_t* doc_query;
     int64_t nd, docs_per_query; int vec_len;
     // FMAP mode
-    const float* Q; const float* cand; const float* X; const int64_t* idx; int64_t C; int D;
+    const float* Q; const float* cand; const float* X; const int64_t* idx; int64_t N; int64_t C; int D;
     int nq, n, layers;
     int64_t docs_per_cta;
     double* out; float* out32;
@@ -276,7 +276,7 @@ __global__ void sv_cta_kernel(const SvCtaParams p) {
             dsrc = p.cand + (size_t)j * len;
         } else {
             const int64_t id = p.idx[j];
-            missing = id < 0;
+            missing = id < 0 || id >= p.N;
             dsrc = p.X + (size_t)(missing ? 0 : id) * len;
         }
         bool d_zero;
@@ -330,21 +330,21 @@ static int launch_sv_cta(SvCtaParams p, cudaStream_t st) {
     return QRAG_OK;
 }
 
-int fmap_warp_try(const float* Q, int nq, const float* cand, const float* X, const int64_t* idx, int64_t C, int D,
+int fmap_warp_try(const float* Q, int nq, const float* cand, const float* X, int64_t N, const int64_t* idx, int64_t C, int D,
                   int n_qubits, int layers, double* out64, float* out32, cudaStream_t st, bool* handled);  // fmap_warp.cu
 
-int fmap_fidelity(const float* Q, int nq, const float* cand, const float* X, const int64_t* idx, int64_t C, int D,
+int fmap_fidelity(const float* Q, int nq, const float* cand, const float* X, int64_t N, const int64_t* idx, int64_t C, int D,
                   int n_qubits, int layers, double* out64, float* out32, cudaStream_t st) {
     QRAG_REQUIRE(n_qubits <= QRAG_MAX_QUBITS, QRAG_ERR_UNSUPPORTED, "feature map: n_qubits=%d > %d", n_qubits,
                  QRAG_MAX_QUBITS);
     QRAG_REQUIRE(layers <= 64, QRAG_ERR_UNSUPPORTED, "feature map: layers=%d > 64", layers);
     if (fmap_kernel_mode() == QRAG_FMAP_AUTO) {
         bool handled = false;
-        const int rc = fmap_warp_try(Q, nq, cand, X, idx, C, D, n_qubits, layers, out64, out32, st, &handled);
+        const int rc = fmap_warp_try(Q, nq, cand, X, N, idx, C, D, n_qubits, layers, out64, out32, st, &handled);
         if (rc || handled) return rc;
     }
     SvCtaParams p{};
-    p.Q = Q; p.cand = cand; p.X = X; p.idx = idx; p.C = C; p.D = D; p.nq = nq; p.n = n_qubits; p.layers = layers;
+    p.Q = Q; p.cand = cand; p.X = X; p.idx = idx; p.N = N; p.C = C; p.D = D; p.nq = nq; p.n = n_qubits; p.layers = layers;
     p.out = out64; p.out32 = out32;
     return launch_sv_cta<1>(p, st);
 }

@@ -18,6 +18,7 @@ Extensions (all default to the reference behaviour):
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
@@ -51,7 +52,14 @@ class QuantumReranker:
         self.embedding_key = self.config.get("embedding_key", "embedding")
         # the reference builds a ClassicalReranker from the same dict (quantum.py:37); kept as an attribute
         self.classical_fallback = ClassicalReranker(config)
-        self._embedding_memo: Dict[int, np.ndarray] = {}
+        # memo of the text-hash embeddings, keyed by sum(ord(c)); bounded (LRU) so that a long-running /rerank service
+        # does not grow without limit -- an evicted seed is simply recomputed (same bits: the stream is seeded)
+        self._embedding_memo: "OrderedDict[int, np.ndarray]" = OrderedDict()
+        self._memo_cap = int(self.config.get("embedding_memo_size", 65536))
+        if self.encoding == "angle" and not 1 <= int(self.n_qubits) <= 12:
+            # the reference accepts any n its simulator can hold; the statevector kernels stage 2^n complex128
+            # amplitudes in shared memory, which ends at n = 12 (QRAG_MAX_QUBITS).  Say so up front, not at rerank().
+            raise ValueError(f"n_qubits={self.n_qubits}: the B200 statevector kernels support 1 <= n_qubits <= 12")
 
     # ------------------------------------------------------------------ API
     def rerank(self, query: str, documents: List[Document], top_k: int = None) -> List[Tuple[Document, float]]:
@@ -77,6 +85,10 @@ class QuantumReranker:
             raw = np.random.RandomState(seed).random_sample(self.n_qubits * 2)
             vec = raw / np.linalg.norm(raw)
             self._embedding_memo[seed] = vec
+            if len(self._embedding_memo) > self._memo_cap:
+                self._embedding_memo.popitem(last=False)
+        else:
+            self._embedding_memo.move_to_end(seed)
         return vec
 
     def _text_embeddings(self, query: str, documents: List[Document]):

@@ -44,7 +44,7 @@ def test_version_and_error_text(libqrag):
 
 def test_argument_validation_happens_before_any_cuda_call(libqrag):
     # null pointers are rejected on the host side, so this is safe without a device
-    assert libqrag.qrag_amp_fidelity(None, 1, None, None, None, 1, 4, 2, 0, None, None, None) == -1
+    assert libqrag.qrag_amp_fidelity(None, 1, None, None, 0, None, 1, 4, 2, 0, None, None, None) == -1
     assert libqrag.qrag_sv_fidelity_angle(None, 1, None, 1, None, 1, 4, 4, 1, None, None) == -1
     assert libqrag.qrag_topk_merge(None, None, 1, 1, 1, 1, 0, None, None, None, 0, None) == -1
 

@@ -229,3 +229,18 @@ def test_numa_binding_helpers(tmp_path):
     cpus = hostmem.node_cpus(1, sysfs=str(tmp_path))
     assert len(cpus) == 112 and cpus[0] == 56 and cpus[-1] == 223
     assert hostmem.node_cpus(7, sysfs=str(tmp_path)) == []
+
+
+def test_embedding_memo_is_bounded_and_qubit_range_is_checked_up_front():
+    """the text-hash memo of a long-running service must not grow without bound; n_qubits beyond what the
+    kernels stage (12) is refused at construction, not at the first rerank."""
+    from src.reranker.quantum import QuantumReranker
+    q = QuantumReranker({"embedding_memo_size": 8})
+    first = q._mock_embedding("a").copy()
+    for i in range(100):
+        q._mock_embedding("x" * (i + 2))
+    assert len(q._embedding_memo) <= 8
+    assert np.array_equal(q._mock_embedding("a"), first)             # evicted and recomputed: same bits (seeded stream)
+    with pytest.raises(ValueError, match="n_qubits"):
+        QuantumReranker({"n_qubits": 13})
+    assert QuantumReranker({"n_qubits": 12}).n_qubits == 12

@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--overlap", default="0,1,2")
     ap.add_argument("--gather", action="store_true", help="candidates named by random ids into a resident corpus")
     a = ap.parse_args()
-    _lib.build()
+    _lib.build(force=True, tuning=True)       # the switches below only exist in a -DQRAG_TUNING build
     lib = _lib.load()
     g = torch.Generator().manual_seed(7)
     nsets = max(2, int(520e6 / (a.nq * a.C * a.D * 4)) + 1)
@@ -45,10 +45,10 @@ def main():
     def step(i):
         Q, c = sets[i % nsets]
         if a.gather:
-            _lib.check(lib.qrag_amp_rerank(api._ptr(Q), a.nq, None, api._ptr(corpus), api._ptr(idxs[i % nsets]), a.C, a.D,
+            _lib.check(lib.qrag_amp_rerank(api._ptr(Q), a.nq, None, api._ptr(corpus), corpus.shape[0], api._ptr(idxs[i % nsets]), a.C, a.D,
                                            api.qubits_for(a.D), a.k, api._ptr(scores), api._ptr(pos), None, api._stream()))
             return
-        _lib.check(lib.qrag_amp_rerank(api._ptr(Q), a.nq, api._ptr(c), None, None, a.C, a.D, api.qubits_for(a.D), a.k,
+        _lib.check(lib.qrag_amp_rerank(api._ptr(Q), a.nq, api._ptr(c), None, 0, None, a.C, a.D, api.qubits_for(a.D), a.k,
                                        api._ptr(scores), api._ptr(pos), None, api._stream()))
 
     ref = None
