@@ -31,7 +31,14 @@ L2_BYTES = 126 * 2**20
 NCU_DRAM_BYTES_PER_LAUNCH = 155.188736e6 + 3.671296e6     # one ncu --set full capture of the timed kernel (profiles/)
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, overlap="interleaved"):
+    cfg = _workload_config(n_gpus)
+    if overlap != "interleaved":
+        cfg["launch"] = f"one fused kernel per step, programmatic dependent launch, overlap policy '{overlap}' (include/qrag.h)"
+    return cfg
+
+
+def _workload_config(n_gpus):
     return {
         "workload": "config 2: quantum rerank, 1000 queries x 100 candidates, 384-d fp32 embeddings, "
                     "amplitude encoding on 9 qubits, stable sort + top-10",
@@ -39,8 +46,10 @@ def workload_config(n_gpus):
         "per_gpu_batch": f"{NQ}x{C}", "sharding": f"by query, {n_gpus} rank(s), no data-path collective",
         "l2": "4 input sets of 155.1 MB rotated every step (465 MB of other traffic before a set is reused; L2 is 126 MB)",
         "seed": SEED,
-        "launch": "one fused kernel per step, programmatic dependent launch, QRAG_OVERLAP_INPUTS_STABLE "
-                  "(inputs resident and not written during the timed region; output writes of step i+1 wait for step i)",
+        "launch": "one fused kernel per step, programmatic dependent launch, QRAG_OVERLAP_INTERLEAVED: half-size CTAs, "
+                  "one per SM and launch, so consecutive steps share every SM two deep and one step's start-up / drain "
+                  "is covered by the other's streaming (inputs resident and not written during the timed region; a "
+                  "step's results are staged in shared memory and written after the previous step's kernel completed)",
     }
 
 
@@ -425,7 +434,9 @@ def run_b200(args):
         dist.barrier()
     from quantum_rag_b200 import _lib, api
     lib = _lib.load()
-    api.set_overlap(api.OVERLAP_INPUTS_STABLE)        # see config["launch"]
+    headline_overlap = {"stable": api.OVERLAP_INPUTS_STABLE, "interleaved": api.OVERLAP_INTERLEAVED,
+                        "safe": api.OVERLAP_SAFE}[args.overlap]
+    api.set_overlap(headline_overlap)                 # see config["launch"]
 
     def barrier():
         if world > 1:
@@ -572,7 +583,7 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world, args.overlap),
             "reranked_queries_per_s": value / C,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
@@ -591,12 +602,12 @@ def run_b200(args):
             "timing": {"what": "median over the timed regions of K steps each (CUDA events, max over ranks per region)",
                        "ms_per_step_min": region_ms[0] / args.steps, "ms_per_step_max": region_ms[-1] / args.steps,
                        "region_ms": [round(x, 5) for x in region_ms]},
-            "kernels": ["qrag::amp_stream_kernel<3,4> (1 launch per step; TMA bulk-copy ring, warp-specialised "
-                        "producer / converter / 16 consumers / 2 rankers, fused rank)"],
+            "kernels": ["qrag::amp_stream_kernel<3,4,8> (1 launch per step; TMA bulk-copy ring, warp-specialised "
+                        "producer / converter / 8 consumers / 2 rankers, fused rank; <3,4,16> with --overlap stable)"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full, profiles/r01_amp_stream_key_metrics.csv "
                          "(dram__bytes_read.sum 155.19 MB + dram__bytes_write.sum 3.67 MB per launch)",
-                         "kernel": "amp_stream_kernel<3,4>",
+                         "kernel": "amp_stream_kernel<3,4,8>" if args.overlap == "interleaved" else "amp_stream_kernel<3,4,16>",
                          "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_score": BYTES_PER_SCORE,
                          "peak_source": peak_src},
             "clocks": clocks,
@@ -621,7 +632,7 @@ def run_b200(args):
             cpu_dt = time.perf_counter() - t0
             faithful, fpairs = cpu_faithful_rate(Qn, cn, 2000)
             # the CPU pass doubles as a parity check of what the GPU just computed on set 0
-            api.set_overlap(api.OVERLAP_INPUTS_STABLE)
+            api.set_overlap(headline_overlap)
             step(0)
             torch.cuda.synchronize()
             want = np.concatenate([r for r in ranks if r is not None], axis=0)
@@ -672,6 +683,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: a single untimed-quality e2e pass")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (configs 3, 4 and 5)")
     ap.add_argument("--no-spinup", action="store_true", help="profiling runs: skip the 0.2 s clock spin-up")
+    ap.add_argument("--overlap", default="interleaved", choices=["interleaved", "stable", "safe"],
+                    help="stream-overlap policy of the headline kernel (include/qrag.h)")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the e2e staging buffers to the GPU's NUMA node")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="slices of the end-to-end pipeline")
     args = ap.parse_args()

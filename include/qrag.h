@@ -69,10 +69,16 @@ int qrag_probe_fp64_fma_rate(double* fma_per_s, double* scratch, void* stream);
  *                  start as soon as an SM is free.  The caller promises that Q / cand / X /
  *                  idx are not produced by the kernel immediately preceding it on the stream
  *                  (copies and events are unaffected: only kernel -> kernel edges relax).
+ *   INTERLEAVED    INPUTS_STABLE with half-size CTAs (half an SM's shared memory each, still one CTA per SM
+ *                  and launch): the free half of every SM is taken by the NEXT launch on the stream, so
+ *                  back-to-back batches run two deep, staggered by half a batch, and each one's start-up and
+ *                  drain are covered by the other's streaming.  For steady streams of equal batches; a single
+ *                  isolated launch gains nothing.  Same promise about the inputs as INPUTS_STABLE.
  * ------------------------------------------------------------------------- */
 #define QRAG_OVERLAP_NONE          0
 #define QRAG_OVERLAP_SAFE          1
 #define QRAG_OVERLAP_INPUTS_STABLE 2
+#define QRAG_OVERLAP_INTERLEAVED   3
 int qrag_set_overlap(int mode);
 int qrag_get_overlap(void);
 

@@ -63,7 +63,7 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-OVERLAP_NONE, OVERLAP_SAFE, OVERLAP_INPUTS_STABLE = 0, 1, 2
+OVERLAP_NONE, OVERLAP_SAFE, OVERLAP_INPUTS_STABLE, OVERLAP_INTERLEAVED = 0, 1, 2, 3
 
 
 def set_overlap(mode: int) -> int:

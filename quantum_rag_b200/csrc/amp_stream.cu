@@ -30,13 +30,17 @@
 
 namespace qrag {
 
+// Two CTA shapes.  CW = 16 consumer warps (640 threads, the whole SM's shared memory, one CTA per SM), and the
+// INTERLEAVED shape CW = 8 (384 threads, half the shared memory, two CTAs per SM) whose grid is still one CTA per SM:
+// the second slot of every SM is taken by the NEXT launch on the stream (programmatic dependent launch), so
+// consecutive batches run staggered by half a period and one batch's start-up and drain (first HBM round trip, last
+// ranking: ~3 us of a 29 us batch) are covered by the other's streaming.  Only with QRAG_OVERLAP_INPUTS_STABLE
+// (reads may start before the previous kernel completes); writes still wait for it.
 constexpr int AS_CWARPS = 16;
+constexpr int AS_CWARPS_HALF = 8;
 constexpr int AS_RWARPS = 2;
 constexpr int AS_RTHREADS = AS_RWARPS * 32;
-constexpr int AS_WARP_RANK = AS_CWARPS;                  // first ranker warp
-constexpr int AS_WARP_CONV = AS_CWARPS + AS_RWARPS;
-constexpr int AS_WARP_PROD = AS_WARP_CONV + 1;
-constexpr int AS_THREADS = (AS_WARP_PROD + 1) * 32;      // 640
+__host__ __device__ constexpr int as_threads(int cw) { return (cw + AS_RWARPS + 2) * 32; }      // consumers, rankers, converter, producer
 constexpr int AS_MAX_STAGES = 64;
 constexpr int AS_MAX_QSLOTS = 8;
 constexpr int AS_MAX_SBUFS = 8;
@@ -62,6 +66,8 @@ struct AmpStreamParams {
     double* out64; float* out32;
     int top_k; double* out_scores; int32_t* out_pos; int64_t* out_ids;
     int overlap;        // QRAG_OVERLAP_*: where the kernel orders itself after the previous kernel on the stream
+    int out_stage_q;    // interleaved shape: results of up to this many queries per CTA are staged in shared memory and
+                        // written after the previous kernel has completed (0 = write each query's result at once)
 };
 
 // Transposed butterfly over the NV = 2*RB per-lane partials v[2*r] = q.d of row r, v[2*r+1] = |d|^2
@@ -125,8 +131,12 @@ __device__ void bitonic_sort_aos(double2* a, int P, int tid, int nt, int bar) {
 
 // NCHUNK > 0: D == 128 * NCHUNK, query cached in registers.  NCHUNK == 0: any D % 4 == 0, query read
 // from its fp64 slot in shared memory.  RB = candidate rows per tile (one consumer warp per tile).
-template <int NCHUNK, int RB>
-__global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStreamParams p) {
+template <int NCHUNK, int RB, int CW>
+__global__ void __launch_bounds__(as_threads(CW), CW == AS_CWARPS ? 1 : 2) amp_stream_kernel(const AmpStreamParams p) {
+    constexpr int AS_WARP_RANK = CW;                         // first ranker warp
+    constexpr int AS_WARP_CONV = CW + AS_RWARPS;
+    constexpr int AS_WARP_PROD = AS_WARP_CONV + 1;
+    constexpr int AS_THREADS = as_threads(CW);
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + AS_MAX_STAGES;
@@ -145,29 +155,36 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
     unsigned char* ring = reinterpret_cast<unsigned char*>(sc + (p.fused ? (size_t)NB * P : 0));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        for (int s = 0; s < S; ++s) {
+    // Start-up: the PRODUCER warp initialises the barriers (one per lane, not one thread in a loop), makes them visible
+    // and goes straight to issuing the first bulk copies; it only ARRIVES on the start barrier, the other warps wait on
+    // it.  The first HBM round trip therefore overlaps the rest of the CTA's prologue instead of following it.
+    constexpr int AS_BAR_START = 2;
+    if (warp == AS_WARP_PROD) {
+        for (int s = lane; s < S; s += 32) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], (uint32_t)G);
         }
-        for (int s = 0; s < QS; ++s) {
+        for (int s = lane; s < QS; s += 32) {
             mbar_init(&qfull[s], 1);
             mbar_init(&qready[s], 1);
         }
-        for (int s = 0; s < NB; ++s) {
+        for (int s = lane; s < NB; s += 32) {
             mbar_init(&sfull[s], p.fused ? (uint32_t)(tpq * G) : 1u);
             mbar_init(&sempty[s], AS_RWARPS);
         }
         fence_barrier_init();
+        __syncwarp();
+        asm volatile("bar.arrive %0, %1;" ::"r"(AS_BAR_START), "r"(AS_THREADS) : "memory");
+    } else {
+        named_bar_sync(AS_BAR_START, AS_THREADS);
     }
-    __syncthreads();
     // Programmatic dependent launch: let the next kernel on the stream start filling SMs as this
     // grid's CTAs retire.  QRAG_OVERLAP_SAFE orders every global access of this kernel after the
     // previous kernel (only launch latency and this prologue overlap); QRAG_OVERLAP_INPUTS_STABLE
     // orders only the writes, so streaming starts while the previous grid drains.
     if (p.overlap != QRAG_OVERLAP_NONE && tid == 0) griddep_launch_dependents();
     const bool wait_reads = p.overlap == QRAG_OVERLAP_SAFE;
-    const bool wait_writes = p.overlap == QRAG_OVERLAP_INPUTS_STABLE;
+    const bool wait_writes = p.overlap >= QRAG_OVERLAP_INPUTS_STABLE;
 
     // tile range [g0, g1) of this CTA in the global sequence (query-major, tpq tiles per query)
     int64_t g0, g1;
@@ -274,15 +291,24 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
         if (!p.fused) return;
         const int rt = tid - AS_WARP_RANK * 32;
         const int top_k = p.top_k;
-        bool ordered = !wait_writes;
+        // Interleaved shape: this launch runs beside the previous one for most of its life, so its global writes (which
+        // must follow that kernel's completion: both may write the same output arrays) are staged in shared memory --
+        // top_k (score, position, id) per query, a few hundred bytes -- and flushed after griddepcontrol.wait at the
+        // end, instead of stalling the ranking of the first query until the neighbour is done.
+        const bool staged = p.out_stage_q > 0;
+        double* st_s = reinterpret_cast<double*>(ring + (size_t)S * p.stage_bytes);
+        long long* st_i = reinterpret_cast<long long*>(st_s + (size_t)p.out_stage_q * top_k);
+        int32_t* st_p = reinterpret_cast<int32_t*>(st_i + (size_t)p.out_stage_q * top_k);
+        bool ordered = !wait_writes || staged;
         for (int qs = 0; qs < nqueries; ++qs) {
             const int buf = qs % NB;
             const int64_t q = qfirst + qs;
             double2* sb = sc + (size_t)buf * P;
             mbar_wait(&sfull[buf], (uint32_t)(qs / NB) & 1u);
-            double* os = p.out_scores + (size_t)q * top_k;
-            int32_t* op = p.out_pos + (size_t)q * top_k;
-            int64_t* oi = p.out_ids ? p.out_ids + (size_t)q * top_k : nullptr;
+            double* os = staged ? st_s + (size_t)qs * top_k : p.out_scores + (size_t)q * top_k;
+            int32_t* op = staged ? st_p + (size_t)qs * top_k : p.out_pos + (size_t)q * top_k;
+            int64_t* oi = !p.out_ids ? nullptr
+                                     : (staged ? reinterpret_cast<int64_t*>(st_i) + (size_t)qs * top_k : p.out_ids + (size_t)q * top_k);
             if (!ordered) { griddep_wait(); ordered = true; }       // first write of this thread
             if (C <= AS_RANK_COUNT_MAX) {
                 // rank by counting; thread rt owns candidates rt and rt + 64
@@ -330,6 +356,17 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
             }
             __syncwarp();                                   // this warp's reads of sb are complete
             if (lane == 0) mbar_arrive(&sempty[buf]);
+        }
+        if (staged) {
+            named_bar_sync(AS_BAR_RANK, AS_RTHREADS);       // both ranker warps have staged all their entries
+            if (wait_writes) griddep_wait();                // the previous kernel is complete: its writes are behind ours
+            const int total = nqueries * top_k;
+            for (int i = rt; i < total; i += AS_RTHREADS) {
+                const size_t o = (size_t)qfirst * top_k + i;
+                p.out_scores[o] = st_s[i];
+                p.out_pos[o] = st_p[i];
+                if (p.out_ids) p.out_ids[o] = st_i[i];
+            }
         }
         return;
     }
@@ -450,13 +487,13 @@ __global__ void __launch_bounds__(AS_THREADS, 1) amp_stream_kernel(const AmpStre
     }
 }
 
-template <int NCHUNK, int RB>
-static int launch_stream(const AmpStreamParams& p, size_t smem_bytes, int grid, cudaStream_t st) {
-    auto kern = amp_stream_kernel<NCHUNK, RB>;
+template <int NCHUNK, int RB, int CW>
+static int launch_stream_cw(const AmpStreamParams& p, size_t smem_bytes, int grid, cudaStream_t st) {
+    auto kern = amp_stream_kernel<NCHUNK, RB, CW>;
     QRAG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(AS_THREADS);
+    cfg.blockDim = dim3(as_threads(CW));
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -469,8 +506,14 @@ static int launch_stream(const AmpStreamParams& p, size_t smem_bytes, int grid, 
     return QRAG_OK;
 }
 
+template <int NCHUNK, int RB>
+static int launch_stream(const AmpStreamParams& p, size_t smem_bytes, int grid, int cw, cudaStream_t st) {
+    return cw == AS_CWARPS ? launch_stream_cw<NCHUNK, RB, AS_CWARPS>(p, smem_bytes, grid, st)
+                           : launch_stream_cw<NCHUNK, RB, AS_CWARPS_HALF>(p, smem_bytes, grid, st);
+}
+
 // Shared-memory plan for a given tile height; returns the number of stages (0 = does not fit).
-static int plan_stream(AmpStreamParams& p, int rb, int g, bool fused, size_t budget, size_t* smem_bytes) {
+static int plan_stream(AmpStreamParams& p, int rb, int g, int cw, int nbuf_want, bool fused, size_t budget, size_t* smem_bytes) {
     const int D = p.D;
     p.G = g;
     p.R = g * rb;
@@ -482,6 +525,7 @@ static int plan_stream(AmpStreamParams& p, int rb, int g, bool fused, size_t bud
     p.nbuf = 2;
     if (fused) {
         int want = (int)((size_t)(192 * 1024) / p.stage_bytes / p.tpq) + 3;
+        if (nbuf_want > want) want = nbuf_want;
         if (want > AS_MAX_SBUFS) want = AS_MAX_SBUFS;
         while (want > 2 && (size_t)want * p.P * 16 > 32 * 1024) --want;
         p.nbuf = want;
@@ -503,7 +547,7 @@ static int plan_stream(AmpStreamParams& p, int rb, int g, bool fused, size_t bud
     if (fixed + 2 * (size_t)p.stage_bytes > budget) return 0;
     stages = (int)((budget - fixed) / p.stage_bytes);
     if (stages > AS_MAX_STAGES) stages = AS_MAX_STAGES;
-    p.teams = stages < AS_CWARPS / g ? stages : AS_CWARPS / g;
+    p.teams = stages < cw / g ? stages : cw / g;
     stages -= stages % p.teams;
     p.qslots = qs;
     p.stages = stages;
@@ -540,25 +584,36 @@ int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, in
     p.overlap = overlap_mode();
 
     const bool nchunk_path = (D == 128 || D == 256 || D == 384 || D == 512);
-    const size_t budget = (size_t)dp.max_smem_optin;
+    // CTA shape: the interleaved half-size shape when the caller asked for it (QRAG_OVERLAP_INTERLEAVED) and every SM
+    // gets a CTA; its shared-memory budget is half an SM's (two CTAs of consecutive launches share the SM)
+    const int q_per_cta = (int)ceil_div(nq, dp.sm_count);
+    const size_t out_stage = (size_t)q_per_cta * top_k * 20 + 16;      // staged results: fp64 score, int64 id, int32 position
+    const bool half = p.overlap == QRAG_OVERLAP_INTERLEAVED && fused && nq >= dp.sm_count && out_stage <= 8 * 1024;
+    const int cw = half ? AS_CWARPS_HALF : AS_CWARPS;
+    const size_t budget = half ? ((size_t)dp.max_smem_optin + 1024) / 2 - 1024 - out_stage : (size_t)dp.max_smem_optin;
+    const size_t tile_cap = half ? 12 * 1024 : 24 * 1024;
+    // score buffers of the interleaved shape: one per query of the CTA, so that the stream never waits for the rankers
+    const int nbuf_want = half ? q_per_cta + 1 : 0;
+    p.out_stage_q = half ? q_per_cta : 0;
     // rows per warp: 4 while a warp's slice stays <= 8 KB, else 2, else 1; team size: the widest
     // tile (one bulk copy, one barrier pair) of <= 24 KB, so that >= 8 tiles are in flight per SM
     int rb = 4;
     while (rb > 1 && (size_t)rb * D * 4 > 8 * 1024) rb >>= 1;
-    int g = AS_CWARPS;
-    while (g > 1 && (size_t)g * rb * D * 4 > 24 * 1024) g >>= 1;
+    int g = cw;
+    while (g > 1 && (size_t)g * rb * D * 4 > tile_cap) g >>= 1;
 #ifdef QRAG_TUNING
     if (const char* e = getenv("QRAG_AMP_STREAM_RB")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) rb = v; }
-    if (const char* e = getenv("QRAG_AMP_STREAM_G")) { const int v = atoi(e); if (v >= 1 && v <= 16 && !(v & (v - 1))) g = v; }
+    if (const char* e = getenv("QRAG_AMP_STREAM_G")) { const int v = atoi(e); if (v >= 1 && v <= cw && !(v & (v - 1))) g = v; }
 #endif
     size_t smem_bytes = 0;
-    while (plan_stream(p, rb, g, fused, budget, &smem_bytes) < 2) {
+    while (plan_stream(p, rb, g, cw, nbuf_want, fused, budget, &smem_bytes) < 2) {
         if (g > 1) g >>= 1;
         else if (rb > 1 && !nchunk_path) rb >>= 1;
         else return QRAG_OK;
     }
     // per-CTA tile counts are kept in 32 bits
     if ((int64_t)p.tpq * nq / dp.sm_count > ((int64_t)1 << 30)) return QRAG_OK;
+    if (half) smem_bytes += out_stage;                        // the staging area sits behind the ring
 
     int grid = dp.sm_count;
     if (fused) {
@@ -569,17 +624,17 @@ int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, in
     }
     *handled = true;
     switch ((nchunk_path ? D / 128 : 0) * 8 + rb) {
-        case 0 * 8 + 4: return launch_stream<0, 4>(p, smem_bytes, grid, st);
-        case 0 * 8 + 2: return launch_stream<0, 2>(p, smem_bytes, grid, st);
-        case 0 * 8 + 1: return launch_stream<0, 1>(p, smem_bytes, grid, st);
-        case 1 * 8 + 4: return launch_stream<1, 4>(p, smem_bytes, grid, st);
-        case 1 * 8 + 2: return launch_stream<1, 2>(p, smem_bytes, grid, st);
-        case 2 * 8 + 4: return launch_stream<2, 4>(p, smem_bytes, grid, st);
-        case 2 * 8 + 2: return launch_stream<2, 2>(p, smem_bytes, grid, st);
-        case 3 * 8 + 4: return launch_stream<3, 4>(p, smem_bytes, grid, st);
-        case 3 * 8 + 2: return launch_stream<3, 2>(p, smem_bytes, grid, st);
-        case 4 * 8 + 4: return launch_stream<4, 4>(p, smem_bytes, grid, st);
-        case 4 * 8 + 2: return launch_stream<4, 2>(p, smem_bytes, grid, st);
+        case 0 * 8 + 4: return launch_stream<0, 4>(p, smem_bytes, grid, cw, st);
+        case 0 * 8 + 2: return launch_stream<0, 2>(p, smem_bytes, grid, cw, st);
+        case 0 * 8 + 1: return launch_stream<0, 1>(p, smem_bytes, grid, cw, st);
+        case 1 * 8 + 4: return launch_stream<1, 4>(p, smem_bytes, grid, cw, st);
+        case 1 * 8 + 2: return launch_stream<1, 2>(p, smem_bytes, grid, cw, st);
+        case 2 * 8 + 4: return launch_stream<2, 4>(p, smem_bytes, grid, cw, st);
+        case 2 * 8 + 2: return launch_stream<2, 2>(p, smem_bytes, grid, cw, st);
+        case 3 * 8 + 4: return launch_stream<3, 4>(p, smem_bytes, grid, cw, st);
+        case 3 * 8 + 2: return launch_stream<3, 2>(p, smem_bytes, grid, cw, st);
+        case 4 * 8 + 4: return launch_stream<4, 4>(p, smem_bytes, grid, cw, st);
+        case 4 * 8 + 2: return launch_stream<4, 2>(p, smem_bytes, grid, cw, st);
         default: break;
     }
     *handled = false;        // (NCHUNK, RB) pair without an instantiation: the caller uses the plain kernel

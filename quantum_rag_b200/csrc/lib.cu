@@ -65,8 +65,8 @@ extern "C" int qrag_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 extern "C" int qrag_set_overlap(int mode) {
-    QRAG_REQUIRE(mode >= QRAG_OVERLAP_NONE && mode <= QRAG_OVERLAP_INPUTS_STABLE, QRAG_ERR_INVALID,
-                 "overlap mode %d (expected QRAG_OVERLAP_NONE / _SAFE / _INPUTS_STABLE)", mode);
+    QRAG_REQUIRE(mode >= QRAG_OVERLAP_NONE && mode <= QRAG_OVERLAP_INTERLEAVED, QRAG_ERR_INVALID,
+                 "overlap mode %d (expected QRAG_OVERLAP_NONE / _SAFE / _INPUTS_STABLE / _INTERLEAVED)", mode);
     qrag::g_overlap.store(mode, std::memory_order_relaxed);
     return QRAG_OK;
 }

@@ -312,3 +312,40 @@ def test_long_stable_sort_vs_oracle(cuda, nq, C, top_k, descending):
             sorted(range(C), key=lambda i: scores[q, i])[:k]             # Python's sort is stable either way
         assert perm[q].cpu().tolist() == want
         assert np.array_equal(srt[q].cpu().numpy(), scores[q][want])
+
+
+def test_interleaved_overlap_mode_back_to_back_batches(cuda):
+    """QRAG_OVERLAP_INTERLEAVED: half-size CTAs, two consecutive launches share every SM, results staged in shared
+    memory and written after the previous kernel completed.  Back-to-back batches into the SAME output arrays (the
+    write-after-write case the staging exists for) and into fresh ones: every batch equals the oracle's ranking."""
+    import ctypes
+    import torch
+    from quantum_rag_b200 import _lib, api
+    rng = np.random.RandomState(31)
+    nq, C, D, k = 300, 100, 384, 10
+    batches = []
+    for b in range(6):
+        Q = rng.standard_normal((nq, D)).astype(np.float32)
+        cand = rng.standard_normal((nq, C, D)).astype(np.float32)
+        cand[:, 40] = cand[:, 7]                                     # exact ties
+        batches.append((torch.from_numpy(Q).cuda(), torch.from_numpy(cand).cuda(), Q, cand))
+    old = api.set_overlap(api.OVERLAP_INTERLEAVED)
+    try:
+        fresh = [api.quantum_rerank_batch(Qd, cand=cd, top_k=k, n_qubits=9) for Qd, cd, _, _ in batches]
+        lib = _lib.load()
+        scores = torch.empty((nq, k), dtype=torch.float64, device="cuda")
+        pos = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+        snaps = []
+        for Qd, cd, _, _ in batches:                                 # same outputs every launch, copied out in stream order
+            _lib.check(lib.qrag_amp_rerank(api._ptr(Qd), nq, api._ptr(cd), None, 0, None, C, D, 9, k, api._ptr(scores),
+                                           api._ptr(pos), None, api._stream()))
+            snaps.append((scores.clone(), pos.clone()))
+        torch.cuda.synchronize()
+    finally:
+        api.set_overlap(old)
+    for (s1, p1, _), (s2, p2), (_, _, Q, cand) in zip(fresh, snaps, batches):
+        want = oq.amplitude_fidelity_batch(Q, cand)
+        order = oq.rank_rows(want, k)
+        assert np.array_equal(p1.cpu().numpy(), order) and np.array_equal(p2.cpu().numpy(), order)
+        assert np.allclose(s1.cpu().numpy(), np.take_along_axis(want, order, 1), rtol=REL)
+        assert torch.equal(s1, s2)
