@@ -181,10 +181,11 @@ int qrag_search_topk(const float* Q, int nq, const float* X, int64_t N, int D, i
                      double* out_scores, int64_t* out_ids,
                      void* workspace, size_t workspace_bytes, void* stream);
 
-/* bf16 shadow of the corpus for one metric, built once per index (shard):
- *   Xb [N, Kp] bf16 with Kp from qrag_index_prepared_dims (IP: x; cosine: x/|x|;
- *   L2: [x, hi(|x|^2), lo(|x|^2)]), aux [4] floats (aux[0] = max |x|, aux[1] = max over rows of
- *   the measured bf16 rounding-error norm |b - bf16(b)|: the filter's error bound uses both). */
+/* 16-bit shadow of the corpus for one metric, built once per index (shard):
+ *   Xb [N, Kp] 16-bit words with Kp from qrag_index_prepared_dims (IP: x as bf16; cosine: x/|x| as fp16 --
+ *   normalised rows fit fp16's range and keep 3 more bits; L2: [x, hi(|x|^2), lo(|x|^2)] as bf16),
+ *   aux [4] floats (aux[0] = max |x|, aux[1] = max over rows of the MEASURED rounding-error norm
+ *   |b - round16(b)|: the filter's error bound uses both). */
 int qrag_index_prepared_dims(int D, int metric, int* Kp);
 int qrag_index_prepare(const float* X, int64_t N, int D, int metric,
                        uint16_t* Xb, float* aux, void* stream);
@@ -194,7 +195,7 @@ int qrag_search_topk_tc(const float* Q, int nq, const float* X, const uint16_t* 
                         double* out_scores, int64_t* out_ids, int32_t* status,
                         void* workspace, size_t workspace_bytes, void* stream);
 
-/* Diagnostic: out [nq, N] = every approximate score of the filter GEMM (bf16 operands, fp32 accumulation in
+/* Diagnostic: out [nq, N] = every approximate score of the filter GEMM (16-bit operands, fp32 accumulation in
  * tensor memory), in the units the filter thresholds use (IP / cosine: the similarity; L2: 2 q.x - |x|^2).  This is
  * the quantity the filter's error bound is a bound on; tests measure the bound's terms with it.  Workspace as for
  * qrag_search_tc_workspace(nq, N, D, 1, metric, 1). */

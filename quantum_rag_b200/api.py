@@ -273,7 +273,9 @@ class FlatIndexTC:
         kp = ctypes.c_int(0)
         _lib.check(lib.qrag_index_prepared_dims(self.D, self.metric, ctypes.byref(kp)))
         self.Kp = kp.value
-        self.Xb = torch.empty((max(self.N, 1), self.Kp), dtype=torch.bfloat16, device=self.X.device)
+        # 16-bit shadow: bf16 (inner product, L2) or fp16 (cosine) -- opaque to the host, typed only for debugging views
+        self.shadow_dtype = torch.float16 if self.metric == METRIC_COSINE else torch.bfloat16
+        self.Xb = torch.empty((max(self.N, 1), self.Kp), dtype=self.shadow_dtype, device=self.X.device)
         self.aux = torch.empty(4, dtype=torch.float32, device=self.X.device)
         _lib.check(lib.qrag_index_prepare(_ptr(self.X), self.N, self.D, self.metric, _ptr(self.Xb), _ptr(self.aux),
                                           _stream()))

@@ -8,9 +8,10 @@
 // A bf16 tensor-core product cannot give fp32-exact order, so the GEMM is used as a FILTER with a
 // proven error bound, and only the survivors are scored exactly:
 //
-//   prepare (once per index)  Xb = bf16 shadow of the corpus, shaped so that every metric is a plain
-//                             inner product: IP: x; cosine: x/|x|; L2: [x, hi(|x|^2), lo(|x|^2)]
-//                             against [2q, -1, -1], i.e. s' = 2 q.x - |x|^2 (descending = nearer).
+//   prepare (once per index)  Xb = 16-bit shadow of the corpus, shaped so that every metric is a plain
+//                             inner product: IP: x (bf16); cosine: x/|x| against q/|q| (fp16: both sides are
+//                             normalised, so the range is safe and the rounding error 8x smaller than bf16's);
+//                             L2: [x, hi(|x|^2), lo(|x|^2)] against [2q, -1, -1] (bf16), i.e. s' = 2 q.x - |x|^2.
 //   pass 1  sim_gemm<BUCKET>  S = Qb Xb^T over every `sample`-th 256-document tile; the epilogue keeps
 //                             only the maximum of each 32-document bucket.
 //   tau     per query, m_k = k-th largest bucket maximum.  At least k documents have approximate
@@ -36,6 +37,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace qrag {
@@ -63,6 +65,7 @@ struct TcGemmParams {
     int kchunks;            // ceil(Kp / 64)
     int ksteps_last;        // tcgen05.mma K-steps in the last chunk (1..4)
     int stages;             // ring depth
+    int fp16;               // operands are fp16 (cosine: both sides normalised, so the range is safe) instead of bf16
     int a_resident;         // 1: the query tile (all K chunks) stays in shared memory; 0: its chunks stream with B
     int stage_bytes;        // 32 KB (B chunk) or 48 KB (B chunk + A chunk)
     int groups;             // query groups (of 128) in this launch
@@ -285,8 +288,9 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     } else if (warp == 1) {
         if (rank == 0) {
             // ------------------------------- MMA issuer: the whole warp runs the loop, one elected lane issues
-            // instruction descriptor: D fp32, A/B bf16, both K-major, N = 256, M = 128 (256 across a pair)
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+            // instruction descriptor: D fp32, A/B bf16 or fp16, both K-major, N = 256, M = 128 (256 across a pair)
+            // (bit 4: D fp32; bits 7 / 10: A / B format, 0 = fp16, 1 = bf16)
+            const uint32_t idesc = (1u << 4) | (p.fp16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(TC_BN >> 3) << 17) |
                                    ((uint32_t)((TC_BM * CG) >> 4) << 24);
             // The issuing thread has 128 cycles per MMA: descriptors are built once and advanced by adding the
             // byte offset (>> 4) to their address field, the four K-steps of a chunk are unrolled.
@@ -438,20 +442,42 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------- operand preparation
-// one warp per corpus row: |x|^2 in fp64, then the bf16 shadow row for the metric
+// The 16-bit operand format per metric.  Cosine normalises BOTH sides (rows in the shadow, the query in
+// query_prepare), so every component is in [-1, 1] and fp16 -- 11 significant bits against bf16's 8 -- is safe; its
+// rounding error, and with it the filter margin 2 eps and the number of rows rescored exactly, is 8x smaller.
+// Inner product and L2 work on raw data of any scale and keep bf16's fp32 range.
+__host__ __device__ __forceinline__ bool tc_operand_fp16(int metric) { return metric == QRAG_METRIC_COSINE; }
+
+// v rounded to the operand format: its 16 bits and the value they stand for.  fp16 values below the smallest normal
+// (2^-14) are flushed to zero here, so that no subnormal reaches the tensor core and the MEASURED rounding error is
+// the error of what is really multiplied.
+__device__ __forceinline__ unsigned short tc_round_operand(float v, bool fp16, float* back) {
+    if (fp16) {
+        if (fabsf(v) < 6.103515625e-05f) { *back = 0.f; return 0; }
+        const __half h = __float2half_rn(v);
+        *back = __half2float(h);
+        return __half_as_ushort(h);
+    }
+    const __nv_bfloat16 r = __float2bfloat16_rn(v);
+    *back = __bfloat162float(r);
+    return __bfloat16_as_ushort(r);
+}
+
+// one warp per corpus row: |x|^2 in fp64, then the 16-bit shadow row for the metric
 __global__ void __launch_bounds__(256) index_prepare_kernel(const float* __restrict__ X, int64_t N, int D, int Kp, int metric,
-                                                            __nv_bfloat16* __restrict__ Xb, float* __restrict__ aux) {
+                                                            unsigned short* __restrict__ Xb, float* __restrict__ aux) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= N) return;
+    const bool fp16 = tc_operand_fp16(metric);
     const float* x = X + (size_t)row * D;
     double part = 0.0;
     for (int j = lane; j < D; j += 32) { const double v = (double)x[j]; part = fma(v, v, part); }
     const double n2 = warp_sum(part);
     const double nrm = sqrt(n2);
-    __nv_bfloat16* o = Xb + (size_t)row * Kp;
-    double err2 = 0.0;                                           // |b - bf16(b)|^2 over the D data columns (exact: the
-    for (int j = lane; j < Kp; j += 32) {                        // difference of an fp32 and its bf16 rounding is an fp32)
+    unsigned short* o = Xb + (size_t)row * Kp;
+    double err2 = 0.0;                                           // |b - round(b)|^2 over the D data columns (exact: the
+    for (int j = lane; j < Kp; j += 32) {                        // difference of an fp32 and its 16-bit rounding is an fp32)
         float v = 0.f;
         if (j < D) {
             v = x[j];
@@ -461,9 +487,9 @@ __global__ void __launch_bounds__(256) index_prepare_kernel(const float* __restr
             const float hi = __bfloat162float(__float2bfloat16_rn(n2f));
             v = (j == D) ? hi : (n2f - hi);
         }
-        const __nv_bfloat16 r = __float2bfloat16_rn(v);
-        o[j] = r;
-        if (j < D) { const double d = (double)(v - __bfloat162float(r)); err2 = fma(d, d, err2); }
+        float back;
+        o[j] = tc_round_operand(v, fp16, &back);
+        if (j < D) { const double d = (double)(v - back); err2 = fma(d, d, err2); }
     }
     err2 = warp_sum(err2);
     if (lane == 0) {
@@ -474,37 +500,51 @@ __global__ void __launch_bounds__(256) index_prepare_kernel(const float* __restr
     }
 }
 
-// one warp per query row: bf16 query operand for the metric, |q| rounded up
+// one warp per query row: 16-bit query operand for the metric, its norm (rounded up) and its rounding-error norm.
+// Cosine: the operand is q / |q| (the score is then the cosine itself, and the operand fits fp16 whatever the
+// scale of q); inner product: q; L2: [2q, -1, -1].
 __global__ void __launch_bounds__(256) query_prepare_kernel(const float* __restrict__ Q, int nq, int nq_pad, int D, int Kp,
-                                                            int metric, __nv_bfloat16* __restrict__ Qb,
+                                                            int metric, unsigned short* __restrict__ Qb,
                                                             float* __restrict__ qnorm, float* __restrict__ qerr) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= nq_pad) return;
-    __nv_bfloat16* o = Qb + (size_t)row * Kp;
+    unsigned short* o = Qb + (size_t)row * Kp;
     if (row >= nq) {
-        for (int j = lane; j < Kp; j += 32) o[j] = __float2bfloat16_rn(0.f);
+        for (int j = lane; j < Kp; j += 32) o[j] = 0;
         return;
     }
+    const bool fp16 = tc_operand_fp16(metric);
     const float* x = Q + (size_t)row * D;
+    double nrm = 1.0;
+    if (metric == QRAG_METRIC_COSINE) {
+        double p2 = 0.0;
+        for (int j = lane; j < D; j += 32) { const double v = (double)x[j]; p2 = fma(v, v, p2); }
+        nrm = sqrt(warp_sum(p2));
+    }
     double part = 0.0, err2 = 0.0;
     for (int j = lane; j < Kp; j += 32) {
         float v = 0.f;
+        unsigned short bits = 0;
         if (j < D) {
             v = x[j];
+            if (metric == QRAG_METRIC_COSINE) v = nrm > 0.0 ? (float)((double)v / nrm) : 0.f;
             part = fma((double)v, (double)v, part);
-            const double d = (double)(v - __bfloat162float(__float2bfloat16_rn(v)));    // q - bf16(q), exact
+            float back;
+            bits = tc_round_operand(v, fp16, &back);
+            const double d = (double)(v - back);                 // a - round(a), exact
             err2 = fma(d, d, err2);
-            if (metric == QRAG_METRIC_L2) v *= 2.f;              // exact in bf16: bf16(2q) == 2 bf16(q)
+            if (metric == QRAG_METRIC_L2) bits = tc_round_operand(2.f * v, fp16, &back);   // exact: bf16(2q) == 2 bf16(q)
         } else if (metric == QRAG_METRIC_L2 && j < D + 2) {
-            v = -1.f;
+            float back;
+            bits = tc_round_operand(-1.f, fp16, &back);
         }
-        o[j] = __float2bfloat16_rn(v);
+        o[j] = bits;
     }
     part = warp_sum(part);
     err2 = warp_sum(err2);
     if (lane == 0) {
-        qnorm[row] = __double2float_ru(sqrt(part));
+        qnorm[row] = __double2float_ru(sqrt(part) * 1.000001);
         qerr[row] = __double2float_ru(sqrt(err2) * 1.000001);
     }
 }
@@ -524,8 +564,10 @@ __device__ __forceinline__ float tc_eps(int metric, int Kp, float qn, float qe, 
         const float xt = xmax + xe;                              // |x~| <= |x| + |x~ - x|
         e = qe * xt + qn * xe + g * (qn + qe) * xt;
     } else if (metric == QRAG_METRIC_COSINE) {
-        const float xt = 1.0000002f + xe;                        // rows are normalised in fp32 before the rounding
-        e = qe * xt + qn * (xe + 2.4e-7f) + g * (qn + qe) * xt;
+        // both operands are normalised in fp32 before the 16-bit rounding (2.4e-7 each: the fp32 division and the
+        // norm); qn is the norm of the normalised query operand, ~1
+        const float xt = 1.0000002f + xe;
+        e = (qe + 2.4e-7f * qn) * xt + qn * (xe + 2.4e-7f) + g * (qn + qe) * xt;
     } else {
         // s' = 2 q.x - |x|^2 with |x|^2 split into hi + lo (relative error 2^-15, generous) in two extra columns
         const float xt = xmax + xe;
@@ -1107,14 +1149,14 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // [rows, Kp] bf16 row-major, box = 64 x box_rows, 128-byte swizzle, zero fill out of bounds
-static int make_map(CUtensorMap* map, const void* base, int64_t rows, int Kp, int box_rows) {
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int Kp, int box_rows, bool fp16) {
     EncodeTiledFn fn = encode_tiled_fn();
     QRAG_REQUIRE(fn != nullptr, QRAG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)Kp * 2};
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+    const CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     QRAG_REQUIRE(r == CUDA_SUCCESS, QRAG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld Kp=%d", (int)r,
@@ -1130,6 +1172,7 @@ struct TcPlan {
     int Kp, kchunks, ksteps_last, stages, a_resident, stage_bytes, cg, nq_pad, groups, ntiles, sample, nsample_tiles, nbuckets;
     int cand_cap, cap;
     int kt;                 // entries of the threshold lists the shards exchange (tc_exchange_len)
+    int fp16;               // 16-bit operand format of this metric (tc_operand_fp16)
     size_t smem_gemm, smem_final;
     size_t off_qb, off_qnorm, off_bmax, off_tau, off_eps, off_hinv, off_hist, off_cnt, off_surv, off_crow, off_ckey,
         off_cfid, off_cm, total;
@@ -1205,6 +1248,7 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPl
     if (cand_cap > TC_MAX_CAND) cand_cap = TC_MAX_CAND;
     pl->cand_cap = cand_cap;
     pl->kt = tc_exchange_len(k, shards);
+    pl->fp16 = tc_operand_fp16(metric) ? 1 : 0;
     const int Dpad = (D + 3) & ~3;
     pl->smem_final = (size_t)(Dpad + XS_WARPS) * 8;           // tc_rescore: the staged query (tc_sort: 12 B per candidate)
     QRAG_REQUIRE(pl->smem_final <= budget, QRAG_ERR_UNSUPPORTED, "D=%d too large for the rescoring stage", D);
@@ -1229,7 +1273,7 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPl
 // workspace carved the same way by every phase of one search (the phases share state through it)
 struct TcWs {
     TcPlan pl;
-    __nv_bfloat16* Qb; float* qnorm; float* bmax; float* tau; float* eps; float* hinv; int* hist; unsigned int* cnt;
+    unsigned short* Qb; float* qnorm; float* bmax; float* tau; float* eps; float* hinv; int* hist; unsigned int* cnt;
     float2* surv;
     int* crow; double* ckey; double* cfid; int* cm;
     float* dump = nullptr;  // qrag_search_tc_scores only
@@ -1243,7 +1287,7 @@ static int tc_ws(int nq, int64_t N, int D, int k, int metric, int shards, void* 
                  "workspace too small: need %zu bytes, got %zu", w->pl.total, workspace_bytes);
     unsigned char* ws = reinterpret_cast<unsigned char*>(align_up((size_t)workspace, 256));
     const TcPlan& pl = w->pl;
-    w->Qb = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_qb);
+    w->Qb = reinterpret_cast<unsigned short*>(ws + pl.off_qb);
     w->qnorm = reinterpret_cast<float*>(ws + pl.off_qnorm);
     w->bmax = reinterpret_cast<float*>(ws + pl.off_bmax);
     w->tau = reinterpret_cast<float*>(ws + pl.off_tau);
@@ -1305,13 +1349,13 @@ template <int MODE, class After>
 static int tc_gemm_pass(const TcWs& w, int nq, int64_t N, const uint16_t* Xb, cudaStream_t st, After after) {
     const TcPlan& pl = w.pl;
     CUtensorMap mapA, mapB;
-    int rc = make_map(&mapA, w.Qb, pl.nq_pad, pl.Kp, TC_BM);
+    int rc = make_map(&mapA, w.Qb, pl.nq_pad, pl.Kp, TC_BM, pl.fp16 != 0);
     if (rc) return rc;
-    rc = make_map(&mapB, Xb, N, pl.Kp, TC_BN / pl.cg);
+    rc = make_map(&mapB, Xb, N, pl.Kp, TC_BN / pl.cg, pl.fp16 != 0);
     if (rc) return rc;
     TcGemmParams gp{};
     gp.kchunks = pl.kchunks; gp.ksteps_last = pl.ksteps_last; gp.stages = pl.stages;
-    gp.a_resident = pl.a_resident; gp.stage_bytes = pl.stage_bytes;
+    gp.a_resident = pl.a_resident; gp.stage_bytes = pl.stage_bytes; gp.fp16 = pl.fp16;
     gp.nq = nq; gp.N = N; gp.ntiles = pl.ntiles; gp.sample = pl.sample; gp.nbuckets = pl.nbuckets;
     gp.tau = w.tau; gp.bmax = w.bmax; gp.cnt = w.cnt; gp.surv = w.surv; gp.dump = w.dump;
 #ifdef QRAG_TUNING
@@ -1357,7 +1401,7 @@ extern "C" int qrag_index_prepare(const float* X, int64_t N, int D, int metric, 
     QRAG_CUDA_CHECK(cudaMemsetAsync(aux, 0, 4 * sizeof(float), st));
     if (N == 0) return QRAG_OK;
     const int Kp = tc_kp(D, metric);
-    index_prepare_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(X, N, D, Kp, metric, reinterpret_cast<__nv_bfloat16*>(Xb),
+    index_prepare_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(X, N, D, Kp, metric, reinterpret_cast<unsigned short*>(Xb),
                                                                   aux);
     QRAG_LAUNCH_CHECK("index_prepare_kernel");
     return QRAG_OK;

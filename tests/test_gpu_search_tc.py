@@ -231,3 +231,40 @@ def test_approx_scores_within_eps_of_exact(cuda):
     err = (S - exact).abs().max(dim=1).values
     assert torch.all(err <= eps), (err / eps).max().item()
     assert (err / eps).max().item() > 0.01                                         # and it is not vacuous by orders of magnitude
+
+
+def test_cosine_fp16_operands_bound_and_flush_to_zero(cuda):
+    """Cosine runs the filter GEMM on fp16 operands (both sides normalised).  (a) |approximate - exact cosine| <= eps
+    for every pair, eps recomputed from the published formula and the measured rounding-error norms; (b) rows whose
+    normalised components fall below fp16's smallest normal (flushed to zero in the shadow, counted in the measured
+    error) and queries of extreme scale (1e-30 ... 1e+30: the operand is q/|q|) still give the exact search's bits."""
+    import torch
+    from quantum_rag_b200 import api
+    g = torch.Generator(device="cuda").manual_seed(8)
+    N, nq, D = 20000, 64, 384
+    X = torch.randn(N, D, generator=g, device="cuda") * torch.rand(N, 1, generator=g, device="cuda") * 3
+    Q = torch.randn(nq, D, generator=g, device="cuda")
+    index = api.FlatIndexTC(X, "cosine")
+    assert index.Xb.dtype == torch.float16
+    S = index.approx_scores(Q).double()
+    Xd, Qd = X.double(), Q.double()
+    exact = (Qd @ Xd.T) / (Qd.norm(dim=1)[:, None] * Xd.norm(dim=1)[None, :])
+    a = (Qd / Qd.norm(dim=1, keepdim=True)).float()                        # the query operand before the fp16 rounding
+    back = a.half().float()
+    back[a.abs() < 2.0 ** -14] = 0.0
+    qn, qe = a.double().norm(dim=1), (a - back).double().norm(dim=1)
+    xe = float(index.aux[1])
+    gk, xt = 384 * 2.4e-7, 1.0000002 + xe
+    eps = (qe + 2.4e-7 * qn) * xt + qn * (xe + 2.4e-7) + gk * (qn + qe) * xt
+    err = (S - exact).abs().max(dim=1).values
+    assert torch.all(err <= eps), (err / eps).max().item()
+    assert xe < 1e-3                                                       # fp16: ~2e-4 |x| (bf16 would measure ~1.7e-3)
+    # (b) extreme dynamic range inside a row, extreme scale across queries
+    rng = np.random.RandomState(12)
+    Xh = (rng.standard_normal((30000, 128)) * 1e-6).astype(np.float32)
+    Xh[np.arange(30000), rng.randint(0, 128, 30000)] += rng.choice([-1.0, 1.0], 30000).astype(np.float32)
+    Qh = (rng.standard_normal((40, 128))).astype(np.float32)
+    Qh[:10] *= 1e30
+    Qh[10:20] *= 1e-30
+    Qh[20] = 0.0
+    _compare_with_exact(api, Qh, Xh, 50, "cosine", allow_fallback=True)
