@@ -912,7 +912,7 @@ __global__ void __launch_bounds__(XS_THREADS) tc_collect_kernel(const TcFinalPar
 // (2) exact rescoring, grid (queries, chunks of XS_RESCORE_ROWS candidates): small CTAs, many resident, so the row
 // gathers run at memory-level parallelism instead of behind one CTA's select and sort.  Same device code as the
 // CUDA-core search (exact_score.cuh): a row's key does not depend on which kernel or batch scored it.
-constexpr int XS_RESCORE_ROWS = 256;
+constexpr int XS_RESCORE_ROWS = 128;
 template <bool VEC>
 __global__ void __launch_bounds__(XS_THREADS) tc_rescore_kernel(const TcFinalParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1120,13 +1120,68 @@ __global__ void __launch_bounds__(1024) owner_finalize_kernel(const OwnerParams 
         }
     }
     __syncthreads();
-    bitonic_sort_kt<double, int>(mkey, mtag, P);
-    for (int i = tid; i < k2; i += blockDim.x) {
-        double f = -pos_inf();
-        long long id = -1;
-        if (i < members && mtag[i] != 0x7fffffff) { f = -mkey[i]; id = ids[mslot[mtag[i]]]; }
-        out[i] = __double_as_longlong(f);
-        out[k2 + i] = id;
+    const int nwarps = blockDim.x >> 5, lane = tid & 31, warp = tid >> 5;
+    if (k2 <= nwarps && P <= (int)blockDim.x) {
+        // Few winners out of many members: no sort.  The k2-th largest of the per-warp maxima is a lower bound of the
+        // k2-th best fidelity (k2 warps each hold a member at least that good), so only members reaching it -- a few
+        // dozen -- can be winners; they are compacted and ranked among themselves by counting.  4 block barriers
+        // instead of the ~55 of a bitonic sort of 1024 (ncu: the sort's barriers were half of this kernel's stalls).
+        __shared__ double s_wmax[32];
+        __shared__ double s_low;
+        __shared__ int s_ns;
+        double* skey = reinterpret_cast<double*>(mslot + P);                // [P] survivors' keys (space: see host side)
+        int* stag = reinterpret_cast<int*>(skey + P);                      // [P] survivors' ranks in the merged list
+        const double mine = tid < P ? mkey[tid] : pos_inf();               // -fidelity (ascending = better), +inf = empty
+        double wbest = mine;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wbest = fmin(wbest, __shfl_xor_sync(FULL_MASK, wbest, o));
+        if (lane == 0) s_wmax[warp] = wbest;
+        if (tid == 0) s_ns = 0;
+        __syncthreads();
+        if (warp == 0) {
+            const double v = lane < nwarps ? s_wmax[lane] : pos_inf();
+            int better = 0;                                                // warps whose best beats this warp's best
+            for (int j = 0; j < 32; ++j) {
+                const double o = __shfl_sync(FULL_MASK, v, j);
+                better += (o < v) || (o == v && j < lane);
+            }
+            if (better == k2 - 1) s_low = v;                               // exactly one lane: the k2-th best warp maximum
+        }
+        __syncthreads();
+        const double low = s_low;
+        if (tid < P && mine <= low && mtag[tid] != 0x7fffffff) {
+            const int at = atomicAdd(&s_ns, 1);
+            skey[at] = mine;
+            stag[at] = mtag[tid];
+        }
+        __syncthreads();
+        const int ns = s_ns;
+        for (int i = tid; i < ns; i += blockDim.x) {
+            const double ki = skey[i];
+            const int ti = stag[i];
+            int rank = 0;
+            for (int j = 0; j < ns; ++j) {
+                const double kj = skey[j];
+                rank += (kj < ki) || (kj == ki && stag[j] < ti);
+            }
+            if (rank < k2) {
+                out[rank] = __double_as_longlong(-ki);
+                out[k2 + rank] = ids[mslot[ti]];
+            }
+        }
+        for (int i = ns + tid; i < k2; i += blockDim.x) {                  // fewer members than k2: padding
+            out[i] = __double_as_longlong(-pos_inf());
+            out[k2 + i] = -1;
+        }
+    } else {
+        bitonic_sort_kt<double, int>(mkey, mtag, P);
+        for (int i = tid; i < k2; i += blockDim.x) {
+            double f = -pos_inf();
+            long long id = -1;
+            if (i < members && mtag[i] != 0x7fffffff) { f = -mkey[i]; id = ids[mslot[mtag[i]]]; }
+            out[i] = __double_as_longlong(f);
+            out[k2 + i] = id;
+        }
     }
     if (tid == 0) out[2 * k2] = s_bad;
 }
@@ -1567,7 +1622,8 @@ extern "C" int qrag_owner_finalize(const int64_t* recv, int G, int per, int kk, 
     QRAG_REQUIRE(dp.ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
     const int64_t slots = (int64_t)G * kk;
     const int members_max = (int)(slots < k1 ? slots : k1);
-    const size_t smem = (size_t)slots * 16 + (size_t)next_pow2(members_max) * 16;
+    const size_t smem = (size_t)slots * 16 + (size_t)next_pow2(members_max) * 28;   // (key, id) per slot; per member: key,
+                                                                                       // rank, slot + the winners' (key, rank)
     QRAG_REQUIRE(smem + 2048 <= (size_t)dp.max_smem_optin, QRAG_ERR_UNSUPPORTED,
                  "owner merge of %d lists x %d entries needs %zu B of shared memory", G, kk, smem);
     if (smem > 40 * 1024)                                  // the kernel also holds ~1 KB of static shared memory
