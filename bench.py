@@ -28,7 +28,7 @@ METRIC = "query-candidate scores/sec"
 UNIT = "scores/s"
 BYTES_PER_SCORE = 4 * D + 4 * D / C + TOPK * 12 / C      # candidate row + amortised query + amortised outputs
 L2_BYTES = 126 * 2**20
-NCU_DRAM_BYTES_PER_LAUNCH = 155.188736e6 + 3.671296e6     # one ncu --set full capture of the timed kernel (profiles/)
+NCU_DRAM_BYTES_PER_LAUNCH = 155.198976e6 + 4.453376e6     # one ncu --set full capture of the timed kernel (profiles/r02_*)
 
 
 def workload_config(n_gpus, overlap="interleaved"):
@@ -339,9 +339,13 @@ def bench_sharded(world, rank, steps=10):
     sub = torch.arange(0, nq, nq // 8, device=dev)[:8]
     ref = path.exact_reference(Q[sub], k1, k2)
     same = bool(torch.equal(ref.ids, res.ids[sub]) and torch.equal(ref.scores, res.scores[sub]))
-    path.profile = {}
-    path(Q, k1, k2)
+    for _ in range(3):                          # per-stage CUDA-event times of one batch (the last of three: ranks in step)
+        if world > 1:
+            dist.barrier()
+        path.profile = {}
+        path(Q, k1, k2)
     stages = {k: round(v, 4) for k, v in path.profile.items()}
+    path.profile = None
     out = {"workload": "config 4: 10,000,000 docs x 384-d row-sharded, 1024 queries, per-shard top-1000 (rerank fidelity "
                        "fused into the exact rescoring) -> NCCL all-to-all to the query's owner -> merge -> quantum "
                        "rerank (9 qubits) -> top-10", "n_gpus": world, "scaling": "strong",
@@ -605,8 +609,8 @@ def run_b200(args):
             "kernels": ["qrag::amp_stream_kernel<3,4,8> (1 launch per step; TMA bulk-copy ring, warp-specialised "
                         "producer / converter / 8 consumers / 2 rankers, fused rank; <3,4,16> with --overlap stable)"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full, profiles/r01_amp_stream_key_metrics.csv "
-                         "(dram__bytes_read.sum 155.19 MB + dram__bytes_write.sum 3.67 MB per launch)",
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full, profiles/r02_amp_stream_key_metrics.csv "
+                         "(dram__bytes_read.sum 155.20 MB + dram__bytes_write.sum 4.45 MB per launch)",
                          "kernel": "amp_stream_kernel<3,4,8>" if args.overlap == "interleaved" else "amp_stream_kernel<3,4,16>",
                          "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_score": BYTES_PER_SCORE,
                          "peak_source": peak_src},
