@@ -285,6 +285,29 @@ def bench_feature_map(api, fma_rate, steps=3):
                         "note": "3.7e3 FP64 warp instructions per state (profiles/r01_fmap_warp_*); HBM traffic is the "
                                 "4 KB candidate row, far from the HBM roofline"},
            "kernels": ["qrag::fmap_warp_kernel<256> (warp per state, 32 amplitudes per lane in registers)"]}
+    # the same workload as a RERANK (top-10 of the 1000 candidates per query): complex64 filter pass over every
+    # candidate + complex128 certification of the candidates within the filter's error margin of the top-k boundary
+    # (include/qrag.h: qrag_fmap_rerank); rankings and returned scores are the complex128 path's, bit for bit
+    top_k = 10
+    api.quantum_rerank_batch(Q, cand=cand, top_k=top_k, n_qubits=n, layers=L)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        rs, rp, _ = api.quantum_rerank_batch(Q, cand=cand, top_k=top_k, n_qubits=n, layers=L)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_r = e0.elapsed_time(e1) / steps
+    sub = slice(0, 64)
+    es, ep, _ = api.quantum_rerank_batch(Q[sub], cand=cand[sub], top_k=top_k, n_qubits=n, layers=L, certify=False)
+    res["rerank_top10"] = {
+        "ms_per_batch": ms_r, "scores_per_s": nq * C / (ms_r * 1e-3), "reranked_queries_per_s": nq / (ms_r * 1e-3),
+        "identical_to_complex128_path_64_queries": bool(torch.equal(rp[sub], ep) and torch.equal(rs[sub], es)),
+        "filter_error_bound": api.fmap_filter_error_bound(L),
+        "kernels": ["qrag::fmap_warp_kernel<384, float> (filter: complex64 state, fp64 overlap)", "qrag::fr_select_kernel",
+                    "qrag::fmap_warp_kernel<256, double> (certify: the candidates within 2 delta of the k-th best)",
+                    "qrag::fr_final_kernel"],
+        "note": "every candidate is scored (in complex64) and the top-10 certified in complex128; includes the host's "
+                "read of the per-query status after each batch"}
     del cand, Q
     torch.cuda.empty_cache()
     return res

@@ -141,6 +141,28 @@ int qrag_amp_rerank(const float* Q, int nq,
                     void* stream);
 
 /* ---------------------------------------------------------------------------
+ * (1c') Feature-map rerank: amplitude state + `layers` reference blocks at n_qubits == 10 (D <= 1024), top_k of
+ * C <= QRAG_MAX_SORT_LEN candidates per query, by FILTER-THEN-CERTIFY: every candidate evolved in complex64
+ * (fp64 normalisation, gate parameters and overlap), |F32 - F| <= delta = qrag_fmap_filter_error_bound(layers);
+ * the candidates within 2 delta of the k-th best approximate score (a superset of the exact top_k and of everything
+ * tied with its last member, typically k + 1..2 of them) re-evolved in complex128 by the kernel qrag_amp_fidelity
+ * runs; sorted by (exact score desc, position asc).  Rankings and returned scores are those of the all-complex128
+ * path, bit for bit.  status[q] != 0: the query's candidate list overflowed (more than max(64, 2 top_k + 32) within
+ * the margin) -- never silent: rerun that query with qrag_amp_fidelity + qrag_sort_scores_stable.
+ *   out_scores [nq, top_k] fp64, out_pos [nq, top_k] (-1 padding), out_ids [nq, top_k] = idx[q, pos] (optional).
+ * qrag_fmap_filter_scores is the filter pass alone (diagnostic: tests measure its error against delta).
+ * ------------------------------------------------------------------------- */
+int qrag_fmap_rerank_workspace(int nq, int64_t C, int top_k, size_t* bytes);
+int qrag_fmap_filter_error_bound(int layers, double* delta);
+int qrag_fmap_filter_scores(const float* Q, int nq, const float* cand, const float* X, int64_t N, const int64_t* idx,
+                            int64_t C, int D, int n_qubits, int layers, double* out64, void* stream);
+int qrag_fmap_rerank(const float* Q, int nq,
+                     const float* cand, const float* X, int64_t N, const int64_t* idx,
+                     int64_t C, int D, int n_qubits, int layers, int top_k,
+                     double* out_scores, int32_t* out_pos, int64_t* out_ids, int32_t* status,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
  * (1d) Stable segmented sort: the `sorted(scored, key=score, reverse=True)[:top_k]`
  * of quantum.py:70-76 / classical.py:302-308 for nq lists of C scores.
  *   descending != 0: (score desc, position asc); else (score asc, position asc).

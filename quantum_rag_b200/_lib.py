@@ -16,7 +16,7 @@ from typing import Dict, List, Optional
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libqrag.so")
-SOURCES = ["lib.cu", "probe.cu", "amp_fidelity.cu", "amp_stream.cu", "sv_kernels.cu", "sort_scores.cu", "fmap_warp.cu", "search_exact.cu", "search_tc.cu"]
+SOURCES = ["lib.cu", "probe.cu", "amp_fidelity.cu", "amp_stream.cu", "sv_kernels.cu", "sort_scores.cu", "fmap_warp.cu", "fmap_rerank.cu", "search_exact.cu", "search_tc.cu"]
 # Kernel-tuning hooks (environment switches that skip or re-shape work inside product kernels) compile only with
 # -DQRAG_TUNING, which is NOT in these flags: the shipped library reads no environment variable.
 NVCC_FLAGS = [
@@ -39,6 +39,12 @@ PROTOTYPES: Dict[str, tuple] = {
                                   c_void_p, c_void_p, c_void_p]),
     "qrag_amp_rerank": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "qrag_fmap_rerank_workspace": (c_int, [c_int, c_int64, c_int, POINTER(c_size_t)]),
+    "qrag_fmap_filter_error_bound": (c_int, [c_int, POINTER(c_double)]),
+    "qrag_fmap_filter_scores": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
+                                        c_void_p, c_void_p]),
+    "qrag_fmap_rerank": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "qrag_sort_scores_workspace": (c_int, [c_int, c_int64, POINTER(c_size_t)]),
     "qrag_sort_scores_stable": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                         c_void_p]),

@@ -192,7 +192,7 @@ def sort_scores(scores: ArrayLike, top_k: Optional[int] = None, descending: bool
 
 def quantum_rerank_batch(Q: ArrayLike, cand: Optional[ArrayLike] = None, X: Optional[ArrayLike] = None,
                          idx: Optional[ArrayLike] = None, top_k: Optional[int] = None,
-                         n_qubits: Optional[int] = None, layers: int = 0):
+                         n_qubits: Optional[int] = None, layers: int = 0, certify: bool = True):
     """Tensor-level ``QuantumReranker.rerank`` with amplitude encoding.
 
     Returns ``(scores fp64 [nq, k], pos int32 [nq, k], ids int64 [nq, k] | None)`` ordered
@@ -210,12 +210,50 @@ def quantum_rerank_batch(Q: ArrayLike, cand: Optional[ArrayLike] = None, X: Opti
         _lib.check(lib.qrag_amp_rerank(_ptr(Qd), nq, _ptr(c), _ptr(Xd), _nrows(Xd), _ptr(i), C, D, n, k, _ptr(scores),
                                        _ptr(pos), _ptr(ids), _stream()))
         return scores, pos, ids
+    if layers >= 1 and n == 10 and D <= 1024 and 1 <= C <= MAX_SORT_LEN and k >= 1 and certify:
+        # filter-then-certify (include/qrag.h: qrag_fmap_rerank): complex64 evolution of every candidate, complex128
+        # re-evolution of the few within the error margin of the top-k boundary; same bits as the all-complex128 path
+        scores = torch.empty((nq, k), dtype=torch.float64, device=Qd.device)
+        pos = torch.empty((nq, k), dtype=torch.int32, device=Qd.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=Qd.device) if i is not None else None
+        status = torch.empty(nq, dtype=torch.int32, device=Qd.device)
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.qrag_fmap_rerank_workspace(nq, C, k, ctypes.byref(nbytes)))
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=Qd.device)
+        _lib.check(lib.qrag_fmap_rerank(_ptr(Qd), nq, _ptr(c), _ptr(Xd), _nrows(Xd), _ptr(i), C, D, n, layers, k, _ptr(scores),
+                                        _ptr(pos), _ptr(ids), _ptr(status), _ptr(ws), nbytes.value, _stream()))
+        flagged = torch.nonzero(status).flatten()                # synchronises; the certificate is never skipped
+        if flagged.numel():                                      # a margin too crowded for the list: those queries exactly
+            fs, fp, fi = quantum_rerank_batch(Qd[flagged], cand=c[flagged] if c is not None else None, X=Xd,
+                                              idx=i[flagged] if i is not None else None, top_k=k, n_qubits=n, layers=layers,
+                                              certify=False)
+            scores[flagged], pos[flagged] = fs, fp
+            if ids is not None:
+                ids[flagged] = fi
+        return scores, pos, ids
     full = torch.empty((nq, C), dtype=torch.float64, device=Qd.device)
     _lib.check(lib.qrag_amp_fidelity(_ptr(Qd), nq, _ptr(c), _ptr(Xd), _nrows(Xd), _ptr(i), C, D, n, layers, _ptr(full), None,
                                      _stream()))
     pos, scores = sort_scores(full, k)
     ids = torch.gather(i, 1, pos.long()) if i is not None else None
     return scores, pos, ids
+
+
+def fmap_filter_scores(Q: ArrayLike, cand: Optional[ArrayLike] = None, X: Optional[ArrayLike] = None,
+                       idx: Optional[ArrayLike] = None, layers: int = 4) -> torch.Tensor:
+    """Diagnostic (include/qrag.h): the complex64 filter pass of the feature-map rerank alone, fp64 [nq, C]."""
+    Qd, c, Xd, i, C = _cand_args(Q, cand, X, idx)
+    nq, D = Qd.shape
+    out = torch.empty((nq, C), dtype=torch.float64, device=Qd.device)
+    _lib.check(_lib.load().qrag_fmap_filter_scores(_ptr(Qd), nq, _ptr(c), _ptr(Xd), _nrows(Xd), _ptr(i), C, D, 10, layers,
+                                                   _ptr(out), _stream()))
+    return out
+
+
+def fmap_filter_error_bound(layers: int) -> float:
+    d = ctypes.c_double(0.0)
+    _lib.check(_lib.load().qrag_fmap_filter_error_bound(int(layers), ctypes.byref(d)))
+    return d.value
 
 
 def mock_embedding(seeds: ArrayLike, n_qubits: int = 4) -> torch.Tensor:

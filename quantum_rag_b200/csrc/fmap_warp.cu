@@ -53,7 +53,17 @@ struct FmapWarpParams {
     double* out; float* out32;
 };
 
-struct FwGate { double c, s, cp, sp; };                      // RY half-angle cos/sin, RZ half-angle cos/sin
+// The state's scalar type: double (exact path, complex128) or float (the FILTER pass of the rerank: complex64 evolution,
+// fp64 overlap; its error bound and the certification of the top-k boundary are in fmap_rerank.cu).
+template <typename R> struct Real2;
+template <> struct Real2<double> { using type = double2; };
+template <> struct Real2<float> { using type = float2; };
+template <typename R> using R2 = typename Real2<R>::type;
+template <typename R> __device__ __forceinline__ R2<R> make_r2(R x, R y) { R2<R> v; v.x = x; v.y = y; return v; }
+__device__ __forceinline__ double shfl_xor_r(double v, int m) { return __shfl_xor_sync(FULL_MASK, v, m); }
+__device__ __forceinline__ float shfl_xor_r(float v, int m) { return __shfl_xor_sync(FULL_MASK, v, m); }
+
+template <typename R> struct FwGate { R c, s, cp, sp; };      // RY half-angle cos/sin, RZ half-angle cos/sin
 
 __host__ __device__ constexpr int fw_pxor5(int x) {          // CX chain on five bits: y_k = x_0 ^ ... ^ x_k
     x ^= x << 1; x ^= x << 2; x ^= x << 4;
@@ -64,29 +74,29 @@ __host__ __device__ constexpr int fw_parity5(int x) { return (x ^ (x >> 1) ^ (x 
 // RY on the five qubits that are bits of the register index.
 // FAST: RY = c * [[1, -t], [t, 1]], t = tan(half angle); the factor c goes into the phase table, so a
 // complex pair costs 4 FMAs instead of 8 flops.  Used when every |t| <= 1 (|a| <= 1/2), else the direct form.
-template <bool FAST>
-__device__ __forceinline__ void fw_ry5(double2 (&a)[32], const FwGate* __restrict__ g, const double* __restrict__ tn) {
+template <bool FAST, typename R>
+__device__ __forceinline__ void fw_ry5(R2<R> (&a)[32], const FwGate<R>* __restrict__ g, const R* __restrict__ tn) {
 #pragma unroll
     for (int b = 0; b < 5; ++b) {
         if (FAST) {
-            const double t = tn[b];
+            const R t = tn[b];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 if (j & (1 << b)) continue;
                 const int k = j | (1 << b);
-                const double2 a0 = a[j], a1 = a[k];
+                const R2<R> a0 = a[j], a1 = a[k];
                 a[j].x = fma(-t, a1.x, a0.x);
                 a[j].y = fma(-t, a1.y, a0.y);
                 a[k].x = fma(t, a0.x, a1.x);
                 a[k].y = fma(t, a0.y, a1.y);
             }
         } else {
-            const double c = g[b].c, s = g[b].s;
+            const R c = g[b].c, s = g[b].s;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 if (j & (1 << b)) continue;
                 const int k = j | (1 << b);
-                const double2 a0 = a[j], a1 = a[k];
+                const R2<R> a0 = a[j], a1 = a[k];
                 a[j].x = fma(-s, a1.x, c * a0.x);
                 a[j].y = fma(-s, a1.y, c * a0.y);
                 a[k].x = fma(s, a0.x, c * a1.x);
@@ -96,17 +106,17 @@ __device__ __forceinline__ void fw_ry5(double2 (&a)[32], const FwGate* __restric
     }
 }
 
-template <bool FAST>
-__device__ __forceinline__ void fw_ry5_real(double (&r)[32], const FwGate* __restrict__ g,
-                                            const double* __restrict__ tn) {
+template <bool FAST, typename R>
+__device__ __forceinline__ void fw_ry5_real(R (&r)[32], const FwGate<R>* __restrict__ g,
+                                            const R* __restrict__ tn) {
 #pragma unroll
     for (int b = 0; b < 5; ++b) {
-        const double t = tn[b], c = g[b].c, s = g[b].s;
+        const R t = tn[b], c = g[b].c, s = g[b].s;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             if (j & (1 << b)) continue;
             const int k = j | (1 << b);
-            const double a0 = r[j], a1 = r[k];
+            const R a0 = r[j], a1 = r[k];
             if (FAST) {
                 r[j] = fma(-t, a1, a0);
                 r[k] = fma(t, a0, a1);
@@ -120,19 +130,21 @@ __device__ __forceinline__ void fw_ry5_real(double (&r)[32], const FwGate* __res
 
 // Phase table of five RZ gates: entry j = prod_b (bit b of j ? e^{+i phi_b/2} : e^{-i phi_b/2}),
 // times the RY scale prod_b c_b in the FAST form.
-template <bool FAST>
-__device__ __forceinline__ double2 fw_phase(const FwGate* __restrict__ g, int j) {
-    double2 p = make_double2(1.0, 0.0);
+template <bool FAST, typename R>
+__device__ __forceinline__ R2<R> fw_phase(const FwGate<R>* __restrict__ g, int j) {
+    // evaluated in R: for R = float that is 5 complex products of rounded unit factors (<= 4u each) and, in the
+    // scaled form, 5 real factors -- accounted for in the filter's error bound (fmap_rerank.cu)
+    R2<R> p = make_r2<R>((R)1, (R)0);
 #pragma unroll
     for (int b = 0; b < 5; ++b) {
-        const double cr = g[b].cp;
-        const double ci = ((j >> b) & 1) ? g[b].sp : -g[b].sp;
-        const double nx = p.x * cr - p.y * ci;
-        const double ny = p.x * ci + p.y * cr;
+        const R cr = g[b].cp;
+        const R ci = ((j >> b) & 1) ? g[b].sp : -g[b].sp;
+        const R nx = p.x * cr - p.y * ci;
+        const R ny = p.x * ci + p.y * cr;
         p.x = nx; p.y = ny;
     }
     if (FAST) {
-        const double sc = g[0].c * g[1].c * g[2].c * g[3].c * g[4].c;
+        const R sc = g[0].c * g[1].c * g[2].c * g[3].c * g[4].c;
         p.x *= sc; p.y *= sc;
     }
     return p;
@@ -140,12 +152,13 @@ __device__ __forceinline__ double2 fw_phase(const FwGate* __restrict__ g, int j)
 
 // a[j] *= tab[j] * cst: the RZ diagonal of a whole layer, split as (uniform table over the register
 // index) x (per-lane constant for the lane's own row / column).
-__device__ __forceinline__ void fw_diag(double2 (&a)[32], const double2* __restrict__ tab, const double2 cst) {
+template <typename R>
+__device__ __forceinline__ void fw_diag(R2<R> (&a)[32], const R2<R>* __restrict__ tab, const R2<R> cst) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        const double2 p = tab[j], v = a[j];
-        const double wx = p.x * cst.x - p.y * cst.y;
-        const double wy = fma(p.x, cst.y, p.y * cst.x);
+        const R2<R> p = tab[j], v = a[j];
+        const R wx = p.x * cst.x - p.y * cst.y;
+        const R wy = fma(p.x, cst.y, p.y * cst.x);
         a[j].x = v.x * wx - v.y * wy;
         a[j].y = fma(v.x, wy, v.y * wx);
     }
@@ -166,29 +179,29 @@ __device__ __forceinline__ void fw_diag(double2 (&a)[32], const double2* __restr
 //   pxor5(h) ^ (parity(l) ? 31 : 0) means the odd-parity registers belong to the row of lane ^ 1:
 //   one __shfl_xor of 16 amplitudes.
 // Ends in layout B (layers odd) or A (layers even); the same for both states of an overlap.
-template <bool FAST>
-__device__ __forceinline__ void fw_layers(double (&r)[32], double2 (&a)[32], int layers, double2* __restrict__ st,
-                                          const FwGate* __restrict__ gates, const double* __restrict__ tn,
-                                          double2* __restrict__ tab) {
+template <bool FAST, typename R>
+__device__ __forceinline__ void fw_layers(R (&r)[32], R2<R> (&a)[32], int layers, R2<R>* __restrict__ st,
+                                          const FwGate<R>* __restrict__ gates, const R* __restrict__ tn,
+                                          R2<R>* __restrict__ tab) {
     const int lane = threadIdx.x & 31;
     const bool odd_lane = __popc(lane) & 1;
     const int lcol = fw_pxor5(lane);                         // column label after a B-side CX
     int hrow = lane;                                         // row label (changes after an A-side CX)
     // ---- layer 0 on the REAL amplitudes: A, transpose, B, then the diagonal makes them complex
     {
-        tab[lane] = fw_phase<FAST>(gates + 5, lane);
-        const double2 cst = fw_phase<FAST>(gates, lane);
-        fw_ry5_real<FAST>(r, gates, tn);
-        double* sr = reinterpret_cast<double*>(st);
+        tab[lane] = fw_phase<FAST, R>(gates + 5, lane);
+        const R2<R> cst = fw_phase<FAST, R>(gates, lane);
+        fw_ry5_real<FAST, R>(r, gates, tn);
+        R* sr = reinterpret_cast<R*>(st);
 #pragma unroll
         for (int j = 0; j < 32; ++j) sr[lane * 33 + j] = r[j];
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = sr[j * 33 + lane];
-        fw_ry5_real<FAST>(r, gates + 5, tn + 5);
+        fw_ry5_real<FAST, R>(r, gates + 5, tn + 5);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            const double2 p = tab[j];
+            const R2<R> p = tab[j];
             a[j].x = r[j] * (p.x * cst.x - p.y * cst.y);
             a[j].y = r[j] * fma(p.x, cst.y, p.y * cst.x);
         }
@@ -199,7 +212,7 @@ __device__ __forceinline__ void fw_layers(double (&r)[32], double2 (&a)[32], int
     for (int layer = 1; layer < layers; ++layer) {
         const bool odd = layer & 1;
         if (odd) {   // B-side CX chain, in registers
-            double2 b[32];
+            R2<R> b[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) b[fw_pxor5(j)] = a[j];
 #pragma unroll
@@ -210,13 +223,13 @@ __device__ __forceinline__ void fw_layers(double (&r)[32], double2 (&a)[32], int
                 a[31 - j].y = odd_lane ? b[j].y : b[31 - j].y;
             }
         } else {     // A-side CX chain: odd-parity registers come from lane ^ 1, then the renaming
-            double2 b[32];
+            R2<R> b[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                double2 v = a[j];
+                R2<R> v = a[j];
                 if (fw_parity5(j)) {
-                    v.x = __shfl_xor_sync(FULL_MASK, v.x, 1);
-                    v.y = __shfl_xor_sync(FULL_MASK, v.y, 1);
+                    v.x = shfl_xor_r(v.x, 1);
+                    v.y = shfl_xor_r(v.y, 1);
                 }
                 b[fw_pxor5(j)] = v;
             }
@@ -224,23 +237,23 @@ __device__ __forceinline__ void fw_layers(double (&r)[32], double2 (&a)[32], int
             for (int j = 0; j < 32; ++j) a[j] = b[j];
             hrow = lcol;
         }
-        const FwGate* g = gates + layer * FW_N;
-        const double* t = tn + layer * FW_N;
+        const FwGate<R>* g = gates + layer * FW_N;
+        const R* t = tn + layer * FW_N;
         const int o1 = odd ? 5 : 0, o2 = 5 - o1;
-        tab[lane] = fw_phase<FAST>(g + o2, lane);
-        const double2 cst = fw_phase<FAST>(g + o1, lane);
-        fw_ry5<FAST>(a, g + o1, t + o1);
-        double2* sp = st + (odd ? lcol : hrow * 33);
+        tab[lane] = fw_phase<FAST, R>(g + o2, lane);
+        const R2<R> cst = fw_phase<FAST, R>(g + o1, lane);
+        fw_ry5<FAST, R>(a, g + o1, t + o1);
+        R2<R>* sp = st + (odd ? lcol : hrow * 33);
         const int ss = odd ? 33 : 1;
 #pragma unroll
         for (int j = 0; j < 32; ++j) sp[j * ss] = a[j];
         __syncwarp();
-        const double2* lp = st + (odd ? lane * 33 : lane);
+        const R2<R>* lp = st + (odd ? lane * 33 : lane);
         const int ls = odd ? 1 : 33;
 #pragma unroll
         for (int j = 0; j < 32; ++j) a[j] = lp[j * ls];
-        fw_ry5<FAST>(a, g + o2, t + o2);
-        fw_diag(a, tab, cst);
+        fw_ry5<FAST, R>(a, g + o2, t + o2);
+        fw_diag<R>(a, tab, cst);
         __syncwarp();                                    // reads of st and tab are complete
     }
 }
@@ -268,10 +281,11 @@ __device__ __forceinline__ void fw_prefetch_row(const float* __restrict__ row, i
 
 // `stage` holds the row if `staged` (prefetched by the previous call), else it is loaded here.  `next_row` (or
 // nullptr) is prefetched into `stage` as soon as this row has been consumed; returns through `*next_staged`.
-__device__ __forceinline__ bool fw_evolve(const float* __restrict__ row, int D, int layers, double2 (&a)[32],
-                                       double2* __restrict__ st, float* __restrict__ stage, bool staged,
+template <typename R>
+__device__ __forceinline__ bool fw_evolve(const float* __restrict__ row, int D, int layers, R2<R> (&a)[32],
+                                       R2<R>* __restrict__ st, float* __restrict__ stage, bool staged,
                                        const float* __restrict__ next_row, bool* next_staged,
-                                       FwGate* __restrict__ gates, double* __restrict__ tn, double2* __restrict__ tab) {
+                                       FwGate<R>* __restrict__ gates, R* __restrict__ tn, R2<R>* __restrict__ tab) {
     const int lane = threadIdx.x & 31;
     // ---- row -> padded staging (coalesced; 4 floats of padding per 32)
     const bool vec = fw_row_vec(row, D);
@@ -290,66 +304,71 @@ __device__ __forceinline__ bool fw_evolve(const float* __restrict__ row, int D, 
     }
     __syncwarp();
     // ---- my 32 real amplitudes (basis index (lane << 5) | j), |row|^2 in fp64
-    double r[32];
+    double rd[32];
     double n2 = 0.0;
     {
         const float4* src = reinterpret_cast<const float4*>(stage + lane * 36);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const float4 v = src[u];
-            r[4 * u + 0] = (double)v.x; r[4 * u + 1] = (double)v.y;
-            r[4 * u + 2] = (double)v.z; r[4 * u + 3] = (double)v.w;
+            rd[4 * u + 0] = (double)v.x; rd[4 * u + 1] = (double)v.y;
+            rd[4 * u + 2] = (double)v.z; rd[4 * u + 3] = (double)v.w;
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) n2 = fma(r[j], r[j], n2);
+        for (int j = 0; j < 32; ++j) n2 = fma(rd[j], rd[j], n2);
     }
     n2 = warp_sum(n2);
     const double nrm = sqrt(n2);
     const bool zero = !(nrm > 0.0);
     const double inv = zero ? 1.0 : 1.0 / nrm;              // one division per state; x * inv is within 1 ulp of x / nrm
+    R r[32];                                                 // (normalised in double, then rounded to R once)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) r[j] *= inv;
-    // ---- gate parameters: layer l, qubit i takes a = x^[(l*n + i) % D]  (quantum.py:160-161: ry(a pi), rz(a pi/2))
+    for (int j = 0; j < 32; ++j) r[j] = (R)(rd[j] * inv);
+    // ---- gate parameters: layer l, qubit i takes a = x^[(l*n + i) % D]  (quantum.py:160-161: ry(a pi), rz(a pi/2));
+    // evaluated in double whatever R is (a few dozen per state), rounded to R once
     bool small = true;
     for (int t = lane; t < layers * FW_N; t += 32) {
         const int comp = t % D;
         const double an = (double)stage[comp + (comp >> 5) * 4] * inv;
-        FwGate g;
-        sincospi(0.25 * an, &g.sp, &g.cp);                   // RZ half angle a pi / 4; the RY half angle is twice that:
-        g.s = 2.0 * g.sp * g.cp;                             // sin 2x = 2 sin x cos x
-        g.c = fma(-2.0 * g.sp, g.sp, 1.0);                   // cos 2x = 1 - 2 sin^2 x (|x| <= pi/4: no cancellation
-        gates[t] = g;                                        //  beyond 1e-16 absolute)
-        tn[t] = g.s / g.c;
+        double sp, cp;
+        sincospi(0.25 * an, &sp, &cp);                       // RZ half angle a pi / 4; the RY half angle is twice that:
+        const double sn = 2.0 * sp * cp;                     // sin 2x = 2 sin x cos x
+        const double cs = fma(-2.0 * sp, sp, 1.0);           // cos 2x = 1 - 2 sin^2 x (|x| <= pi/4: no cancellation
+        FwGate<R> g;                                         //  beyond 1e-16 absolute)
+        g.sp = (R)sp; g.cp = (R)cp; g.s = (R)sn; g.c = (R)cs;
+        gates[t] = g;
+        tn[t] = (R)(sn / cs);
         small = small && (fabs(an) <= 0.5);
     }
     const bool fast = __all_sync(FULL_MASK, small);
     __syncwarp();                                            // gates visible; staging fully consumed
     *next_staged = next_row != nullptr && fw_row_vec(next_row, D);
     if (*next_staged) fw_prefetch_row(next_row, D, stage);
-    if (fast) fw_layers<true>(r, a, layers, st, gates, tn, tab);
-    else      fw_layers<false>(r, a, layers, st, gates, tn, tab);
+    if (fast) fw_layers<true, R>(r, a, layers, st, gates, tn, tab);
+    else      fw_layers<false, R>(r, a, layers, st, gates, tn, tab);
     return zero;
 }
 
 // One CTA = W warps; a unit = (query, chunk of its candidates).  Item 0 of a unit is the query
 // itself, item t >= 1 candidate t-1; warp w takes items w, w + W, ...  Warp 0 evolves the query
 // state while the others already evolve their first candidate.
-template <int MAXT>
+template <int MAXT, typename R>
 __global__ void __launch_bounds__(MAXT, 1) fmap_warp_kernel(const FmapWarpParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double2* qstate = reinterpret_cast<double2*>(smem_raw);
-    double2* st = qstate + FW_ST + (size_t)warp * FW_ST;
-    double2* tab = qstate + FW_ST + (size_t)W * FW_ST + warp * 32;
-    FwGate* gates = reinterpret_cast<FwGate*>(qstate + FW_ST + (size_t)W * (FW_ST + 32)) + warp * p.layers * FW_N;
-    double* tn = reinterpret_cast<double*>(reinterpret_cast<FwGate*>(qstate + FW_ST + (size_t)W * (FW_ST + 32)) +
-                                           (size_t)W * p.layers * FW_N) + warp * p.layers * FW_N;
-    float* stage = reinterpret_cast<float*>(reinterpret_cast<double*>(reinterpret_cast<FwGate*>(
-                       qstate + FW_ST + (size_t)W * (FW_ST + 32)) + (size_t)W * p.layers * FW_N) +
-                   (size_t)W * p.layers * FW_N) + (size_t)warp * FW_STAGE;
+    // layout (the same order as fmap_warp_smem): query state | W states | W tables | W x layers x 10 gates | tangents | staging
+    R2<R>* qstate = reinterpret_cast<R2<R>*>(smem_raw);
+    R2<R>* st = qstate + FW_ST + (size_t)warp * FW_ST;
+    R2<R>* tab = qstate + FW_ST + (size_t)W * FW_ST + warp * 32;
+    FwGate<R>* gates0 = reinterpret_cast<FwGate<R>*>(qstate + FW_ST + (size_t)W * (FW_ST + 32));
+    FwGate<R>* gates = gates0 + warp * p.layers * FW_N;
+    R* tn0 = reinterpret_cast<R*>(gates0 + (size_t)W * p.layers * FW_N);
+    R* tn = tn0 + warp * p.layers * FW_N;
+    // (W * layers * 10 tangents; the staging rows need 16-byte alignment: round the float count up to 4)
+    float* stage = reinterpret_cast<float*>(tn0 + (((size_t)W * p.layers * FW_N + 3) & ~(size_t)3)) + (size_t)warp * FW_STAGE;
     __shared__ int q_zero;
 
-    double2 a[32];
+    R2<R> a[32];
     for (int64_t u = blockIdx.x; u < p.units; u += gridDim.x) {
         const int64_t qi = u / p.chunks_per_q;
         const int64_t c0 = (u % p.chunks_per_q) * p.chunk;
@@ -371,12 +390,16 @@ __global__ void __launch_bounds__(MAXT, 1) fmap_warp_kernel(const FmapWarpParams
             const bool active = t <= cnt;
             const int64_t j = qi * p.C + c0 + (t - 1);
             bool missing = false, zero = false;
-            if (active) {
+            if (active) row_of(t, &missing);
+            if (active && missing) {                         // padding candidate (warp-uniform): no state to evolve
+                if (staged) asm volatile("cp.async.wait_group 0;" ::: "memory");
+                staged = false;
+            } else if (active) {
                 const float* row = row_of(t, &missing);
                 bool nmiss = false;
                 const float* next_row = (t + W <= cnt) ? row_of(t + W, &nmiss) : nullptr;
                 bool next_staged = false;
-                zero = fw_evolve(row, p.D, p.layers, a, st, stage, staged, next_row, &next_staged, gates, tn, tab);
+                zero = fw_evolve<R>(row, p.D, p.layers, a, st, stage, staged, next_row, &next_staged, gates, tn, tab);
                 staged = next_staged;
                 if (t == 0) {
 #pragma unroll
@@ -389,9 +412,10 @@ __global__ void __launch_bounds__(MAXT, 1) fmap_warp_kernel(const FmapWarpParams
                 double re = 0.0, im = 0.0;                   // <psi_d | psi_q> = sum conj(d) q
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
-                    const double2 q = qstate[k * 33 + lane], d = a[k];
-                    re = fma(d.x, q.x, re); re = fma(d.y, q.y, re);
-                    im = fma(d.x, q.y, im); im = fma(-d.y, q.x, im);
+                    const R2<R> qr = qstate[k * 33 + lane];          // fp64 accumulation of the overlap whatever R is
+                    const double qx = (double)qr.x, qy = (double)qr.y, dx = (double)a[k].x, dy = (double)a[k].y;
+                    re = fma(dx, qx, re); re = fma(dy, qy, re);
+                    im = fma(dx, qy, im); im = fma(-dy, qx, im);
                 }
                 re = warp_sum(re);
                 im = warp_sum(im);
@@ -408,25 +432,25 @@ __global__ void __launch_bounds__(MAXT, 1) fmap_warp_kernel(const FmapWarpParams
     }
 }
 
-}  // namespace
 
-size_t fmap_warp_smem(int W, int layers) {
-    return (size_t)(1 + W) * FW_ST * sizeof(double2) + (size_t)W * 32 * sizeof(double2) +
-           (size_t)W * layers * FW_N * (sizeof(FwGate) + sizeof(double)) + (size_t)W * FW_STAGE * sizeof(float);
+template <typename R>
+static size_t fmap_warp_smem(int W, int layers) {
+    const size_t tn = (((size_t)W * layers * FW_N + 3) & ~(size_t)3);
+    return (size_t)(1 + W) * FW_ST * sizeof(R2<R>) + (size_t)W * 32 * sizeof(R2<R>) +
+           (size_t)W * layers * FW_N * sizeof(FwGate<R>) + tn * sizeof(R) + (size_t)W * FW_STAGE * sizeof(float);
 }
 
-// Returns QRAG_OK and sets *handled when the shape is served by this kernel (n = 10).
-int fmap_warp_try(const float* Q, int nq, const float* cand, const float* X, int64_t N, const int64_t* idx, int64_t C, int D,
-                  int n_qubits, int layers, double* out64, float* out32, cudaStream_t st, bool* handled) {
-    *handled = false;
-    if (n_qubits != FW_N || layers < 1 || D < 1 || D > FW_DIM) return QRAG_OK;
+template <typename R, int MAXW>
+static int fmap_warp_launch(const float* Q, int nq, const float* cand, const float* X, int64_t N, const int64_t* idx, int64_t C,
+                            int D, int layers, double* out64, float* out32, cudaStream_t st, bool* handled) {
     const DeviceProps& dp = device_props();
     QRAG_REQUIRE(dp.ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
-    // 8 warps = 2 per scheduler at 255 registers.  Measured on B200 (512 x 1000 x 1024, L = 4): 7.9e7 scores/s;
+    // complex128: 8 warps = 2 per scheduler at 255 registers.  Measured on B200 (512 x 1000 x 1024, L = 4): 7.9e7 scores/s;
     // 11 warps at 168 registers 6.6e7 (spills, unbalanced schedulers); the 168-register build at 8 warps 6.2e7.
-    int W = 8;
-    while (W > 1 && fmap_warp_smem(W, layers) + 64 > (size_t)dp.max_smem_optin) --W;
-    if (fmap_warp_smem(W, layers) + 64 > (size_t)dp.max_smem_optin) return QRAG_OK;    // layers too deep: generic kernel
+    // complex64 (the rerank's filter pass): half the registers and half the shared memory per state, 12 warps.
+    int W = MAXW;
+    while (W > 1 && fmap_warp_smem<R>(W, layers) + 64 > (size_t)dp.max_smem_optin) --W;
+    if (fmap_warp_smem<R>(W, layers) + 64 > (size_t)dp.max_smem_optin) return QRAG_OK;    // layers too deep: generic kernel
     FmapWarpParams p{};
     p.Q = Q; p.cand = cand; p.X = X; p.idx = idx; p.N = N; p.C = C; p.D = D; p.nq = nq; p.layers = layers;
     p.out = out64; p.out32 = out32;
@@ -439,13 +463,32 @@ int fmap_warp_try(const float* Q, int nq, const float* cand, const float* X, int
     p.chunks_per_q = (int)ceil_div(C, p.chunk);
     p.units = (int64_t)nq * p.chunks_per_q;
     const int64_t grid = p.units < dp.sm_count ? p.units : dp.sm_count;
-    const size_t smem = fmap_warp_smem(W, layers);
-    auto kern = fmap_warp_kernel<256>;
+    const size_t smem = fmap_warp_smem<R>(W, layers);
+    auto kern = fmap_warp_kernel<MAXW * 32, R>;
     QRAG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, W * 32, smem, st>>>(p);
     QRAG_LAUNCH_CHECK("fmap_warp_kernel");
     *handled = true;
     return QRAG_OK;
+}
+
+}  // namespace
+
+// Returns QRAG_OK and sets *handled when the shape is served by this kernel (n = 10).
+int fmap_warp_try(const float* Q, int nq, const float* cand, const float* X, int64_t N, const int64_t* idx, int64_t C, int D,
+                  int n_qubits, int layers, double* out64, float* out32, cudaStream_t st, bool* handled) {
+    *handled = false;
+    if (n_qubits != FW_N || layers < 1 || D < 1 || D > FW_DIM) return QRAG_OK;
+    return fmap_warp_launch<double, 8>(Q, nq, cand, X, N, idx, C, D, layers, out64, out32, st, handled);
+}
+
+// The same evolution with the state in complex64 (fp64 normalisation, gate parameters and overlap): the FILTER pass of
+// qrag_fmap_rerank.  |F32 - F| <= fmap_filter_error_bound(layers) (fmap_rerank.cu); never a result by itself.
+int fmap_warp_filter_try(const float* Q, int nq, const float* cand, const float* X, int64_t N, const int64_t* idx, int64_t C,
+                         int D, int n_qubits, int layers, double* out64, cudaStream_t st, bool* handled) {
+    *handled = false;
+    if (n_qubits != FW_N || layers < 1 || D < 1 || D > FW_DIM) return QRAG_OK;
+    return fmap_warp_launch<float, 12>(Q, nq, cand, X, N, idx, C, D, layers, out64, nullptr, st, handled);
 }
 
 }  // namespace qrag

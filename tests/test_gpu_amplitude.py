@@ -349,3 +349,94 @@ def test_interleaved_overlap_mode_back_to_back_batches(cuda):
         assert np.array_equal(p1.cpu().numpy(), order) and np.array_equal(p2.cpu().numpy(), order)
         assert np.allclose(s1.cpu().numpy(), np.take_along_axis(want, order, 1), rtol=REL)
         assert torch.equal(s1, s2)
+
+
+def test_feature_map_filter_error_is_inside_the_bound(cuda):
+    """The complex64 filter pass of the feature-map rerank against the complex128 kernel: max |F32 - F| MEASURED and
+    compared with delta = qrag_fmap_filter_error_bound(layers).  Ordinary data (scaled-rotation path), large angles
+    (direct-rotation path: some |x^_i| > 1/2), near-duplicates of the query (fidelity ~ 1, where the bound's factor
+    2 |<d|q>| is largest), short rows (D = 7) and the deepest circuit the register kernel takes."""
+    import torch
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(3)
+    worst = 0.0
+    for D, layers in ((1024, 4), (1024, 1), (600, 6), (7, 5), (1024, 9)):
+        nq, C = 6, 200
+        Q = rng.standard_normal((nq, D)).astype(np.float32)
+        cand = rng.standard_normal((nq, C, D)).astype(np.float32)
+        cand[:, :20] = Q[:, None, :] + 1e-2 * rng.standard_normal((nq, 20, D)).astype(np.float32)   # fidelity near 1
+        cand[:, 20] = Q
+        if D >= 600:
+            cand[:, 21:40, 3] = 40.0                                        # dominant component: |x^_3| > 1/2, direct rotations
+        f64 = api.amp_fidelity(Q, cand=cand, n_qubits=10, layers=layers)
+        f32 = api.fmap_filter_scores(Q, cand=cand, layers=layers)
+        delta = api.fmap_filter_error_bound(layers)
+        err = float((f32 - f64).abs().max())
+        assert err <= delta, (D, layers, err, delta)
+        assert err > 0.0                                                    # it IS a different arithmetic
+        worst = max(worst, err / delta)
+    assert worst < 0.5, worst                                              # the bound has room (worst-case analysis x 2)
+    print(f"feature-map filter: max |F32 - F| = {worst:.3f} delta")
+
+
+@pytest.mark.parametrize("C,top_k,gathered", [(1000, 10, False), (300, 40, True), (64, 64, False), (4096, 5, False)])
+def test_feature_map_rerank_equals_the_complex128_path(cuda, C, top_k, gathered):
+    """qrag_fmap_rerank (complex64 filter + complex128 certification of the top-k boundary) returns the positions,
+    ids and score BITS of the all-complex128 path (qrag_amp_fidelity + stable sort): exact duplicates tie in input
+    order, near-ties closer than the filter's error are certified, padding ids sort last."""
+    import torch
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(C + top_k)
+    nq, D, L = 5, 1024, 4
+    Q = rng.standard_normal((nq, D)).astype(np.float32)
+    if gathered:
+        X = rng.standard_normal((500, D)).astype(np.float32)
+        idx = rng.randint(0, 500, size=(nq, C)).astype(np.int64)          # C of 500 rows: repeated rows = exact ties
+        idx[2, 17:25] = -1                                                 # padding
+        idx[4, 3] = 10 ** 9                                                # out of range = padding
+        kw = {"X": X, "idx": idx}
+        rows = X[np.where((idx >= 0) & (idx < 500), idx, 0)]
+    else:
+        cand = rng.standard_normal((nq, C, D)).astype(np.float32)
+        cand[:, 5] = cand[:, 2]                                            # exact tie
+        cand[1, 9] = cand[1, 2] * (1 + 1e-7)                               # near-tie far inside the filter's error
+        kw = {"cand": cand}
+    scores, pos, ids = api.quantum_rerank_batch(Q, top_k=top_k, n_qubits=10, layers=L, **kw)
+    es, ep, ei = api.quantum_rerank_batch(Q, top_k=top_k, n_qubits=10, layers=L, certify=False, **kw)
+    assert torch.equal(pos, ep) and torch.equal(scores, es)
+    if gathered:
+        assert torch.equal(ids, ei)
+        assert int(pos[2].min()) >= 0 or top_k > C - 8                     # padding never beats a real candidate
+    # and against the oracle on a few entries: the ranking is the oracle's
+    q0 = 1
+    want = np.array([oq.feature_map_fidelity(Q[q0], (rows if gathered else cand)[q0, int(p)], 10, L)
+                     for p in pos[q0, :min(top_k, 6)].cpu().tolist()])
+    assert np.allclose(scores[q0, :min(top_k, 6)].cpu().numpy(), want, rtol=1e-11)
+
+
+def test_feature_map_rerank_crowded_margin_is_flagged_and_rerun(cuda):
+    """More candidates inside the filter's error margin than the certify list holds (here: one row repeated 300 times
+    at the top): status flags the query and the API reruns it through the exact path -- same answer, never silent."""
+    import ctypes
+    import torch
+    from quantum_rag_b200 import _lib, api
+    rng = np.random.RandomState(5)
+    nq, C, D, L, k = 3, 400, 1024, 2, 10
+    Q = rng.standard_normal((nq, D)).astype(np.float32)
+    cand = rng.standard_normal((nq, C, D)).astype(np.float32)
+    cand[1, 50:350] = Q[1]                                                 # 300 exact copies of the query: all tie at F = 1
+    Qd, cd = torch.from_numpy(Q).cuda(), torch.from_numpy(cand).cuda()
+    lib = _lib.load()
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(lib.qrag_fmap_rerank_workspace(nq, C, k, ctypes.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
+    s = torch.empty((nq, k), dtype=torch.float64, device="cuda")
+    p = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    st = torch.empty(nq, dtype=torch.int32, device="cuda")
+    _lib.check(lib.qrag_fmap_rerank(api._ptr(Qd), nq, api._ptr(cd), None, 0, None, C, D, 10, L, k, api._ptr(s), api._ptr(p), None,
+                                    api._ptr(st), api._ptr(ws), nbytes.value, api._stream()))
+    assert st.cpu().tolist() == [0, 1, 0]
+    scores, pos, _ = api.quantum_rerank_batch(Q, cand=cand, top_k=k, n_qubits=10, layers=L)
+    es, ep, _ = api.quantum_rerank_batch(Q, cand=cand, top_k=k, n_qubits=10, layers=L, certify=False)
+    assert torch.equal(pos, ep) and torch.equal(scores, es)
+    assert pos[1].cpu().tolist() == list(range(50, 60))                    # the first ten copies, in input order
