@@ -47,6 +47,11 @@ def main():
     print(f"config 5 shape: {a.nq} x {a.C} x {a.D}, n={n}, L={a.layers}: {ms:.3f} ms, {scores / ms * 1e3:.3e} scores/s, "
           f"{scores * flop / ms / 1e9:.2f} TFLOP/s fp64-equivalent ({flop} flop/score), "
           f"{scores * 4 * a.D / ms / 1e6:.1f} GB/s of candidate rows")
+    if n == 10:
+        msf = timed(lambda: api.fmap_filter_scores(Q, cand=cand, layers=a.layers), a.steps)
+        print(f"complex64 filter pass alone: {msf:.3f} ms, {scores / msf * 1e3:.3e} scores/s")
+        msr = timed(lambda: api.quantum_rerank_batch(Q, cand=cand, top_k=10, n_qubits=n, layers=a.layers), a.steps)
+        print(f"rerank top-10, filter + certify: {msr:.3f} ms, {scores / msr * 1e3:.3e} scores/s")
     ms0 = timed(lambda: api.amp_fidelity(Q, cand=cand, n_qubits=n, layers=0), a.steps)
     print(f"same shape, layers=0 (HBM-bound streaming kernel): {ms0:.3f} ms, {scores / ms0 * 1e3:.3e} scores/s, "
           f"{scores * 4 * a.D / ms0 / 1e6:.1f} GB/s")
