@@ -1243,6 +1243,8 @@ static int tc_exchange_len(int k, int shards) {
     return kt < k ? (int)kt : k;
 }
 
+static int tc_sm_units(int cg);
+
 static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPlan* pl) {
     QRAG_REQUIRE(nq >= 0 && N >= 0 && D > 0, QRAG_ERR_INVALID, "bad sizes nq=%d N=%lld D=%d", nq, (long long)N, D);
     QRAG_REQUIRE(metric >= 0 && metric <= 2, QRAG_ERR_INVALID, "unknown metric %d", metric);
@@ -1276,8 +1278,20 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPl
     pl->groups = pl->nq_pad / TC_BM;
     pl->ntiles = (int)ceil_div(N > 0 ? N : 1, TC_BN);
     int cap = TC_CAP_MIN;
-    while (cap < 64 * k && cap < TC_CAP_MAX) cap <<= 1;
-    pl->cap = cap;
+    while (cap < 64 * k && cap < TC_CAP_MAX) cap <<= 1;       // sized for the expected survivors (the sample rate below uses it)
+    {
+        // ... and for CLUSTERED corpora: the list is split into one segment per (CTA of the query's group, column
+        // quarter), and near-duplicates stored in adjacent rows put most of a query's neighbours into one 256-row
+        // tile, i.e. into one CTA's four segments.  Give every segment room for 256 survivors where memory allows
+        // (few queries = many CTAs per group = many short segments: 27 slots each before this).
+        const int su = tc_sm_units(pl->cg);
+        int ug = pl->groups / pl->cg;
+        if (ug > su) ug = su;
+        const int nseg = TC_EPI_SPLIT * (su / (ug > 0 ? ug : 1));
+        int64_t want = next_pow2((int64_t)256 * nseg);
+        while (want > cap && (int64_t)pl->nq_pad * want * 8 > ((int64_t)1 << 30)) want >>= 1;   // at most 1 GiB of lists
+        pl->cap = want > cap ? (int)want : cap;
+    }
     // pass 1 samples every `sample`-th tile: survivors ~ sample * k per query, kept well under the capacity,
     // and the sample must hold many more buckets than k for the bound to be tight
     // (the threshold comes from the union of all shards' samples, so a shard of a G-way search samples G x less)
@@ -1316,7 +1330,7 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPl
     pl->off_hinv = off; off = align_up(off + (size_t)pl->nq_pad * 4, 256);
     pl->off_hist = off; off = align_up(off + (size_t)pl->nq_pad * TC_HIST_BINS * 4, 256);
     pl->off_cnt = off; off = align_up(off + (size_t)pl->nq_pad * TC_MAX_SEGS * 4, 256);
-    pl->off_surv = off; off = align_up(off + (size_t)pl->nq_pad * cap * 8, 256);
+    pl->off_surv = off; off = align_up(off + (size_t)pl->nq_pad * pl->cap * 8, 256);
     pl->off_crow = off; off = align_up(off + (size_t)pl->nq_pad * cand_cap * 4, 256);
     pl->off_ckey = off; off = align_up(off + (size_t)pl->nq_pad * cand_cap * 8, 256);
     pl->off_cfid = off; off = align_up(off + (size_t)pl->nq_pad * cand_cap * 8, 256);

@@ -268,3 +268,22 @@ def test_cosine_fp16_operands_bound_and_flush_to_zero(cuda):
     Qh[10:20] *= 1e-30
     Qh[20] = 0.0
     _compare_with_exact(api, Qh, Xh, 50, "cosine", allow_fallback=True)
+
+
+@pytest.mark.parametrize("nq", [4, 200])
+def test_clustered_corpus_does_not_fall_back(cuda, nq):
+    """near-duplicates stored in ADJACENT rows put a query's whole top-k into one 256-row tile, i.e. into
+    the four survivor segments of one CTA.  The segments are sized for that (256 slots each where memory allows), so a
+    clustered corpus is searched by the tensor-core path without the exact rerun (which re-reads the corpus per query)."""
+    import torch
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(17)
+    N, D, k = 60000, 384, 100
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Q = rng.standard_normal((nq, D)).astype(np.float32)
+    for q in range(min(nq, 8)):                       # 230 near-copies of query q in adjacent rows of one tile
+        base = 256 * (10 + 7 * q) + 5
+        X[base:base + 230] = Q[q] + 0.02 * rng.standard_normal((230, D)).astype(np.float32)
+    for name in ("cosine", "ip", "l2"):
+        index = _compare_with_exact(api, Q, X, k, name)          # asserts last_fallback == 0 and identity with the exact search
+        assert index.last_fallback == 0
