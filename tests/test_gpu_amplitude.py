@@ -440,3 +440,29 @@ def test_feature_map_rerank_crowded_margin_is_flagged_and_rerun(cuda):
     es, ep, _ = api.quantum_rerank_batch(Q, cand=cand, top_k=k, n_qubits=10, layers=L, certify=False)
     assert torch.equal(pos, ep) and torch.equal(scores, es)
     assert pos[1].cpu().tolist() == list(range(50, 60))                    # the first ten copies, in input order
+
+
+def test_host_pipelines_equal_the_device_api(cuda):
+    """The two end-to-end forms the bench times (pinned host buffers in, pinned host results out, slices on two
+    streams): dense candidates, and candidate ids against a resident corpus.  Same bits as the one-launch device API."""
+    import torch
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(23)
+    nq, C, D, k = 203, 60, 384, 7                                        # 203 queries: the last slice is ragged
+    Q = torch.from_numpy(rng.standard_normal((nq, D)).astype(np.float32)).pin_memory()
+    cand = torch.from_numpy(rng.standard_normal((nq, C, D)).astype(np.float32)).pin_memory()
+    pipe = api.HostRerankPipeline(nq, C, D, k, 9, chunks=4)
+    hS, hP = pipe(Q, cand)
+    s, p, _ = api.quantum_rerank_batch(Q, cand=cand, top_k=k, n_qubits=9)
+    assert torch.equal(hS, s.cpu()) and torch.equal(hP, p.cpu())
+    X = torch.from_numpy(rng.standard_normal((5000, D)).astype(np.float32))
+    idx = torch.from_numpy(rng.randint(0, 5000, size=(nq, C)).astype(np.int64)).pin_memory()
+    idx[5, 10:20] = -1
+    s2, p2, i2 = api.quantum_rerank_batch(Q, X=X, idx=idx, top_k=k, n_qubits=9)
+    for chunks in (1, 3):
+        idp = api.HostIdRerankPipeline(X, nq, C, k, 9, chunks=chunks)
+        for _ in range(2):                                                # reusable: the second call gives the same answer
+            hS2, hO2 = idp(Q, idx)
+        assert torch.equal(hS2, s2.cpu()) and torch.equal(hO2, i2.cpu())
+    want = oq.rank_rows(oq.amplitude_fidelity_batch(Q.numpy()[:3], X.numpy()[idx.numpy()[:3]]), k)
+    assert np.array_equal(p2[:3].cpu().numpy(), want)
