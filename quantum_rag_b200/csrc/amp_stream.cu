@@ -182,6 +182,11 @@ __global__ void __launch_bounds__(as_threads(CW), CW == AS_CWARPS ? 1 : 2) amp_s
     // grid's CTAs retire.  QRAG_OVERLAP_SAFE orders every global access of this kernel after the
     // previous kernel (only launch latency and this prologue overlap); QRAG_OVERLAP_INPUTS_STABLE
     // orders only the writes, so streaming starts while the previous grid drains.
+    // The interleaved shape triggers here too: two consecutive launches then start together, share every SM and end
+    // together, so each pair pays ONE start-up and drain.  Delaying the trigger to the CTA's midpoint, which staggers
+    // consecutive launches by half a batch, was measured and is worse (0.80-0.82 of the HBM peak against 0.88 in the same
+    // run): a staggered launch cannot write its results until its predecessor completes half a batch later, and holds
+    // its half of the SM idle meanwhile.
     if (p.overlap != QRAG_OVERLAP_NONE && tid == 0) griddep_launch_dependents();
     const bool wait_reads = p.overlap == QRAG_OVERLAP_SAFE;
     const bool wait_writes = p.overlap >= QRAG_OVERLAP_INPUTS_STABLE;
