@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--configs", default="default,4x4,8x4,8x2")
-    ap.add_argument("--overlap", default="0,1,2")
+    ap.add_argument("--overlap", default="0,1,2,3")
     ap.add_argument("--gather", action="store_true", help="candidates named by random ids into a resident corpus")
     a = ap.parse_args()
     _lib.build(force=True, tuning=True)       # the switches below only exist in a -DQRAG_TUNING build
@@ -80,4 +80,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    finally:
+        _lib.build(force=True)                # never leave the tuning build in the tree: what ships reads no environment
