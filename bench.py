@@ -189,8 +189,12 @@ def bench_search(api, peaks, steps=20, oracle_check=False):
            "flagged_queries": int(st.count_nonzero()),
            "identical_to_exact_search": bool(torch.equal(i[sub], ei) and torch.equal(s[sub], es)),
            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                        "peak_sustained": peaks.get("bf16_tflops_sustained"),
+                        "frac_of_sustained": (tf / float(peaks["bf16_tflops_sustained"])) if peaks.get("bf16_tflops_sustained") else None,
                         "note": "algorithmic flops (2*D per score) / wall time of the whole search (bucket pass, "
-                                "threshold, filter pass, exact rescoring); peak = measured cuBLAS bf16 burst"},
+                                "threshold, filter pass, exact rescoring); peak = measured cuBLAS bf16 burst; the timed loop "
+                                "(20 batches back to back) runs under the power cap, for which the sustained cuBLAS figure "
+                                "is the fairer ceiling: both fractions are given"},
            "kernels": ["qrag::sim_gemm_kernel<0> (sampled bucket-max pass)", "qrag::tau_union_kernel",
                        "qrag::sim_gemm_kernel<1> (filter pass)", "qrag::surv_hist_kernel",
                        "qrag::tc_collect_kernel / tc_rescore_kernel / tc_sort_kernel (candidates, exact fp64 rescoring, sort)"]}
