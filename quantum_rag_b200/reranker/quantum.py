@@ -65,6 +65,16 @@ class QuantumReranker:
     def rerank(self, query: str, documents: List[Document], top_k: int = None) -> List[Tuple[Document, float]]:
         if not documents:                                           # quantum.py:63-64
             return []
+        if (self.method == "state_fidelity" and self.encoding == "amplitude" and isinstance(top_k, int)
+                and 0 < top_k < len(documents) <= 4096):
+            # only the top_k are wanted: the fused kernels score, rank and cut on the device (layers == 0: one
+            # streaming launch; layers >= 1 at 10 qubits: complex64 filter + complex128 certification) -- the same
+            # documents, order and score bits as ranking everything and slicing
+            from .. import api
+            q, x = self._real_embeddings(query, documents)
+            n = max(self.n_qubits, api.qubits_for(q.shape[1])) if "n_qubits" not in self.config else self.n_qubits
+            scores, pos, _ = api.quantum_rerank_batch(q, cand=x[None, :, :], top_k=top_k, n_qubits=n, layers=self.layers)
+            return [(documents[i], s) for i, s in zip(pos[0].cpu().tolist(), scores[0].cpu().tolist())]
         order, scores = self._rank(query, documents)
         ranked = [(documents[i], s) for i, s in zip(order, scores)]
         if top_k is not None:                                       # quantum.py:75-76 (plain slice)

@@ -147,3 +147,25 @@ def test_classical_embedding_methods_long_list(cuda, method, mid):
     s, i = osr.exact_search(qv[None], emb, 100, mid)
     sign = -1.0 if method == "l2" else 1.0
     assert order[:100] == i[0].tolist() and np.allclose(sc[:100], sign * s[0], rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("dim,layers", [(384, 0), (1024, 3), (1000, 1)])
+def test_quantum_reranker_amplitude_topk_uses_fused_kernels_same_answer(cuda, dim, layers):
+    """``QuantumReranker.rerank(..., top_k=k)`` with amplitude encoding hands top-k to the fused kernels (streaming rerank;
+    at 10 qubits with layers: complex64 filter + complex128 certification).  Same Document objects, order and score bits as
+    ranking everything and slicing (quantum.py:70-76), exact ties in input order."""
+    rng = np.random.RandomState(dim + layers)
+    emb = rng.standard_normal((60, dim)).astype(np.float32)
+    emb[31] = emb[4]
+    emb[50] = emb[4]
+    qv = rng.standard_normal(dim).astype(np.float32)
+    docs = [Document(str(i), f"doc {i}", metadata={"embedding": emb[i]}) for i in range(60)]
+    rr = QuantumReranker({"encoding": "amplitude", "layers": layers, "query_embedding": qv})
+    full = rr.rerank("q", docs)                                   # top_k None: everything, the generic path
+    assert len(full) == 60
+    for k in (1, 7, 59):
+        got = rr.rerank("q", docs, top_k=k)
+        assert [d is w for (d, _), (w, _) in zip(got, full[:k])] == [True] * k
+        assert [s for _, s in got] == [s for _, s in full[:k]]
+    assert rr.rerank("q", docs, top_k=0) == [] and len(rr.rerank("q", docs, top_k=60)) == 60
+    assert rr.rerank("q", docs, top_k=-3) == full[:-3]            # plain Python slice semantics
