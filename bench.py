@@ -366,6 +366,10 @@ def bench_sharded(world, rank, steps=10):
     sub = torch.arange(0, nq, nq // 8, device=dev)[:8]
     ref = path.exact_reference(Q[sub], k1, k2)
     same = bool(torch.equal(ref.ids, res.ids[sub]) and torch.equal(ref.scores, res.scores[sub]))
+    # ... and the all-gather form (the rerun route) over the same group: same answer, lists equal to the exact search
+    full = path(Q, k1, k2, return_search_lists=True)
+    same_full = bool(torch.equal(full.ids, res.ids) and torch.equal(full.scores, res.scores) and
+                     torch.equal(full.search_ids[sub], ref.search_ids))
     for _ in range(3):                          # per-stage CUDA-event times of one batch (the last of three: ranks in step)
         if world > 1:
             dist.barrier()
@@ -381,7 +385,7 @@ def bench_sharded(world, rank, steps=10):
                      "inside the timed region; CUDA events, max over ranks",
            "ms_per_batch_runs": [round(x, 4) for x in reps], "ms_per_batch_one_at_a_time": ms_sync,
            "rerun_all_gather_form": path.last_rerun, "equals_exact_route_on_8_queries": same,
-           "collectives_per_batch": 0 if world == 1 else 4, "stage_ms_rank0": stages,
+           "all_gather_form_equal": same_full, "collectives_per_batch": 0 if world == 1 else 4, "stage_ms_rank0": stages,
            "result_sha256": h.hexdigest(), "note": "result_sha256 must not depend on n_gpus (bit-identical rankings)"}
     del path, X
     torch.cuda.empty_cache()

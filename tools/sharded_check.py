@@ -105,11 +105,16 @@ def main():
     sub = torch.arange(0, a.nq, max(1, a.nq // 8), device=dev)[:8]
     ref = path.exact_reference(Q[sub], a.k1, a.k2)
     same = bool(torch.equal(ref.ids, res.ids[sub]) and torch.equal(ref.scores, res.scores[sub]))
+    # ... and the all-gather form (the rerun route: thresholds exchanged, per-shard lists all-gathered, merged on every rank)
+    full = path(Q, a.k1, a.k2, return_search_lists=True)
+    same_full = bool(torch.equal(full.ids, res.ids) and torch.equal(full.scores, res.scores))
+    sub_ok = bool(torch.equal(full.search_ids[sub], ref.search_ids) and torch.equal(full.search_scores[sub], ref.search_scores))
     if rank == 0:
         ms = ms_sync
         print(json.dumps({"gpus": world, "modes": modes, "N": a.N, "nq": a.nq, "k1": a.k1, "k2": a.k2, "ms_per_batch": ms,
                           "search_scores_per_s": a.nq * a.N / ms * 1e3, "reranked_queries_per_s": a.nq / ms * 1e3,
                           "rerun_all_gather_form": path.last_rerun, "equals_exact_route_on_8_queries": same,
+                          "all_gather_form_equal": same_full, "all_gather_form_lists_equal_exact_search": sub_ok,
                           "stage_ms_rank0": prof, "result_sha256": h.hexdigest()}), flush=True)
     if world > 1:
         dist.barrier()
