@@ -190,7 +190,7 @@ int qrag_mock_embedding(const uint32_t* seeds, int64_t n, int n_qubits, double* 
  * accumulation, order (best, id asc), ids = id_base + row, -1 padding if k > N.
  *
  *   qrag_search_topk       CUDA-core exact path (any nq; the checker for the tensor-core path).
- *   qrag_search_topk_tc    tcgen05 path: bf16 GEMM used as a filter with a proven error bound
+ *   qrag_search_topk_tc    tcgen05 path: 16-bit (bf16 / fp16) GEMM used as a filter with a proven error bound
  *                          (bucket-maximum pass -> per-query threshold -> filter pass; the score
  *                          matrix never leaves TMEM), exact fp64 rescoring of the survivors with the
  *                          same code as the CUDA-core path, so scores and ids are bit-identical to

@@ -292,7 +292,7 @@ def search_topk(Q: ArrayLike, X: ArrayLike, k: int, metric="l2", id_base: int = 
 
 
 class FlatIndexTC:
-    """A flat index (shard) prepared for the tcgen05 search: fp32 rows plus their bf16 shadow.
+    """A flat index (shard) prepared for the tcgen05 search: fp32 rows plus their 16-bit shadow (bf16; fp16 for cosine).
 
     ``search(Q, k)`` returns exactly what ``search_topk`` returns (same fp64 scores, same ids, same
     order): the tensor cores only filter, survivors are rescored by the exact code.  Queries whose

@@ -70,7 +70,7 @@ class CudaEngine:
         return self.index.search(Q, k)
 
     def sync_corpus_bound(self, all_reduce_max):
-        """The filter's error bound uses max |x| and the largest bf16 rounding-error norm over the WHOLE corpus
+        """The filter's error bound uses max |x| and the largest 16-bit rounding-error norm over the WHOLE corpus
         (aux[0], aux[1]): reduce them once per index."""
         all_reduce_max(self.index.aux[:2])
 
@@ -372,14 +372,14 @@ def sharded_search_rerank(q, X_shard, k1: int = 1000, k2: int = 10, group: Optio
                           metric: str = "cosine", n_total: Optional[int] = None) -> ShardedResult:
     """Functional form named in SURVEY.md section 8b: ``sharded_search_rerank(q, X_shard, k1, k2, group)``.
 
-    The prepared shard (bf16 shadow, corpus bound) is cached per (shard tensor, metric, group), so repeated calls pay
+    The prepared shard (16-bit shadow, corpus bound) is cached per (shard tensor, metric, group), so repeated calls pay
     only for the search.  ``n_total`` defaults to the sum of the shard sizes over the group (one small all-reduce on the
     first call); shards must follow ``shard_bounds`` (contiguous, balanced).
     """
     key = (X_shard.data_ptr(), tuple(X_shard.shape), metric, id(group))
     hit = _PATHS.get(key)
     # the cache entry keeps the shard tensor alive, so a matching pointer means the same storage; rows modified in
-    # place after the first call need a fresh ShardedSearchRerank (the bf16 shadow is built once)
+    # place after the first call need a fresh ShardedSearchRerank (the 16-bit shadow is built once)
     path = hit[1] if hit is not None and hit[0] is X_shard else None
     if path is None:
         if n_total is None:
