@@ -156,7 +156,7 @@ def corpus_rows(lo, hi, dim, device):
 def bench_search(api, peaks, steps=20, oracle_check=False):
     """BASELINE config 3 on one GPU: cosine top-100 over 1M x 384 docs (tcgen05 filter GEMM + exact rescoring) for
     1024 queries (the config), and for 1 and 4096 queries.  Reported beside the headline; the tensor
-    roofline uses the ALGORITHMIC flops 2*D per score, the HBM roofline (nq = 1) the bf16 shadow read once."""
+    roofline uses the ALGORITHMIC flops 2*D per score, the HBM roofline (nq = 1) the 16-bit shadow read once."""
     import torch
     N, k = 1_000_000, 100
     X = corpus_rows(0, N, D, torch.device("cuda"))
@@ -209,7 +209,7 @@ def bench_search(api, peaks, steps=20, oracle_check=False):
     gbs = N * index.Kp * 2 / (ms1 * 1e-3) / 1e9
     out["nq_1"] = {"ms_per_batch": ms1, "scores_per_s": N / (ms1 * 1e-3), "flagged_queries": int(st1.count_nonzero()),
                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
-                                "note": "one query: the bf16 shadow of the corpus (768 MB) is read once per pass, and there "
+                                "note": "one query: the fp16 shadow of the corpus (768 MB) is read once per pass, and there "
                                         "are two passes' worth of work (sampled bucket pass + filter pass); bytes = N*Kp*2"}}
     ms4, _, _, _, st4 = timed(4096, max(3, steps // 4))
     tf4 = 2.0 * D * 4096 * N / (ms4 * 1e-3) / 1e12
