@@ -237,3 +237,48 @@ def test_phased_search_cut_and_fallback_routes(skew, flag):
         scores, ids, fell_back = out[rank]
         assert np.array_equal(ids, want.ids.numpy()) and np.array_equal(scores, want.scores.numpy()), rank
         assert fell_back == (skew or flag)            # the all-gather form materialises the merged search lists
+
+
+def _pipelined_worker(rank, world, port, n, d, nq, k1, k2, metric, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        X, _ = _data(n, d, nq)
+        lo, hi = shard_bounds(n, world, rank)
+        rng = np.random.RandomState(77)
+        batches = [torch.from_numpy(rng.standard_normal((nq, d)).astype(np.float32)) for _ in range(4)]
+        # batch 2 is flagged by the last rank (its certificate fails): it alone reruns through the all-gather form,
+        # in the middle of the queue, identically on every rank
+        engines = [PhasedOracleEngine(X[lo:hi], metric, lo, flag_query=(0 if b == 2 and rank == world - 1 else None))
+                   for b in range(4)]
+        path = ShardedSearchRerank(torch.from_numpy(X[lo:hi]), n, metric, engine=engines[0])
+        pend = []
+        for b, Q in enumerate(batches):
+            path.engine = engines[b]
+            pend.append(path.submit(Q, k1, k2))
+        res = []
+        for b, p in enumerate(pend):
+            path.engine = engines[b]
+            res.append(p.result())
+        out[rank] = [(r.scores.numpy(), r.ids.numpy(), r.search_ids is not None) for r in res]
+    finally:
+        dist.destroy_process_group()
+
+
+def test_submit_keeps_several_batches_in_flight_and_reruns_only_the_flagged_one():
+    """``submit`` queues batches back to back (shared exchange buffers, results copied out per batch); ``result()`` reads
+    each batch's certificate later.  Four different batches in flight over 3 gloo ranks, the third one flagged."""
+    world, metric, n, d, nq, k1, k2 = 3, osr.METRIC_L2, 600, 12, 5, 60, 8
+    X, _ = _data(n, d, nq)
+    rng = np.random.RandomState(77)
+    batches = [rng.standard_normal((nq, d)).astype(np.float32) for _ in range(4)]
+    eng = OracleEngine(X, metric, 0)
+    single = ShardedSearchRerank(torch.from_numpy(X), n, metric, engine=eng)
+    want = [single(torch.from_numpy(Q), k1, k2) for Q in batches]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_pipelined_worker, args=(world, _free_port(), n, d, nq, k1, k2, metric, out), nprocs=world, join=True)
+    for rank in range(world):
+        for b, (scores, ids, reran) in enumerate(out[rank]):
+            assert np.array_equal(ids, want[b].ids.numpy()) and np.array_equal(scores, want[b].scores.numpy()), (rank, b)
+            assert reran == (b == 2)
