@@ -59,9 +59,18 @@ __device__ __forceinline__ double xs_stage_query(const float* __restrict__ qrow,
     return nq2;
 }
 
+// 16 bytes of a row: from global memory through the streaming read-only path, or (STREAM = false) from wherever
+// the caller staged the row -- shared memory filled by a bulk copy in tc_rescore_bulk_kernel.  The values, hence
+// the scores, are the same.
+template <bool STREAM>
+__device__ __forceinline__ float4 xs_load4(const float4* p) {
+    if (STREAM) return ldg_stream(p);
+    return *p;
+}
+
 // One warp scores XS_ROWS rows.  l2: acc = sum (q - d)^2; otherwise acc = q.d and |d|^2.
 // Returns the transposed-reduced value (see xs_reduce4pairs); nd2 receives |d|^2 of the same row.
-template <bool VEC>
+template <bool VEC, bool STREAM = true>
 __device__ __forceinline__ double xs_score4(const float* const (&rp)[XS_ROWS], const double* qs, int D, bool l2,
                                             int lane, double& nd2) {
     double acc[8];
@@ -73,7 +82,7 @@ __device__ __forceinline__ double xs_score4(const float* const (&rp)[XS_ROWS], c
         for (int j = lane; j < D4; j += 32) {
             float4 v[XS_ROWS];
 #pragma unroll
-            for (int i = 0; i < XS_ROWS; ++i) v[i] = ldg_stream(reinterpret_cast<const float4*>(rp[i]) + j);
+            for (int i = 0; i < XS_ROWS; ++i) v[i] = xs_load4<STREAM>(reinterpret_cast<const float4*>(rp[i]) + j);
             const double2 qa = *reinterpret_cast<const double2*>(qs + 4 * j);
             const double2 qb = *reinterpret_cast<const double2*>(qs + 4 * j + 2);
             const double qv[4] = {qa.x, qa.y, qb.x, qb.y};
@@ -117,7 +126,7 @@ __device__ __forceinline__ double xs_score4(const float* const (&rp)[XS_ROWS], c
 // amplitude fidelity of an L2 candidate from the one read of its row).  The L2 sum goes through the same
 // instruction sequence as in xs_score4, q.d and |d|^2 through the sequence of the non-L2 form, so all three
 // agree bit for bit with what the separate kernels compute.
-template <bool VEC>
+template <bool VEC, bool STREAM = true>
 __device__ __forceinline__ double xs_score4_l2dot(const float* const (&rp)[XS_ROWS], const double* qs, int D, int lane,
                                                   double& nd2, double& dot) {
     double acc[8], acd[8];
@@ -129,7 +138,7 @@ __device__ __forceinline__ double xs_score4_l2dot(const float* const (&rp)[XS_RO
         for (int j = lane; j < D4; j += 32) {
             float4 v[XS_ROWS];
 #pragma unroll
-            for (int i = 0; i < XS_ROWS; ++i) v[i] = ldg_stream(reinterpret_cast<const float4*>(rp[i]) + j);
+            for (int i = 0; i < XS_ROWS; ++i) v[i] = xs_load4<STREAM>(reinterpret_cast<const float4*>(rp[i]) + j);
             const double2 qa = *reinterpret_cast<const double2*>(qs + 4 * j);
             const double2 qb = *reinterpret_cast<const double2*>(qs + 4 * j + 2);
             const double qv[4] = {qa.x, qa.y, qb.x, qb.y};

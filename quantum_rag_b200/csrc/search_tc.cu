@@ -197,6 +197,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ float neg_inf_f() { return __int_as_float(0xff800000); }
 
 // ------------------------------------------------------------------------------- the GEMM
+// First statement of every per-batch kernel (see launch_chained): let the next kernel of the stream start launching,
+// then wait until everything before this kernel has completed and is visible.  No-ops in a plain launch.
+__device__ __forceinline__ void pdl_enter() {
+    griddep_launch_dependents();
+    griddep_wait();
+}
+
 // CG == 1: one CTA computes 128 queries x 256 documents per tile.  CG == 2: a CTA pair computes 256 queries x 256
 // documents per tile with tcgen05.mma.cta_group::2: each CTA keeps its own 128 query rows resident and loads HALF of
 // every document tile (128 rows); the pair's tensor cores read both halves.  Per SM that halves the L2->SM bytes per
@@ -237,6 +244,7 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (CG == 2) cluster_sync_all();                              // the peer's barriers exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_enter();                                                  // barriers and TMEM are set up while the previous kernel drains
 
     // work of this CTA (pair): query group g, tiles u0, u0 + cpg, ... (pass 1: of the sampled tiles)
     const int unit_id = blockIdx.x / CG;                          // CTA (CG 1) or pair (CG 2) index
@@ -506,6 +514,7 @@ __global__ void __launch_bounds__(256) index_prepare_kernel(const float* __restr
 __global__ void __launch_bounds__(256) query_prepare_kernel(const float* __restrict__ Q, int nq, int nq_pad, int D, int Kp,
                                                             int metric, unsigned short* __restrict__ Qb,
                                                             float* __restrict__ qnorm, float* __restrict__ qerr) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= nq_pad) return;
@@ -696,13 +705,45 @@ __device__ void block_topk_values(RadixSel& rs, int k, int total, ForEach for_ea
     for (int i = rs.count + threadIdx.x; i < k; i += blockDim.x) out[i] = t;       // ties with the k-th / padding
 }
 
+// The select kernels make four radix passes (and the top-k form a fifth, collecting) over the same few thousand
+// values: read them from global memory once into shared memory when they fit (ncu r02: tau_union barrier- and
+// scoreboard-bound, 40 registers = 6 CTAs per SM = 1.15 waves of 1024 queries; now 8 CTAs per SM, one wave).
+constexpr int SEL_CACHE = 3072;
+template <class Load>
+__device__ __forceinline__ void sel_fill(float* sv, int total, Load load) {
+    for (int i = threadIdx.x; i < total; i += 8 * blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = i + u * blockDim.x;
+            v[u] = j < total ? load(j) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = i + u * blockDim.x;
+            if (j < total) sv[j] = v[u];
+        }
+    }
+    __syncthreads();
+}
+
 // per query: the k largest bucket maxima of this shard -> bm_top [nq, k]
-__global__ void __launch_bounds__(256) bucket_topk_kernel(const float* __restrict__ bmax, int nbuckets, int k,
-                                                          float* __restrict__ bm_top) {
+__global__ void __launch_bounds__(256, 8) bucket_topk_kernel(const float* __restrict__ bmax, int nbuckets, int k,
+                                                             float* __restrict__ bm_top) {
+    pdl_enter();
     __shared__ RadixSel rs;
+    __shared__ float sv[SEL_CACHE];
     const int q = blockIdx.x;
     const float* row = bmax + (size_t)q * nbuckets;
-    auto fe = [&](auto f) { for_strided<8>(threadIdx.x, nbuckets, blockDim.x, [&](int j) { return row[j]; }, f); };
+    const bool cached = nbuckets <= SEL_CACHE;
+    if (cached) sel_fill(sv, nbuckets, [&](int j) { return row[j]; });
+    auto fe = [&](auto f) {
+        if (cached) {
+            for (int j = threadIdx.x; j < nbuckets; j += blockDim.x) f(sv[j]);
+        } else {
+            for_strided<8>(threadIdx.x, nbuckets, blockDim.x, [&](int j) { return row[j]; }, f);
+        }
+    };
     block_topk_values(rs, k, nbuckets, fe, bm_top + (size_t)q * k);
 }
 
@@ -710,31 +751,48 @@ __global__ void __launch_bounds__(256) bucket_topk_kernel(const float* __restric
 // (single shard: bm_top_all == nullptr and the k-th largest is taken straight from this shard's bucket maxima).
 // Also lays out the query's survivor histogram (surv_hist_kernel): TC_HIST_BINS uniform bins from tau up to the
 // largest sampled bucket maximum (scores above it land in the last bin).
-__global__ void __launch_bounds__(256) tau_union_kernel(const float* __restrict__ bm_top_all, int G, int nq, int k, int kt,
-                                                        int metric,
-                                                        int Kp, const float* __restrict__ qnorm, const float* __restrict__ qerr,
-                                                        const float* __restrict__ aux,
-                                                        const float* __restrict__ bmax, int nbuckets,
-                                                        float* __restrict__ tau, float* __restrict__ eps,
-                                                        float* __restrict__ hinv) {
+__global__ void __launch_bounds__(256, 8) tau_union_kernel(const float* __restrict__ bm_top_all, int G, int nq, int k, int kt,
+                                                           int metric,
+                                                           int Kp, const float* __restrict__ qnorm, const float* __restrict__ qerr,
+                                                           const float* __restrict__ aux,
+                                                           const float* __restrict__ bmax, int nbuckets,
+                                                           float* __restrict__ tau, float* __restrict__ eps,
+                                                           float* __restrict__ hinv) {
+    pdl_enter();
     __shared__ RadixSel rs;
     __shared__ float s_max[8];
+    __shared__ float sv[SEL_CACHE];
     const int q = blockIdx.x;
     float mk = neg_inf_f(), top = neg_inf_f();
     auto track = [&](auto f) { return [&top, f](float v) { top = fmaxf(top, v); f(v); }; };
-    if (bm_top_all != nullptr) {
-        auto fe = [&](auto f) {
+    const int64_t total = bm_top_all != nullptr ? (int64_t)G * kt : (int64_t)nbuckets;
+    const bool cached = total <= SEL_CACHE;
+    if (cached) {
+        if (bm_top_all != nullptr) {
+            sel_fill(sv, (int)total, [&](int j) {
+                const int g = j / kt;
+                return bm_top_all[((size_t)g * nq + q) * kt + (j - g * kt)];
+            });
+        } else {
+            const float* row = bmax + (size_t)q * nbuckets;
+            sel_fill(sv, (int)total, [&](int j) { return row[j]; });
+        }
+    }
+    auto fe = [&](auto f) {
+        if (cached) {
+            auto tf = track(f);
+            for (int j = threadIdx.x; j < (int)total; j += blockDim.x) tf(sv[j]);
+        } else if (bm_top_all != nullptr) {
             for (int g = 0; g < G; ++g) {
                 const float* row = bm_top_all + ((size_t)g * nq + q) * kt;
                 for_strided<4>(threadIdx.x, kt, blockDim.x, [&](int j) { return row[j]; }, track(f));
             }
-        };
-        if ((int64_t)G * kt >= k) mk = block_kth_largest(rs, k, fe);
-    } else if (nbuckets >= k) {
-        const float* row = bmax + (size_t)q * nbuckets;
-        auto fe = [&](auto f) { for_strided<8>(threadIdx.x, nbuckets, blockDim.x, [&](int j) { return row[j]; }, track(f)); };
-        mk = block_kth_largest(rs, k, fe);
-    }
+        } else {
+            const float* row = bmax + (size_t)q * nbuckets;
+            for_strided<8>(threadIdx.x, nbuckets, blockDim.x, [&](int j) { return row[j]; }, track(f));
+        }
+    };
+    if (total >= k) mk = block_kth_largest(rs, k, fe);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) top = fmaxf(top, __shfl_xor_sync(FULL_MASK, top, o));
     if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = top;
@@ -760,24 +818,59 @@ __global__ void __launch_bounds__(256) tau_union_kernel(const float* __restrict_
 // hinv come from the all-gathered bucket maxima), and the highest bin edge with k survivors at or above it bounds
 // the k-th best approximate score from below, which is all the candidate cut needs.  (int)NaN == 0, +inf saturates.
 // (Counting in the filter GEMM's epilogue instead was measured: +14 % on the GEMM, whose epilogue is its critical path.)
+// f(entry) for every survivor of one query.  seg_n [nseg] (shared memory) = entries per segment.  The lists are many
+// short segments (config 3: 72 segments of ~22 survivors), so walking them one segment per warp at a time is a chain
+// of dependent-latency loads (ncu r02: both kernels below latency-bound at 12-15 us for 13 MB).  Here a warp has the
+// first 32 entries of FOUR segments in flight at once, then mops up the rare longer segments four loads deep.
+template <class F>
+__device__ __forceinline__ void for_each_survivor(const float2* __restrict__ sv, const int* seg_n, int nseg, int seg_cap, F f) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int s0 = 4 * warp; s0 < nseg; s0 += 4 * nwarps) {
+        float2 e[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int sg = s0 + u;
+            ok[u] = sg < nseg && lane < seg_n[sg];
+            e[u] = ok[u] ? sv[(size_t)sg * seg_cap + lane] : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (ok[u]) f(e[u]);
+    }
+    for (int sg = warp; sg < nseg; sg += nwarps) {
+        const int n = seg_n[sg];
+        const float2* sp = sv + (size_t)sg * seg_cap;
+        for (int i0 = 32 + lane; i0 < n; i0 += 128) {
+            float2 e[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) e[u] = (i0 + 32 * u < n) ? sp[i0 + 32 * u] : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + 32 * u < n) f(e[u]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) surv_hist_kernel(const unsigned int* __restrict__ cnt, const float2* __restrict__ surv,
                                                         int q0, int nseg, int seg_cap, int cap,
                                                         const float* __restrict__ tau, const float* __restrict__ hinv,
                                                         int* __restrict__ hist) {
+    pdl_enter();
     __shared__ int h[TC_HIST_BINS];
+    __shared__ int seg_n[TC_MAX_SEGS];
     const int q = q0 + blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int tid = threadIdx.x;
     for (int i = tid; i < TC_HIST_BINS; i += blockDim.x) h[i] = 0;
-    __syncthreads();
-    const float t = tau[q], hv = hinv[q];
-    const float2* sv = surv + (size_t)q * cap;
-    for (int sgi = warp; sgi < nseg; sgi += nwarps) {
+    for (int sgi = tid; sgi < nseg; sgi += blockDim.x) {
         const unsigned int c = cnt[(size_t)q * TC_MAX_SEGS + sgi];
-        const int n = c < (unsigned)seg_cap ? (int)c : seg_cap;
-        const float2* sp = sv + (size_t)sgi * seg_cap;
-        for_strided<4>(lane, n, 32, [&](int j) { return sp[j].x; },
-                       [&](float v) { atomicAdd(&h[max(0, min(TC_HIST_BINS - 1, (int)((v - t) * hv)))], 1); });
+        seg_n[sgi] = c < (unsigned)seg_cap ? (int)c : seg_cap;
     }
+    const float t = tau[q], hv = hinv[q];
+    __syncthreads();
+    for_each_survivor(surv + (size_t)q * cap, seg_n, nseg, seg_cap, [&](float2 e) {
+        atomicAdd(&h[max(0, min(TC_HIST_BINS - 1, (int)((e.x - t) * hv)))], 1);
+    });
     __syncthreads();
     for (int i = tid; i < TC_HIST_BINS; i += blockDim.x) hist[(size_t)q * TC_HIST_BINS + i] = h[i];
 }
@@ -793,6 +886,10 @@ struct TcFinalParams {
     int* cand_rows; double* cand_key; int* cand_m;     // [nq, cand_cap], [nq, cand_cap], [nq, 2] (count, overflow)
     double* cand_fid;                                  // [nq, cand_cap] amplitude fidelity of the row (packed form) or null
     long long* pack; int kk;                           // packed form: [nq, 3 kk + 1] records cut to kk entries, or null
+    int fuse_sort;                                     // tc_rescore_bulk_kernel sorts and writes the list itself (grid.y == 1)
+#ifdef QRAG_TUNING
+    int tune;                                          // 2: register form of tc_rescore even where the bulk form fits; 4: never fuse the sort
+#endif
 };
 
 template <typename K, typename T>
@@ -820,6 +917,7 @@ __device__ void bitonic_sort_kt(K* key, T* tag, int P) {
 // survivor histogram the filter pass built (summed over the shards by the caller): the highest bin edge that still
 // has k survivors at or above it.  Candidates = this shard's survivors >= a_k - 2 eps -> cand_rows, cand_m.
 __global__ void __launch_bounds__(XS_THREADS) tc_collect_kernel(const TcFinalParams p) {
+    pdl_enter();
     __shared__ int seg_n[TC_MAX_SEGS];
     __shared__ int s_m, s_bad;
     __shared__ float s_ak;
@@ -878,28 +976,17 @@ __global__ void __launch_bounds__(XS_THREADS) tc_collect_kernel(const TcFinalPar
     float thr = ak - 2.f * p.eps[q];                                        // -inf stays -inf
     thr = thr - fabsf(thr) * 2.4e-7f - 1e-37f;
     // candidates (any order: the final sort is a total order on (score, id))
-    for (int sgi = warp; sgi < p.nseg; sgi += XS_WARPS) {
-        const float2* sp = sv + (size_t)sgi * p.seg_cap;
-        const int sn = seg_n[sgi];
-        for (int i0 = lane; i0 < sn; i0 += 128) {
-            float2 ev[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) ev[u] = (i0 + 32 * u < sn) ? sp[i0 + 32 * u] : make_float2(neg_inf_f(), 0.f);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float2 e = ev[u];
-                if (i0 + 32 * u < sn && e.x >= thr) {
-                    const unsigned am = __activemask();             // one atomic per converged group
-                    const int leader = __ffs(am) - 1;
-                    int base = 0;
-                    if (lane == leader) base = atomicAdd(&s_m, __popc(am));
-                    base = __shfl_sync(am, base, leader);
-                    const int pos = base + __popc(am & ((1u << lane) - 1u));
-                    if (pos < p.cand_cap) cand[pos] = __float_as_int(e.y);
-                }
-            }
+    for_each_survivor(sv, seg_n, p.nseg, p.seg_cap, [&](float2 e) {
+        if (e.x >= thr) {
+            const unsigned am = __activemask();                             // one atomic per converged group
+            const int leader = __ffs(am) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&s_m, __popc(am));
+            base = __shfl_sync(am, base, leader);
+            const int pos = base + __popc(am & ((1u << lane) - 1u));
+            if (pos < p.cand_cap) cand[pos] = __float_as_int(e.y);
         }
-    }
+    });
     __syncthreads();
     if (tid == 0) {
         int m = s_m, bad = s_bad;
@@ -909,63 +996,17 @@ __global__ void __launch_bounds__(XS_THREADS) tc_collect_kernel(const TcFinalPar
     }
 }
 
-// (2) exact rescoring, grid (queries, chunks of XS_RESCORE_ROWS candidates): small CTAs, many resident, so the row
-// gathers run at memory-level parallelism instead of behind one CTA's select and sort.  Same device code as the
-// CUDA-core search (exact_score.cuh): a row's key does not depend on which kernel or batch scored it.
-constexpr int XS_RESCORE_ROWS = 128;
-template <bool VEC>
-__global__ void __launch_bounds__(XS_THREADS) tc_rescore_kernel(const TcFinalParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int q = p.q0 + blockIdx.x;
-    const int m = p.cand_m[2 * q];
-    const int c0 = blockIdx.y * XS_RESCORE_ROWS;
-    if (c0 >= m) return;
-    const int D = p.D, Dpad = (D + 3) & ~3;
-    double* qs = reinterpret_cast<double*>(smem_raw);
-    double* red = qs + Dpad;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool l2 = p.metric == QRAG_METRIC_L2;
-    const int* cand = p.cand_rows + (size_t)q * p.cand_cap;
-    double* ckey = p.cand_key + (size_t)q * p.cand_cap;
-    const double nq2 = xs_stage_query(p.Q + (size_t)q * D, D, qs, red);     // ends with __syncthreads()
-    const int c1 = (c0 + XS_RESCORE_ROWS < m) ? c0 + XS_RESCORE_ROWS : m;
-    for (int r0 = c0 + warp * XS_ROWS; r0 < c1; r0 += XS_WARPS * XS_ROWS) {
-        const float* rp[XS_ROWS];
-#pragma unroll
-        for (int i = 0; i < XS_ROWS; ++i) {
-            const int r = (r0 + i < c1) ? r0 + i : r0;
-            rp[i] = p.X + (size_t)cand[r] * D;
-        }
-        double nd2, dot;
-        double tot;
-        if (l2 && p.cand_fid != nullptr) {
-            tot = xs_score4_l2dot<VEC>(rp, qs, D, lane, nd2, dot);
-        } else {
-            tot = xs_score4<VEC>(rp, qs, D, l2, lane, nd2);
-            dot = tot;
-        }
-        if ((lane & 7) == 0) {
-            const int r = r0 + (lane >> 3);
-            if (r < c1) {
-                ckey[r] = xs_key(p.metric, tot, nd2, nq2);
-                // the rerank's fidelity from the same read of the row (bit-identical to amp_fidelity.cu)
-                if (p.cand_fid != nullptr) p.cand_fid[(size_t)q * p.cand_cap + r] = xs_fidelity(dot, nd2, nq2);
-            }
-        }
-    }
-}
-
-// (3) one CTA per query: sort the (key, row) pairs by (score, id), write the shard's list and its status.
-__global__ void __launch_bounds__(1024) tc_sort_kernel(const TcFinalParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+// (3) one CTA per query: sort the (key, row) pairs by (score, id), write the shard's list and its status.  The body
+// is shared by the stand-alone kernel and by the rescoring kernel, which runs it itself when one CTA scored the
+// whole list of its query (tc_rescore_bulk_kernel, fuse_sort).  `smem` holds 12 bytes per (power-of-two) list slot.
+__device__ __forceinline__ void tc_sort_body(const TcFinalParams& p, int q, unsigned char* smem) {
     const int tid = threadIdx.x;
-    const int q = p.q0 + blockIdx.x;
     const int k = p.k;
     const bool l2 = p.metric == QRAG_METRIC_L2;
     const int m = p.cand_m[2 * q];
     int P2 = 1;
     while (P2 < m) P2 <<= 1;
-    double* ckey = reinterpret_cast<double*>(smem_raw);                     // [P2]
+    double* ckey = reinterpret_cast<double*>(smem);                         // [P2]
     int* ctag = reinterpret_cast<int*>(ckey + P2);                          // [P2] corpus rows = the sort tags
     const int* cand = p.cand_rows + (size_t)q * p.cand_cap;
     const double* gkey = p.cand_key + (size_t)q * p.cand_cap;
@@ -990,19 +1031,17 @@ __global__ void __launch_bounds__(1024) tc_sort_kernel(const TcFinalParams p) {
 // (3') packed form of (3) for the search + rerank path: the sorted list goes straight into the record the exchange
 // sends to the query's owner -- [0] header (valid entries | bad << 32), then kk score bits, kk ids, kk fidelity bits
 // -- cut to the kk best entries.  The sort tag is row << 13 | candidate slot (rows are unique within a list, so the
-// order is still (score, id)); the slot finds the row's fidelity after the sort.
+// order is still (score, id)); the slot finds the row's fidelity after the sort.  16 bytes of `smem` per list slot.
 constexpr int TC_SLOT_BITS = 13;
 static_assert((1 << TC_SLOT_BITS) >= TC_MAX_CAND, "a candidate slot must fit the tag");
-__global__ void __launch_bounds__(1024) tc_sort_pack_kernel(const TcFinalParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void tc_sort_pack_body(const TcFinalParams& p, int q, unsigned char* smem) {
     const int tid = threadIdx.x;
-    const int q = p.q0 + blockIdx.x;
     const int k = p.k, kk = p.kk;
     const bool l2 = p.metric == QRAG_METRIC_L2;
     const int m = p.cand_m[2 * q];
     int P2 = 1;
     while (P2 < m) P2 <<= 1;
-    double* ckey = reinterpret_cast<double*>(smem_raw);                     // [P2]
+    double* ckey = reinterpret_cast<double*>(smem);                         // [P2]
     long long* ctag = reinterpret_cast<long long*>(ckey + P2);              // [P2]
     const int* cand = p.cand_rows + (size_t)q * p.cand_cap;
     const double* gkey = p.cand_key + (size_t)q * p.cand_cap;
@@ -1034,6 +1073,181 @@ __global__ void __launch_bounds__(1024) tc_sort_pack_kernel(const TcFinalParams 
     }
 }
 
+__global__ void __launch_bounds__(1024) tc_sort_kernel(const TcFinalParams p) {
+    pdl_enter();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    tc_sort_body(p, p.q0 + blockIdx.x, smem_raw);
+}
+
+__global__ void __launch_bounds__(1024) tc_sort_pack_kernel(const TcFinalParams p) {
+    pdl_enter();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    tc_sort_pack_body(p, p.q0 + blockIdx.x, smem_raw);
+}
+
+// (2) exact rescoring, grid (queries, y): CTA (q, y) takes the chunks y, y + gridDim.y, ... of XS_RESCORE_ROWS
+// candidates of query q (y = 1 when the queries alone fill the machine: no CTAs that only find nothing to do).  A warp
+// scores batches of XS_ROWS rows; lane l reads the row number of the warp's batch l >> 2, slot l & 3 of the chunk up
+// front.  Same device code as the CUDA-core search (exact_score.cuh): a row's key does not depend on which kernel or
+// batch scored it.
+//
+// Two forms.  tc_rescore_bulk_kernel (rows a multiple of 16 bytes and short enough for two CTAs per SM): a warp
+// brings its batch into shared memory with one bulk async copy per row (UBLKCP, completion on the warp's own
+// mbarrier) and scores it from there.  The gather is latency-bound when every load instruction waits for its own
+// lines -- ncu r02 on the register form at k = 100: three exposed waits per batch (the compiler keeps 4 of the 12
+// LDG.128 of a batch in flight at 80 registers), 66 % of the stall samples in that loop, 3.3 TB/s -- while a bulk
+// copy has the whole batch (6 KB at D = 384) in flight per warp and needs no registers for it: 4 CTAs per SM,
+// 32 batches = 192 KB in flight per SM, one wait per batch.  The first batch is requested before the query is staged.
+// tc_rescore_kernel is the register form (any D, any alignment).
+constexpr int XS_RESCORE_ROWS = 128;
+constexpr int XS_RESCORE_BATCHES = XS_RESCORE_ROWS / (XS_WARPS * XS_ROWS);      // per warp and chunk
+static_assert(XS_RESCORE_BATCHES * XS_ROWS <= 32, "one lane per row of the warp's share of a chunk");
+
+__device__ __forceinline__ int rescore_fetch(const int* cand, int c, int m, int lane, int warp) {
+    const int off = XS_ROWS * (warp + XS_WARPS * (lane >> 2)) + (lane & 3);     // this lane's row within a chunk
+    return (lane < XS_RESCORE_BATCHES * XS_ROWS && c + off < m) ? cand[c + off] : -1;
+}
+
+__device__ __forceinline__ void rescore_emit(const TcFinalParams& p, int q, int r0, int c1, int lane, double tot, double nd2,
+                                             double dot, double nq2) {
+    if ((lane & 7) == 0) {
+        const int r = r0 + (lane >> 3);
+        if (r < c1) {
+            p.cand_key[(size_t)q * p.cand_cap + r] = xs_key(p.metric, tot, nd2, nq2);
+            // the rerank's fidelity from the same read of the row (bit-identical to amp_fidelity.cu)
+            if (p.cand_fid != nullptr) p.cand_fid[(size_t)q * p.cand_cap + r] = xs_fidelity(dot, nd2, nq2);
+        }
+    }
+}
+
+static size_t rescore_bulk_smem(int D) {                       // staged query + reduction scratch + barriers + row stages
+    return (size_t)(D + 2 * XS_WARPS) * 8 + (size_t)XS_WARPS * XS_ROWS * D * 4;
+}
+
+__global__ void __launch_bounds__(XS_THREADS, 4) tc_rescore_bulk_kernel(const TcFinalParams p) {
+    pdl_enter();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int q = p.q0 + blockIdx.x;
+    const int m = p.cand_m[2 * q];
+    int cc = blockIdx.y * XS_RESCORE_ROWS;
+    if (cc >= m && !p.fuse_sort) return;                        // (fused: an empty list still writes its padding)
+    const int D = p.D;                                          // a multiple of 4 (the caller checks)
+    double* qs = reinterpret_cast<double*>(smem_raw);
+    double* red = qs + D;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + XS_WARPS);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* stage = reinterpret_cast<float*>(bars + XS_WARPS) + (size_t)warp * XS_ROWS * D;
+    uint64_t* bar = bars + warp;
+    const uint32_t row_bytes = (uint32_t)D * 4u;
+    const bool l2 = p.metric == QRAG_METRIC_L2;
+    const int* cand = p.cand_rows + (size_t)q * p.cand_cap;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    int my = rescore_fetch(cand, cc, m, lane, warp);
+    int c1 = (cc + XS_RESCORE_ROWS < m) ? cc + XS_RESCORE_ROWS : m;
+    // lane 0 starts the copies of the warp's batch t of the chunk at cc (the stage is free: see the __syncwarp below)
+    auto issue = [&](int t) {
+        int id[XS_ROWS];
+#pragma unroll
+        for (int i = 0; i < XS_ROWS; ++i) id[i] = __shfl_sync(FULL_MASK, my, XS_ROWS * t + i);
+        if (lane == 0) {
+            const int left = c1 - (cc + XS_ROWS * (warp + XS_WARPS * t));
+            const int n = left < XS_ROWS ? left : XS_ROWS;
+            mbar_arrive_expect_tx(bar, (uint32_t)n * row_bytes);
+#pragma unroll
+            for (int i = 0; i < XS_ROWS; ++i)
+                if (i < n) bulk_g2s(stage + (size_t)i * D, p.X + (size_t)id[i] * D, row_bytes, bar);
+        }
+    };
+    bool ahead = cc + XS_ROWS * warp < c1;                      // the first batch is requested before the query is staged
+    if (ahead) issue(0);
+    const double nq2 = xs_stage_query(p.Q + (size_t)q * D, D, qs, red);     // ends with __syncthreads()
+    uint32_t parity = 0;
+    while (cc < m) {
+#pragma unroll 1
+        for (int t = 0; t < XS_RESCORE_BATCHES; ++t) {
+            const int r0 = cc + XS_ROWS * (warp + XS_WARPS * t);
+            if (r0 >= c1) break;                                // warp-uniform
+            if (!ahead) issue(t);
+            ahead = false;
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            const float* rp[XS_ROWS];
+#pragma unroll
+            for (int i = 0; i < XS_ROWS; ++i) rp[i] = stage + (size_t)(r0 + i < c1 ? i : 0) * D;   // past the end: row 0 again, unused
+            double nd2, dot, tot;
+            if (l2 && p.cand_fid != nullptr) {
+                tot = xs_score4_l2dot<true, false>(rp, qs, D, lane, nd2, dot);
+            } else {
+                tot = xs_score4<true, false>(rp, qs, D, l2, lane, nd2);
+                dot = tot;
+            }
+            rescore_emit(p, q, r0, c1, lane, tot, nd2, dot, nq2);
+            __syncwarp();                                       // every lane has read the stage before it is refilled
+        }
+        cc += gridDim.y * XS_RESCORE_ROWS;
+        if (cc >= m) break;                                     // CTA-uniform
+        c1 = (cc + XS_RESCORE_ROWS < m) ? cc + XS_RESCORE_ROWS : m;
+        my = rescore_fetch(cand, cc, m, lane, warp);
+    }
+    if (p.fuse_sort) {
+        // this CTA scored the query's whole list (grid.y == 1): sort it here, in the row stages (every copy into them
+        // has been waited for), instead of in a kernel of its own
+        __syncthreads();
+        unsigned char* sort_smem = reinterpret_cast<unsigned char*>(bars + XS_WARPS);
+        if (p.pack != nullptr) tc_sort_pack_body(p, q, sort_smem);
+        else                   tc_sort_body(p, q, sort_smem);
+    }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(XS_THREADS) tc_rescore_kernel(const TcFinalParams p) {
+    pdl_enter();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int q = p.q0 + blockIdx.x;
+    const int m = p.cand_m[2 * q];
+    int cc = blockIdx.y * XS_RESCORE_ROWS;
+    if (cc >= m) return;
+    const int D = p.D, Dpad = (D + 3) & ~3;
+    double* qs = reinterpret_cast<double*>(smem_raw);
+    double* red = qs + Dpad;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool l2 = p.metric == QRAG_METRIC_L2;
+    const int* cand = p.cand_rows + (size_t)q * p.cand_cap;
+    int my = rescore_fetch(cand, cc, m, lane, warp);
+    const double nq2 = xs_stage_query(p.Q + (size_t)q * D, D, qs, red);     // ends with __syncthreads()
+    while (true) {
+        const int c1 = (cc + XS_RESCORE_ROWS < m) ? cc + XS_RESCORE_ROWS : m;
+#pragma unroll 1
+        for (int t = 0; t < XS_RESCORE_BATCHES; ++t) {
+            const int r0 = cc + XS_ROWS * (warp + XS_WARPS * t);
+            if (r0 >= c1) break;                               // warp-uniform
+            const float* rp[XS_ROWS];
+            const int id0 = __shfl_sync(FULL_MASK, my, XS_ROWS * t);
+#pragma unroll
+            for (int i = 0; i < XS_ROWS; ++i) {
+                int id = __shfl_sync(FULL_MASK, my, XS_ROWS * t + i);
+                if (id < 0) id = id0;                          // past the end of the list: score row r0 again, unused
+                rp[i] = p.X + (size_t)id * D;
+            }
+            double nd2, dot, tot;
+            if (l2 && p.cand_fid != nullptr) {
+                tot = xs_score4_l2dot<VEC>(rp, qs, D, lane, nd2, dot);
+            } else {
+                tot = xs_score4<VEC>(rp, qs, D, l2, lane, nd2);
+                dot = tot;
+            }
+            rescore_emit(p, q, r0, c1, lane, tot, nd2, dot, nq2);
+        }
+        cc += gridDim.y * XS_RESCORE_ROWS;
+        if (cc >= m) break;                                    // CTA-uniform
+        my = rescore_fetch(cand, cc, m, lane, warp);
+    }
+}
+
 // Owner side of the search + rerank exchange: one CTA per owned query.  recv [G, per, 3 kk + 1] holds, from every
 // shard, the record tc_sort_pack_kernel wrote for this query.  The G sorted lists are merged by RANK -- an entry's
 // position in the global (score, id) order is its own position plus, for every other list, the number of entries
@@ -1046,6 +1260,7 @@ struct OwnerParams {
 };
 constexpr int OWNER_MAX_G = 256;
 __global__ void __launch_bounds__(1024) owner_finalize_kernel(const OwnerParams p) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_valid[OWNER_MAX_G];
     __shared__ int s_bad, s_total;
@@ -1221,6 +1436,29 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int Kp, in
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Every per-batch kernel of the search is launched with programmatic stream serialization and begins with pdl_enter()
+// (below): its CTAs may become resident -- launch latency, scheduling, and in the GEMM the barrier / TMEM set-up --
+// while the kernel before it drains, and touch nothing that kernel wrote until it has completed.  A batch is 7-8
+// short dependent kernels around one long one; the boundaries were ~20 us of it (a CUDA-graph replay measured 3 %
+// faster than plain launches; this gets the same without asking the caller for fixed pointers).
+template <class... P, class... A>
+static cudaError_t launch_chained(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+#ifdef QRAG_TUNING
+    if (const char* e = getenv("QRAG_TC_TUNE")) if (atoi(e) & 8) cfg.numAttrs = 0;
+#endif
+    return cudaLaunchKernelEx(&cfg, kern, P(args)...);
+}
+
 static int tc_kp(int D, int metric) { return (int)align_up((size_t)D + (metric == QRAG_METRIC_L2 ? 2 : 0), 16); }
 
 struct TcPlan {
@@ -1302,6 +1540,9 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPl
     const int64_t by_buckets = N * shards / ((int64_t)256 * k);
     if (sample > by_buckets) sample = by_buckets;
     if (sample < 1) sample = 1;
+#ifdef QRAG_TUNING
+    if (const char* e = getenv("QRAG_TC_SAMPLE")) sample = atoi(e) > 0 ? atoi(e) : sample;
+#endif
     pl->sample = (int)sample;
     const int sample_i = (int)sample;
     pl->nsample_tiles = (pl->ntiles + sample_i - 1) / sample_i;
@@ -1382,13 +1623,18 @@ static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const T
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // see launch_chained
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = CG;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = CG > 1 ? 1 : 0;
+    cfg.numAttrs = CG > 1 ? 2 : 1;
+#ifdef QRAG_TUNING
+    if (const char* e = getenv("QRAG_TC_TUNE")) if (atoi(e) & 8) { cfg.attrs = attr + 1; cfg.numAttrs = CG > 1 ? 1 : 0; }
+#endif
     QRAG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mapA, mapB, gp));
     QRAG_LAUNCH_CHECK("sim_gemm_kernel");
     return QRAG_OK;
@@ -1496,13 +1742,13 @@ extern "C" int qrag_search_tc_begin(const float* Q, int nq, const uint16_t* Xb, 
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const TcPlan& pl = w.pl;
-    query_prepare_kernel<<<(unsigned)ceil_div(pl.nq_pad, 8), 256, 0, st>>>(Q, nq, pl.nq_pad, D, pl.Kp, metric, w.Qb, w.qnorm,
-                                                                           w.qnorm + pl.nq_pad);
+    QRAG_CUDA_CHECK(launch_chained(query_prepare_kernel, dim3((unsigned)ceil_div(pl.nq_pad, 8)), dim3(256), 0, st, Q, nq, pl.nq_pad, D, pl.Kp, metric, w.Qb, w.qnorm,
+                                   w.qnorm + pl.nq_pad));
     QRAG_LAUNCH_CHECK("query_prepare_kernel");
     rc = tc_gemm_pass<TC_MODE_BUCKET>(w, nq, N, Xb, st, [](int, int, int, int) { return QRAG_OK; });
     if (rc) return rc;
     if (bm_top != nullptr) {                                   // single shard: the threshold kernel reads bmax itself
-        bucket_topk_kernel<<<nq, 256, 0, st>>>(w.bmax, pl.nbuckets, pl.kt, bm_top);
+        QRAG_CUDA_CHECK(launch_chained(bucket_topk_kernel, dim3(nq), dim3(256), 0, st, w.bmax, pl.nbuckets, pl.kt, bm_top));
         QRAG_LAUNCH_CHECK("bucket_topk_kernel");
     }
     return QRAG_OK;
@@ -1519,8 +1765,8 @@ extern "C" int qrag_search_tc_scores(const float* Q, int nq, const uint16_t* Xb,
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const TcPlan& pl = w.pl;
-    query_prepare_kernel<<<(unsigned)ceil_div(pl.nq_pad, 8), 256, 0, st>>>(Q, nq, pl.nq_pad, D, pl.Kp, metric, w.Qb, w.qnorm,
-                                                                           w.qnorm + pl.nq_pad);
+    QRAG_CUDA_CHECK(launch_chained(query_prepare_kernel, dim3((unsigned)ceil_div(pl.nq_pad, 8)), dim3(256), 0, st, Q, nq, pl.nq_pad, D, pl.Kp, metric, w.Qb, w.qnorm,
+                                   w.qnorm + pl.nq_pad));
     QRAG_LAUNCH_CHECK("query_prepare_kernel");
     w.dump = out;
     return tc_gemm_pass<TC_MODE_DUMP>(w, nq, N, Xb, st, [](int, int, int, int) { return QRAG_OK; });
@@ -1538,11 +1784,11 @@ extern "C" int qrag_search_tc_filter(int nq, const uint16_t* Xb, const float* au
     if (rc) return rc;
     if (hist != nullptr) w.hist = hist;
     cudaStream_t st = (cudaStream_t)stream;
-    tau_union_kernel<<<nq, 256, 0, st>>>(bm_top_all, G, nq, k, w.pl.kt, metric, w.pl.Kp, w.qnorm, w.qnorm + w.pl.nq_pad, aux,
-                                         w.bmax, w.pl.nbuckets, w.tau, w.eps, w.hinv);
+    QRAG_CUDA_CHECK(launch_chained(tau_union_kernel, dim3(nq), dim3(256), 0, st, bm_top_all, G, nq, k, w.pl.kt, metric, w.pl.Kp, w.qnorm, w.qnorm + w.pl.nq_pad, aux,
+                                   w.bmax, w.pl.nbuckets, w.tau, w.eps, w.hinv));
     QRAG_LAUNCH_CHECK("tau_union_kernel");
     return tc_gemm_pass<TC_MODE_FILTER>(w, nq, N, Xb, st, [&](int q0, int q1, int nseg, int seg_cap) {
-        surv_hist_kernel<<<q1 - q0, 256, 0, st>>>(w.cnt, w.surv, q0, nseg, seg_cap, w.pl.cap, w.tau, w.hinv, w.hist);
+        QRAG_CUDA_CHECK(launch_chained(surv_hist_kernel, dim3(q1 - q0), dim3(256), 0, st, w.cnt, w.surv, q0, nseg, seg_cap, w.pl.cap, w.tau, w.hinv, w.hist));
         QRAG_LAUNCH_CHECK("surv_hist_kernel");
         return QRAG_OK;
     });
@@ -1571,29 +1817,68 @@ static int tc_finish_impl(const float* Q, int nq, const float* X, int64_t N, int
                          pl.cap, pl.cand_cap, hist_all ? hist_all : w.hist, w.tau, w.hinv, w.cnt, w.surv, w.eps, out_scores,
                          out_ids, status,
                          w.crow, w.ckey, w.cm, pack ? w.cfid : nullptr, pack, kk};
-        tc_collect_kernel<<<q1 - q0, XS_THREADS, 0, st>>>(fp);
+#ifdef QRAG_TUNING
+        fp.tune = getenv("QRAG_TC_TUNE") ? atoi(getenv("QRAG_TC_TUNE")) : 0;
+#endif
+        QRAG_CUDA_CHECK(launch_chained(tc_collect_kernel, dim3(q1 - q0), dim3(XS_THREADS), 0, st, fp));
         QRAG_LAUNCH_CHECK("tc_collect_kernel");
-        const dim3 rgrid((unsigned)(q1 - q0), (unsigned)ceil_div(pl.cand_cap, XS_RESCORE_ROWS));
-        if (pl.smem_final > 48 * 1024) {
-            QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_rescore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_final));
-            QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_rescore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_final));
+        // the bulk-copy form when the rows allow it and two CTAs still share an SM
+        const size_t smem_bulk = rescore_bulk_smem(D);
+        bool bulk = vec && 2 * (smem_bulk + 1024) <= (size_t)device_props().max_smem_optin + 1024;
+#ifdef QRAG_TUNING
+        if (fp.tune & 2) bulk = false;
+#endif
+        int per_sm = 3;                                        // resident CTAs per SM: registers / shared memory
+        if (bulk) {
+            per_sm = (int)((228 * 1024) / (smem_bulk + 1024));
+            if (per_sm > 4) per_sm = 4;
         }
-        if (vec) tc_rescore_kernel<true><<<rgrid, XS_THREADS, pl.smem_final, st>>>(fp);
-        else     tc_rescore_kernel<false><<<rgrid, XS_THREADS, pl.smem_final, st>>>(fp);
+        // chunks of one query side by side only as far as it takes to fill the machine once
+        int ry = (int)ceil_div((int64_t)per_sm * device_props().sm_count, q1 - q0);
+        const int rchunks = (int)ceil_div(pl.cand_cap, XS_RESCORE_ROWS);
+        if (ry > rchunks) ry = rchunks;
+#ifdef QRAG_TUNING
+        if (const char* e = getenv("QRAG_TC_RESCORE_Y")) ry = atoi(e) > 0 ? (atoi(e) < rchunks ? atoi(e) : rchunks) : ry;
+#endif
+        const dim3 rgrid((unsigned)(q1 - q0), (unsigned)ry);
+        // one CTA per query and a list that fits the row stages: the rescoring kernel sorts too
+        fp.fuse_sort = (bulk && ry == 1 && (size_t)pl.cand_cap * 16 <= (size_t)XS_WARPS * XS_ROWS * D * 4) ? 1 : 0;
+#ifdef QRAG_TUNING
+        if (fp.tune & 4) fp.fuse_sort = 0;
+#endif
+        if (bulk) {
+            if (smem_bulk > 48 * 1024)
+                QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_rescore_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bulk));
+            QRAG_CUDA_CHECK(launch_chained(tc_rescore_bulk_kernel, rgrid, dim3(XS_THREADS), smem_bulk, st, fp));
+        } else {
+            if (pl.smem_final > 48 * 1024) {
+                QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_rescore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_final));
+                QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_rescore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_final));
+            }
+            if (vec) QRAG_CUDA_CHECK(launch_chained(tc_rescore_kernel<true>, rgrid, dim3(XS_THREADS), pl.smem_final, st, fp));
+            else     QRAG_CUDA_CHECK(launch_chained(tc_rescore_kernel<false>, rgrid, dim3(XS_THREADS), pl.smem_final, st, fp));
+        }
         QRAG_LAUNCH_CHECK("tc_rescore_kernel");
-        // one compare-exchange per thread and stage: half the candidate capacity, within [256, 1024] threads
-        const int sort_threads = pl.cand_cap / 2 < 256 ? 256 : (pl.cand_cap / 2 > 1024 ? 1024 : pl.cand_cap / 2);
+        // about one compare-exchange per thread and stage for the list length to EXPECT (this shard's share of k plus
+        // the margin; the capacity is several times that), within [256, 1024] threads: small CTAs for short lists,
+        // so that 1024 queries are one wave
+        const int64_t expect = next_pow2(((int64_t)k + G - 1) / G * 5 / 4 + 16);
+        int sort_threads = (int)(expect / 2 < 256 ? 256 : (expect / 2 > 1024 ? 1024 : expect / 2));
+#ifdef QRAG_TUNING
+        if (const char* e = getenv("QRAG_TC_SORT_THREADS")) sort_threads = atoi(e);
+#endif
+        if (fp.fuse_sort) continue;
         if (pack != nullptr) {
             const size_t smem_sort = (size_t)pl.cand_cap * 16;
             if (smem_sort > 48 * 1024)
                 QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_sort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
-            tc_sort_pack_kernel<<<q1 - q0, sort_threads, smem_sort, st>>>(fp);
+            QRAG_CUDA_CHECK(launch_chained(tc_sort_pack_kernel, dim3(q1 - q0), dim3(sort_threads), smem_sort, st, fp));
             QRAG_LAUNCH_CHECK("tc_sort_pack_kernel");
         } else {
             const size_t smem_sort = (size_t)pl.cand_cap * 12;
             if (smem_sort > 48 * 1024)
                 QRAG_CUDA_CHECK(cudaFuncSetAttribute(tc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
-            tc_sort_kernel<<<q1 - q0, sort_threads, smem_sort, st>>>(fp);
+            QRAG_CUDA_CHECK(launch_chained(tc_sort_kernel, dim3(q1 - q0), dim3(sort_threads), smem_sort, st, fp));
             QRAG_LAUNCH_CHECK("tc_sort_kernel");
         }
     }
@@ -1644,7 +1929,7 @@ extern "C" int qrag_owner_finalize(const int64_t* recv, int G, int per, int kk, 
         QRAG_CUDA_CHECK(cudaFuncSetAttribute(owner_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     OwnerParams op{reinterpret_cast<const long long*>(recv), G, per, kk, k1, k2, metric == QRAG_METRIC_L2 ? 1 : 0, q_base,
                    nq, reinterpret_cast<long long*>(out)};
-    owner_finalize_kernel<<<per, 1024, smem, (cudaStream_t)stream>>>(op);
+    QRAG_CUDA_CHECK(launch_chained(owner_finalize_kernel, dim3(per), dim3(1024), smem, (cudaStream_t)stream, op));
     QRAG_LAUNCH_CHECK("owner_finalize_kernel");
     return QRAG_OK;
 }

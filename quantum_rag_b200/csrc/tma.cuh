@@ -55,6 +55,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+// Ask L2 for a contiguous global range without a destination (SASS UBLKPF): one instruction per row of a gather,
+// issued long before the loads that consume it.  src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // programmatic dependent launch (PDL): allow the next kernel on the stream to begin launching /
 // block until every kernel this one depends on has completed and its writes are visible
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
