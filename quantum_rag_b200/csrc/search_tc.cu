@@ -708,7 +708,7 @@ __device__ void block_topk_values(RadixSel& rs, int k, int total, ForEach for_ea
 // The select kernels make four radix passes (and the top-k form a fifth, collecting) over the same few thousand
 // values: read them from global memory once into shared memory when they fit (ncu r02: tau_union barrier- and
 // scoreboard-bound, 40 registers = 6 CTAs per SM = 1.15 waves of 1024 queries; now 8 CTAs per SM, one wave).
-constexpr int SEL_CACHE = 3072;
+constexpr int SEL_CACHE = 5120;                // 20 KB: eight CTAs of a select kernel still share an SM
 template <class Load>
 __device__ __forceinline__ void sel_fill(float* sv, int total, Load load) {
     for (int i = threadIdx.x; i < total; i += 8 * blockDim.x) {
@@ -1532,11 +1532,14 @@ static int tc_plan(int nq, int64_t N, int D, int k, int metric, int shards, TcPl
     }
     // pass 1 samples every `sample`-th tile: survivors ~ sample * k per query, kept well under the capacity,
     // and the sample must hold many more buckets than k for the bound to be tight
-    // (the threshold comes from the union of all shards' samples, so a shard of a G-way search samples G x less)
+    // (the threshold comes from the union of all shards' samples: a shard of a G-way search expects sample * k / G)
     QRAG_REQUIRE(shards >= 1 && shards <= 1024, QRAG_ERR_INVALID, "shards=%d", shards);
     int64_t sample = (int64_t)cap * shards / (4 * (int64_t)k);
-    if (sample > 64) sample = 64;
-    if (sample > 16 * (int64_t)shards) sample = 16 * (int64_t)shards;
+    // every 16th tile at most, whatever the shard count: pass 1 costs ~ (filter pass) / sample, the survivors it leaves
+    // the filter pass cost ~ 0.002 ms per unit of `sample` (k = 1000, measured per stage with tools/shard_stage_probe.py
+    // --samples at G = 1, 2, 4, 8): the sum is flat between 12 and 24 and rises beyond (G = 4: 1.85 ms at 16, 1.93 at
+    // 32, 2.06 at 64; round 2 sampled G x more sparsely on a G-way shard)
+    if (sample > 16) sample = 16;
     const int64_t by_buckets = N * shards / ((int64_t)256 * k);
     if (sample > by_buckets) sample = by_buckets;
     if (sample < 1) sample = 1;

@@ -24,7 +24,10 @@ def _compare_with_exact(api, Q, X, k, name, id_base=0, allow_fallback=False):
 @pytest.mark.parametrize("name,mid", METRICS)
 @pytest.mark.parametrize("nq,N,D,k", [(5, 3000, 64, 10), (130, 20000, 384, 100), (1, 70000, 384, 100),
                                       (300, 66000, 128, 37), (64, 50000, 96, 1000), (7, 9000, 40, 7),
-                                      (33, 30011, 1536, 20), (9, 5000, 50, 12), (3, 4000, 33, 5)])   # D % 4 != 0: scalar rows
+                                      (33, 30011, 1536, 20), (9, 5000, 50, 12), (3, 4000, 33, 5),     # D % 4 != 0: scalar rows
+                                      # >= 592 queries: one rescoring CTA per query, which loops over the list's chunks
+                                      # and (rows long enough to hold the list in their stages) sorts it too
+                                      (640, 40000, 384, 300), (600, 20000, 64, 200)])
 def test_tc_search_equals_exact_search(cuda, name, mid, nq, N, D, k):
     from quantum_rag_b200 import api
     rng = np.random.RandomState(nq + N + D + k)

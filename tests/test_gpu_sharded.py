@@ -120,6 +120,36 @@ def test_sharded_path_matches_oracle_and_single_shard(cuda, metric):
         assert torch.equal(ids, res.ids) and torch.equal(top, res.scores), f"packed G={G}"
 
 
+@pytest.mark.parametrize("metric", ["cosine", "l2"])
+def test_sharded_path_many_queries(cuda, metric):
+    """Enough queries that one CTA rescoring a query's whole list also sorts and packs it (the fused tail of
+    tc_rescore_bulk_kernel, lists of several 128-candidate chunks); fewer queries take the separate sort kernels."""
+    import torch
+    from quantum_rag_b200.sharded import ShardedSearchRerank
+    rng = np.random.RandomState(14)
+    n, d, nq, k1, k2 = 24000, 384, 640, 200, 10
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((nq, d)).astype(np.float32)
+    X[n - 3] = X[2]
+    Q[5] = X[2]
+    Xd, Qd = torch.from_numpy(X).cuda(), torch.from_numpy(Q).cuda()
+    path = ShardedSearchRerank(Xd, n, metric)
+    res = path(Qd, k1, k2, return_search_lists=True)
+    own = path(Qd, k1, k2)
+    assert path.last_rerun == 0
+    assert torch.equal(own.ids, res.ids) and torch.equal(own.scores, res.scores)
+    mid = {"cosine": osr.METRIC_COSINE, "l2": osr.METRIC_L2}[metric]
+    rs, ri = osr.exact_search(Q, X, k1, mid)
+    assert np.array_equal(res.search_ids.cpu().numpy(), ri)
+    f = oq.amplitude_fidelity_batch(Q, X[ri])
+    order = oq.rank_rows(f, k2)
+    assert np.array_equal(res.ids.cpu().numpy(), np.take_along_axis(ri, order, 1))
+    assert np.allclose(res.scores.cpu().numpy(), np.take_along_axis(f, order, 1), rtol=1e-12, atol=1e-16)
+    for G in (2, 8):
+        top, ids = _emulated_packed(Xd, Qd, G, k1, k2, metric)
+        assert torch.equal(ids, res.ids) and torch.equal(top, res.scores), f"packed G={G}"
+
+
 def test_owner_finalize_vs_oracle_random_records(cuda):
     """qrag_owner_finalize against the NumPy restatement on synthetic records: ties in score (id decides) and in
     fidelity (merged position decides), short and empty lists, flagged shards, padding queries, k2 == k1."""

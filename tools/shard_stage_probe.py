@@ -28,8 +28,24 @@ def main():
     ap.add_argument("--k1", type=int, default=1000)
     ap.add_argument("--k2", type=int, default=10)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--samples", default="", help="comma-separated pass-1 sample rates to compare (QRAG_TC_SAMPLE: "
+                    "builds libqrag with -DQRAG_TUNING for the run and restores the product build afterwards)")
     a = ap.parse_args()
-    _lib.build()
+    if not a.samples:
+        _lib.build()
+        probe(a)
+        return
+    _lib.build(force=True, tuning=True)
+    try:
+        for smp in a.samples.split(","):
+            os.environ["QRAG_TC_SAMPLE"] = smp
+            probe(a, {"sample": int(smp)})
+    finally:
+        os.environ.pop("QRAG_TC_SAMPLE", None)
+        _lib.build(force=True)
+
+
+def probe(a, extra=None):
     G, nq, k1, k2 = a.G, a.nq, a.k1, a.k2
     n = a.N // G
     g = torch.Generator(device="cuda").manual_seed(1238)
@@ -102,7 +118,7 @@ def main():
         batch()
     rep = timed(graph.replay)
     hdr = send[:nq, 0]
-    res = {"G": G, "shard_rows": n, "nq": nq, "k1": k1, "k2": k2, "kk": kk, "stage_ms": {k: round(v, 4) for k, v in stage.items()},
+    res = {**(extra or {}), "G": G, "shard_rows": n, "nq": nq, "k1": k1, "k2": k2, "kk": kk, "stage_ms": {k: round(v, 4) for k, v in stage.items()},
            "eager_ms": round(eager, 4), "graph_replay_ms": round(rep, 4),
            "valid_entries_max": int((hdr & 0xFFFFFFFF).max()), "flagged": int((hdr >> 32).count_nonzero())}
     print(json.dumps(res))
