@@ -320,6 +320,15 @@ class FlatIndexTC:
         self._ws = None
         self.last_fallback = 0          # queries the last search() had to rerun exactly
 
+    def fork(self) -> "FlatIndexTC":
+        """A second handle on the same rows and shadow with its own search workspace and phase state (nothing is
+        copied): two searches can then be between their exchange points at once (sharded.py lanes)."""
+        import copy
+        f = copy.copy(self)
+        f._ws = None
+        f._phase = None
+        return f
+
     def _workspace(self, nq: int, k: int, shards: int = 1) -> torch.Tensor:
         lib = _lib.load()
         nbytes = ctypes.c_size_t(0)

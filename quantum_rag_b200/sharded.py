@@ -34,6 +34,7 @@ and it raises without a GPU -- there is no CPU fallback in the product path.
 """
 from __future__ import annotations
 
+import copy
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -65,6 +66,16 @@ class CudaEngine:
         self.index = api.FlatIndexTC(X_shard, metric, id_base=id_base)
         self.metric = metric
         self.device = self.index.X.device
+        self._views = [self]
+
+    def lane(self, i: int) -> "CudaEngine":
+        """View number ``i`` of this engine: the same rows and 16-bit shadow, its own search workspace and phase
+        state, so that two batches can be between their exchange points at the same time (view 0 is the engine)."""
+        while len(self._views) <= i:
+            v = copy.copy(self)
+            v.index = self.index.fork()
+            self._views.append(v)
+        return self._views[i]
 
     def search(self, Q, k):
         return self.index.search(Q, k)
@@ -119,13 +130,19 @@ class PendingResult:
     host synchronisation of the path) and, if some shard could not certify a query or had to cut a list, reruns the
     batch through the all-gather form -- identically on every rank, because the flag was all-gathered with the result."""
 
-    def __init__(self, path, Q, k1, k2, top, ids, flag):
+    def __init__(self, path, Q, k1, k2, top, ids, flag, event=None):
         self.path, self.Q, self.k1, self.k2 = path, Q, k1, k2
         self.top, self.ids, self.flag = top, ids, flag
+        self.event = event            # end of the batch on its lane's stream (None: queued on the caller's stream)
         self._done = None
 
     def result(self) -> ShardedResult:
         if self._done is None:
+            if self.event is not None:
+                cur = torch.cuda.current_stream()
+                cur.wait_event(self.event)
+                for t in (self.top, self.ids, self.flag):   # allocated on the lane's stream, read on the caller's
+                    t.record_stream(cur)
             bad = int(self.flag.item())
             self.path._flush_marks()
             if bad:
@@ -143,7 +160,7 @@ class ShardedSearchRerank:
     """Search the row-sharded corpus, merge over the process group, quantum-rerank the merged list."""
 
     def __init__(self, X_shard, n_total: int, metric: str = "cosine", group: Optional[dist.ProcessGroup] = None,
-                 engine=None):
+                 engine=None, lanes: Optional[int] = None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -157,12 +174,32 @@ class ShardedSearchRerank:
         self.metric = metric
         self.profile = None          # set to {} to collect per-stage CUDA-event timings (ms) of the next call
         self._marks = []
-        self._bufs = {}
         self._graphs = {}
         self.last_rerun = 0          # 1 if the last call had to rerun through the all-gather form
         self.engine = engine if engine is not None else CudaEngine(X_shard, metric, self.lo)
         if hasattr(self.engine, "sync_corpus_bound"):
             self.engine.sync_corpus_bound(self._all_reduce_max)
+        # Lanes: ``submit`` alternates between `lanes` independent (stream, process group, workspace, exchange buffers)
+        # sets, so that one batch's collectives and per-query kernels run beside the next batch's filter GEMM instead
+        # of in front of it.  Each lane has its own communicator: NCCL runs a communicator's collectives in issue
+        # order on one internal stream, and a single one would chain the two batches together again.  Every rank
+        # creates the groups here, in the same order (new_group is collective).
+        can = hasattr(self.engine, "lane")
+        self.n_lanes = max(1, int(lanes)) if lanes is not None else (2 if can else 1)
+        if self.n_lanes > 1 and not can:
+            raise ValueError("this engine has no lane() views: lanes must be 1")
+        self._lane_groups = [group]
+        for _ in range(1, self.n_lanes):
+            g = None
+            if self.world > 1:
+                g = dist.new_group(ranks=dist.get_process_group_ranks(group) if group is not None else None)
+            self._lane_groups.append(g)
+        dev = getattr(self.engine, "device", None)
+        on_gpu = dev is not None and torch.device(dev).type == "cuda"
+        self._lane_streams = [torch.cuda.Stream(device=dev) if (on_gpu and self.n_lanes > 1) else None
+                              for _ in range(self.n_lanes)]
+        self._lane_bufs = [dict() for _ in range(self.n_lanes)]
+        self._next_lane = 0
 
     def close(self) -> None:
         """Drop the captured CUDA graphs (``submit(graph=True)``).  Call it before ``destroy_process_group``: a graph
@@ -183,17 +220,17 @@ class ShardedSearchRerank:
             self._marks = []
 
     # ------------------------------------------------------------------ exchange steps
-    def _all_gather(self, t: torch.Tensor) -> torch.Tensor:
+    def _all_gather(self, t: torch.Tensor, group=None) -> torch.Tensor:
         if self.world == 1:
             return t[None]
         t = t.contiguous()
         out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t, group=self.group)           # concatenation along dim 0
+        dist.all_gather_into_tensor(out, t, group=group or self.group)  # concatenation along dim 0
         return out.view((self.world,) + tuple(t.shape))
 
-    def _all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+    def _all_reduce_sum(self, t: torch.Tensor, group=None) -> torch.Tensor:
         if self.world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group or self.group)
         return t
 
     def _all_reduce_max(self, t: torch.Tensor) -> torch.Tensor:
@@ -258,10 +295,11 @@ class ShardedSearchRerank:
         top, ids = self.rerank(Q, si, min(k2, k1))
         return ShardedResult(top, ids, ss, si)
 
-    def _buffers(self, nq: int, kk: int, k2: int, device):
-        """Exchange buffers of the packed path, allocated once per shape (send rows beyond nq stay zero: empty records)."""
+    def _buffers(self, lane: int, nq: int, kk: int, k2: int, device):
+        """Exchange buffers of the packed path, one set per lane, allocated once per shape (send rows beyond nq stay
+        zero: empty records)."""
         key = (nq, kk, k2, str(device))
-        b = self._bufs.get(key)
+        b = self._lane_bufs[lane].get(key)
         if b is None:
             per = -(-nq // self.world)
             rec, orec = 3 * kk + 1, 2 * k2 + 1
@@ -270,31 +308,34 @@ class ShardedSearchRerank:
                  "recv": torch.empty((self.world, per, rec), dtype=torch.int64, device=device),
                  "out": torch.empty((per, orec), dtype=torch.int64, device=device),
                  "res": torch.empty((self.world, per, orec), dtype=torch.int64, device=device)}
-            self._bufs = {key: b}
+            self._lane_bufs[lane] = {key: b}
         return b
 
-    def _enqueue_packed(self, Q, k1: int, k2: int):
-        """Queue one batch of the packed path on the current stream (no host synchronisation):
+    def _enqueue_packed(self, Q, k1: int, k2: int, lane: int = 0):
+        """Queue one batch of the packed path on the current stream (no host synchronisation), with lane ``lane``'s
+        workspace, exchange buffers and process group:
         search phases with their two threshold exchanges, ONE all-to-all of per-query records to the query's owner,
         one owner kernel, one small all-gather.  Returns (fidelity [nq, k2], ids [nq, k2], flag [1]) device tensors;
         flag != 0 means some shard could not certify a query or had to cut a list."""
-        G, eng = self.world, self.engine
+        G = self.world
+        eng = self.engine.lane(lane) if self.n_lanes > 1 else self.engine
+        grp = self._lane_groups[lane]
         nq = Q.shape[0]
         kk = exchange_len(k1, G)
         bm = eng.packed_begin(Q, k1, G)
-        bm_all = self._all_gather(bm) if G > 1 else None
+        bm_all = self._all_gather(bm, grp) if G > 1 else None
         self._mark("begin+gather")
         hist = eng.packed_filter(bm_all)
         if G > 1:
-            self._all_reduce_sum(hist)
+            self._all_reduce_sum(hist, grp)
         self._mark("filter+reduce")
         dev = getattr(eng, "device", Q.device)
-        buf = self._buffers(nq, kk, k2, dev)
+        buf = self._buffers(lane, nq, kk, k2, dev)
         per = buf["per"]
         eng.packed_finish(hist, kk, buf["send"])
         self._mark("finish_packed")
         if G > 1:
-            dist.all_to_all_single(buf["recv"].view(G * per, -1), buf["send"], group=self.group)
+            dist.all_to_all_single(buf["recv"].view(G * per, -1), buf["send"], group=grp)
             recv = buf["recv"]
         else:
             recv = buf["send"].view(1, per, -1)
@@ -302,7 +343,7 @@ class ShardedSearchRerank:
         out = eng.owner_finalize(recv, kk, k1, k2, self.rank * per, nq, buf["out"])
         self._mark("owner_finalize")
         if G > 1:
-            dist.all_gather_into_tensor(buf["res"].view(G * per, -1), out, group=self.group)
+            dist.all_gather_into_tensor(buf["res"].view(G * per, -1), out, group=grp)
             res = buf["res"].view(G * per, -1)[:nq]
         else:
             res = out[:nq]
@@ -323,9 +364,25 @@ class ShardedSearchRerank:
             Q = torch.as_tensor(Q)
         k2 = min(k2, k1)
         if not graph:
-            self._mark("start")
-            top, ids, flag = self._enqueue_packed(Q, k1, k2)
-            return PendingResult(self, Q, k1, k2, top, ids, flag)
+            lane = self._next_lane
+            self._next_lane = (lane + 1) % self.n_lanes
+            side = self._lane_streams[lane]
+            if side is None:
+                self._mark("start")
+                top, ids, flag = self._enqueue_packed(Q, k1, k2, lane)
+                return PendingResult(self, Q, k1, k2, top, ids, flag)
+            if Q.device != side.device:
+                Q = Q.to(side.device, non_blocking=True)
+            side.wait_stream(torch.cuda.current_stream())           # Q may have been produced on the caller's stream
+            with torch.cuda.stream(side):
+                self._mark("start")
+                top, ids, flag = self._enqueue_packed(Q, k1, k2, lane)
+                done = torch.cuda.Event()
+                done.record(side)
+            return PendingResult(self, Q, k1, k2, top, ids, flag, done)
+        for side in self._lane_streams:                             # the replay shares lane 0's workspace and buffers
+            if side is not None:
+                torch.cuda.current_stream().wait_stream(side)
         key = (tuple(Q.shape), k1, k2)
         g = self._graphs.get(key)
         if g is None:

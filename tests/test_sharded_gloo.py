@@ -282,3 +282,56 @@ def test_submit_keeps_several_batches_in_flight_and_reruns_only_the_flagged_one(
         for b, (scores, ids, reran) in enumerate(out[rank]):
             assert np.array_equal(ids, want[b].ids.numpy()) and np.array_equal(scores, want[b].scores.numpy()), (rank, b)
             assert reran == (b == 2)
+
+
+class LanedOracleEngine(PhasedOracleEngine):
+    """OracleEngine with ``lane()`` views (separate per-batch state), which switches ShardedSearchRerank to two lanes:
+    alternate batches go through alternate process groups, workspaces and exchange buffers."""
+
+    def lane(self, i):
+        views = self.__dict__.setdefault("_views", {})
+        if i not in views:
+            import copy
+            v = copy.copy(self)
+            v.lane_id = i
+            views[i] = v
+        return views[i]
+
+
+def _laned_worker(rank, world, port, n, d, nq, k1, k2, metric, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        X, _ = _data(n, d, nq)
+        lo, hi = shard_bounds(n, world, rank)
+        rng = np.random.RandomState(91)
+        batches = [torch.from_numpy(rng.standard_normal((nq, d)).astype(np.float32)) for _ in range(5)]
+        path = ShardedSearchRerank(torch.from_numpy(X[lo:hi]), n, metric, engine=LanedOracleEngine(X[lo:hi], metric, lo))
+        assert path.n_lanes == 2 and path._lane_groups[1] is not None and path._lane_groups[1] is not path._lane_groups[0]
+        pend = [path.submit(Q, k1, k2) for Q in batches]
+        used = sorted(v.lane_id for v in path.engine._views.values())
+        res = [p.result() for p in pend]
+        again = path(batches[1], k1, k2)                     # one at a time after the queue drained
+        out[rank] = ([(r.scores.numpy(), r.ids.numpy()) for r in res + [again]], used,
+                     [len(b) for b in path._lane_bufs])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_lanes_alternate_process_groups_and_give_the_single_rank_result():
+    world, metric, n, d, nq, k1, k2 = 3, osr.METRIC_COSINE, 500, 10, 6, 40, 7
+    X, _ = _data(n, d, nq)
+    rng = np.random.RandomState(91)
+    batches = [rng.standard_normal((nq, d)).astype(np.float32) for _ in range(5)]
+    single = ShardedSearchRerank(torch.from_numpy(X), n, metric, engine=OracleEngine(X, metric, 0))
+    assert single.n_lanes == 1
+    want = [single(torch.from_numpy(Q), k1, k2) for Q in batches]
+    want.append(want[1])
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_laned_worker, args=(world, _free_port(), n, d, nq, k1, k2, metric, out), nprocs=world, join=True)
+    for rank in range(world):
+        got, used, nbufs = out[rank]
+        assert used == [0, 1] and nbufs == [1, 1]            # both lanes ran, each with its own exchange buffers
+        for b, (scores, ids) in enumerate(got):
+            assert np.array_equal(ids, want[b].ids.numpy()) and np.array_equal(scores, want[b].scores.numpy()), (rank, b)

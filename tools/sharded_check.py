@@ -85,8 +85,21 @@ def main():
     ms_sync, res = timed(lambda: [path(Q, a.k1, a.k2) for _ in range(a.steps)][-1])
     # (2) a serving loop: batches queued back to back, certificates read afterwards (all inside the timed region)
     ms_pipe, res_p = timed(lambda: [p.result() for p in [path.submit(Q, a.k1, a.k2) for _ in range(a.steps)]][-1])
-    modes = {"sync_per_batch_ms": ms_sync, "pipelined_ms": ms_pipe,
-             "pipelined_equal": bool(torch.equal(res_p.ids, res.ids) and torch.equal(res_p.scores, res.scores))}
+    lanes = path.n_lanes
+    queue = lambda: [p.result() for p in [path.submit(Q, a.k1, a.k2) for _ in range(a.steps)]][-1]
+    two, one = [ms_pipe], []
+    for _ in range(3):                                     # A/B, alternating: the same queue through one lane / two lanes
+        path.n_lanes, path._next_lane = 1, 0
+        t, res_1 = timed(queue)
+        one.append(t)
+        path.n_lanes = lanes
+        two.append(timed(queue)[0])
+    ms_one, ms_pipe2 = sorted(one)[1], sorted(two)[len(two) // 2]
+    modes = {"sync_per_batch_ms": ms_sync, "pipelined_ms": ms_pipe, "pipelined_again_ms": ms_pipe2, "lanes": lanes,
+             "pipelined_single_lane_ms": ms_one,
+             "runs_two_lanes": [round(x, 4) for x in two], "runs_single_lane": [round(x, 4) for x in one],
+             "pipelined_equal": bool(torch.equal(res_p.ids, res.ids) and torch.equal(res_p.scores, res.scores) and
+                                     torch.equal(res_1.ids, res.ids) and torch.equal(res_1.scores, res.scores))}
     if a.graph:
         for _ in range(2):
             path.submit(Q, a.k1, a.k2, graph=True).result()
