@@ -223,14 +223,23 @@ def bench_search(api, peaks, steps=20, oracle_check=False):
 def bench_circuit(api, fma_rate, steps=20):
     """K1, the reference circuit itself (quantum.py:138-167: RY/RZ per qubit + CX chain, exact complex128 statevector,
     |<psi_d|psi_q>|^2): (a) the string-API shape, n = 4 qubits, 1000 queries x 100 documents of 8-component mock
-    embeddings; (b) the angle-circuit variant of config 2: n = 9 qubits on the first 9 components of the
-    384-d embeddings.  Bound: FP64 pipe; flops per score = 12 n 2^n + 8 2^n, peak = 2 x the measured FMA rate."""
+    embeddings (one call is two short launches: host-bound at this size, so the same shape at 10x the queries is timed
+    too); (b) the angle-circuit variant of config 2: n = 9 qubits on the first 9 components of the 384-d
+    embeddings.  Bound: FP64 pipe / instruction issue.  Two figures: `dense_equivalent_tflops` = SURVEY 8d's dense count
+    (12 n 2^n + 8 2^n flops per score) over the time -- the kernels skip the amplitudes that are still exactly zero while
+    the first block of gates is applied to |0..0>, so this is NOT a pipe utilisation and can exceed the peak -- and
+    `roofline` = the FP64 instructions the kernel really executes per score (counted in its SASS: the single-block path is
+    straight-line code) against the FMA rate measured in this run."""
     import torch
+    # FP64 thread-instructions per score, cuobjdump -sass of sva_thread_kernel<4,0,0> (DFMA+DMUL+DADD per thread) and
+    # sva_warp_kernel<9,0,0> (per warp x 32 lanes); the query states add 1/C of that and are left out
+    executed = {4: 332 + 128 + 12, 9: (227 + 95 + 18) * 32}
     res = {}
-    for name, n, vec_len in (("n4_string_api_shape", 4, 8), ("n9_config2_angle_variant", 9, 9)):
+    for name, n, vec_len, nq in (("n4_string_api_shape", 4, 8, NQ), ("n4_string_api_shape_x10", 4, 8, 10 * NQ),
+                                 ("n9_config2_angle_variant", 9, 9, NQ)):
         g = torch.Generator(device="cuda").manual_seed(1234 + 20 + n)
-        q = torch.rand(NQ, vec_len, generator=g, device="cuda", dtype=torch.float64)
-        d = torch.rand(NQ * C, vec_len, generator=g, device="cuda", dtype=torch.float64)
+        q = torch.rand(nq, vec_len, generator=g, device="cuda", dtype=torch.float64)
+        d = torch.rand(nq * C, vec_len, generator=g, device="cuda", dtype=torch.float64)
         for _ in range(3):
             out = api.sv_fidelity_angle(q, d, docs_per_query=C, n_qubits=n, layers=1)
         torch.cuda.synchronize()
@@ -242,16 +251,20 @@ def bench_circuit(api, fma_rate, steps=20):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         flops = (12 * n + 8) * (1 << n)
-        rate = NQ * C / (ms * 1e-3)
+        rate = nq * C / (ms * 1e-3)
         q2 = q[:1].repeat(2, 1)
         self_f = float(api.sv_fidelity_angle(q2[:1], q2[1:], docs_per_query=1, n_qubits=n, layers=1)[0])
-        res[name] = {"n_qubits": n, "pairs": NQ * C, "ms_per_batch": ms, "scores_per_s": rate,
+        res[name] = {"n_qubits": n, "pairs": nq * C, "ms_per_batch": ms, "scores_per_s": rate,
                      "self_fidelity_err": abs(self_f - 1.0), "in_unit_interval": bool(((out >= -1e-12) & (out <= 1 + 1e-12)).all()),
-                     "roofline": {"bound": "fp64 pipe", "achieved": rate * flops / 1e12, "peak": 2 * fma_rate / 1e12,
-                                  "unit": "TFLOP/s (fp64)", "frac": rate * flops / (2 * fma_rate),
-                                  "flops_per_score": flops, "peak_source": "qrag_probe_fp64_fma_rate, measured in this run"}}
-    res["kernels"] = ["qrag::sv_angle_warp_kernel (n <= 5: one warp per state, shuffles)",
-                      "qrag::sv_cta_kernel (n >= 6: 2^n complex128 amplitudes staged in shared memory)"]
+                     "dense_equivalent_tflops": rate * flops / 1e12, "dense_flops_per_score": flops,
+                     "roofline": {"bound": "fp64 pipe", "achieved": rate * executed[n], "peak": fma_rate,
+                                  "unit": "FP64 thread-instructions/s", "frac": rate * executed[n] / fma_rate,
+                                  "fp64_instr_per_score": executed[n],
+                                  "peak_source": "qrag_probe_fp64_fma_rate, measured in this run"}}
+    res["kernels"] = ["qrag::sva_thread_kernel<n> (n <= 5: one thread per state, 2^n amplitudes in registers; pass 1 query "
+                      "states, pass 2 document states + overlap, chained by programmatic dependent launch)",
+                      "qrag::sva_warp_kernel<n> (6 <= n <= 10: one warp per state, 2^(n-5) amplitudes per lane)",
+                      "qrag::sv_cta_kernel (n = 11, 12: amplitudes staged in shared memory)"]
     return res
 
 

@@ -16,7 +16,7 @@ from typing import Dict, List, Optional
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libqrag.so")
-SOURCES = ["lib.cu", "probe.cu", "amp_fidelity.cu", "amp_stream.cu", "sv_kernels.cu", "sort_scores.cu", "fmap_warp.cu", "fmap_rerank.cu", "search_exact.cu", "search_tc.cu"]
+SOURCES = ["lib.cu", "probe.cu", "amp_fidelity.cu", "amp_stream.cu", "sv_kernels.cu", "sv_angle.cu", "sort_scores.cu", "fmap_warp.cu", "fmap_rerank.cu", "search_exact.cu", "search_tc.cu"]
 # Kernel-tuning hooks (environment switches that skip or re-shape work inside product kernels) compile only with
 # -DQRAG_TUNING, which is NOT in these flags: the shipped library reads no environment variable.
 NVCC_FLAGS = [

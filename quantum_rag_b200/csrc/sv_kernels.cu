@@ -4,11 +4,8 @@
 // pair): QuantumReranker._quantum_similarity / _vector_to_circuit,
 // /root/reference/src/reranker/quantum.py:108-167.
 //
-// Two kernels, both complex128:
-//  * sv_angle_warp_kernel  (n_qubits <= 5): 2^n lanes hold one amplitude each of the
-//    query state and of the document state; gates are __shfl_xor exchanges, the CX
-//    chain is a single arbitrary-lane shuffle, the overlap a shuffle butterfly.
-//  * sv_cta_kernel (n_qubits <= 12): the 2^n amplitudes are staged in shared memory
+// complex128 throughout.  n_qubits <= 10 runs with the states in registers (sv_angle.cu); here:
+//  * sv_cta_kernel (n_qubits = 11, 12, and the fall-back of the feature map): the 2^n amplitudes are staged in shared memory
 //    (double2, XOR-swizzled so that all radix-8 passes are bank-conflict free); each
 //    pass applies up to three qubits' RY/RZ in registers; the pass that finishes a
 //    layer scatters through the CX-chain permutation into the other buffer.
@@ -47,78 +44,6 @@ __device__ __forceinline__ void apply_gate(const GateParams& g, double2& a0, dou
 __device__ __forceinline__ int prefix_xor(int x) {
     x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8;
     return x;
-}
-
-// ===========================================================================
-// warp path, n <= 5
-// ===========================================================================
-struct SvAngleParams {
-    const double* qvec; const double* dvec; const int32_t* doc_query;
-    int64_t nd, docs_per_query; int nq, vec_len, n, layers;
-    double* out;
-};
-
-__device__ __forceinline__ double group_sum(double v, int n) {
-    for (int o = 1; o < (1 << n); o <<= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
-    return v;
-}
-
-__global__ void __launch_bounds__(128) sv_angle_warp_kernel(const SvAngleParams p) {
-    const int n = p.n, dim = 1 << n;
-    const int lane = threadIdx.x & 31;
-    const int a = lane & (dim - 1);                       // amplitude index owned by this lane
-    const int per_warp = 32 >> n;
-    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t jraw = warp_global * per_warp + (lane >> n);
-    const bool live = jraw < p.nd;
-    const int64_t j = live ? jraw : p.nd - 1;             // clamp so every lane joins the shuffles
-    const int64_t qi = p.doc_query ? (int64_t)p.doc_query[j] : j / p.docs_per_query;
-    const double* v[2] = {p.qvec + qi * p.vec_len, p.dvec + j * p.vec_len};
-
-    double vnorm[2];
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        double n2 = 0.0;
-        for (int i = 0; i < p.vec_len; ++i) n2 = fma(v[s][i], v[s][i], n2);
-        const double nrm = sqrt(n2);
-        vnorm[s] = nrm;                                    // divide by it like quantum.py:151
-    }
-    double2 st[2];
-    st[0] = make_double2(a == 0 ? 1.0 : 0.0, 0.0);
-    st[1] = st[0];
-    const int limit = p.vec_len < n ? p.vec_len : n;       // quantum.py:158
-    const int src_lane = (lane & ~(dim - 1)) | ((a ^ (a << 1)) & (dim - 1));   // CX chain: new[y] = old[y ^ (y<<1)]
-    for (int layer = 0; layer < p.layers; ++layer) {
-        for (int k = 0; k < n; ++k) {
-            if (p.layers == 1 && k >= limit) continue;
-            const int comp = (layer * n + k) % p.vec_len;
-            const bool hi = (a >> k) & 1;
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const double x = v[s][comp];
-                const double an = vnorm[s] > 0.0 ? x / vnorm[s] : x;
-                const GateParams g = gate_params(an);
-                double2 other;
-                other.x = __shfl_xor_sync(FULL_MASK, st[s].x, 1 << k);
-                other.y = __shfl_xor_sync(FULL_MASK, st[s].y, 1 << k);
-                double2 a0 = hi ? other : st[s];
-                double2 a1 = hi ? st[s] : other;
-                apply_gate(g, a0, a1);
-                st[s] = hi ? a1 : a0;
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            st[s].x = __shfl_sync(FULL_MASK, st[s].x, src_lane);
-            st[s].y = __shfl_sync(FULL_MASK, st[s].y, src_lane);
-        }
-    }
-    // <psi_d | psi_q> = sum conj(d) q
-    double re = st[1].x * st[0].x + st[1].y * st[0].y;
-    double im = st[1].x * st[0].y - st[1].y * st[0].x;
-    re = group_sum(re, n);
-    im = group_sum(im, n);
-    if (live && a == 0) p.out[j] = re * re + im * im;
 }
 
 // ===========================================================================
@@ -330,6 +255,9 @@ static int launch_sv_cta(SvCtaParams p, cudaStream_t st) {
     return QRAG_OK;
 }
 
+int sv_angle_registers(const double* qvec, int nq, const double* dvec, int64_t nd, const int32_t* doc_query,
+                       int64_t docs_per_query, int vec_len, int n_qubits, int layers, double* out, cudaStream_t st);  // sv_angle.cu
+
 int fmap_warp_try(const float* Q, int nq, const float* cand, const float* X, int64_t N, const int64_t* idx, int64_t C, int D,
                   int n_qubits, int layers, double* out64, float* out32, cudaStream_t st, bool* handled);  // fmap_warp.cu
 
@@ -409,15 +337,10 @@ extern "C" int qrag_sv_fidelity_angle(const double* qvec, int nq, const double* 
     const DeviceProps& dp = device_props();
     QRAG_REQUIRE(dp.ok, QRAG_ERR_CUDA, "no CUDA device available (libqrag has no CPU fallback)");
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_qubits <= 5) {
-        SvAngleParams p{qvec, dvec, doc_query, nd, docs_per_query, nq, vec_len, n_qubits, layers, out_scores};
-        const int per_warp = 32 >> n_qubits;
-        const int64_t warps = ceil_div(nd, per_warp);
-        const int64_t grid = ceil_div(warps, 4);
-        QRAG_REQUIRE(grid <= 0x7fffffff, QRAG_ERR_UNSUPPORTED, "too many documents for one launch");
-        sv_angle_warp_kernel<<<(unsigned)grid, 128, 0, st>>>(p);
-        QRAG_LAUNCH_CHECK("sv_angle_warp_kernel");
-        return QRAG_OK;
+    if (n_qubits <= 10) {                                   // states in registers (sv_angle.cu)
+        QRAG_REQUIRE(ceil_div(nd, 128) <= 0x7fffffff, QRAG_ERR_UNSUPPORTED, "too many documents for one launch");
+        return sv_angle_registers(qvec, nq, dvec, nd, doc_query, doc_query ? 1 : docs_per_query, vec_len, n_qubits,
+                                  layers, out_scores, st);
     }
     SvCtaParams p{};
     p.qvec = qvec; p.dvec = dvec; p.doc_query = doc_query; p.nd = nd;
