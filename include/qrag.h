@@ -140,6 +140,20 @@ int qrag_amp_rerank(const float* Q, int nq,
                     double* out_scores, int32_t* out_pos, int64_t* out_ids,
                     void* stream);
 
+/* (1c, host form) The same rerank called with HOST buffers -- what a serving process behind a retrieval step holds
+ * (the string API's documents, quantum.py:44-78, resolved to row ids): queries hQ [nq, D] fp32 and candidate ids
+ * hIdx [nq, C] int64 in (pinned) host memory, the corpus X [N, D] resident on the device.  One call enqueues on
+ * `stream`: the two host->device copies into `workspace` (device memory, 256-byte aligned, at least
+ * qrag_amp_rerank_host_workspace bytes), the fused kernel of qrag_amp_rerank, and the device->host copies of
+ * hScores [nq, top_k] fp64 and hIds [nq, top_k] int64.  Nothing is synchronised: the outputs are valid once the
+ * stream has reached this point (record an event after the call).  Several calls on different streams with
+ * different workspaces overlap copy and kernel. */
+int qrag_amp_rerank_host_workspace(int nq, int64_t C, int D, int top_k, size_t* bytes);
+int qrag_amp_rerank_host(const float* hQ, int nq, const int64_t* hIdx, int64_t C,
+                         const float* X, int64_t N, int D, int n_qubits, int top_k,
+                         void* workspace, size_t workspace_bytes,
+                         double* hScores, int64_t* hIds, void* stream);
+
 /* ---------------------------------------------------------------------------
  * (1c') Feature-map rerank: amplitude state + `layers` reference blocks at n_qubits == 10 (D <= 1024), top_k of
  * C <= QRAG_MAX_SORT_LEN candidates per query, by FILTER-THEN-CERTIFY: every candidate evolved in complex64

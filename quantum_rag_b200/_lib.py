@@ -39,6 +39,9 @@ PROTOTYPES: Dict[str, tuple] = {
                                   c_void_p, c_void_p, c_void_p]),
     "qrag_amp_rerank": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "qrag_amp_rerank_host_workspace": (c_int, [c_int, c_int64, c_int, c_int, POINTER(c_size_t)]),
+    "qrag_amp_rerank_host": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
+                                     c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "qrag_fmap_rerank_workspace": (c_int, [c_int, c_int64, c_int, POINTER(c_size_t)]),
     "qrag_fmap_filter_error_bound": (c_int, [c_int, POINTER(c_double)]),
     "qrag_fmap_filter_scores": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,

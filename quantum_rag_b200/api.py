@@ -556,61 +556,69 @@ class HostRerankPipeline:
 class HostIdRerankPipeline:
     """End-to-end rerank of candidates named by ID against a corpus resident on the GPU.
 
-    This is the serving shape behind a retrieval step (faiss-style ids in, reranked ids out): per call
-    the host sends the queries [nq, D] fp32 and the candidate ids [nq, C] int64 from pinned memory, the
-    kernel gathers the rows from the resident corpus, and (score, id) top-k come back to pinned
-    host memory.  ``chunks`` > 1 sends the queries in slices on two streams (the copy of slice i+1 overlaps the
-    kernel of slice i); for batches the size of BASELINE config 2 -- 2.3 MB in, 0.12 ms per call -- the host's cost per
-    slice outweighs the overlap (measured: 0.31 ms with 4 slices), so the default is one slice on the current stream.
-    ``__call__`` returns after everything has landed on the host.
+    This is the serving shape behind a retrieval step (faiss-style ids in, reranked ids out): per batch the host
+    sends the queries [nq, D] fp32 and the candidate ids [nq, C] int64 from pinned memory, the kernel gathers the rows
+    from the resident corpus, and (score, id) top-k come back to pinned host memory.  One batch is ONE library call
+    (include/qrag.h: qrag_amp_rerank_host enqueues both copies in, the fused kernel and both copies out).
+
+    ``submit(Q_host, idx_host)`` queues a batch on the next of ``depth`` slots (each with its own stream, device
+    workspace and pinned outputs) and returns a ticket; ``result(ticket)`` waits for that batch only and returns its
+    pinned (scores, ids).  With two or more batches in flight the host->device copy of one overlaps the kernel of
+    another: for batches the size of BASELINE config 2 (2.3 MB in, ~45 us of copy, ~40 us of kernel) the steady state is
+    bound by the copy.  ``__call__`` is submit + result: one batch, host waits (the latency form).
     """
 
-    def __init__(self, X: ArrayLike, nq: int, C: int, top_k: int, n_qubits: Optional[int] = None, chunks: int = 1):
+    def __init__(self, X: ArrayLike, nq: int, C: int, top_k: int, n_qubits: Optional[int] = None, depth: int = 3):
         self.X = _dev(X, torch.float32)
         dev = self.X.device
         self.nq, self.C, self.D, self.k = nq, C, self.X.shape[1], top_k
         self.n = qubits_for(self.D) if n_qubits is None else n_qubits
-        self.chunks = max(1, min(chunks, nq))
-        self.step = -(-nq // self.chunks)
-        self.streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-        self.dQ = torch.empty((nq, self.D), dtype=torch.float32, device=dev)
-        self.dI = torch.empty((nq, C), dtype=torch.int64, device=dev)
-        self.dS = torch.empty((nq, top_k), dtype=torch.float64, device=dev)
-        self.dP = torch.empty((nq, top_k), dtype=torch.int32, device=dev)
-        self.dO = torch.empty((nq, top_k), dtype=torch.int64, device=dev)
-        self.hS = torch.empty((nq, top_k), dtype=torch.float64).pin_memory()
-        self.hO = torch.empty((nq, top_k), dtype=torch.int64).pin_memory()
+        self.depth = max(1, int(depth))
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(_lib.load().qrag_amp_rerank_host_workspace(nq, C, self.D, top_k, ctypes.byref(nbytes)))
+        self._slots = []
+        for _ in range(self.depth):
+            self._slots.append({"stream": torch.cuda.Stream(device=dev), "event": torch.cuda.Event(),
+                                "ws": torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=dev),
+                                "hS": torch.empty((nq, top_k), dtype=torch.float64).pin_memory(),
+                                "hO": torch.empty((nq, top_k), dtype=torch.int64).pin_memory(), "busy": False})
+        self._next = 0
         self.h2d_bytes = nq * self.D * 4 + nq * C * 8
         self.d2h_bytes = nq * top_k * 16
-        self.launches_per_call = self.chunks
+        self.launches_per_call = 1
+
+    def submit(self, Q_host: torch.Tensor, idx_host: torch.Tensor) -> int:
+        """Queue one batch; at most ``depth`` may be outstanding (collect the oldest with ``result`` first)."""
+        if Q_host.is_cuda or idx_host.is_cuda:
+            raise ValueError("HostIdRerankPipeline takes HOST tensors (use amp_rerank for device tensors)")
+        if Q_host.dtype != torch.float32 or tuple(Q_host.shape) != (self.nq, self.D) or not Q_host.is_contiguous():
+            raise ValueError(f"Q_host must be a contiguous float32 [{self.nq}, {self.D}] tensor")
+        if idx_host.dtype != torch.int64 or tuple(idx_host.shape) != (self.nq, self.C) or not idx_host.is_contiguous():
+            raise ValueError(f"idx_host must be a contiguous int64 [{self.nq}, {self.C}] tensor")
+        t = self._next
+        slot = self._slots[t]
+        if slot["busy"]:
+            raise RuntimeError(f"{self.depth} batches already in flight: call result() on the oldest ticket first")
+        self._next = (t + 1) % self.depth
+        ws = slot["ws"]
+        _lib.check(_lib.load().qrag_amp_rerank_host(
+            Q_host.data_ptr(), self.nq, idx_host.data_ptr(), self.C, _ptr(self.X), self.X.shape[0], self.D, self.n, self.k,
+            _ptr(ws), ws.numel(), slot["hS"].data_ptr(), slot["hO"].data_ptr(),
+            ctypes.c_void_p(slot["stream"].cuda_stream)))
+        slot["event"].record(slot["stream"])
+        slot["busy"] = True
+        slot["inputs"] = (Q_host, idx_host)          # keep the host buffers alive until the copies have run
+        return t
+
+    def result(self, ticket: int):
+        """Pinned (scores [nq, k] fp64, ids [nq, k] int64) of that batch; valid until the slot is submitted to again."""
+        slot = self._slots[ticket]
+        if not slot["busy"]:
+            raise RuntimeError("no batch outstanding on this ticket")
+        slot["event"].synchronize()
+        slot["busy"] = False
+        slot["inputs"] = None
+        return slot["hS"], slot["hO"]
 
     def __call__(self, Q_host: torch.Tensor, idx_host: torch.Tensor):
-        lib = _lib.load()
-        if self.chunks == 1:
-            self.dQ.copy_(Q_host, non_blocking=True)
-            self.dI.copy_(idx_host, non_blocking=True)
-            _lib.check(lib.qrag_amp_rerank(_ptr(self.dQ), self.nq, None, _ptr(self.X), self.X.shape[0], _ptr(self.dI), self.C,
-                                           self.D, self.n, self.k, _ptr(self.dS), _ptr(self.dP), _ptr(self.dO), _stream()))
-            self.hS.copy_(self.dS, non_blocking=True)
-            self.hO.copy_(self.dO, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return self.hS, self.hO
-        cur = torch.cuda.current_stream()
-        for s in self.streams:
-            s.wait_stream(cur)
-        for c in range(self.chunks):
-            a, b = c * self.step, min(self.nq, (c + 1) * self.step)
-            if a >= b:
-                break
-            s = self.streams[c & 1]
-            with torch.cuda.stream(s):
-                self.dQ[a:b].copy_(Q_host[a:b], non_blocking=True)
-                self.dI[a:b].copy_(idx_host[a:b], non_blocking=True)
-                _lib.check(lib.qrag_amp_rerank(_ptr(self.dQ[a:b]), b - a, None, _ptr(self.X), self.X.shape[0],
-                                               _ptr(self.dI[a:b]), self.C, self.D, self.n, self.k, _ptr(self.dS[a:b]),
-                                               _ptr(self.dP[a:b]), _ptr(self.dO[a:b]), ctypes.c_void_p(s.cuda_stream)))
-                self.hS[a:b].copy_(self.dS[a:b], non_blocking=True)
-                self.hO[a:b].copy_(self.dO[a:b], non_blocking=True)
-        for s in self.streams:
-            s.synchronize()
-        return self.hS, self.hO
+        return self.result(self.submit(Q_host, idx_host))

@@ -346,3 +346,53 @@ extern "C" int qrag_amp_rerank(const float* Q, int nq, const float* cand, const 
     p.top_k = top_k; p.out_scores = out_scores; p.out_pos = out_pos; p.out_ids = out_ids;
     return amp_fidelity_fused(p, (cudaStream_t)stream);
 }
+
+// ---- the rerank called with HOST buffers: copies in, kernel, copies out, all enqueued by one call ----
+namespace {
+inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+struct HostWs { size_t q, idx, s, o, p, total; };
+HostWs host_ws(int nq, int64_t C, int D, int top_k) {
+    HostWs w;
+    w.q = 0;
+    w.idx = w.q + up256((size_t)nq * D * sizeof(float));
+    w.s = w.idx + up256((size_t)nq * C * sizeof(int64_t));
+    w.o = w.s + up256((size_t)nq * top_k * sizeof(double));
+    w.p = w.o + up256((size_t)nq * top_k * sizeof(int64_t));
+    w.total = w.p + up256((size_t)nq * top_k * sizeof(int32_t));
+    return w;
+}
+}  // namespace
+
+extern "C" int qrag_amp_rerank_host_workspace(int nq, int64_t C, int D, int top_k, size_t* bytes) {
+    QRAG_REQUIRE(bytes != nullptr, QRAG_ERR_INVALID, "bytes is null");
+    QRAG_REQUIRE(nq >= 0 && C >= 1 && D >= 1 && top_k >= 1, QRAG_ERR_INVALID, "bad sizes nq=%d C=%lld D=%d top_k=%d", nq,
+                 (long long)C, D, top_k);
+    *bytes = host_ws(nq, C, D, top_k).total;
+    return QRAG_OK;
+}
+
+extern "C" int qrag_amp_rerank_host(const float* hQ, int nq, const int64_t* hIdx, int64_t C, const float* X, int64_t N,
+                                    int D, int n_qubits, int top_k, void* workspace, size_t workspace_bytes,
+                                    double* hScores, int64_t* hIds, void* stream) {
+    QRAG_REQUIRE(hQ && hIdx && X && workspace && hScores && hIds, QRAG_ERR_INVALID, "null pointer argument");
+    QRAG_REQUIRE(nq >= 0 && C >= 1 && D >= 1 && top_k >= 1, QRAG_ERR_INVALID, "bad sizes nq=%d C=%lld D=%d top_k=%d", nq,
+                 (long long)C, D, top_k);
+    QRAG_REQUIRE(((uintptr_t)workspace & 255) == 0, QRAG_ERR_INVALID, "workspace must be 256-byte aligned");
+    const HostWs w = host_ws(nq, C, D, top_k);
+    QRAG_REQUIRE(workspace_bytes >= w.total, QRAG_ERR_INVALID, "workspace of %zu bytes, %zu needed", workspace_bytes, w.total);
+    if (nq == 0) return QRAG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = static_cast<char*>(workspace);
+    float* dQ = reinterpret_cast<float*>(base + w.q);
+    int64_t* dI = reinterpret_cast<int64_t*>(base + w.idx);
+    double* dS = reinterpret_cast<double*>(base + w.s);
+    int64_t* dO = reinterpret_cast<int64_t*>(base + w.o);
+    int32_t* dP = reinterpret_cast<int32_t*>(base + w.p);
+    QRAG_CUDA_CHECK(cudaMemcpyAsync(dQ, hQ, (size_t)nq * D * sizeof(float), cudaMemcpyHostToDevice, st));
+    QRAG_CUDA_CHECK(cudaMemcpyAsync(dI, hIdx, (size_t)nq * C * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    const int rc = qrag_amp_rerank(dQ, nq, nullptr, X, N, dI, C, D, n_qubits, top_k, dS, dP, dO, stream);
+    if (rc) return rc;
+    QRAG_CUDA_CHECK(cudaMemcpyAsync(hScores, dS, (size_t)nq * top_k * sizeof(double), cudaMemcpyDeviceToHost, st));
+    QRAG_CUDA_CHECK(cudaMemcpyAsync(hIds, dO, (size_t)nq * top_k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    return QRAG_OK;
+}

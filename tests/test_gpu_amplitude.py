@@ -459,10 +459,25 @@ def test_host_pipelines_equal_the_device_api(cuda):
     idx = torch.from_numpy(rng.randint(0, 5000, size=(nq, C)).astype(np.int64)).pin_memory()
     idx[5, 10:20] = -1
     s2, p2, i2 = api.quantum_rerank_batch(Q, X=X, idx=idx, top_k=k, n_qubits=9)
-    for chunks in (1, 3):
-        idp = api.HostIdRerankPipeline(X, nq, C, k, 9, chunks=chunks)
+    for depth in (1, 3):
+        idp = api.HostIdRerankPipeline(X, nq, C, k, 9, depth=depth)
         for _ in range(2):                                                # reusable: the second call gives the same answer
             hS2, hO2 = idp(Q, idx)
         assert torch.equal(hS2, s2.cpu()) and torch.equal(hO2, i2.cpu())
+    # several batches in flight (one library call each: copies in, kernel, copies out on the slot's stream); every
+    # ticket returns its own batch; a fourth submit before any result() is refused
+    Qb = [torch.from_numpy(rng.standard_normal((nq, D)).astype(np.float32)).pin_memory() for _ in range(3)]
+    Ib = [torch.from_numpy(rng.randint(-2, 5003, size=(nq, C)).astype(np.int64)).pin_memory() for _ in range(3)]
+    tickets = [idp.submit(q, i) for q, i in zip(Qb, Ib)]
+    with pytest.raises(RuntimeError):
+        idp.submit(Qb[0], Ib[0])
+    for t, q, i in zip(tickets, Qb, Ib):
+        hS3, hO3 = idp.result(t)
+        s3, _, i3 = api.quantum_rerank_batch(q, X=X, idx=i, top_k=k, n_qubits=9)
+        assert torch.equal(hS3, s3.cpu()) and torch.equal(hO3, i3.cpu())
+    with pytest.raises(RuntimeError):
+        idp.result(tickets[0])
+    with pytest.raises(ValueError):
+        idp.submit(Qb[0][:5], Ib[0][:5])
     want = oq.rank_rows(oq.amplitude_fidelity_batch(Q.numpy()[:3], X.numpy()[idx.numpy()[:3]]), k)
     assert np.array_equal(p2[:3].cpu().numpy(), want)
