@@ -28,7 +28,27 @@ METRIC = "query-candidate scores/sec"
 UNIT = "scores/s"
 BYTES_PER_SCORE = 4 * D + 4 * D / C + TOPK * 12 / C      # candidate row + amortised query + amortised outputs
 L2_BYTES = 126 * 2**20
-NCU_DRAM_BYTES_PER_LAUNCH = 155.198976e6 + 4.453376e6     # one ncu --set full capture of the timed kernel (profiles/r02_*)
+NCU_CAPTURE = "profiles/r02b_amp_stream_key_metrics.csv"  # one ncu --set full capture of the timed kernel, same command line
+
+
+def ncu_dram_bytes_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the timed kernel, read from the committed ncu extract (so the
+    figure follows the capture, not a pasted constant); (None, why) when the extract is missing."""
+    import csv
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    got = {}
+    try:
+        with open(os.path.join(ROOT, NCU_CAPTURE)) as fh:
+            for row in csv.DictReader(fh):
+                if row["metric"] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and "amp_stream" in row["kernel"]:
+                    got[row["metric"]] = float(row["value"]) * scale[row["unit"]]
+    except Exception as exc:
+        return None, f"{NCU_CAPTURE}: {exc}"
+    if len(got) != 2:
+        return None, f"{NCU_CAPTURE}: counters not found"
+    return got["dram__bytes_read.sum"] + got["dram__bytes_write.sum"], (
+        f"ncu --set full, {NCU_CAPTURE} (dram__bytes_read.sum {got['dram__bytes_read.sum'] / 1e6:.2f} MB + "
+        f"dram__bytes_write.sum {got['dram__bytes_write.sum'] / 1e6:.2f} MB per launch)")
 
 
 def workload_config(n_gpus, overlap="interleaved"):
@@ -744,8 +764,7 @@ def run_b200(args):
             "kernels": ["qrag::amp_stream_kernel<3,4,8> (1 launch per step; TMA bulk-copy ring, warp-specialised "
                         "producer / converter / 8 consumers / 2 rankers, fused rank; <3,4,16> with --overlap stable)"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "ncu --set full, profiles/r02_amp_stream_key_metrics.csv "
-                         "(dram__bytes_read.sum 155.20 MB + dram__bytes_write.sum 4.45 MB per launch)",
+                         "traffic": ncu_dram_bytes_per_launch()[0], "traffic_source": ncu_dram_bytes_per_launch()[1],
                          "kernel": "amp_stream_kernel<3,4,8>" if args.overlap == "interleaved" else "amp_stream_kernel<3,4,16>",
                          "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_score": BYTES_PER_SCORE,
                          "peak_source": peak_src},
