@@ -852,7 +852,13 @@ __device__ __forceinline__ void for_each_survivor(const float2* __restrict__ sv,
     }
 }
 
-__global__ void __launch_bounds__(256) surv_hist_kernel(const unsigned int* __restrict__ cnt, const float2* __restrict__ surv,
+// CTA size of the two kernels that walk one query's survivor segments.  A few queries over a large shard (nq <= 128:
+// the single-CTA GEMM form, one segment per (SM, column quarter) = 592 of them) leave each walking CTA a long chain of
+// dependent-latency loads -- 23 + 28 us of a 211 us one-query search at 8 warps (profiles/r02b_search_nq1_launches.csv)
+// -- so those run 32 warps wide; many queries with short segment lists keep 8 warps (more CTAs per SM).
+static inline int seg_walk_threads(int nseg) { return nseg >= 256 ? 1024 : 256; }
+
+__global__ void __launch_bounds__(1024) surv_hist_kernel(const unsigned int* __restrict__ cnt, const float2* __restrict__ surv,
                                                         int q0, int nseg, int seg_cap, int cap,
                                                         const float* __restrict__ tau, const float* __restrict__ hinv,
                                                         int* __restrict__ hist) {
@@ -916,7 +922,7 @@ __device__ void bitonic_sort_kt(K* key, T* tag, int P) {
 // (1) one CTA per query: a_k = a lower bound of the k-th best approximate score over all shards, read off the
 // survivor histogram the filter pass built (summed over the shards by the caller): the highest bin edge that still
 // has k survivors at or above it.  Candidates = this shard's survivors >= a_k - 2 eps -> cand_rows, cand_m.
-__global__ void __launch_bounds__(XS_THREADS) tc_collect_kernel(const TcFinalParams p) {
+__global__ void __launch_bounds__(1024) tc_collect_kernel(const TcFinalParams p) {
     pdl_enter();
     __shared__ int seg_n[TC_MAX_SEGS];
     __shared__ int s_m, s_bad;
@@ -929,7 +935,7 @@ __global__ void __launch_bounds__(XS_THREADS) tc_collect_kernel(const TcFinalPar
 
     if (tid == 0) { s_m = 0; s_bad = 0; }
     __syncthreads();
-    for (int sgi = tid; sgi < p.nseg; sgi += XS_THREADS) {
+    for (int sgi = tid; sgi < p.nseg; sgi += blockDim.x) {
         const unsigned int c = p.cnt[(size_t)q * TC_MAX_SEGS + sgi];
         seg_n[sgi] = c < (unsigned)p.seg_cap ? (int)c : p.seg_cap;
         if (c > (unsigned)p.seg_cap) s_bad = 1;
@@ -1791,7 +1797,7 @@ extern "C" int qrag_search_tc_filter(int nq, const uint16_t* Xb, const float* au
                                    w.bmax, w.pl.nbuckets, w.tau, w.eps, w.hinv));
     QRAG_LAUNCH_CHECK("tau_union_kernel");
     return tc_gemm_pass<TC_MODE_FILTER>(w, nq, N, Xb, st, [&](int q0, int q1, int nseg, int seg_cap) {
-        QRAG_CUDA_CHECK(launch_chained(surv_hist_kernel, dim3(q1 - q0), dim3(256), 0, st, w.cnt, w.surv, q0, nseg, seg_cap, w.pl.cap, w.tau, w.hinv, w.hist));
+        QRAG_CUDA_CHECK(launch_chained(surv_hist_kernel, dim3(q1 - q0), dim3(seg_walk_threads(nseg)), 0, st, w.cnt, w.surv, q0, nseg, seg_cap, w.pl.cap, w.tau, w.hinv, w.hist));
         QRAG_LAUNCH_CHECK("surv_hist_kernel");
         return QRAG_OK;
     });
@@ -1823,7 +1829,7 @@ static int tc_finish_impl(const float* Q, int nq, const float* X, int64_t N, int
 #ifdef QRAG_TUNING
         fp.tune = getenv("QRAG_TC_TUNE") ? atoi(getenv("QRAG_TC_TUNE")) : 0;
 #endif
-        QRAG_CUDA_CHECK(launch_chained(tc_collect_kernel, dim3(q1 - q0), dim3(XS_THREADS), 0, st, fp));
+        QRAG_CUDA_CHECK(launch_chained(tc_collect_kernel, dim3(q1 - q0), dim3(seg_walk_threads(fp.nseg)), 0, st, fp));
         QRAG_LAUNCH_CHECK("tc_collect_kernel");
         // the bulk-copy form when the rows allow it and two CTAs still share an SM
         const size_t smem_bulk = rescore_bulk_smem(D);
