@@ -202,9 +202,21 @@ class ShardedSearchRerank:
         self._next_lane = 0
 
     def close(self) -> None:
-        """Drop the captured CUDA graphs (``submit(graph=True)``).  Call it before ``destroy_process_group``: a graph
-        that holds NCCL kernels must not outlive the communicator (observed: the teardown hangs otherwise)."""
+        """Drop the captured CUDA graphs (``submit(graph=True)``) and the extra lanes' communicators; the object then
+        runs on one lane.  Call it before ``destroy_process_group``: a graph that holds NCCL kernels must not outlive
+        the communicator (observed: the teardown hangs otherwise)."""
         self._graphs = {}
+        for side in getattr(self, "_lane_streams", []):
+            if side is not None:
+                side.synchronize()
+        groups, self._lane_groups = self._lane_groups, self._lane_groups[:1]
+        self.n_lanes, self._next_lane = 1, 0
+        for g in groups[1:]:                                  # the extra lanes' communicators (collective: every rank closes)
+            if g is not None:
+                try:
+                    dist.destroy_process_group(g)
+                except Exception:
+                    pass
 
     def _mark(self, name: str) -> None:
         if self.profile is not None:

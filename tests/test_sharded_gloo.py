@@ -312,8 +312,11 @@ def _laned_worker(rank, world, port, n, d, nq, k1, k2, metric, out):
         used = sorted(v.lane_id for v in path.engine._views.values())
         res = [p.result() for p in pend]
         again = path(batches[1], k1, k2)                     # one at a time after the queue drained
-        out[rank] = ([(r.scores.numpy(), r.ids.numpy()) for r in res + [again]], used,
-                     [len(b) for b in path._lane_bufs])
+        nbufs = [len(b) for b in path._lane_bufs]
+        path.close()                                         # drops the second lane's group: one lane from here on
+        assert path.n_lanes == 1 and len(path._lane_groups) == 1
+        closed = path(batches[2], k1, k2)
+        out[rank] = ([(r.scores.numpy(), r.ids.numpy()) for r in res + [again, closed]], used, nbufs)
     finally:
         dist.destroy_process_group()
 
@@ -327,6 +330,7 @@ def test_two_lanes_alternate_process_groups_and_give_the_single_rank_result():
     assert single.n_lanes == 1
     want = [single(torch.from_numpy(Q), k1, k2) for Q in batches]
     want.append(want[1])
+    want.append(want[2])
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_laned_worker, args=(world, _free_port(), n, d, nq, k1, k2, metric, out), nprocs=world, join=True)
