@@ -446,12 +446,12 @@ def bench_sharded(world, rank, steps=10):
     # A/B in the same run: the same queue through ONE lane (one stream, one communicator: every collective and
     # per-query kernel in front of the next batch's filter GEMM)
     lanes = path.n_lanes
-    path.n_lanes, path._next_lane = 1, 0
+    path.use_lanes(1)
     reps1 = []
     for _ in range(3):
         ms_r, res1 = timed(lambda: [p.result() for p in [path.submit(Q, k1, k2) for _ in range(steps)]][-1])
         reps1.append(ms_r)
-    path.n_lanes = lanes
+    path.use_lanes(lanes)
     assert torch.equal(res1.ids, res.ids) and torch.equal(res1.scores, res.scores)
     ms_sync, res_sync = timed(lambda: [path(Q, k1, k2) for _ in range(steps)][-1])
     assert torch.equal(res_sync.ids, res.ids) and torch.equal(res_sync.scores, res.scores)

@@ -29,6 +29,8 @@
 #include "common.cuh"
 #include "tma.cuh"
 
+#include <mutex>
+
 namespace qrag {
 
 struct SvaParams {
@@ -264,6 +266,8 @@ __global__ void __launch_bounds__(SVA_WARP_THREADS) sva_warp_kernel(const SvaPar
 // back to the driver at every synchronisation).
 static int sva_pool(cudaMemPool_t* out) {
     static cudaMemPool_t pools[64] = {};
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
     int dev = 0;
     QRAG_CUDA_CHECK(cudaGetDevice(&dev));
     QRAG_REQUIRE(dev >= 0 && dev < 64, QRAG_ERR_UNSUPPORTED, "device ordinal %d", dev);
@@ -300,9 +304,14 @@ static int sva_launch(K kern, const SvaParams& p, int64_t grid, int threads, boo
 template <typename K>
 static int sva_warp_grid(K kern, int64_t states, int64_t* grid) {
     const DeviceProps& dp = device_props();
-    int per_sm = 0;
-    QRAG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SVA_WARP_THREADS, 0));
-    const int64_t cap = (int64_t)dp.sm_count * (per_sm > 0 ? per_sm : 1);    // every CTA resident; warps stride over the states
+    static int per_sm_cached = 0;                          // one per instantiation of this template (= per kernel)
+    int per_sm = per_sm_cached;
+    if (per_sm == 0) {
+        QRAG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SVA_WARP_THREADS, 0));
+        if (per_sm < 1) per_sm = 1;
+        per_sm_cached = per_sm;
+    }
+    const int64_t cap = (int64_t)dp.sm_count * per_sm;     // every CTA resident; warps stride over the states
     const int64_t need = ceil_div(states, SVA_WARP_THREADS / 32);
     *grid = need < cap ? need : cap;
     return QRAG_OK;
@@ -332,7 +341,6 @@ static int sva_run_n(const SvaParams& p, cudaStream_t st) {
 // n_qubits in [1, 10]; arguments already validated by qrag_sv_fidelity_angle (sv_kernels.cu)
 int sv_angle_registers(const double* qvec, int nq, const double* dvec, int64_t nd, const int32_t* doc_query,
                        int64_t docs_per_query, int vec_len, int n_qubits, int layers, double* out, cudaStream_t st) {
-    QRAG_REQUIRE((int64_t)nq * (int64_t)sizeof(double2) <= (int64_t)1 << 50, QRAG_ERR_UNSUPPORTED, "nq=%d", nq);
     cudaMemPool_t pool;
     int rc = sva_pool(&pool);
     if (rc) return rc;

@@ -218,6 +218,13 @@ class ShardedSearchRerank:
                 except Exception:
                     pass
 
+    def use_lanes(self, n: int) -> None:
+        """Run the following ``submit`` calls over the first ``n`` lanes (1 = every batch behind the previous one on one
+        stream and one communicator; the bench's A/B).  Every rank must make the same call, between batches."""
+        if not 1 <= int(n) <= len(self._lane_groups):
+            raise ValueError(f"lanes must be in [1, {len(self._lane_groups)}]")
+        self.n_lanes, self._next_lane = int(n), 0
+
     def _mark(self, name: str) -> None:
         if self.profile is not None:
             ev = torch.cuda.Event(enable_timing=True)
@@ -330,7 +337,7 @@ class ShardedSearchRerank:
         one owner kernel, one small all-gather.  Returns (fidelity [nq, k2], ids [nq, k2], flag [1]) device tensors;
         flag != 0 means some shard could not certify a query or had to cut a list."""
         G = self.world
-        eng = self.engine.lane(lane) if self.n_lanes > 1 else self.engine
+        eng = self.engine.lane(lane) if hasattr(self.engine, "lane") else self.engine
         grp = self._lane_groups[lane]
         nq = Q.shape[0]
         kk = exchange_len(k1, G)

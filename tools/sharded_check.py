@@ -89,10 +89,10 @@ def main():
     queue = lambda: [p.result() for p in [path.submit(Q, a.k1, a.k2) for _ in range(a.steps)]][-1]
     two, one = [ms_pipe], []
     for _ in range(3):                                     # A/B, alternating: the same queue through one lane / two lanes
-        path.n_lanes, path._next_lane = 1, 0
+        path.use_lanes(1)
         t, res_1 = timed(queue)
         one.append(t)
-        path.n_lanes = lanes
+        path.use_lanes(lanes)
         two.append(timed(queue)[0])
     ms_one, ms_pipe2 = sorted(one)[1], sorted(two)[len(two) // 2]
     modes = {"sync_per_batch_ms": ms_sync, "pipelined_ms": ms_pipe, "pipelined_again_ms": ms_pipe2, "lanes": lanes,
