@@ -253,7 +253,7 @@ def bench_circuit(api, fma_rate, steps=20):
     import torch
     # FP64 thread-instructions per score, cuobjdump -sass of sva_thread_kernel<4,0,0> (DFMA+DMUL+DADD per thread) and
     # sva_warp_kernel<9,0,0> (per warp x 32 lanes); the query states add 1/C of that and are left out
-    executed = {4: 332 + 128 + 12, 9: (227 + 95 + 18) * 32}
+    executed = {4: 332 + 128 + 12, 9: (362 + 164 + 27) * 32 // 2}      # n = 9: one pass of the warp loop is two states
     res = {}
     for name, n, vec_len, nq in (("n4_string_api_shape", 4, 8, NQ), ("n4_string_api_shape_x10", 4, 8, 10 * NQ),
                                  ("n9_config2_angle_variant", 9, 9, NQ)):

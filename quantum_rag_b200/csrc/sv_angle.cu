@@ -13,8 +13,8 @@
 //    arithmetic, the CX chain a register renaming).  No shuffles, no redundant trigonometry: every thread owns a
 //    different vector.
 //  * 6 <= n <= 10: one WARP per state, 2^(n-5) amplitudes per lane (qubits 0..n-6 inside a lane, the top five
-//    across lanes).  Lane k evaluates the gate of qubit k (one sincospi pair per gate per state) and the warp
-//    shares it by shuffles; the CX chain is one shuffle per amplitude (source register static, source lane
+//    across lanes).  Lane k evaluates the gate of qubit k (one sincospi pair per gate per state; the first block's
+//    gates of TWO states per pass, one state per half-warp) and the warp shares it by shuffles; the CX chain is one shuffle per amplitude (source register static, source lane
 //    lane ^ (lane << 1) ^ carry).
 //
 // The first block of gates acts on |0...0>: when qubit k's RY/RZ is applied, every amplitude with a bit >= k set is
@@ -164,36 +164,53 @@ __device__ __forceinline__ void warp_cx(double2 (&st)[1 << (N - 5)], int lane) {
     for (int r = 0; r < R; ++r) st[r] = t[r];
 }
 
-template <int N, bool MULTI>
-__device__ __forceinline__ void warp_state(const double* __restrict__ v, int vec_len, int layers, int lane,
-                                           double2 (&st)[1 << (N - 5)]) {
-    constexpr int M = N - 5, R = 1 << M;
+// Gates of the first block for TWO states at once: lanes 0..15 serve state A, lanes 16..31 state B (n <= 10 < 16 gates
+// per state).  The chain  load -> |v| -> divide -> two sincospi  is the fixed cost of a state (about half of the time at
+// n = 9, nearly all of it at n = 6); evaluated for a pair it is paid once per two states.  Lane 16 h + k returns
+// (alpha_k, beta_k) of its state:  RZ RY |0> = alpha |0> + beta |1>,  alpha = c e^{-i phi/2},  beta = s e^{+i phi/2}.
+template <int N>
+__device__ __forceinline__ void warp_gates2(const double* __restrict__ vA, const double* __restrict__ vB, int vec_len,
+                                            int layers, int lane, double2& al, double2& be, double& nrm) {
+    const int k = lane & 15;
+    const double* __restrict__ v = (lane & 16) ? vB : vA;
     double part = 0.0;
-    for (int i = lane; i < vec_len; i += 32) part = fma(v[i], v[i], part);
-    const double nrm = sqrt(warp_sum(part));
-    {
-        // layer 0 on |0..0>: lane k holds qubit k's (alpha, beta); the state is their tensor product
-        const SvaGate g = sva_gate(lane < N ? sva_angle(v, vec_len, nrm, N, layers, 0, lane) : 0.0);
-        const double2 al = make_double2(g.c * g.cp, -g.c * g.sp), be = make_double2(g.s * g.cp, g.s * g.sp);
-        double2 f = make_double2(1.0, 0.0);                // this lane's factor: the five qubits across lanes
+    for (int i = k; i < vec_len; i += 16) part = fma(v[i], v[i], part);
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const double2 a = shfl_d2(al, M + j), b = shfl_d2(be, M + j);
-            f = cmul(((lane >> j) & 1) ? b : a, f);
-        }
-        st[0] = f;
+    for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(FULL_MASK, part, o);   // within the 16-lane half
+    nrm = sqrt(part);
+    const SvaGate g = sva_gate(k < N ? sva_angle(v, vec_len, nrm, N, layers, 0, k) : 0.0);
+    al = make_double2(g.c * g.cp, -g.c * g.sp);
+    be = make_double2(g.s * g.cp, g.s * g.sp);
+}
+
+// First block on |0..0> from the gates held by lanes base .. base + N - 1: the state is their tensor product.
+template <int N>
+__device__ __forceinline__ void warp_first_block(double2 al, double2 be, int base, int lane, double2 (&st)[1 << (N - 5)]) {
+    constexpr int M = N - 5;
+    double2 f = make_double2(1.0, 0.0);                    // this lane's factor: the five qubits across lanes
 #pragma unroll
-        for (int k = 0; k < M; ++k) {
-            const double2 a = shfl_d2(al, k), b = shfl_d2(be, k);
-#pragma unroll
-            for (int x = 0; x < (1 << k); ++x) {
-                st[x | (1 << k)] = cmul(b, st[x]);
-                st[x] = cmul(a, st[x]);
-            }
-        }
-        warp_cx<N>(st, lane);
+    for (int j = 0; j < 5; ++j) {
+        const double2 a = shfl_d2(al, base + M + j), b = shfl_d2(be, base + M + j);
+        f = cmul(((lane >> j) & 1) ? b : a, f);
     }
-    if (!MULTI) return;
+    st[0] = f;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        const double2 a = shfl_d2(al, base + k), b = shfl_d2(be, base + k);
+#pragma unroll
+        for (int x = 0; x < (1 << k); ++x) {
+            st[x | (1 << k)] = cmul(b, st[x]);
+            st[x] = cmul(a, st[x]);
+        }
+    }
+    warp_cx<N>(st, lane);
+}
+
+// Blocks 1 .. layers-1 (dense): lane k evaluates qubit k's gate of the block.
+template <int N>
+__device__ __forceinline__ void warp_more_blocks(const double* __restrict__ v, int vec_len, double nrm, int layers, int lane,
+                                                 double2 (&st)[1 << (N - 5)]) {
+    constexpr int M = N - 5, R = 1 << M;
     for (int layer = 1; layer < layers; ++layer) {
         const SvaGate g = sva_gate(lane < N ? sva_angle(v, vec_len, nrm, N, layers, layer, lane) : 0.0);
 #pragma unroll
@@ -233,29 +250,47 @@ __global__ void __launch_bounds__(SVA_WARP_THREADS) sva_warp_kernel(const SvaPar
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t total = QUERY ? (int64_t)p.nq : p.nd;
+    const double* __restrict__ vecs = QUERY ? p.qvec : p.dvec;
     if (QUERY) griddep_launch_dependents();
     bool waited = false;
-    for (int64_t j = warp0; j < total; j += nwarps) {
-        double2 st[R];
-        warp_state<N, MULTI>((QUERY ? p.qvec : p.dvec) + j * p.vec_len, p.vec_len, p.layers, lane, st);
-        if (QUERY) {
+    // PAIR: states 2 jj and 2 jj + 1 share one gate pass.  Measured (1000 x 100 pairs): n = 6 68 -> 53 us, n = 8 91 -> 77,
+    // n = 9 128 -> 111; at n = 10 and in the multi-block kernels the extra registers cost more than the pass saves
+    // (214 -> 225 us; n = 9, 3 blocks: 1.34 -> 1.58 ms), so those take one state per pass.
+    constexpr bool PAIR = !MULTI && N <= 9;
+    constexpr int PER = PAIR ? 2 : 1;
+    for (int64_t jj = warp0; PER * jj < total; jj += nwarps) {
+        const int64_t jA = PER * jj;
+        const bool hasB = PAIR && jA + 1 < total;
+        const int64_t jB = hasB ? jA + 1 : jA;
+        double2 al, be;
+        double nrm;
+        warp_gates2<N>(vecs + jA * p.vec_len, vecs + jB * p.vec_len, p.vec_len, p.layers, lane, al, be, nrm);
 #pragma unroll
-            for (int r = 0; r < R; ++r) p.qstate[(j * R + r) * 32 + lane] = st[r];
-            continue;
-        }
-        const int64_t qi = p.doc_query ? (int64_t)p.doc_query[j] : j / p.docs_per_query;
-        if (!waited) { griddep_wait(); waited = true; }    // the query states are pass 1's output
-        const double2* __restrict__ q = p.qstate + qi * R * 32 + lane;
-        double re = 0.0, im = 0.0;
+        for (int h = 0; h < PER; ++h) {
+            if (h == 1 && !hasB) break;
+            const int64_t j = h ? jB : jA;
+            double2 st[R];
+            warp_first_block<N>(al, be, 16 * h, lane, st);
+            if (MULTI) warp_more_blocks<N>(vecs + j * p.vec_len, p.vec_len, shfl_d(nrm, 16 * h), p.layers, lane, st);
+            if (QUERY) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const double2 d = st[r], a = q[r * 32];
-            re = fma(d.x, a.x, fma(d.y, a.y, re));
-            im = fma(d.x, a.y, fma(-d.y, a.x, im));
+                for (int r = 0; r < R; ++r) p.qstate[(j * R + r) * 32 + lane] = st[r];
+                continue;
+            }
+            const int64_t qi = p.doc_query ? (int64_t)p.doc_query[j] : j / p.docs_per_query;
+            if (!waited) { griddep_wait(); waited = true; }    // the query states are pass 1's output
+            const double2* __restrict__ q = p.qstate + qi * R * 32 + lane;
+            double re = 0.0, im = 0.0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const double2 d = st[r], a = q[r * 32];
+                re = fma(d.x, a.x, fma(d.y, a.y, re));
+                im = fma(d.x, a.y, fma(-d.y, a.x, im));
+            }
+            re = warp_sum(re);
+            im = warp_sum(im);
+            if (lane == 0) p.out[j] = re * re + im * im;
         }
-        re = warp_sum(re);
-        im = warp_sum(im);
-        if (lane == 0) p.out[j] = re * re + im * im;
     }
 }
 
@@ -302,7 +337,7 @@ static int sva_launch(K kern, const SvaParams& p, int64_t grid, int threads, boo
 }
 
 template <typename K>
-static int sva_warp_grid(K kern, int64_t states, int64_t* grid) {
+static int sva_warp_grid(K kern, int64_t states, int per_pass, int64_t* grid) {
     const DeviceProps& dp = device_props();
     static int per_sm_cached = 0;                          // one per instantiation of this template (= per kernel)
     int per_sm = per_sm_cached;
@@ -312,7 +347,7 @@ static int sva_warp_grid(K kern, int64_t states, int64_t* grid) {
         per_sm_cached = per_sm;
     }
     const int64_t cap = (int64_t)dp.sm_count * per_sm;     // every CTA resident; warps stride over the states
-    const int64_t need = ceil_div(states, SVA_WARP_THREADS / 32);
+    const int64_t need = ceil_div(ceil_div(states, per_pass), SVA_WARP_THREADS / 32);   // a warp takes per_pass states per step
     *grid = need < cap ? need : cap;
     return QRAG_OK;
 }
@@ -325,8 +360,9 @@ static int sva_run(const SvaParams& p, cudaStream_t st) {
         return sva_launch(sva_thread_kernel<N, false, MULTI>, p, ceil_div(p.nd, 128), 128, true, st);
     } else {
         int64_t gq = 1, gd = 1;
-        int rc = sva_warp_grid(sva_warp_kernel<N, true, MULTI>, p.nq, &gq);
-        if (!rc) rc = sva_warp_grid(sva_warp_kernel<N, false, MULTI>, p.nd, &gd);
+        constexpr int per_pass = (!MULTI && N <= 9) ? 2 : 1;             // = PAIR in sva_warp_kernel
+        int rc = sva_warp_grid(sva_warp_kernel<N, true, MULTI>, p.nq, per_pass, &gq);
+        if (!rc) rc = sva_warp_grid(sva_warp_kernel<N, false, MULTI>, p.nd, per_pass, &gd);
         if (!rc) rc = sva_launch(sva_warp_kernel<N, true, MULTI>, p, gq, SVA_WARP_THREADS, false, st);
         if (rc) return rc;
         return sva_launch(sva_warp_kernel<N, false, MULTI>, p, gd, SVA_WARP_THREADS, true, st);
