@@ -94,7 +94,8 @@ int qrag_get_overlap(void);
  *   layers == 1 is the reference circuit: RY(pi v_i), RZ(pi v_i / 2) on qubit
  *   i < min(vec_len, n_qubits), then CX(i, i+1) for i = 0..n-2.  layers > 1
  *   repeats the block, layer l reading v[(l*n + i) % vec_len].
- *   out_scores[j] = |<psi_d|psi_q>|^2  (qiskit state_fidelity).
+ *   out_scores[j] = |<psi_d|psi_q>|^2  (qiskit state_fidelity); NaN where doc_query[j] is outside [0, nq)
+ *   (n_qubits <= 10; never an out-of-bounds read).
  * ------------------------------------------------------------------------- */
 int qrag_sv_fidelity_angle(const double* qvec, int nq,
                            const double* dvec, int64_t nd,

@@ -60,6 +60,8 @@ __device__ __forceinline__ double sva_angle(const double* __restrict__ v, int ve
     return nrm > 0.0 ? x / nrm : x;                        // quantum.py:149-151
 }
 
+__device__ __forceinline__ double sva_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(128) sva_thread_kernel(const SvaParams p) {
         return;
     }
     const int64_t qi = p.doc_query ? (int64_t)p.doc_query[j] : j / p.docs_per_query;
+    if (qi < 0 || qi >= p.nq) { p.out[j] = sva_nan(); return; }   // a doc_query entry that names no query: never an OOB read
     griddep_wait();                                        // the query states are pass 1's output
     const double2* __restrict__ q = p.qstate + qi * DIM;
     double re = 0.0, im = 0.0;                             // <psi_d|psi_q> = sum conj(d) q
@@ -278,6 +281,10 @@ __global__ void __launch_bounds__(SVA_WARP_THREADS) sva_warp_kernel(const SvaPar
                 continue;
             }
             const int64_t qi = p.doc_query ? (int64_t)p.doc_query[j] : j / p.docs_per_query;
+            if (qi < 0 || qi >= p.nq) {                        // a doc_query entry that names no query: never an OOB read
+                if (lane == 0) p.out[j] = sva_nan();
+                continue;
+            }
             if (!waited) { griddep_wait(); waited = true; }    // the query states are pass 1's output
             const double2* __restrict__ q = p.qstate + qi * R * 32 + lane;
             double re = 0.0, im = 0.0;

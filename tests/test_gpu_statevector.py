@@ -45,6 +45,19 @@ def test_ragged_doc_query_map_and_ties(cuda, n):
     assert got[5] == got[20] == got[36]             # bit-identical, so the stable sort ties exactly
 
 
+@pytest.mark.parametrize("n", [4, 9])
+def test_doc_query_entry_outside_the_queries_gives_nan_not_a_wild_read(cuda, n):
+    from quantum_rag_b200 import api
+    rng = np.random.RandomState(50 + n)
+    qv, dv = rng.random_sample((3, n)), rng.random_sample((9, n))
+    dq = np.array([0, 1, 2, 7, -1, 2, 1, 3, 0], dtype=np.int32)           # 7, -1 and 3 name no query
+    got = api.sv_fidelity_angle(qv, dv, doc_query=dq, n_qubits=n).cpu().numpy()
+    bad = (dq < 0) | (dq >= 3)
+    assert np.isnan(got[bad]).all()
+    want = _oracle_scores(qv, dv[~bad], dq[~bad], n, 1)
+    assert np.allclose(got[~bad], want, rtol=REL)
+
+
 def test_known_answers(cuda, kat):
     from quantum_rag_b200 import api
     s = kat["survey"]
