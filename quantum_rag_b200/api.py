@@ -59,7 +59,14 @@ def _nrows(t: Optional[torch.Tensor]) -> int:
     return int(t.shape[0]) if t is not None else 0
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """The caller's current CUDA stream as a ``cudaStream_t``.  The raw accessor skips building a ``torch.cuda.Stream``
+    object (several microseconds per call, which shows in the 20-document string API); same stream either way."""
+    if _raw_stream is not None:
+        return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -169,13 +176,21 @@ def sort_scores(scores: ArrayLike, top_k: Optional[int] = None, descending: bool
 
     scores [nq, C] fp64 -> (perm int32 [nq, k], sorted fp64 [nq, k]).
     """
+    return _sort_scores(scores, top_k, descending)[:2]
+
+
+def _sort_scores(scores: ArrayLike, top_k: Optional[int], descending: bool):
+    """(perm, sorted, the one uint8 buffer both are views of)."""
     s = _dev(scores, torch.float64)
     if s.dim() == 1:
         s = s[None, :]
     nq, C = s.shape
     k = C if top_k is None else max(0, min(int(top_k), C))
-    perm = torch.empty((nq, k), dtype=torch.int32, device=s.device)
-    srt = torch.empty((nq, k), dtype=torch.float64, device=s.device)
+    # one allocation for both outputs (sorted scores first: 8-byte aligned), so that a caller who wants them on the host
+    # can bring both back with one copy (sort_scores_host)
+    both = torch.empty(nq * k * 12, dtype=torch.uint8, device=s.device)
+    srt = both[: nq * k * 8].view(torch.float64).view(nq, k)
+    perm = both[nq * k * 8:].view(torch.int32).view(nq, k)
     lib = _lib.load()
     # lists longer than the shared-memory sort (the reference sorts any length, quantum.py:70-72) go through the
     # library's block-sort + global-memory merge, which needs a workspace; lists of 65535+ queries go in slices
@@ -187,7 +202,16 @@ def sort_scores(scores: ArrayLike, top_k: Optional[int] = None, descending: bool
         b = min(nq, a + step)
         _lib.check(lib.qrag_sort_scores_stable(_ptr(s[a:b]), b - a, C, k, 1 if descending else 0, _ptr(perm[a:b]),
                                                _ptr(srt[a:b]), _ptr(ws), nbytes.value, _stream()))
-    return perm, srt
+    return perm, srt, both
+
+
+def sort_scores_host(scores: ArrayLike, top_k: Optional[int] = None, descending: bool = True):
+    """``sort_scores`` with the result on the host as two NumPy arrays (perm int32 [nq, k], sorted fp64 [nq, k]):
+    one device-to-host copy for both (what the string API needs for its list of tuples)."""
+    perm, _, both = _sort_scores(scores, top_k, descending)
+    nq, k = perm.shape
+    host = both.cpu().numpy()
+    return host[nq * k * 8:].view(np.int32).reshape(nq, k), host[: nq * k * 8].view(np.float64).reshape(nq, k)
 
 
 def quantum_rerank_batch(Q: ArrayLike, cand: Optional[ArrayLike] = None, X: Optional[ArrayLike] = None,

@@ -32,9 +32,12 @@ QISKIT_AVAILABLE = True
 
 
 def _char_sum(text: str) -> int:
-    """sum(ord(c)) -- quantum.py:182 (vectorised over the UTF-32 code units)."""
+    """sum(ord(c)) -- quantum.py:182.  ASCII text: the byte sum (one C loop); anything else: vectorised over the
+    UTF-32 code units."""
     if not text:
         return 0
+    if text.isascii():
+        return sum(text.encode("ascii"))
     return int(np.frombuffer(text.encode("utf-32-le", "surrogatepass"), dtype="<u4").sum(dtype=np.uint64))
 
 
@@ -102,14 +105,19 @@ class QuantumReranker:
         return vec
 
     def _text_embeddings(self, query: str, documents: List[Document]):
+        import torch
         from .. import api
         if self.embedding_backend == "device":
             seeds = np.array([_char_sum(query)] + [_char_sum(d.content) for d in documents], dtype=np.int64)
             emb = api.mock_embedding(seeds, self.n_qubits)
             return emb[:1], emb[1:]
-        q = self._mock_embedding(query)[None, :]
-        d = np.stack([self._mock_embedding(doc.content) for doc in documents])
-        return q, d
+        # query and documents in ONE array: one host-to-device copy, sliced on the device
+        both = np.empty((1 + len(documents), 2 * self.n_qubits), dtype=np.float64)
+        both[0] = self._mock_embedding(query)
+        for i, doc in enumerate(documents):
+            both[i + 1] = self._mock_embedding(doc.content)
+        dev = api._dev(both, torch.float64)
+        return dev[:1], dev[1:]
 
     def _real_embeddings(self, query: str, documents: List[Document]):
         docs_e = [d.metadata.get(self.embedding_key) if isinstance(d.metadata, dict) else None for d in documents]
@@ -146,5 +154,5 @@ class QuantumReranker:
         """(input positions, scores) in final order: score desc, input position asc."""
         from .. import api
         scores = self._scores(query, documents)
-        perm, srt = api.sort_scores(scores[None, :], None, descending=True)
-        return perm[0].cpu().tolist(), srt[0].cpu().tolist()
+        perm, srt = api.sort_scores_host(scores[None, :], None, descending=True)     # one device-to-host copy for both
+        return perm[0].tolist(), srt[0].tolist()
