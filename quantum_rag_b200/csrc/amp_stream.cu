@@ -591,7 +591,14 @@ int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, in
     const bool nchunk_path = (D == 128 || D == 256 || D == 384 || D == 512);
     // CTA shape: the interleaved half-size shape when the caller asked for it (QRAG_OVERLAP_INTERLEAVED) and every SM
     // gets a CTA; its shared-memory budget is half an SM's (two CTAs of consecutive launches share the SM)
-    const int q_per_cta = (int)ceil_div(nq, dp.sm_count);
+    // CTAs per SM and launch in the interleaved shape (tuning build: QRAG_AMP_STREAM_CPS=2 fills both slots of every
+    // SM from ONE launch, so a launch with no neighbour on the stream still uses the whole SM)
+    int cps = 1;
+#ifdef QRAG_TUNING
+    if (const char* e = getenv("QRAG_AMP_STREAM_CPS")) { const int v = atoi(e); if (v == 1 || v == 2) cps = v; }
+#endif
+    if (nq < cps * dp.sm_count) cps = 1;
+    const int q_per_cta = (int)ceil_div(nq, (int64_t)dp.sm_count * cps);
     const size_t out_stage = (size_t)q_per_cta * top_k * 20 + 16;      // staged results: fp64 score, int64 id, int32 position
     const bool half = p.overlap == QRAG_OVERLAP_INTERLEAVED && fused && nq >= dp.sm_count && out_stage <= 8 * 1024;
     const int cw = half ? AS_CWARPS_HALF : AS_CWARPS;
@@ -620,7 +627,7 @@ int amp_stream_try(const float* Q, int nq, const float* cand, const float* X, in
     if ((int64_t)p.tpq * nq / dp.sm_count > ((int64_t)1 << 30)) return QRAG_OK;
     if (half) smem_bytes += out_stage;                        // the staging area sits behind the ring
 
-    int grid = dp.sm_count;
+    int grid = half ? dp.sm_count * cps : dp.sm_count;
     if (fused) {
         if (grid > nq) grid = nq;
     } else {

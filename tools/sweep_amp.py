@@ -26,8 +26,13 @@ def main():
     ap.add_argument("--configs", default="default,4x4,8x4,8x2")
     ap.add_argument("--overlap", default="0,1,2,3")
     ap.add_argument("--gather", action="store_true", help="candidates named by random ids into a resident corpus")
+    ap.add_argument("--region", type=int, default=0, help="also time regions of this many steps with a synchronise "
+                    "between them (what bench.py --steps K measures), median of 15")
+    ap.add_argument("--cps", default="1", help="comma list of QRAG_AMP_STREAM_CPS values (CTAs per SM and launch, interleaved shape)")
+    ap.add_argument("--no-build", action="store_true", help="the tuning build is already in the tree (built where nvcc is fast)")
     a = ap.parse_args()
-    _lib.build(force=True, tuning=True)       # the switches below only exist in a -DQRAG_TUNING build
+    if not a.no_build:
+        _lib.build(force=True, tuning=True)   # the switches below only exist in a -DQRAG_TUNING build
     lib = _lib.load()
     g = torch.Generator().manual_seed(7)
     nsets = max(2, int(520e6 / (a.nq * a.C * a.D * 4)) + 1)
@@ -52,8 +57,9 @@ def main():
                                        api._ptr(scores), api._ptr(pos), None, api._stream()))
 
     ref = None
-    for cfg, ov in [(c, int(o)) for c in a.configs.split(",") for o in a.overlap.split(",")]:
+    for cfg, ov, cps in [(c, int(o), x) for c in a.configs.split(",") for o in a.overlap.split(",") for x in a.cps.split(",")]:
         api.set_overlap(ov)
+        os.environ["QRAG_AMP_STREAM_CPS"] = cps
         os.environ.pop("QRAG_AMP_STREAM_G", None)
         os.environ.pop("QRAG_AMP_STREAM_RB", None)
         if cfg != "default":
@@ -76,11 +82,25 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / a.steps
-        print(f"GxRB={cfg:8s} overlap={ov} {us:8.2f} us/launch  {nbytes / us / 1e3:8.1f} GB/s  same_as_first={same}", flush=True)
+        reg = ""
+        if a.region:
+            ts = []
+            for _ in range(15):
+                torch.cuda.synchronize()
+                e0.record()
+                for i in range(a.region):
+                    step(i)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e3 / a.region)
+            ts.sort()
+            reg = f"  regions of {a.region}: median {ts[7]:.2f} us/launch ({nbytes / ts[7] / 1e3:.0f} GB/s), min {ts[0]:.2f}"
+        print(f"GxRB={cfg:8s} overlap={ov} cps={cps} {us:8.2f} us/launch  {nbytes / us / 1e3:8.1f} GB/s  same_as_first={same}{reg}", flush=True)
 
 
 if __name__ == "__main__":
     try:
         main()
     finally:
-        _lib.build(force=True)                # never leave the tuning build in the tree: what ships reads no environment
+        if "--no-build" not in sys.argv:
+            _lib.build(force=True)            # never leave the tuning build in the tree: what ships reads no environment
