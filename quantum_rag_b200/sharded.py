@@ -218,6 +218,14 @@ class ShardedSearchRerank:
                 except Exception:
                     pass
 
+    def _join_lanes(self) -> None:
+        """Order the caller's stream after everything queued on the lanes.  The all-gather form (``search``: the rerun
+        route, ``return_search_lists=True``) runs on the caller's stream with lane 0's search workspace, which a batch
+        still in flight on lane 0's own stream may be using."""
+        for side in self._lane_streams:
+            if side is not None:
+                torch.cuda.current_stream().wait_stream(side)
+
     def use_lanes(self, n: int) -> None:
         """Run the following ``submit`` calls over the first ``n`` lanes (1 = every batch behind the previous one on one
         stream and one communicator; the bench's A/B).  Every rank must make the same call, between batches."""
@@ -265,6 +273,7 @@ class ShardedSearchRerank:
         an all-reduce inside the search), so that each shard rescores only its ~1/G share of the
         global list; any query a shard could not certify makes every rank rerun it exactly.
         """
+        self._join_lanes()
         if self.world > 1 and hasattr(self.engine, "search_sharded"):
             s, i, status = self.engine.search_sharded(Q, k1, self._all_gather, self._all_reduce_sum, self.world)
             self._mark("search_phases")
@@ -399,9 +408,7 @@ class ShardedSearchRerank:
                 done = torch.cuda.Event()
                 done.record(side)
             return PendingResult(self, Q, k1, k2, top, ids, flag, done)
-        for side in self._lane_streams:                             # the replay shares lane 0's workspace and buffers
-            if side is not None:
-                torch.cuda.current_stream().wait_stream(side)
+        self._join_lanes()                                          # the replay shares lane 0's workspace and buffers
         key = (tuple(Q.shape), k1, k2)
         g = self._graphs.get(key)
         if g is None:
