@@ -252,12 +252,12 @@ class ShardedSearchRerank:
             return t[None]
         t = t.contiguous()
         out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t, group=group or self.group)  # concatenation along dim 0
+        dist.all_gather_into_tensor(out, t, group=self.group if group is None else group)  # concatenation along dim 0
         return out.view((self.world,) + tuple(t.shape))
 
     def _all_reduce_sum(self, t: torch.Tensor, group=None) -> torch.Tensor:
         if self.world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group or self.group)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group if group is None else group)
         return t
 
     def _all_reduce_max(self, t: torch.Tensor) -> torch.Tensor:
