@@ -313,6 +313,15 @@ def _laned_worker(rank, world, port, n, d, nq, k1, k2, metric, out):
         res = [p.result() for p in pend]
         again = path(batches[1], k1, k2)                     # one at a time after the queue drained
         nbufs = [len(b) for b in path._lane_bufs]
+        with pytest.raises(ValueError):
+            path.use_lanes(3)                                # only two lanes were created
+        path.use_lanes(1)                                    # the bench's A/B: the same queue through lane 0 alone
+        one = [path.submit(Q, k1, k2) for Q in batches[:2]]
+        assert path._next_lane == 0
+        for b, p_ in enumerate(one):
+            r = p_.result()
+            assert torch.equal(r.ids, res[b].ids) and torch.equal(r.scores, res[b].scores)
+        path.use_lanes(2)
         path.close()                                         # drops the second lane's group: one lane from here on
         assert path.n_lanes == 1 and len(path._lane_groups) == 1
         closed = path(batches[2], k1, k2)
