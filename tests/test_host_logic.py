@@ -244,3 +244,19 @@ def test_embedding_memo_is_bounded_and_qubit_range_is_checked_up_front():
     with pytest.raises(ValueError, match="n_qubits"):
         QuantumReranker({"n_qubits": 13})
     assert QuantumReranker({"n_qubits": 12}).n_qubits == 12
+
+
+def test_char_sum_fast_paths_agree_with_the_definition():
+    """sum(ord(c)) (quantum.py:182): the ASCII byte-sum path and the UTF-32 path against the definition, on random
+    strings that mix ASCII, Latin-1, BMP and astral code points (and the lone-surrogate case Python strings allow)."""
+    rng = np.random.RandomState(5)
+    pools = [(32, 127), (128, 256), (0x400, 0x500), (0x4E00, 0x4F00), (0x1F600, 0x1F650)]
+    for trial in range(300):
+        n = int(rng.randint(0, 60))
+        chars = []
+        for _ in range(n):
+            lo, hi = pools[int(rng.randint(0, len(pools) if trial % 3 else 1))]
+            chars.append(chr(int(rng.randint(lo, hi))))
+        text = "".join(chars)
+        assert _char_sum(text) == sum(ord(c) for c in text), repr(text)
+    assert _char_sum("\ud800x") == 0xD800 + ord("x")
